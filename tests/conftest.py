@@ -1,0 +1,50 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line(
+        'markers', 'gpu: needs a CUDA device (run with -m gpu on a B200)')
+    config.addinivalue_line(
+        'markers', 'reference: needs the real reference at /root/reference')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+@pytest.fixture(scope='session')
+def golden():
+    return load_golden
+
+
+def reference_pints():
+    """The real reference, when it is mounted (build container only)."""
+    ref = os.environ.get('PINTS_REFERENCE', '/root/reference')
+    if not os.path.isdir(os.path.join(ref, 'pints')):
+        return None
+    if ref not in sys.path:
+        sys.path.append(ref)
+    sys.dont_write_bytecode = True
+    try:
+        import pints
+        import pints.toy  # noqa: F401
+    except Exception:
+        return None
+    return pints
+
+
+@pytest.fixture(scope='session')
+def pints_ref():
+    p = reference_pints()
+    if p is None:
+        pytest.skip('reference not available')
+    return p
