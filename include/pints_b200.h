@@ -1,0 +1,238 @@
+/*
+ * pints_b200.h -- C ABI of the B200-native batched evaluation engine for PINTS.
+ *
+ * This is the drop-in boundary of the one hot path this repository
+ * accelerates: scoring N parameter vectors as
+ *
+ *     model.simulate(x, times) -> residual -> sum of squares -> objective
+ *
+ * in one fused launch, plus the per-iteration state update of two MCMC
+ * samplers.  The reference (pints-team/pints v0.6.2) is pure Python and has no
+ * FFI of its own; every entry point below names the reference function
+ * (file:line, relative to the reference root) whose work it replaces.  The
+ * binding a maintainer would add is the ctypes shim in
+ * pints_b200/_lib.py (shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, scalars.  No C++ or torch types.
+ *  - every function returns 0 on success and a negative PB200_E* code on
+ *    failure; pb200_last_error() returns a thread-local message.  Nothing is
+ *    thrown across the boundary and nothing aborts.
+ *  - pointers named d_* are DEVICE pointers owned by the caller (in this
+ *    repository: torch tensors).  The library never allocates or frees device
+ *    memory; a pb200_problem is a small host object holding constants and the
+ *    caller's d_series pointer, which must stay valid while it is used.
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream).  All work
+ *    is enqueued asynchronously on it; the caller synchronises.
+ *  - like the reference evaluators (pints/_evaluation.py:156-158) one problem
+ *    handle must not be used from several host threads at once; distinct
+ *    handles and streams are independent.
+ *  - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef PINTS_B200_H
+#define PINTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_VERSION 100           /* 0.1.0 */
+
+/* error codes */
+#define PB200_OK            0
+#define PB200_EINVAL       -1       /* bad argument                        */
+#define PB200_EUNSUPPORTED -2       /* model/objective/size not supported   */
+#define PB200_ECUDA        -3       /* CUDA runtime error (see last_error)  */
+#define PB200_ENOMEM       -4       /* host allocation failed               */
+
+/* forward models (pints/toy/...) */
+#define PB200_MODEL_LOGISTIC        0   /* _logistic_model.py:62-86            */
+#define PB200_MODEL_HH_IK           1   /* _hh_ik_model.py:135-214             */
+#define PB200_MODEL_CONSTANT        2   /* _constant_model.py:75-93            */
+#define PB200_MODEL_FHN             3   /* _fitzhugh_nagumo_model.py:111-117   */
+#define PB200_MODEL_LOTKA_VOLTERRA  4   /* _lotka_volterra_model.py:91-97      */
+#define PB200_MODEL_SIR             5   /* _sir_model.py:96-111                */
+#define PB200_N_MODELS              6
+
+/* objectives */
+#define PB200_OBJ_SSE                   0  /* pints/_error_measures.py:373-376     */
+#define PB200_OBJ_GAUSSIAN_KNOWN_SIGMA  1  /* pints/_log_likelihoods.py:1012-1041  */
+#define PB200_OBJ_GAUSSIAN              2  /* pints/_log_likelihoods.py:1110-1129  */
+#define PB200_N_OBJECTIVES              3
+
+#define PB200_MAX_OUTPUTS   8
+#define PB200_MAX_PARAMS    16      /* model parameters + sigma parameters  */
+#define PB200_MAX_EVENTS    64      /* HH-IK protocol events                */
+
+typedef struct pb200_problem pb200_problem;
+
+/* Adaptive Dormand-Prince 5(4) controls for the ODE models.  The reference
+ * integrates with scipy's LSODA at rtol = atol = 1.49012e-8
+ * (pints/toy/_toy_classes.py:225-233); the defaults here match that. */
+typedef struct pb200_solver_opts {
+    double  rtol;        /* <= 0 -> 1.49012e-8                               */
+    double  atol;        /* <= 0 -> 1.49012e-8                               */
+    double  h0;          /* first step; <= 0 -> automatic                    */
+    int32_t max_steps;   /* attempted steps per vector; <= 0 -> 1000000.     */
+                         /* A vector that exceeds it scores NaN.             */
+    int32_t block;       /* threads per block; <= 0 -> automatic             */
+} pb200_solver_opts;
+
+int         pb200_version(void);
+const char *pb200_last_error(void);
+
+/* Number of doubles the packed series buffer must hold (see below). */
+int64_t pb200_series_len(int32_t n_times, int32_t n_outputs);
+
+/*
+ * Describe one inference problem: a forward model, the observed series and an
+ * objective.  Replaces the object graph
+ *   ErrorMeasure/LogPDF -> Single/MultiOutputProblem -> ForwardModel
+ * (pints/_core.py:102-327, pints/_log_pdfs.py:134-241).
+ *
+ * d_series   device buffer of pb200_series_len() doubles, 16-byte aligned:
+ *            n_times rows of [t_j, v_j0 .. v_j(n_outputs-1)], zero padded.
+ *            Times must be non-negative and non-decreasing
+ *            (pints/_core.py:129-133, :238-242); the caller checks that.
+ * model_consts (host)
+ *   LOGISTIC        [p0]
+ *   HH_IK           [n0, g_max, E_k, v_hold, n_events, events[n_events],
+ *                    voltages[n_events]]   voltages[i] applies after events[i]
+ *   CONSTANT        []           (n_outputs parameters, output o = p_o*(o+1))
+ *   FHN             [y0_V, y0_R]
+ *   LOTKA_VOLTERRA  [y0_x, y0_y]
+ *   SIR             [y0_S (unused), y0_I, y0_R, truncate_S0 (0|1)]
+ * obj_consts (host)
+ *   SSE                   weights[n_outputs]
+ *   GAUSSIAN_KNOWN_SIGMA  offset[n_outputs], multip[n_outputs]
+ *   GAUSSIAN              [0.5 * n_times * log(2 pi)]
+ * sign       +1, or -1 for ProbabilityBasedError
+ *            (pints/_error_measures.py:183-184)
+ * prior_lower/upper (host, n_prior entries or NULL/0): box of a
+ *            UniformLogPrior combined through LogPosterior
+ *            (pints/_log_pdfs.py:207-212, pints/_log_priors.py:1319-1320);
+ *            log_prior_value is the prior's constant inside the box.
+ */
+int pb200_problem_create(int32_t model, int32_t objective,
+                         int32_t n_times, int32_t n_outputs,
+                         const double *d_series,
+                         const double *model_consts, int32_t n_model_consts,
+                         const double *obj_consts, int32_t n_obj_consts,
+                         double sign,
+                         const double *prior_lower, const double *prior_upper,
+                         int32_t n_prior, double log_prior_value,
+                         pb200_problem **out);
+void pb200_problem_destroy(pb200_problem *p);
+
+/* Row length of a parameter vector for this problem
+ * (model parameters + n_outputs sigmas for GAUSSIAN). */
+int32_t pb200_problem_n_parameters(const pb200_problem *p);
+
+/*
+ * Score n parameter vectors: the fused replacement of
+ *   SequentialEvaluator._evaluate / ParallelEvaluator._evaluate
+ *   (pints/_evaluation.py:478-482, :284-372)
+ * and everything they call per vector.  Trajectories never leave the SM.
+ *
+ * d_params  n rows of `ld` doubles (ld >= n_parameters), row major
+ * d_scores  n doubles
+ * d_steps   n int32 or NULL: attempted RK steps per vector (ODE models),
+ *           0 for closed-form models; used for flop accounting
+ */
+int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n,
+               int64_t ld, double *d_scores, int32_t *d_steps,
+               const pb200_solver_opts *opts, void *stream);
+
+/*
+ * Batched ForwardModel.simulate / Problem.evaluate
+ * (pints/_core.py:147-153, :257-265): writes the n trajectories
+ * d_traj[n][n_times][n_outputs].  Also the first half of the unfused baseline.
+ */
+int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n,
+                   int64_t ld, double *d_traj, int32_t *d_steps,
+                   const pb200_solver_opts *opts, void *stream);
+
+/* Second half of the unfused baseline: objective from stored trajectories. */
+int pb200_score_trajectories(const pb200_problem *p, const double *d_traj,
+                             const double *d_params, int64_t n, int64_t ld,
+                             double *d_scores, void *stream);
+
+/*
+ * Metropolis accept/reject for n chains (bit-exact with the reference given
+ * the same inputs):  accept_j = isfinite-or-not rule AND log_u_j < fx_j - cur_f_j
+ *   require_finite = 1: AdaptiveCovarianceMC.tell
+ *                       (pints/_mcmc/_adaptive_covariance.py:264-278)
+ *   require_finite = 0: DifferentialEvolutionMCMC.tell
+ *                       (pints/_mcmc/_differential_evolution.py:314-326)
+ * Updates d_current[n][d] / d_current_f[n] in place from d_proposed / d_fx and
+ * writes d_accepted[n] (uint8).
+ */
+int pb200_mh_accept(double *d_current, double *d_current_f,
+                    const double *d_proposed, const double *d_fx,
+                    const double *d_log_u, uint8_t *d_accepted,
+                    int64_t n, int32_t d, int32_t require_finite,
+                    void *stream);
+
+/*
+ * Haario-Bardenet adaptation after the accept step
+ * (pints/_mcmc/_adaptive_covariance.py:286-300, :88-107;
+ *  pints/_mcmc/_haario_bardenet_ac.py:65-68), separately rounded products and
+ * sums exactly as NumPy evaluates them.  gamma = (adaptations + 1) ** -eta is
+ * chain independent and computed by the caller.
+ */
+int pb200_hbac_adapt(const double *d_current, const uint8_t *d_accepted,
+                     double *d_mu, double *d_sigma, double *d_log_lambda,
+                     int64_t n, int32_t d, double gamma, double target,
+                     void *stream);
+
+/*
+ * Device-side proposals for the Haario-Bardenet sampler:
+ *   x* = x + L z,  L L^T = sigma * exp(log_lambda)   (Cholesky, in-thread)
+ * The reference factors with LAPACK's SVD inside numpy.random.multivariate_normal
+ * (pints/_mcmc/_haario_bardenet_ac.py:70-73); Cholesky gives a different but
+ * equally distributed proposal, so this entry point is statistical parity
+ * only.  d_z holds n*d standard normals (see pb200_philox_normal).
+ */
+int pb200_hbac_propose(const double *d_current, const double *d_sigma,
+                       const double *d_log_lambda, const double *d_z,
+                       double *d_proposed, int64_t n, int32_t d,
+                       void *stream);
+
+/*
+ * Differential-evolution proposals
+ * (pints/_mcmc/_differential_evolution.py:103-115):
+ *   x*_j = (x_j + gamma * (x_r1 - x_r2)) + eps_j      left to right, no FMA
+ * d_current_all holds the positions of ALL chains (e.g. after an all-gather),
+ * d_r1/d_r2 are int32 chain indices into it; this call proposes for the n
+ * chains [first, first + n), and d_eps/d_r1/d_r2/d_proposed have n rows.
+ */
+int pb200_de_propose(const double *d_current_all, int64_t first,
+                     const double *d_eps, const int32_t *d_r1,
+                     const int32_t *d_r2, double *d_proposed, int64_t n,
+                     int32_t d, double gamma, void *stream);
+
+/* Counter-based RNG (Philox4x32-10): n doubles, N(0,1) or U(0,1), for
+ * (seed, stream_id, offset).  Used only in device-RNG sampler mode. */
+int pb200_philox_normal(double *d_out, int64_t n, uint64_t seed,
+                        uint64_t offset, void *stream);
+int pb200_philox_uniform(double *d_out, int64_t n, uint64_t seed,
+                         uint64_t offset, void *stream);
+/* two distinct indices != j, uniform over the other n_total - 1 chains */
+int pb200_philox_pairs(int32_t *d_r1, int32_t *d_r2, int64_t n,
+                       int64_t first, int64_t n_total, uint64_t seed,
+                       uint64_t offset, void *stream);
+
+/*
+ * FP64 FMA-pipe probe: every thread runs `iters` rounds of 8 independent
+ * dependent-FMA chains.  Executes 16 * iters flop per thread.  The caller
+ * times it with events; used as the measured FP64 roofline denominator.
+ */
+int pb200_fp64_probe(double *d_sink, int32_t blocks, int32_t threads,
+                     int64_t iters, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINTS_B200_H */

@@ -1,0 +1,193 @@
+"""
+Device side of a problem: uploads the packed series, owns the
+``pb200_problem`` handle, and launches the fused kernels on torch-owned device
+buffers.  PyTorch is used for device memory, streams and events only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._spec import ProblemSpec
+
+DEFAULT_RTOL = 1.49012e-8       # scipy odeint's default, used by the reference
+DEFAULT_ATOL = 1.49012e-8
+
+
+def require_cuda(device=None):
+    """The torch device to run on; raises when there is no GPU (there is no
+    CPU implementation behind this package)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            'pints_b200 needs a CUDA device (built for NVIDIA B200, sm_100a); '
+            'no GPU is visible and there is no CPU fallback.')
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('pints_b200 runs on CUDA devices only, got %s'
+                           % device)
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    return device
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def solver_opts(rtol=None, atol=None, h0=None, max_steps=None, block=None):
+    return _lib.SolverOpts(
+        rtol if rtol else DEFAULT_RTOL, atol if atol else DEFAULT_ATOL,
+        h0 if h0 else 0.0, int(max_steps) if max_steps else 0,
+        int(block) if block else 0)
+
+
+class DeviceProblem(object):
+    """A ``ProblemSpec`` resident on one GPU."""
+
+    def __init__(self, spec, device=None, **opts):
+        if not isinstance(spec, ProblemSpec):
+            raise TypeError('spec must be a ProblemSpec')
+        self.spec = spec
+        self.device = require_cuda(device)
+        self._lib = _lib.load()
+        self.opts = solver_opts(**opts)
+        with torch.cuda.device(self.device):
+            self._series = torch.from_numpy(spec.packed_series()).to(
+                self.device)
+            mc, n_mc = _lib.doubles(spec.model_consts)
+            oc, n_oc = _lib.doubles(spec.obj_consts)
+            lo = hi = None
+            n_prior = 0
+            if spec.prior_lower is not None:
+                lo, n_prior = _lib.doubles(spec.prior_lower)
+                hi, _ = _lib.doubles(spec.prior_upper)
+            handle = ctypes.c_void_p()
+            _lib.check(self._lib.pb200_problem_create(
+                spec.model, spec.objective, spec.n_times, spec.n_outputs,
+                _ptr(self._series), mc, n_mc, oc, n_oc, spec.sign, lo, hi,
+                n_prior, spec.log_prior, ctypes.byref(handle)))
+        self._handle = handle
+        self.n_parameters = spec.n_parameters()
+        self.n_model_parameters = spec.n_model_parameters()
+
+    def __del__(self):
+        h = getattr(self, '_handle', None)
+        if h:
+            try:
+                self._lib.pb200_problem_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # ------------------------------------------------------------------
+    def _check_params(self, d_params, width):
+        if d_params.dtype != torch.float64 or d_params.dim() != 2:
+            raise ValueError('parameters must be a 2-d float64 tensor')
+        if d_params.device != self.device:
+            raise ValueError('parameters live on %s, problem on %s'
+                             % (d_params.device, self.device))
+        if d_params.shape[1] < width:
+            raise ValueError(
+                'Expected %d parameters per vector, got %d.'
+                % (width, d_params.shape[1]))
+        if d_params.stride(1) != 1:
+            d_params = d_params.contiguous()
+        return d_params
+
+    def eval(self, d_params, out=None, steps=None):
+        """Scores of the rows of ``d_params`` (device tensor ``(n, d)``);
+        asynchronous on the current stream.  Returns a device tensor."""
+        d_params = self._check_params(d_params, self.n_parameters)
+        n = d_params.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pb200_eval(
+                self._handle, _ptr(d_params), n, d_params.stride(0),
+                _ptr(out), _ptr(steps), ctypes.byref(self.opts),
+                _stream_ptr(self.device)))
+        return out
+
+    def simulate(self, d_params, out=None, steps=None):
+        """Trajectories ``(n, n_times, n_outputs)`` of the rows of
+        ``d_params`` (only the model parameters are read)."""
+        d_params = self._check_params(d_params, self.n_model_parameters)
+        n = d_params.shape[0]
+        if out is None:
+            out = torch.empty((n, self.spec.n_times, self.spec.n_outputs),
+                              dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pb200_simulate(
+                self._handle, _ptr(d_params), n, d_params.stride(0),
+                _ptr(out), _ptr(steps), ctypes.byref(self.opts),
+                _stream_ptr(self.device)))
+        return out
+
+    def score_trajectories(self, d_traj, d_params, out=None):
+        """Unfused baseline, second half: objective from stored
+        trajectories."""
+        d_params = self._check_params(d_params, self.n_parameters)
+        n = d_params.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pb200_score_trajectories(
+                self._handle, _ptr(d_traj), _ptr(d_params), n,
+                d_params.stride(0), _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def new_steps(self, n):
+        return torch.zeros(n, dtype=torch.int32, device=self.device)
+
+
+def positions_to_array(positions, width=None):
+    """Evaluator input -> contiguous float64 ``(n, d)`` host array.  Accepts
+    what the reference's controllers pass: a 2-d (read-only) ndarray or a list
+    of 1-d arrays (pints/_mcmc/__init__.py:718)."""
+    if isinstance(positions, np.ndarray) and positions.ndim == 2:
+        xs = np.ascontiguousarray(positions, dtype=np.float64)
+    else:
+        n = len(positions)
+        if n == 0:
+            return np.zeros((0, width or 0), dtype=np.float64)
+        xs = np.array([np.asarray(x, dtype=np.float64).reshape(-1)
+                       for x in positions], dtype=np.float64)
+        if xs.ndim != 2:
+            raise ValueError('All positions must have the same length.')
+    if width is not None and xs.shape[0] > 0 and xs.shape[1] != width:
+        raise ValueError('Expected positions with %d parameters, got %d.'
+                         % (width, xs.shape[1]))
+    return xs
+
+
+def fp64_probe(device=None, iters=20000, blocks_per_sm=4, threads=256,
+               repeats=3):
+    """Measured FP64 FMA throughput (TFLOP/s) of the device: the roofline
+    denominator for the fused ODE kernel (MEASURED_PEAKS.json has none)."""
+    device = require_cuda(device)
+    lib = _lib.load()
+    props = torch.cuda.get_device_properties(device)
+    blocks = props.multi_processor_count * blocks_per_sm
+    sink = torch.zeros(8, dtype=torch.float64, device=device)
+    best = 0.0
+    with torch.cuda.device(device):
+        for r in range(repeats + 1):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.pb200_fp64_probe(_ptr(sink), blocks, threads,
+                                            iters, _stream_ptr(device)))
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            flops = 16.0 * iters * blocks * threads
+            if r > 0:
+                best = max(best, flops / (ms * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,218 @@
+"""
+Host-side description of one (model, series, objective) problem and the
+introspection that derives it from an objective object.
+
+The reference has no evaluator plug-in hook and no operator registry
+(SURVEY.md section 8b): the function handed to an evaluator is an object graph
+
+    [ProbabilityBasedError] -> [LogPosterior] -> SumOfSquaresError |
+        GaussianKnownSigmaLogLikelihood | GaussianLogLikelihood
+        -> SingleOutputProblem | MultiOutputProblem -> toy model
+
+``describe()`` peels that graph, for reference objects and for the mirror
+classes of this package alike (both keep their state in the same private
+attributes), into a ``ProblemSpec`` whose fields are exactly the arguments of
+``pb200_problem_create``.  Anything it does not recognise raises ``TypeError``:
+there is deliberately no "call the Python function instead" path.
+"""
+import numpy as np
+
+from . import _lib
+
+_OWNERS = ('pints', 'pints_b200')
+
+
+def _owned(obj):
+    mod = type(obj).__module__ or ''
+    return mod.split('.')[0] in _OWNERS
+
+
+def _kind(obj):
+    """Class name of objects defined by the reference or by this package; a
+    user subclass (which may override anything) is not trusted."""
+    return type(obj).__name__ if _owned(obj) else None
+
+
+class ProblemSpec(object):
+    """Plain-data problem description (host arrays only)."""
+
+    def __init__(self, model, model_consts, times, values, objective,
+                 obj_consts, sign=1.0, prior_lower=None, prior_upper=None,
+                 log_prior=0.0, multi_output=None):
+        self.model = int(model)
+        self.model_consts = [float(v) for v in model_consts]
+        self.times = np.ascontiguousarray(times, dtype=np.float64)
+        values = np.asarray(values, dtype=np.float64)
+        if multi_output is None:
+            multi_output = values.ndim == 2
+        self.multi_output = bool(multi_output)
+        if values.ndim == 1:
+            values = values.reshape((-1, 1))
+        self.values = np.ascontiguousarray(values)
+        self.n_times = int(self.times.shape[0])
+        self.n_outputs = int(self.values.shape[1])
+        if self.values.shape[0] != self.n_times:
+            raise ValueError('Times and values arrays must have same length.')
+        self.objective = int(objective)
+        self.obj_consts = [float(v) for v in obj_consts]
+        self.sign = float(sign)
+        self.prior_lower = None if prior_lower is None else \
+            [float(v) for v in prior_lower]
+        self.prior_upper = None if prior_upper is None else \
+            [float(v) for v in prior_upper]
+        self.log_prior = float(log_prior)
+
+    # ------------------------------------------------------------------
+    def n_model_parameters(self):
+        fixed = {_lib.MODEL_LOGISTIC: 2, _lib.MODEL_HH_IK: 5,
+                 _lib.MODEL_FHN: 3, _lib.MODEL_LOTKA_VOLTERRA: 4,
+                 _lib.MODEL_SIR: 3}
+        return fixed.get(self.model, self.n_outputs)
+
+    def n_parameters(self):
+        extra = self.n_outputs if self.objective == _lib.OBJ_GAUSSIAN else 0
+        return self.n_model_parameters() + extra
+
+    def is_ode(self):
+        return self.model in (_lib.MODEL_FHN, _lib.MODEL_LOTKA_VOLTERRA,
+                              _lib.MODEL_SIR)
+
+    def packed_series(self):
+        """Rows ``[t_j, v_j0 ..]`` padded to whole 16-byte units, the layout
+        ``pb200_problem_create`` expects in device memory."""
+        row = 1 + self.n_outputs
+        n = self.n_times * row
+        out = np.zeros((n + 1) & ~1, dtype=np.float64)
+        block = out[:n].reshape((self.n_times, row))
+        block[:, 0] = self.times
+        block[:, 1:] = self.values
+        return out
+
+    def flops_per_eval(self, steps):
+        """Algorithmic FP64 flop of one evaluation given the attempted RK
+        steps: FHN 234 S + 24 n_t, LV 222 S + 24 n_t,
+        SIR 298 S + 32 n_t; closed-form models 8 n_t / 12 n_t + 750."""
+        nt = self.n_times
+        steps = np.asarray(steps, dtype=np.float64)
+        if self.model == _lib.MODEL_FHN:
+            return 234.0 * steps + 24.0 * nt
+        if self.model == _lib.MODEL_LOTKA_VOLTERRA:
+            return 222.0 * steps + 24.0 * nt
+        if self.model == _lib.MODEL_SIR:
+            return 298.0 * steps + 32.0 * nt
+        if self.model == _lib.MODEL_HH_IK:
+            return 0.0 * steps + 12.0 * nt + 750.0
+        return 0.0 * steps + 8.0 * nt * self.n_outputs
+
+
+# ----------------------------------------------------------------------
+# model introspection
+# ----------------------------------------------------------------------
+
+def describe_model(model):
+    """(model id, constants) of a toy model object; ``TypeError`` otherwise."""
+    kind = _kind(model)
+    if kind == 'LogisticModel':
+        return _lib.MODEL_LOGISTIC, [model._p0]
+    if kind == 'HodgkinHuxleyIKModel':
+        events = np.asarray(model._events, dtype=float)
+        volts = np.asarray(model._voltages, dtype=float)
+        if len(events) != len(volts) or len(events) > _lib.MAX_EVENTS:
+            raise TypeError('unsupported voltage protocol')
+        return _lib.MODEL_HH_IK, [model._n0, model._g_max, model._E_k,
+                                  model._v_hold, len(events)] \
+            + list(events) + list(volts)
+    if kind == 'ConstantModel':
+        n = int(model._n)
+        if n > _lib.MAX_OUTPUTS:
+            raise TypeError('ConstantModel with more than %d outputs'
+                            % _lib.MAX_OUTPUTS)
+        if not np.array_equal(np.asarray(model._r), np.arange(1, 1 + n)):
+            raise TypeError('unexpected ConstantModel multipliers')
+        return _lib.MODEL_CONSTANT, []
+    if kind == 'FitzhughNagumoModel':
+        y0 = np.asarray(model._y0, dtype=float)
+        return _lib.MODEL_FHN, [y0[0], y0[1]]
+    if kind == 'LotkaVolterraModel':
+        y0 = np.asarray(model._y0, dtype=float)
+        return _lib.MODEL_LOTKA_VOLTERRA, [y0[0], y0[1]]
+    if kind == 'SIRModel':
+        y0 = np.asarray(model._y0)
+        # an integer y0 (the default) truncates S0 on assignment
+        truncate = 1.0 if y0.dtype.kind in 'iu' else 0.0
+        return _lib.MODEL_SIR, [float(y0[0]), float(y0[1]), float(y0[2]),
+                                truncate]
+    raise TypeError(
+        'CudaEvaluator supports the toy models LogisticModel, '
+        'HodgkinHuxleyIKModel, ConstantModel, FitzhughNagumoModel, '
+        'LotkaVolterraModel and SIRModel; got %s.%s (no CPU fallback).'
+        % (type(model).__module__, type(model).__name__))
+
+
+def describe(function):
+    """``ProblemSpec`` of an objective object graph; ``TypeError`` if any part
+    of it is outside the supported hot path."""
+    sign = 1.0
+    prior = None
+    f = function
+    for _ in range(8):
+        kind = _kind(f)
+        if kind == 'ProbabilityBasedError':
+            sign = -sign
+            f = f._log_pdf
+        elif kind == 'LogPosterior':
+            if prior is not None:
+                raise TypeError('nested LogPosterior is not supported')
+            prior = f._log_prior
+            f = f._log_likelihood
+        else:
+            break
+    kind = _kind(f)
+    if kind not in ('SumOfSquaresError', 'GaussianKnownSigmaLogLikelihood',
+                    'GaussianLogLikelihood'):
+        raise TypeError(
+            'CudaEvaluator supports SumOfSquaresError, '
+            'GaussianKnownSigmaLogLikelihood and GaussianLogLikelihood '
+            '(optionally inside LogPosterior with a UniformLogPrior and/or '
+            'ProbabilityBasedError); got %s.%s (no CPU fallback).'
+            % (type(f).__module__, type(f).__name__))
+    problem = f._problem
+    if _kind(problem) not in ('SingleOutputProblem', 'MultiOutputProblem'):
+        raise TypeError('unsupported problem class %s'
+                        % type(problem).__name__)
+    multi = _kind(problem) == 'MultiOutputProblem'
+    model_id, model_consts = describe_model(problem._model)
+    times = np.asarray(problem._times, dtype=float)
+    values = np.asarray(problem._values, dtype=float)
+    n_outputs = values.shape[1] if values.ndim == 2 else 1
+    n_times = len(times)
+    if kind == 'SumOfSquaresError':
+        objective = _lib.OBJ_SSE
+        obj_consts = list(np.asarray(f._weights, dtype=float))
+    elif kind == 'GaussianKnownSigmaLogLikelihood':
+        objective = _lib.OBJ_GAUSSIAN_KNOWN_SIGMA
+        offset = np.ones(n_outputs) * np.asarray(f._offset, dtype=float)
+        multip = np.ones(n_outputs) * np.asarray(f._multip, dtype=float)
+        obj_consts = list(offset) + list(multip)
+    else:
+        objective = _lib.OBJ_GAUSSIAN
+        obj_consts = [float(f._logn)]
+        if int(f._nt) != n_times or int(f._no) != n_outputs:
+            raise TypeError('inconsistent GaussianLogLikelihood')
+    lower = upper = None
+    log_prior = 0.0
+    if prior is not None:
+        if _kind(prior) != 'UniformLogPrior' or \
+                _kind(prior._boundaries) != 'RectangularBoundaries':
+            raise TypeError(
+                'only UniformLogPrior over RectangularBoundaries is fused '
+                'into the CUDA path; got %s' % type(prior).__name__)
+        lower = np.asarray(prior._boundaries.lower(), dtype=float)
+        upper = np.asarray(prior._boundaries.upper(), dtype=float)
+        log_prior = float(prior._value)
+    spec = ProblemSpec(model_id, model_consts, times, values, objective,
+                       obj_consts, sign, lower, upper, log_prior,
+                       multi_output=multi)
+    if lower is not None and len(lower) != spec.n_parameters():
+        raise TypeError('prior and likelihood dimensions differ')
+    return spec

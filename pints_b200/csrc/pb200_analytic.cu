@@ -1,0 +1,312 @@
+// Closed-form forward models fused with the objective: Logistic, Hodgkin-Huxley
+// IK (piecewise-exponential gate under a voltage-step protocol) and Constant.
+// The time points of one parameter vector are independent, so one WARP owns a
+// vector: lanes stride over the observation times (conflict-free shared-memory
+// reads of the staged series), accumulate residual squares per output, and a
+// shuffle tree produces the sums.  Warps loop over vectors (persistent grid).
+//
+// Replaces (citations relative to the reference root):
+//   LogisticModel._simulate            pints/toy/_logistic_model.py:62-86
+//   HodgkinHuxleyIKModel.simulate      pints/toy/_hh_ik_model.py:175-214
+//   ConstantModel.simulate             pints/toy/_constant_model.py:75-93
+//   Single/MultiOutputProblem.evaluate pints/_core.py:147-153, :257-265
+//   objective __call__                 see objective_finish()
+#include "pb200_common.cuh"
+
+namespace {
+
+constexpr int WARPS = 8;                 // warps per block
+constexpr int SEG_STRIDE = 4;            // doubles per HH-IK segment record
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// ---- per-vector model state (warp-uniform unless noted) -------------------
+struct LogisticEval {
+    double r, k, c;
+    bool zero;
+    __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
+                                            double *, int) {
+        r = x[0]; k = x[1];
+        const double p0 = mc.c[0];
+        zero = (p0 == 0.0) || (k < 0.0);
+        c = __dsub_rn(__ddiv_rn(k, p0), 1.0);
+    }
+    // k / (1 + c * exp(-r t)), products and sums rounded one by one as NumPy
+    __device__ __forceinline__ double value(double t, int, const double *) const {
+        if (zero) return 0.0;
+        const double e = exp(__dmul_rn(-r, t));
+        return __ddiv_rn(k, __dadd_rn(1.0, __dmul_rn(c, e)));
+    }
+};
+
+struct ConstantEval {
+    double p[PB200_MAX_OUTPUTS];
+    __device__ __forceinline__ void prepare(const double *x, const ModelConsts &,
+                                            double *, int no) {
+        for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
+            p[o] = (o < no) ? __dmul_rn(x[o], static_cast<double>(o + 1)) : 0.0;
+    }
+    __device__ __forceinline__ double value(double, int o, const double *) const {
+        return p[o];
+    }
+};
+
+// HH-IK: the protocol has n_ev events -> n_ev + 1 constant-voltage segments.
+// Lane s prepares segment s: rates, time constant, steady state, and the decay
+// over the whole segment; one lane then chains the gate value across events
+// (n_next = inf - (inf - n_start) * decay).  Records go to a per-warp table in
+// shared memory: [inf, n_start, t_start, -1/tau].
+struct HhEval {
+    double g_max, e_k;
+    int n_ev;
+    const double *events;     // in the kernel parameter (constant bank)
+    __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
+                                            double *table, int) {
+        const int lane = threadIdx.x & 31;
+        const double n0 = mc.c[0];
+        g_max = mc.c[1]; e_k = mc.c[2];
+        const double v_hold = mc.c[3];
+        n_ev = static_cast<int>(mc.c[4]);
+        events = &mc.c[5];
+        const double *volts = &mc.c[5 + n_ev];
+        mc_vhold = v_hold;
+        mc_volts = volts;
+        const double p1 = x[0], p2 = x[1], p3 = x[2], p4 = x[3], p5 = x[4];
+        for (int s = lane; s <= n_ev; s += 32) {
+            const double v = (s == 0) ? v_hold : volts[s - 1];
+            const double t_start = (s == 0) ? 0.0 : events[s - 1];
+            // a = p1 * (-(v + 75) + p2) / (exp((-(v + 75) + p2) / p3) - 1)
+            const double q = __dadd_rn(-__dadd_rn(v, 75.0), p2);
+            const double a = __ddiv_rn(__dmul_rn(p1, q),
+                                       __dsub_rn(exp(__ddiv_rn(q, p3)), 1.0));
+            // b = p4 * exp((-v - 75) / p5)
+            const double b = __dmul_rn(p4, exp(__ddiv_rn(__dsub_rn(-v, 75.0), p5)));
+            const double tau = __ddiv_rn(1.0, __dadd_rn(a, b));
+            const double inf = __dmul_rn(a, tau);
+            double decay = 0.0;
+            if (s < n_ev)
+                decay = exp(__ddiv_rn(-__dsub_rn(events[s], t_start), tau));
+            table[s * SEG_STRIDE + 0] = inf;
+            table[s * SEG_STRIDE + 1] = decay;      // replaced by n_start below
+            table[s * SEG_STRIDE + 2] = t_start;
+            table[s * SEG_STRIDE + 3] = tau;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double n_start = n0;
+            for (int s = 0; s <= n_ev; ++s) {
+                const double inf = table[s * SEG_STRIDE + 0];
+                const double decay = table[s * SEG_STRIDE + 1];
+                table[s * SEG_STRIDE + 1] = n_start;
+                n_start = __dsub_rn(inf, __dmul_rn(__dsub_rn(inf, n_start), decay));
+            }
+        }
+        __syncwarp();
+    }
+    // segment of t: number of events <= t  (half-open [t_last, t_next))
+    __device__ __forceinline__ double value(double t, int, const double *table) const {
+        int lo = 0, hi = n_ev;            // answer in [0, n_ev]
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (events[mid] <= t) lo = mid + 1; else hi = mid;
+        }
+        const int s = lo;
+        const double inf = table[s * SEG_STRIDE + 0];
+        const double n_start = table[s * SEG_STRIDE + 1];
+        const double t_start = table[s * SEG_STRIDE + 2];
+        const double tau = table[s * SEG_STRIDE + 3];
+        const double e = exp(__ddiv_rn(-__dsub_rn(t, t_start), tau));
+        const double nn = __dsub_rn(inf, __dmul_rn(__dsub_rn(inf, n_start), e));
+        // g_max * n**4 * (v - E_k)
+        const double volt = (s == 0) ? mc_vhold : mc_volts[s - 1];
+        const double n2 = __dmul_rn(nn, nn);
+        const double n4 = __dmul_rn(n2, n2);
+        return __dmul_rn(__dmul_rn(g_max, n4), __dsub_rn(volt, e_k));
+    }
+    double mc_vhold;
+    const double *mc_volts;
+};
+
+template <class E, bool SMEM, bool TRAJ>
+__global__ void __launch_bounds__(WARPS * 32)
+analytic_kernel(const __grid_constant__ ProblemDev P,
+                const __grid_constant__ ModelConsts mc,
+                const double *__restrict__ params, int64_t n, int64_t ld,
+                double *__restrict__ scores, double *__restrict__ traj) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double seg_table[WARPS][(PB200_MAX_EVENTS + 1) * SEG_STRIDE];
+
+    const int row = P.row, no = P.n_outputs, nt = P.n_times;
+    const double *series;
+    if (SMEM) {
+        const uint32_t bytes = static_cast<uint32_t>(
+            (static_cast<int64_t>(nt) * row * 8 + 15) & ~15ll);
+        stage_series(smem, P.series, bytes, &bar);
+        series = smem;
+    } else {
+        series = P.series;
+    }
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double *table = seg_table[warp];
+    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * WARPS;
+    const int n_read = TRAJ ? P.n_model_params : P.n_params;
+
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * WARPS + warp; i < n;
+         i += warps_total) {
+        double x[PB200_MAX_PARAMS];
+#pragma unroll
+        for (int k = 0; k < PB200_MAX_PARAMS; ++k)
+            x[k] = (k < n_read) ? params[i * ld + k] : 0.0;
+
+        if (!TRAJ) {
+            double early;
+            if (objective_precheck(P, x, &early)) {     // warp-uniform
+                if (lane == 0) scores[i] = early;
+                continue;
+            }
+        }
+        E ev;
+        ev.prepare(x, mc, table, no);
+
+        double ss[PB200_MAX_OUTPUTS];
+#pragma unroll
+        for (int o = 0; o < PB200_MAX_OUTPUTS; ++o) ss[o] = 0.0;
+        double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * no : nullptr;
+
+        for (int j = lane; j < nt; j += 32) {
+            const double t = series[j * row];
+#pragma unroll
+            for (int o = 0; o < PB200_MAX_OUTPUTS; ++o) {
+                if (o < no) {
+                    const double v = ev.value(t, o, table);
+                    if (TRAJ) my_traj[j * no + o] = v;
+                    const double r = __dsub_rn(series[j * row + 1 + o], v);
+                    ss[o] = __dadd_rn(ss[o], __dmul_rn(r, r));
+                }
+            }
+        }
+        if (!TRAJ) {
+#pragma unroll
+            for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
+                if (o < no) ss[o] = warp_sum(ss[o]);
+            if (lane == 0) scores[i] = objective_finish(P, ss, x);
+        }
+        __syncwarp();
+    }
+}
+
+template <class E>
+int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
+                int64_t ld, double *d_scores, double *d_traj, cudaStream_t st) {
+    const int64_t bytes = (static_cast<int64_t>(p->dev.n_times) * p->dev.row * 8 + 15) & ~15ll;
+    const bool use_smem = bytes <= 100 * 1024;
+    const bool traj = d_traj != nullptr;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (n + WARPS - 1) / WARPS;
+    const int64_t cap = static_cast<int64_t>(sms) * 4;   // persistent: 4 blocks/SM
+    if (grid > cap) grid = cap;
+    if (grid <= 0) return PB200_OK;
+#define PB200_LAUNCH(SM, TR)                                                             \
+    do {                                                                                 \
+        auto kern = analytic_kernel<E, SM, TR>;                                          \
+        size_t dyn = SM ? static_cast<size_t>(bytes) : 0;                                \
+        if (dyn > 32 * 1024) {                                                           \
+            int rc = pb200_check_cuda(                                                   \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     static_cast<int>(dyn)),                             \
+                "cudaFuncSetAttribute");                                                 \
+            if (rc) return rc;                                                           \
+        }                                                                                \
+        kern<<<static_cast<unsigned>(grid), WARPS * 32, dyn, st>>>(                      \
+            p->dev, p->mc, d_params, n, ld, d_scores, d_traj);                           \
+    } while (0)
+    if (use_smem) {
+        if (traj) PB200_LAUNCH(true, true); else PB200_LAUNCH(true, false);
+    } else {
+        if (traj) PB200_LAUNCH(false, true); else PB200_LAUNCH(false, false);
+    }
+#undef PB200_LAUNCH
+    return pb200_check_cuda(cudaGetLastError(), "analytic_kernel launch");
+}
+
+// ---- unfused baseline, second half: objective from stored trajectories ----
+__global__ void __launch_bounds__(WARPS * 32)
+score_traj_kernel(const __grid_constant__ ProblemDev P, const double *__restrict__ traj,
+                  const double *__restrict__ params, int64_t n, int64_t ld,
+                  double *__restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int row = P.row, no = P.n_outputs, nt = P.n_times;
+    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * WARPS;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * WARPS + warp; i < n;
+         i += warps_total) {
+        double x[PB200_MAX_PARAMS];
+#pragma unroll
+        for (int k = 0; k < PB200_MAX_PARAMS; ++k)
+            x[k] = (k < P.n_params) ? params[i * ld + k] : 0.0;
+        double early;
+        if (objective_precheck(P, x, &early)) {
+            if (lane == 0) scores[i] = early;
+            continue;
+        }
+        double ss[PB200_MAX_OUTPUTS];
+#pragma unroll
+        for (int o = 0; o < PB200_MAX_OUTPUTS; ++o) ss[o] = 0.0;
+        const double *tr = traj + i * static_cast<int64_t>(nt) * no;
+        // flat, coalesced sweep over the nt*no stored values
+        const int total = nt * no;
+        for (int q = lane; q < total; q += 32) {
+            const int j = q / no, o = q - j * no;
+            const double r = P.series[j * row + 1 + o] - tr[q];
+            const double sq = r * r;
+#pragma unroll
+            for (int oo = 0; oo < PB200_MAX_OUTPUTS; ++oo)
+                if (oo == o) ss[oo] += sq;
+        }
+#pragma unroll
+        for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
+            if (o < no) ss[o] = warp_sum(ss[o]);
+        if (lane == 0) scores[i] = objective_finish(P, ss, x);
+    }
+}
+
+}  // namespace
+
+int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
+                    int64_t ld, double *d_scores, double *d_traj,
+                    cudaStream_t st) {
+    switch (p->dev.model) {
+        case PB200_MODEL_LOGISTIC:
+            return launch_eval<LogisticEval>(p, d_params, n, ld, d_scores, d_traj, st);
+        case PB200_MODEL_HH_IK:
+            return launch_eval<HhEval>(p, d_params, n, ld, d_scores, d_traj, st);
+        case PB200_MODEL_CONSTANT:
+            return launch_eval<ConstantEval>(p, d_params, n, ld, d_scores, d_traj, st);
+    }
+    pb200_set_error("model %d is not a closed-form model", p->dev.model);
+    return PB200_EUNSUPPORTED;
+}
+
+int launch_score_traj(const pb200_problem *p, const double *d_traj,
+                      const double *d_params, int64_t n, int64_t ld,
+                      double *d_scores, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (n + WARPS - 1) / WARPS;
+    if (grid > static_cast<int64_t>(sms) * 8) grid = static_cast<int64_t>(sms) * 8;
+    if (grid <= 0) return PB200_OK;
+    score_traj_kernel<<<static_cast<unsigned>(grid), WARPS * 32, 0, st>>>(
+        p->dev, d_traj, d_params, n, ld, d_scores);
+    return pb200_check_cuda(cudaGetLastError(), "score_traj_kernel launch");
+}

@@ -1,0 +1,227 @@
+// C-ABI entry points (include/pints_b200.h): argument checking, the host-side
+// problem object, and dispatch to the kernel launchers.  No device memory is
+// allocated here and nothing synchronises: work is enqueued on the caller's
+// stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "pb200_common.cuh"
+
+static thread_local char g_error[512] = "";
+
+void pb200_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int pb200_check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return PB200_OK;
+    pb200_set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return PB200_ECUDA;
+}
+
+namespace {
+
+struct ModelInfo {
+    int n_params;      // forward-model parameters (-1: equals n_outputs)
+    int n_outputs;     // -1: any (1..PB200_MAX_OUTPUTS)
+    int min_consts;
+    bool ode;
+};
+
+const ModelInfo kModels[PB200_N_MODELS] = {
+    /* LOGISTIC       */ {2, 1, 1, false},
+    /* HH_IK          */ {5, 1, 5, false},
+    /* CONSTANT       */ {-1, -1, 0, false},
+    /* FHN            */ {3, 2, 2, true},
+    /* LOTKA_VOLTERRA */ {4, 2, 2, true},
+    /* SIR            */ {3, 2, 4, true},
+};
+
+SolverDev resolve_opts(const pb200_solver_opts *o, int *block) {
+    SolverDev s;
+    s.rtol = (o && o->rtol > 0) ? o->rtol : 1.49012e-8;
+    s.atol = (o && o->atol > 0) ? o->atol : 1.49012e-8;
+    s.h0 = (o && o->h0 > 0) ? o->h0 : 0.0;
+    s.max_steps = (o && o->max_steps > 0) ? o->max_steps : 1000000;
+    *block = (o && o->block > 0) ? o->block : 0;
+    return s;
+}
+
+int check_batch(const pb200_problem *p, const void *d_params, int64_t n, int64_t ld,
+                const void *d_out, const char *who, bool model_only = false) {
+    if (!p) { pb200_set_error("%s: problem is NULL", who); return PB200_EINVAL; }
+    if (n < 0) { pb200_set_error("%s: n = %lld < 0", who, (long long)n); return PB200_EINVAL; }
+    if (n == 0) return PB200_OK;
+    if (!d_params || !d_out) { pb200_set_error("%s: NULL device pointer", who); return PB200_EINVAL; }
+    const int need = model_only ? p->dev.n_model_params : p->dev.n_params;
+    if (ld < need) {
+        pb200_set_error("%s: row stride %lld is shorter than the %d parameters of this problem",
+                        who, (long long)ld, need);
+        return PB200_EINVAL;
+    }
+    return PB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb200_version(void) { return PB200_VERSION; }
+
+const char *pb200_last_error(void) { return g_error; }
+
+int64_t pb200_series_len(int32_t n_times, int32_t n_outputs) {
+    if (n_times < 0 || n_outputs < 1) return -1;
+    const int64_t len = static_cast<int64_t>(n_times) * (1 + n_outputs);
+    return (len + 1) & ~1ll;            // whole 16-byte units for the bulk copy
+}
+
+int pb200_problem_create(int32_t model, int32_t objective, int32_t n_times,
+                         int32_t n_outputs, const double *d_series,
+                         const double *model_consts, int32_t n_model_consts,
+                         const double *obj_consts, int32_t n_obj_consts, double sign,
+                         const double *prior_lower, const double *prior_upper,
+                         int32_t n_prior, double log_prior_value, pb200_problem **out) {
+    if (!out) { pb200_set_error("pb200_problem_create: out is NULL"); return PB200_EINVAL; }
+    *out = nullptr;
+    if (model < 0 || model >= PB200_N_MODELS) {
+        pb200_set_error("unknown model id %d", model);
+        return PB200_EUNSUPPORTED;
+    }
+    if (objective < 0 || objective >= PB200_N_OBJECTIVES) {
+        pb200_set_error("unknown objective id %d", objective);
+        return PB200_EUNSUPPORTED;
+    }
+    const ModelInfo &mi = kModels[model];
+    if (n_times < 0) { pb200_set_error("n_times = %d < 0", n_times); return PB200_EINVAL; }
+    if (n_outputs < 1 || n_outputs > PB200_MAX_OUTPUTS ||
+        (mi.n_outputs > 0 && n_outputs != mi.n_outputs)) {
+        pb200_set_error("model %d does not have %d outputs", model, n_outputs);
+        return PB200_EINVAL;
+    }
+    if (n_times > 0 && !d_series) { pb200_set_error("d_series is NULL"); return PB200_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(d_series) & 15) != 0) {
+        pb200_set_error("d_series must be 16-byte aligned");
+        return PB200_EINVAL;
+    }
+    if (n_model_consts < mi.min_consts || n_model_consts > PB200_MAX_MODEL_CONSTS ||
+        (n_model_consts > 0 && !model_consts)) {
+        pb200_set_error("model %d needs at least %d constants, got %d", model,
+                        mi.min_consts, n_model_consts);
+        return PB200_EINVAL;
+    }
+    if (model == PB200_MODEL_HH_IK) {
+        const int n_ev = static_cast<int>(model_consts[4]);
+        if (n_ev < 0 || n_ev > PB200_MAX_EVENTS || n_model_consts != 5 + 2 * n_ev) {
+            pb200_set_error("HH-IK protocol: %d events needs %d constants, got %d", n_ev,
+                            5 + 2 * n_ev, n_model_consts);
+            return PB200_EINVAL;
+        }
+    }
+    const int want_obj = objective == PB200_OBJ_SSE ? n_outputs
+                         : objective == PB200_OBJ_GAUSSIAN_KNOWN_SIGMA ? 2 * n_outputs : 1;
+    if (n_obj_consts != want_obj || !obj_consts) {
+        pb200_set_error("objective %d needs %d constants, got %d", objective, want_obj,
+                        n_obj_consts);
+        return PB200_EINVAL;
+    }
+    const int n_model_params = mi.n_params > 0 ? mi.n_params : n_outputs;
+    const int n_params = n_model_params + (objective == PB200_OBJ_GAUSSIAN ? n_outputs : 0);
+    if (n_params > PB200_MAX_PARAMS) {
+        pb200_set_error("%d parameters exceed the supported %d", n_params, PB200_MAX_PARAMS);
+        return PB200_EUNSUPPORTED;
+    }
+    if (n_prior != 0 && (n_prior != n_params || !prior_lower || !prior_upper)) {
+        pb200_set_error("prior box must have %d entries, got %d", n_params, n_prior);
+        return PB200_EINVAL;
+    }
+    if (!(sign == 1.0 || sign == -1.0)) {
+        pb200_set_error("sign must be +1 or -1");
+        return PB200_EINVAL;
+    }
+    pb200_problem *p = new (std::nothrow) pb200_problem();
+    if (!p) { pb200_set_error("out of host memory"); return PB200_ENOMEM; }
+    memset(p, 0, sizeof(*p));
+    p->dev.model = model;
+    p->dev.objective = objective;
+    p->dev.n_times = n_times;
+    p->dev.n_outputs = n_outputs;
+    p->dev.n_model_params = n_model_params;
+    p->dev.n_params = n_params;
+    p->dev.n_prior = n_prior;
+    p->dev.row = 1 + n_outputs;
+    p->dev.series = d_series;
+    p->dev.sign = sign;
+    p->dev.log_prior = n_prior ? log_prior_value : 0.0;
+    for (int i = 0; i < n_obj_consts; ++i) p->dev.oc[i] = obj_consts[i];
+    for (int i = 0; i < n_prior; ++i) {
+        p->dev.lo[i] = prior_lower[i];
+        p->dev.hi[i] = prior_upper[i];
+    }
+    for (int i = 0; i < n_model_consts; ++i) p->mc.c[i] = model_consts[i];
+    p->n_model_consts = n_model_consts;
+    p->series_bytes = pb200_series_len(n_times, n_outputs) * 8;
+    *out = p;
+    return PB200_OK;
+}
+
+void pb200_problem_destroy(pb200_problem *p) { delete p; }
+
+int32_t pb200_problem_n_parameters(const pb200_problem *p) {
+    return p ? p->dev.n_params : -1;
+}
+
+int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+               double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
+               void *stream) {
+    int rc = check_batch(p, d_params, n, ld, d_scores, "pb200_eval");
+    if (rc || n == 0) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kModels[p->dev.model].ode) {
+        int block;
+        SolverDev s = resolve_opts(opts, &block);
+        return launch_ode(p, d_params, n, ld, d_scores, nullptr, d_steps, s, block, st);
+    }
+    if (d_steps) {
+        rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),
+                              "cudaMemsetAsync(d_steps)");
+        if (rc) return rc;
+    }
+    return launch_analytic(p, d_params, n, ld, d_scores, nullptr, st);
+}
+
+int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+                   double *d_traj, int32_t *d_steps, const pb200_solver_opts *opts,
+                   void *stream) {
+    int rc = check_batch(p, d_params, n, ld, d_traj, "pb200_simulate", true);
+    if (rc || n == 0) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kModels[p->dev.model].ode) {
+        int block;
+        SolverDev s = resolve_opts(opts, &block);
+        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, st);
+    }
+    if (d_steps) {
+        rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),
+                              "cudaMemsetAsync(d_steps)");
+        if (rc) return rc;
+    }
+    return launch_analytic(p, d_params, n, ld, nullptr, d_traj, st);
+}
+
+int pb200_score_trajectories(const pb200_problem *p, const double *d_traj,
+                             const double *d_params, int64_t n, int64_t ld,
+                             double *d_scores, void *stream) {
+    int rc = check_batch(p, d_params, n, ld, d_scores, "pb200_score_trajectories");
+    if (rc || n == 0) return rc;
+    if (!d_traj) { pb200_set_error("pb200_score_trajectories: d_traj is NULL"); return PB200_EINVAL; }
+    return launch_score_traj(p, d_traj, d_params, n, ld, d_scores,
+                             static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Shared device-side definitions of the pints-b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/pints_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pints-b200 kernels are written for sm_100a (Blackwell B200) only"
+#endif
+
+// ---------------------------------------------------------------------------
+// Problem description passed by value as a kernel parameter (constant bank,
+// so every read is a uniform load).
+// ---------------------------------------------------------------------------
+#define PB200_MAX_MODEL_CONSTS (5 + 2 * PB200_MAX_EVENTS)
+
+struct ProblemDev {
+    int32_t model;
+    int32_t objective;
+    int32_t n_times;
+    int32_t n_outputs;
+    int32_t n_model_params;       // parameters consumed by the forward model
+    int32_t n_params;             // row length (adds sigmas for GAUSSIAN)
+    int32_t n_prior;              // 0 = no prior box
+    int32_t row;                  // doubles per series row = 1 + n_outputs
+    const double *series;         // device, packed [n_times][row]
+    double sign;
+    double log_prior;
+    double oc[2 * PB200_MAX_OUTPUTS];      // objective constants
+    double lo[PB200_MAX_PARAMS];
+    double hi[PB200_MAX_PARAMS];
+};
+
+// Model constants live apart so the ODE kernels do not carry the HH-IK table.
+struct ModelConsts {
+    double c[PB200_MAX_MODEL_CONSTS];
+};
+
+struct pb200_problem {
+    ProblemDev dev;
+    ModelConsts mc;
+    int32_t n_model_consts;
+    int64_t series_bytes;         // bytes staged into shared memory
+};
+
+struct SolverDev {
+    double rtol, atol, h0;
+    int32_t max_steps;
+};
+
+// ---------------------------------------------------------------------------
+// Shared-memory staging of the observed series with the bulk-copy engine
+// (cp.async.bulk -> SASS UBLKCP), completion through an mbarrier.
+// One elected thread issues the copy; everybody waits on the barrier phase.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void stage_series(double *dst, const double *src,
+                                             uint32_t bytes, uint64_t *bar) {
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile(
+            "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+            "r"(bytes)
+            : "memory");
+        const uint32_t chunk = 32768u;
+        uint32_t done = 0;
+        while (done < bytes) {
+            uint32_t nb = bytes - done < chunk ? bytes - done : chunk;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst) + done),
+                "l"(reinterpret_cast<const char *>(src) + done), "r"(nb), "r"(bar_a)
+                : "memory");
+            done += nb;
+        }
+    }
+    // wait for phase 0 to complete
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_a)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Objective epilogue.  Products and sums are rounded separately, in the order
+// NumPy evaluates the reference expressions, so closed-form models agree with
+// the reference to the last few ulps:
+//   SSE    np.sum(np.sum((sim - data)**2, axis=0) * weights)
+//          (pints/_error_measures.py:373-376)
+//   KNOWN  np.sum(offset + multip * np.sum(error**2, axis=0))
+//          (pints/_log_likelihoods.py:1039-1041)
+//   GAUSS  np.sum(-logn - nt*log(sigma) - np.sum(error**2, axis=0)/(2 sigma**2))
+//          (pints/_log_likelihoods.py:1123-1129)
+// then LogPosterior adds the prior constant (pints/_log_pdfs.py:207-212) and
+// ProbabilityBasedError flips the sign (pints/_error_measures.py:183-184).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double objective_finish(const ProblemDev &P,
+                                                   const double *ss,
+                                                   const double *x) {
+    double acc = 0.0;
+    const int no = P.n_outputs;
+    if (P.objective == PB200_OBJ_SSE) {
+        for (int o = 0; o < no; ++o) {
+            double term = __dmul_rn(ss[o], P.oc[o]);
+            acc = (o == 0) ? term : __dadd_rn(acc, term);
+        }
+    } else if (P.objective == PB200_OBJ_GAUSSIAN_KNOWN_SIGMA) {
+        for (int o = 0; o < no; ++o) {
+            double term = __dadd_rn(P.oc[o], __dmul_rn(P.oc[no + o], ss[o]));
+            acc = (o == 0) ? term : __dadd_rn(acc, term);
+        }
+    } else {
+        const double logn = P.oc[0];
+        const double nt = static_cast<double>(P.n_times);
+        for (int o = 0; o < no; ++o) {
+            const double sigma = x[P.n_model_params + o];
+            double a = __dsub_rn(-logn, __dmul_rn(nt, log(sigma)));
+            double b = __ddiv_rn(ss[o], __dmul_rn(2.0, __dmul_rn(sigma, sigma)));
+            double term = __dsub_rn(a, b);
+            acc = (o == 0) ? term : __dadd_rn(acc, term);
+        }
+    }
+    if (P.n_prior > 0) acc = __dadd_rn(P.log_prior, acc);
+    return P.sign * acc;
+}
+
+// Checks done before any simulation: the prior box (a point outside scores
+// -inf and is never simulated) and sigma <= 0 for the unknown-sigma
+// likelihood.  Returns true when the vector is decided without a solve.
+__device__ __forceinline__ bool objective_precheck(const ProblemDev &P,
+                                                   const double *x,
+                                                   double *score) {
+    if (P.n_prior > 0) {
+        bool outside = false;
+        for (int i = 0; i < P.n_prior; ++i)
+            outside = outside || (x[i] < P.lo[i]) || (x[i] >= P.hi[i]);
+        if (outside) {
+            *score = P.sign * -INFINITY;
+            return true;
+        }
+    }
+    if (P.objective == PB200_OBJ_GAUSSIAN) {
+        bool bad = false;
+        for (int o = 0; o < P.n_outputs; ++o)
+            bad = bad || (x[P.n_model_params + o] <= 0.0);
+        if (bad) {
+            double v = -INFINITY;
+            if (P.n_prior > 0) v = P.log_prior + v;
+            *score = P.sign * v;
+            return true;
+        }
+    }
+    return false;
+}
+
+// host-side launchers implemented in the kernel translation units
+int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
+               int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
+               const SolverDev &s, int block, cudaStream_t st);
+int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
+                    int64_t ld, double *d_scores, double *d_traj,
+                    cudaStream_t st);
+int launch_score_traj(const pb200_problem *p, const double *d_traj,
+                      const double *d_params, int64_t n, int64_t ld,
+                      double *d_scores, cudaStream_t st);
+void pb200_set_error(const char *fmt, ...);
+int pb200_check_cuda(cudaError_t e, const char *what);

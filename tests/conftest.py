@@ -10,6 +10,16 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
+# Make the real reference importable (when it is mounted) BEFORE pints_b200 is
+# imported, so the mirror classes pick up the reference's base classes.  Set
+# PINTS_B200_NO_PINTS=1 to run the suite as on the GPU box (no reference).
+_REF = os.environ.get('PINTS_REFERENCE', '/root/reference')
+if os.environ.get('PINTS_B200_NO_PINTS') != '1' and \
+        os.path.isdir(os.path.join(_REF, 'pints')) and _REF not in sys.path:
+    sys.path.append(_REF)
+    sys.dont_write_bytecode = True
+
+
 def pytest_configure(config):
     config.addinivalue_line(
         'markers', 'gpu: needs a CUDA device (run with -m gpu on a B200)')
@@ -28,12 +38,8 @@ def golden():
 
 def reference_pints():
     """The real reference, when it is mounted (build container only)."""
-    ref = os.environ.get('PINTS_REFERENCE', '/root/reference')
-    if not os.path.isdir(os.path.join(ref, 'pints')):
+    if os.environ.get('PINTS_B200_NO_PINTS') == '1':
         return None
-    if ref not in sys.path:
-        sys.path.append(ref)
-    sys.dont_write_bytecode = True
     try:
         import pints
         import pints.toy  # noqa: F401

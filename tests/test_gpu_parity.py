@@ -1,0 +1,397 @@
+"""
+Parity of the CUDA path (through the C ABI, ``pints_b200._lib`` ->
+``libpints_b200.so``) against
+
+  * the golden fixtures produced by the real reference (tests/golden), and
+  * the CPU oracle run live on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  closed-form models   1e-12 relative on scores and trajectories
+  ODE models           scores 1e-6 relative; trajectories |d| <= 1e-5 + 1e-6|y|
+                       against the reference's LSODA; and the device must be
+                       at least as close to a tight-tolerance solve ("truth") as
+                       the reference itself is.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pints_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+ANALYTIC_RTOL = 1e-12
+ODE_SCORE_RTOL = 1e-6
+TRAJ_ATOL, TRAJ_RTOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope='module')
+def pb():
+    import pints_b200
+    pints_b200.require_cuda()
+    return pints_b200
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, float), np.asarray(want, float)
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    with np.errstate(invalid='ignore', divide='ignore'):
+        r = np.abs(got - want) / np.abs(want)
+    r[same] = 0.0
+    return r
+
+
+def evaluate(pb, f, xs, **kw):
+    return pb.CudaEvaluator(f, as_list=False, **kw).evaluate(xs)
+
+
+# --------------------------------------------------------------- closed form
+
+def test_logistic_scores_and_trajectories(pb):
+    g = load_golden('logistic')
+    model = pb.toy.LogisticModel()
+    problem = pb.SingleOutputProblem(model, g['times'], g['values'])
+    got = evaluate(pb, pb.SumOfSquaresError(problem), g['xs'])
+    assert np.nanmax(rel_err(got, g['scores'])) < ANALYTIC_RTOL
+    assert np.isnan(got[15]) and np.isnan(g['scores'][15])
+    got = evaluate(pb, pb.GaussianKnownSigmaLogLikelihood(problem, 1.0),
+                   g['xs'])
+    assert np.nanmax(rel_err(got, g['ll_scores'])) < ANALYTIC_RTOL
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs_gauss'])
+    assert got[2] == -np.inf
+    assert np.nanmax(rel_err(got, g['gauss_scores'])) < ANALYTIC_RTOL
+    traj = model.simulate(g['xs'][:16], g['times'])
+    assert traj.shape == (16, 1000)
+    assert np.nanmax(rel_err(traj, g['traj'])) < ANALYTIC_RTOL
+    # single-vector call keeps the reference's shape
+    one = model.simulate(g['xs'][0], g['times'])
+    assert one.shape == (1000,)
+    assert np.array_equal(one, traj[0])
+    # reference unit test values (pints/tests/test_toy_logistic_model.py:93-105)
+    v = pb.toy.LogisticModel(0.5).simulate([0.1, 12], g['unit_times'])
+    assert np.max(rel_err(v, g['unit_values'])) < ANALYTIC_RTOL
+    assert abs(v[1] - 0.5501745273651227) < 1e-15
+    assert np.all(pb.toy.LogisticModel(0).simulate([0.1, 50], [0, 1, 2]) == 0)
+    with pytest.raises(ValueError):
+        model.simulate([0.1, 50], [-1, 0, 1])
+
+
+def test_constant_model_reference_known_answers(pb):
+    g = load_golden('constant')
+    t = g['single_times']
+    p1 = pb.SingleOutputProblem(pb.toy.ConstantModel(1), t, g['single_values'])
+    got = evaluate(pb, pb.SumOfSquaresError(p1), g['single_sse_x'])
+    assert list(got) == [0.0, 3.0, 12.0, 0.75]
+    p3 = pb.MultiOutputProblem(pb.toy.ConstantModel(3), t, g['multi_values'])
+    assert np.array_equal(evaluate(pb, pb.SumOfSquaresError(p3), g['multi_x']),
+                          g['multi_sse'])
+    got = evaluate(pb, pb.SumOfSquaresError(p3, weights=[1, 2, 3]),
+                   g['multi_x'])
+    assert np.max(rel_err(got, g['multi_sse_weighted'])) < ANALYTIC_RTOL
+    got = evaluate(pb, pb.GaussianKnownSigmaLogLikelihood(
+        p3, g['multi_sigma']), g['multi_x'])
+    assert np.max(rel_err(got, g['multi_known'])) < ANALYTIC_RTOL
+    got = evaluate(pb, pb.GaussianLogLikelihood(p3), g['multi_gauss_x'])
+    assert got[2] == -np.inf
+    assert np.max(rel_err(got, g['multi_gauss'])) < ANALYTIC_RTOL
+    # pints/tests/test_log_likelihoods.py:1909-1961
+    data_multi = np.array([[10.7, 3.5, 3.8], [1.1, 3.2, -1.4],
+                           [9.3, 0.0, 4.5], [1.2, -3, -10]])
+    times = [1, 2, 3, 4]
+    ll = pb.GaussianKnownSigmaLogLikelihood(pb.SingleOutputProblem(
+        pb.toy.ConstantModel(1), times, np.arange(1, 5) / 5.0), 1.5)
+    assert abs(ll([-1]) - -7.3420590096957925) < 1e-12
+    ll = pb.GaussianKnownSigmaLogLikelihood(pb.MultiOutputProblem(
+        pb.toy.ConstantModel(3), times, data_multi), 1)
+    assert abs(ll([0, 0, 0]) - -196.9122623984561) < 1e-10
+
+
+def test_hh_ik(pb):
+    g = load_golden('hh_ik')
+    model = pb.toy.HodgkinHuxleyIKModel()
+    assert np.array_equal(model._events, g['events'])
+    assert np.array_equal(model._voltages, g['voltages'])
+    traj = model.simulate(g['xs'][:6, :5], g['times'])
+    assert traj.shape == (6, 4800)
+    assert np.max(rel_err(traj, g['traj'])) < ANALYTIC_RTOL
+    # samples on event times / past the end of the protocol
+    ev = model.simulate(g['xs'][:6, :5], g['event_times'])
+    assert np.max(rel_err(ev, g['event_values'])) < ANALYTIC_RTOL
+    problem = pb.SingleOutputProblem(model, g['times'], g['values'])
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'])
+    assert got[4] == -np.inf
+    assert np.max(rel_err(got, g['scores'])) < ANALYTIC_RTOL
+    problem = pb.SingleOutputProblem(model, g['times_1k'], g['values_1k'])
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'][:16])
+    assert np.max(rel_err(got, g['scores_1k'])) < ANALYTIC_RTOL
+    # reference unit test (pints/tests/test_toy_hh_ik_model.py:44-74)
+    v = model.simulate(model.suggested_parameters(), model.suggested_times())
+    assert abs(v[0] - 3.790799999999997) < 1e-7
+    assert abs(v[390] - 15.9405) < 1e-2
+    with pytest.raises(ValueError):
+        model.simulate(model.suggested_parameters(), [-1, 0, 1])
+
+
+# ----------------------------------------------------------------- ODE models
+
+def check_ode(traj_dev, traj_ref, truth):
+    d = np.abs(traj_dev - traj_ref)
+    assert np.all(d <= TRAJ_ATOL + TRAJ_RTOL * np.abs(traj_ref)), d.max()
+    err_dev = np.abs(traj_dev - truth).max()
+    err_ref = np.abs(traj_ref - truth).max()
+    assert err_dev <= err_ref * 1.05 + 1e-9, (err_dev, err_ref)
+    return err_dev, err_ref
+
+
+def test_fhn_headline(pb):
+    g = load_golden('fhn')
+    model = pb.toy.FitzhughNagumoModel()
+    problem = pb.MultiOutputProblem(model, g['times'], g['values'])
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, float(g['sigma']))
+    ev = pb.CudaEvaluator(ll, as_list=False)
+    got, steps = ev.evaluate_array(g['xs'], return_steps=True)
+    assert np.max(rel_err(got, g['scores'])) < ODE_SCORE_RTOL
+    # closer to the tight-tolerance truth than the reference is
+    assert np.max(rel_err(got, g['truth_scores'])) <= \
+        np.max(rel_err(g['scores'], g['truth_scores']))
+    assert steps.min() > 200 and steps.max() < 1000
+    # ProbabilityBasedError flips the sign, bit for bit
+    neg = evaluate(pb, pb.ProbabilityBasedError(ll), g['xs'][:8])
+    assert np.array_equal(neg, -got[:8])
+    assert np.max(rel_err(neg, g['neg_scores'])) < ODE_SCORE_RTOL
+    traj = model.simulate(g['xs'][:12], g['times'])
+    assert traj.shape == (12, 1000, 2)
+    check_ode(traj, g['traj'], g['truth'])
+    # other objectives on the same series
+    got = evaluate(pb, pb.SumOfSquaresError(problem, g['sse_weights']),
+                   g['xs'][:16])
+    assert np.max(rel_err(got, g['sse_scores'])) < ODE_SCORE_RTOL
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs_gauss'])
+    assert got[3] == -np.inf and got[5] == -np.inf
+    assert np.max(rel_err(got, g['gauss_scores'])) < ODE_SCORE_RTOL
+
+
+def test_fhn_wide_box(pb):
+    g = load_golden('fhn')
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), g['times'],
+                                    g['values'])
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, float(g['sigma']))
+    got = evaluate(pb, ll, g['xs_wide'])
+    assert np.all(np.isfinite(got))
+    # against the truth the device is tight everywhere in the box ...
+    assert np.max(rel_err(got, g['truth_scores_wide'])) < ODE_SCORE_RTOL
+    # ... and at least as good as the reference
+    assert np.max(rel_err(got, g['truth_scores_wide'])) <= \
+        np.max(rel_err(g['scores_wide'], g['truth_scores_wide'])) + 1e-9
+
+
+def test_fhn_reference_unit_test(pb):
+    # pints/tests/test_toy_fitzhugh_nagumo_model.py:51-59
+    g = load_golden('fhn_unit')
+    model = pb.toy.FitzhughNagumoModel(g['y0'])
+    v = model.simulate(g['x'], g['times'])
+    assert v.shape == (201, 2)
+    assert v[0, 0] == -2 and v[0, 1] == 1.5
+    assert round(abs(v[200, 0] - 1.675726), 6) == 0
+    assert round(abs(v[200, 1] - -0.226142), 6) == 0
+    check_ode(v, g['values'], g['truth'])
+    # times not starting at zero: solve still starts at t = 0
+    v = model.simulate(g['x'], g['times_nz'])
+    assert np.all(np.abs(v - g['values_nz'])
+                  <= TRAJ_ATOL + TRAJ_RTOL * np.abs(g['values_nz']))
+    with pytest.raises(ValueError):
+        model.simulate(g['x'], [-1, 0, 1])
+
+
+def test_lotka_volterra(pb):
+    g = load_golden('lotka_volterra')
+    model = pb.toy.LotkaVolterraModel()
+    traj = model.simulate(g['xs'][:8, :4], g['times'])
+    check_ode(traj, g['traj'], g['truth'])
+    problem = pb.MultiOutputProblem(model, g['times'], g['values'])
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'])
+    assert np.max(rel_err(got, g['scores'])) < ODE_SCORE_RTOL
+    # the 21-point hare/lynx series on log scale
+    problem = pb.MultiOutputProblem(model, model.suggested_times(),
+                                    np.log(model.suggested_values()))
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'][:16])
+    assert np.max(rel_err(got, g['small_scores'])) < ODE_SCORE_RTOL
+    # pints/tests/test_toy_lotka_volterra_model.py:42-55
+    v = pb.toy.LotkaVolterraModel(g['unit_y0']).simulate(g['unit_x'],
+                                                         g['unit_times'])
+    assert v[0, 0] == 3 and v[0, 1] == 5
+    assert round(abs(v[1, 0] - 1.929494), 6) == 0
+    assert round(abs(v[1, 1] - 4.806542), 6) == 0
+    assert round(abs(v[100, 0] - 1.277762), 6) == 0
+    assert round(abs(v[100, 1] - 0.000529), 6) == 0
+
+
+def test_sir(pb):
+    g = load_golden('sir')
+    model = pb.toy.SIRModel()
+    traj = model.simulate(g['xs'][:8, :3], g['times'])
+    check_ode(traj, g['traj'], g['truth'])
+    # S0 = 38.9 is truncated to 38 by the default integer y0
+    a = model.simulate([0.026, 0.285, 38.0], g['times'])
+    b = model.simulate([0.026, 0.285, 38.9], g['times'])
+    assert np.array_equal(a, b)
+    problem = pb.MultiOutputProblem(model, g['times'], g['values'])
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'])
+    assert np.max(rel_err(got, g['scores'])) < ODE_SCORE_RTOL
+    problem = pb.MultiOutputProblem(
+        model, np.asarray(model.suggested_times(), float),
+        np.asarray(model.suggested_values(), float))
+    got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'][:16])
+    assert np.max(rel_err(got, g['small_scores'])) < ODE_SCORE_RTOL
+    # pints/tests/test_toy_sir_model.py:48-60, float y0 keeps S0 as given
+    mf = pb.toy.SIRModel(g['unit_y0'])
+    v = mf.simulate([0.05, 0.4, 100], g['unit_times'])
+    assert v[0, 0] == 10 and v[0, 1] == 1
+    assert round(abs(v[1, 0] - 15.61537), 5) == 0
+    assert round(abs(v[100, 1] - 108.542466), 5) == 0
+    vf = mf.simulate([0.05, 0.4, 77.7], g['unit_times'])
+    assert np.all(np.abs(vf - g['unit_values_frac'])
+                  <= TRAJ_ATOL + TRAJ_RTOL * np.abs(g['unit_values_frac']))
+
+
+# ------------------------------------------- live oracle, seeded random inputs
+
+@pytest.mark.parametrize('seed', [101, 102])
+def test_live_oracle_random_problems(pb, seed):
+    rng = np.random.RandomState(seed)
+    # FHN, ragged time grid that does not start at zero, unknown sigma
+    times = np.sort(rng.uniform(0.3, 18, 137))
+    values = po.fhn_simulate([0.15, 0.45, 2.7], times) \
+        + rng.normal(0, 0.3, (137, 2))
+    xs = np.hstack([np.array([0.15, 0.45, 2.7]) * (1 + 0.1 * rng.randn(24, 3)),
+                    rng.uniform(0.2, 0.5, (24, 2))])
+    spec = po.Spec('fhn', times, values, 'gaussian')
+    f = pb.GaussianLogLikelihood(pb.MultiOutputProblem(
+        pb.toy.FitzhughNagumoModel(), times, values))
+    assert np.max(rel_err(evaluate(pb, f, xs), po.scores(spec, xs))) \
+        < ODE_SCORE_RTOL
+    # logistic with a posterior (uniform prior box) and sign flip
+    times = np.linspace(0, 80, 300)
+    values = po.logistic_simulate([0.12, 40], times) + rng.normal(0, 2, 300)
+    xs = np.array([0.12, 40]) * (1 + 0.5 * rng.randn(64, 2))
+    lower, upper = np.array([0.0, 10.0]), np.array([0.3, 60.0])
+    spec = po.Spec('logistic', times, values, 'gaussian_known_sigma', 2.0,
+                   sign=-1.0, prior_box=(lower, upper))
+    post = pb.LogPosterior(
+        pb.GaussianKnownSigmaLogLikelihood(pb.SingleOutputProblem(
+            pb.toy.LogisticModel(), times, values), 2.0),
+        pb.UniformLogPrior(lower, upper))
+    got = evaluate(pb, pb.ProbabilityBasedError(post), xs)
+    want = po.scores(spec, xs)
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    assert np.any(np.isinf(want)) and not np.all(np.isinf(want))
+    assert np.nanmax(rel_err(got, want)) < ANALYTIC_RTOL
+
+
+# ------------------------------------------------------ fused vs unfused path
+
+def test_fused_equals_unfused(pb):
+    g = load_golden('fhn')
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), g['times'],
+                                    g['values'])
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    ev = pb.CudaEvaluator(ll, as_list=False)
+    fused = ev.evaluate(g['xs'])
+    dp = ev.device_problem()
+    d_x = torch.from_numpy(g['xs']).to(dp.device)
+    traj = dp.simulate(d_x)
+    unfused = dp.score_trajectories(traj, d_x).cpu().numpy()
+    assert np.max(rel_err(unfused, fused)) < 1e-12
+
+
+# ------------------------------------------------------------------ edge cases
+
+def test_edge_cases(pb):
+    g = load_golden('fhn')
+    model = pb.toy.FitzhughNagumoModel()
+    problem = pb.MultiOutputProblem(model, g['times'], g['values'])
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    ev = pb.CudaEvaluator(ll)
+    assert ev.evaluate([]) == []
+    one = ev.evaluate([g['xs'][0]])
+    assert isinstance(one, list) and len(one) == 1
+    assert abs(one[0] - g['scores'][0]) < 1e-6 * abs(g['scores'][0])
+    assert ll(g['xs'][0]) == one[0]                 # scalar __call__
+    # list of 1-d arrays, as MCMCController passes (pints/_mcmc/__init__.py:718)
+    lst = ev.evaluate([np.array(x) for x in g['xs'][:5]])
+    assert lst == ev.evaluate(g['xs'][:5])
+    # read-only input, as optimisers pass
+    ro = np.array(g['xs'][:5]); ro.setflags(write=False)
+    assert ev.evaluate(ro) == lst
+    with pytest.raises(ValueError):
+        ev.evaluate(1)
+    with pytest.raises(ValueError):
+        ev.evaluate(np.zeros((3, 2)))
+    # duplicate time points (allowed for multi-output problems)
+    t = np.array([0.0, 0.5, 0.5, 1.0, 1.0, 1.0, 2.5])
+    v = model.simulate(g['xs'][0], t)
+    assert np.array_equal(v[1], v[2]) and np.array_equal(v[3], v[5])
+    assert np.array_equal(v[0], [-1.0, 1.0])
+    # a vector the explicit solver cannot finish within the step cap -> NaN,
+    # never a hang; its neighbours are unaffected
+    bad = np.array(g['xs'][:4]); bad[1] = [0.1, 0.5, 1e7]
+    capped = pb.CudaEvaluator(ll, max_steps=2000, as_list=False).evaluate(bad)
+    assert np.isnan(capped[1]) and np.all(np.isfinite(capped[[0, 2, 3]]))
+    assert np.array_equal(capped[[0, 2, 3]],
+                          np.array(ev.evaluate(g['xs'][:4]))[[0, 2, 3]])
+    nan_in = np.array(g['xs'][:3]); nan_in[2, 0] = np.nan
+    out = pb.CudaEvaluator(ll, max_steps=5000, as_list=False).evaluate(nan_in)
+    assert np.isnan(out[2]) and np.all(np.isfinite(out[:2]))
+
+
+def test_long_series_uses_global_memory_path(pb):
+    # 6000 x 3 doubles = 144 KB > the shared-memory staging limit
+    rng = np.random.RandomState(5)
+    times = np.linspace(0, 20, 6000)
+    values = po.fhn_simulate([0.1, 0.5, 3], times) + rng.normal(0, 0.5, (6000, 2))
+    xs = po.headline_fhn_points(8)
+    spec = po.Spec('fhn', times, values, 'gaussian_known_sigma', 0.5)
+    f = pb.GaussianKnownSigmaLogLikelihood(pb.MultiOutputProblem(
+        pb.toy.FitzhughNagumoModel(), times, values), 0.5)
+    assert np.max(rel_err(evaluate(pb, f, xs), po.scores(spec, xs))) \
+        < ODE_SCORE_RTOL
+    # closed form with a long series (30000 points = 480 KB)
+    times = np.linspace(0, 100, 30000)
+    values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 1, 30000)
+    lx = np.array([0.1, 50]) * (1 + 0.1 * rng.randn(8, 2))
+    spec = po.Spec('logistic', times, values, 'sse')
+    f = pb.SumOfSquaresError(pb.SingleOutputProblem(
+        pb.toy.LogisticModel(), times, values))
+    assert np.max(rel_err(evaluate(pb, f, lx), po.scores(spec, lx))) \
+        < ANALYTIC_RTOL
+
+
+# ------------------------------------------- full size, size-free properties
+
+def test_full_population_properties(pb):
+    spec = po.headline_fhn_spec()
+    n = 65536
+    xs = po.headline_fhn_points(n)
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    ev = pb.CudaEvaluator(ll, as_list=False)
+    scores, steps = ev.evaluate_array(xs, return_steps=True)
+    assert scores.shape == (n,) and np.all(np.isfinite(scores))
+    # order independence: every vector scores the same wherever it sits
+    perm = np.random.RandomState(0).permutation(n)
+    assert np.array_equal(ev.evaluate(xs[perm]), scores[perm])
+    # the golden points are the first rows of this population
+    g = load_golden('fhn')
+    assert np.max(rel_err(scores[:96], g['scores'])) < ODE_SCORE_RTOL
+    # the likelihood is maximal near the generating parameters
+    best = xs[np.argmax(scores)]
+    assert np.all(np.abs(best / np.array([0.1, 0.5, 3]) - 1) < 0.2)
+    # sum of squares and known-sigma LL are affinely related:
+    #   LL = sum_o offset_o + multip * SSE      (same sigma for both outputs)
+    sse = evaluate(pb, pb.SumOfSquaresError(problem), xs[:4096])
+    off = ll._offset.sum()
+    assert np.max(rel_err(off + ll._multip[0] * sse, scores[:4096])) < 1e-12
+    assert 300 < steps.mean() < 600

@@ -1,0 +1,285 @@
+"""
+CPU-only checks: the C-ABI library builds, loads and exports every symbol the
+header declares; the host-side mirror validates like the reference; the
+introspection turns objective graphs (mirror objects and, when mounted, real
+reference objects) into the same problem description; and nothing silently
+falls back to the CPU.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pints_b200 as pb
+from pints_b200 import _lib
+from conftest import ROOT, load_golden
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'pints_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    names = re.findall(r'\b(pb200_[a-z0-9_]+)\s*\(', text)
+    return sorted(set(names))
+
+
+def test_library_builds_loads_and_exports_the_header():
+    from pints_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    declared = header_functions()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), name + ' is declared but not exported'
+    assert sorted(_lib.SIGNATURES) == declared
+    assert lib.pb200_version() == 100
+    assert lib.pb200_series_len(1000, 2) == 3000
+    assert lib.pb200_series_len(3, 2) == 10          # padded to 16-byte units
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH],
+                         stdout=subprocess.PIPE, text=True).stdout
+    archs = set(re.findall(r'sm_\d+a?', out))
+    assert archs == {'sm_100a'}, archs
+
+
+def test_problem_create_argument_errors():
+    import ctypes
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    oc, n_oc = _lib.doubles([1.0, 1.0])
+    mc, n_mc = _lib.doubles([-1.0, 1.0])
+    # unknown model
+    rc = lib.pb200_problem_create(99, 0, 10, 2, None, mc, n_mc, oc, n_oc, 1.0,
+                                  None, None, 0, 0.0, ctypes.byref(h))
+    assert rc == -2 and b'unknown model' in lib.pb200_last_error()
+    # wrong number of outputs for FHN
+    rc = lib.pb200_problem_create(_lib.MODEL_FHN, 0, 0, 3, None, mc, n_mc, oc,
+                                  n_oc, 1.0, None, None, 0, 0.0,
+                                  ctypes.byref(h))
+    assert rc == -1
+    # bad sign
+    rc = lib.pb200_problem_create(_lib.MODEL_FHN, 0, 0, 2, None, mc, n_mc, oc,
+                                  n_oc, 0.5, None, None, 0, 0.0,
+                                  ctypes.byref(h))
+    assert rc == -1 and b'sign' in lib.pb200_last_error()
+    # a valid (empty-series) problem can be created and destroyed without a GPU
+    rc = lib.pb200_problem_create(_lib.MODEL_FHN, 0, 0, 2, None, mc, n_mc, oc,
+                                  n_oc, 1.0, None, None, 0, 0.0,
+                                  ctypes.byref(h))
+    assert rc == 0 and h.value
+    assert lib.pb200_problem_n_parameters(h) == 3
+    # n = 0 is a no-op everywhere, n < 0 an error
+    assert lib.pb200_eval(h, None, 0, 3, None, None, None, None) == 0
+    assert lib.pb200_eval(h, None, -1, 3, None, None, None, None) == -1
+    lib.pb200_problem_destroy(h)
+    with pytest.raises(_lib.LibraryError):
+        _lib.check(-1)
+
+
+def fhn_objects(mod, toy):
+    g = load_golden('fhn')
+    model = toy.FitzhughNagumoModel()
+    problem = mod.MultiOutputProblem(model, g['times'], g['values'])
+    return g, model, problem
+
+
+def test_describe_mirror_objects():
+    g, model, problem = fhn_objects(pb, pb.toy)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    s = pb.describe(ll)
+    assert (s.model, s.objective, s.sign) == (_lib.MODEL_FHN, 1, 1.0)
+    assert s.model_consts == [-1.0, 1.0]
+    assert s.n_parameters() == 3 and s.n_outputs == 2 and s.n_times == 1000
+    off = -0.5 * 1000 * np.log(2 * np.pi) - 1000 * np.log(0.5)
+    assert s.obj_consts == [off, off, -2.0, -2.0]
+    packed = s.packed_series()
+    assert packed.shape == (3000,)
+    assert np.array_equal(packed.reshape(1000, 3)[:, 0], g['times'])
+    assert np.array_equal(packed.reshape(1000, 3)[:, 1:], g['values'])
+    s = pb.describe(pb.ProbabilityBasedError(ll))
+    assert s.sign == -1.0
+    s = pb.describe(pb.GaussianLogLikelihood(problem))
+    assert s.objective == 2 and s.n_parameters() == 5
+    assert s.obj_consts == [0.5 * 1000 * np.log(2 * np.pi)]
+    s = pb.describe(pb.SumOfSquaresError(problem, [1, 2.5]))
+    assert s.objective == 0 and s.obj_consts == [1.0, 2.5]
+    post = pb.LogPosterior(ll, pb.UniformLogPrior([0, 0, 0], [1, 2, 10]))
+    s = pb.describe(pb.ProbabilityBasedError(post))
+    assert s.prior_lower == [0, 0, 0] and s.prior_upper == [1, 2, 10]
+    assert s.log_prior == -np.log(20.0) and s.sign == -1.0
+    # SIR: the default integer y0 sets the truncation flag
+    assert pb.describe_model(pb.toy.SIRModel())[1] == [38.0, 1.0, 0.0, 1.0]
+    assert pb.describe_model(pb.toy.SIRModel([38, 1, 0]))[1][3] == 0.0
+    mid, consts = pb.describe_model(pb.toy.HodgkinHuxleyIKModel())
+    assert mid == _lib.MODEL_HH_IK and consts[:5] == [0.3, 36, -88, -75, 24]
+    assert len(consts) == 5 + 48 and consts[5] == 90 and consts[28] == 1200
+
+
+def test_unsupported_functions_raise_type_error():
+    g, model, problem = fhn_objects(pb, pb.toy)
+
+    class MyModel(pb.toy.FitzhughNagumoModel):     # user subclass: not trusted
+        pass
+
+    with pytest.raises(TypeError):
+        pb.describe(pb.SumOfSquaresError(
+            pb.MultiOutputProblem(MyModel(), g['times'], g['values'])))
+    with pytest.raises(TypeError):
+        pb.describe(lambda x: 0.0)
+    with pytest.raises(TypeError):
+        pb.CudaEvaluator(lambda x: 0.0)
+    with pytest.raises(ValueError):
+        pb.CudaEvaluator(3)                        # not callable
+    with pytest.raises(ValueError):
+        pb.CudaEvaluator(pb.SumOfSquaresError(problem), args=[1])
+    with pytest.raises(ValueError):
+        pb.CudaEvaluator(pb.SumOfSquaresError(problem), args=1)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine without a GPU')
+    g, model, problem = fhn_objects(pb, pb.toy)
+    ev = pb.CudaEvaluator(pb.SumOfSquaresError(problem))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ev.evaluate(g['xs'][:4])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model.simulate(g['xs'][0], g['times'])
+    with pytest.raises(ValueError):
+        ev.evaluate(7)             # contract errors come first, as in pints
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'pints_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, name)).read()
+                assert 'oracle' not in text.replace('no oracle', ''), name
+
+
+def test_mirror_validation_matches_reference_messages():
+    t = [0, 1, 2]
+    with pytest.raises(ValueError, match='Population size'):
+        pb.toy.LogisticModel(-1)
+    with pytest.raises(ValueError, match='size 2'):
+        pb.toy.FitzhughNagumoModel([1, 2, 3])
+    with pytest.raises(ValueError, match='> 0 and < 1'):
+        pb.toy.HodgkinHuxleyIKModel(1.0)
+    with pytest.raises(ValueError, match='negative'):
+        pb.toy.LotkaVolterraModel([-1, 0])
+    with pytest.raises(ValueError, match='size 3'):
+        pb.toy.SIRModel([1, 1])
+    with pytest.raises(ValueError, match='negative'):
+        pb.toy.SIRModel([1, 1, -1])
+    with pytest.raises(ValueError):
+        pb.toy.ConstantModel(0)
+    m = pb.toy.LogisticModel()
+    with pytest.raises(ValueError, match='increasing'):
+        pb.SingleOutputProblem(m, [0, 1, 1], [0, 0, 0])
+    with pytest.raises(ValueError, match='negative'):
+        pb.SingleOutputProblem(m, [-1, 1, 2], [0, 0, 0])
+    with pytest.raises(ValueError, match='same length'):
+        pb.SingleOutputProblem(m, t, [0, 0])
+    with pytest.raises(ValueError, match='single-output'):
+        pb.SingleOutputProblem(pb.toy.FitzhughNagumoModel(), t, [0, 0, 0])
+    f = pb.toy.FitzhughNagumoModel()
+    pb.MultiOutputProblem(f, [0, 1, 1], np.zeros((3, 2)))   # ties allowed
+    with pytest.raises(ValueError, match='non-decreasing'):
+        pb.MultiOutputProblem(f, [0, 2, 1], np.zeros((3, 2)))
+    with pytest.raises(ValueError, match='shape'):
+        pb.MultiOutputProblem(f, t, np.zeros((3, 3)))
+    p = pb.MultiOutputProblem(f, t, np.zeros((3, 2)))
+    with pytest.raises(ValueError, match='greater than zero'):
+        pb.GaussianKnownSigmaLogLikelihood(p, 0)
+    with pytest.raises(ValueError, match='length n_outputs'):
+        pb.GaussianKnownSigmaLogLikelihood(p, [1, 2, 3])
+    with pytest.raises(ValueError, match='weights'):
+        pb.SumOfSquaresError(p, [1, 2, 3])
+    with pytest.raises(ValueError, match='exceed'):
+        pb.RectangularBoundaries([0, 0], [1, 0])
+    b = pb.RectangularBoundaries([0, 0], [1, 2])
+    assert b.check([0, 0]) and not b.check([1, 0]) and not b.check([0.5, 2])
+    assert list(b.check(np.array([[0, 0], [1, 0]]))) == [True, False]
+    prior = pb.UniformLogPrior(b)
+    assert prior([0.5, 1]) == -np.log(2.0) and prior([2, 1]) == -np.inf
+    with pytest.raises(ValueError, match='same dimension'):
+        pb.LogPosterior(pb.GaussianLogLikelihood(p), prior)
+    assert pb.GaussianLogLikelihood(p).n_parameters() == 5
+
+
+# ------------------------------------------------- against the real reference
+
+def test_describe_reference_objects_equals_mirror(pints_ref):
+    pints = pints_ref
+    g = load_golden('fhn')
+
+    def build(mod, toy):
+        out = []
+        m = toy.FitzhughNagumoModel()
+        p = mod.MultiOutputProblem(m, g['times'], g['values'])
+        ll = mod.GaussianKnownSigmaLogLikelihood(p, 0.5)
+        out += [ll, mod.ProbabilityBasedError(ll), mod.GaussianLogLikelihood(p),
+                mod.SumOfSquaresError(p, [1, 2.5]),
+                mod.LogPosterior(ll, mod.UniformLogPrior([0, 0, 0],
+                                                         [1, 2, 10]))]
+        gl = load_golden('logistic')
+        pl = mod.SingleOutputProblem(toy.LogisticModel(3.0), gl['times'],
+                                     gl['values'])
+        out += [mod.SumOfSquaresError(pl), mod.GaussianLogLikelihood(pl)]
+        gh = load_golden('hh_ik')
+        ph = mod.SingleOutputProblem(toy.HodgkinHuxleyIKModel(0.4),
+                                     gh['times'], gh['values'])
+        out += [mod.GaussianLogLikelihood(ph)]
+        gs = load_golden('sir')
+        out += [mod.GaussianLogLikelihood(mod.MultiOutputProblem(
+            toy.SIRModel(), gs['times'], gs['values'])),
+            mod.GaussianLogLikelihood(mod.MultiOutputProblem(
+                toy.SIRModel([30, 2, 1]), gs['times'], gs['values'])),
+            mod.GaussianLogLikelihood(mod.MultiOutputProblem(
+                toy.LotkaVolterraModel(), gs['times'], gs['values']))]
+        gc = load_golden('constant')
+        out += [mod.GaussianKnownSigmaLogLikelihood(mod.MultiOutputProblem(
+            toy.ConstantModel(3), gc['single_times'], gc['multi_values']),
+            gc['multi_sigma'])]
+        return out
+
+    for ref_f, mir_f in zip(build(pints, pints.toy), build(pb, pb.toy)):
+        a, b = pb.describe(ref_f), pb.describe(mir_f)
+        for key in ('model', 'model_consts', 'objective', 'obj_consts', 'sign',
+                    'prior_lower', 'prior_upper', 'log_prior', 'n_times',
+                    'n_outputs', 'multi_output'):
+            assert getattr(a, key) == getattr(b, key), (key, type(ref_f))
+        assert np.array_equal(a.packed_series(), b.packed_series())
+
+
+def test_cuda_evaluator_is_a_pints_evaluator(pints_ref):
+    pints = pints_ref
+    assert issubclass(pb.CudaEvaluator, pints.Evaluator)
+    g = load_golden('fhn')
+    m = pints.toy.FitzhughNagumoModel()
+    p = pints.MultiOutputProblem(m, g['times'], g['values'])
+    ll = pints.GaussianKnownSigmaLogLikelihood(p, 0.5)
+    ev = pb.CudaEvaluator(pints.ProbabilityBasedError(ll))
+    assert isinstance(ev, pints.Evaluator) and ev.spec().sign == -1.0
+    # mirror objectives pass the reference's isinstance checks
+    mm = pb.toy.FitzhughNagumoModel()
+    mp = pb.MultiOutputProblem(mm, g['times'], g['values'])
+    mll = pb.GaussianKnownSigmaLogLikelihood(mp, 0.5)
+    assert isinstance(mll, pints.LogPDF) and isinstance(mm, pints.ForwardModel)
+    pints.ProbabilityBasedError(mll)
+    pints.LogPosterior(mll, pints.UniformLogPrior([0, 0, 0], [1, 1, 10]))
+    # unsupported reference objects are refused, not evaluated on the CPU
+    with pytest.raises(TypeError):
+        pb.CudaEvaluator(pints.MeanSquaredError(p))
+    with pytest.raises(TypeError):
+        pb.CudaEvaluator(pints.toy.RosenbrockError())
+    with pytest.raises(TypeError):
+        pb.CudaEvaluator(pints.GaussianLogLikelihood(pints.MultiOutputProblem(
+            pints.toy.GoodwinOscillatorModel(), g['times'],
+            np.zeros((1000, 3)))))
