@@ -34,6 +34,18 @@ def save(name, **arrays):
     print('%-24s %8.1f KB' % (name + '.npz', os.path.getsize(path) / 1024.0))
 
 
+def gauss_ll_from(sim, values, sigma):
+    """GaussianLogLikelihood of a given (tight-tolerance) trajectory, written
+    with the reference's own expression (pints/_log_likelihoods.py:1127-1129)
+    so that only the trajectory differs."""
+    sigma = np.asarray(sigma)
+    nt = len(values)
+    logn = 0.5 * nt * np.log(2 * np.pi)
+    error = values - sim
+    return np.sum(- logn - nt * np.log(sigma)
+                  - np.sum(error**2, axis=0) / (2 * sigma**2))
+
+
 # --------------------------------------------------------------------------
 # the five benchmark problems of BASELINE.json / SURVEY.md section 8(d)
 # --------------------------------------------------------------------------
@@ -182,6 +194,9 @@ def golden_lv():
     traj = np.array([model.simulate(x[:4], times) for x in xs[:8]])
     truth = np.array([odeint(model._rhs, model._y0, times, (x[:4],), **TRUTH)
                       for x in xs[:8]])
+    truth_scores = np.array([gauss_ll_from(
+        odeint(model._rhs, model._y0, times, (x[:4],), **TRUTH), values,
+        x[4:]) for x in xs])
     # reference unit test (pints/tests/test_toy_lotka_volterra_model.py:42-55)
     mu = pints.toy.LotkaVolterraModel([3, 5])
     tu = np.linspace(0, 5, 101)
@@ -192,7 +207,7 @@ def golden_lv():
     gls = pints.GaussianLogLikelihood(pints.MultiOutputProblem(model, ts, vs))
     ss = np.array(pints.SequentialEvaluator(gls).evaluate(xs[:16]))
     save('lotka_volterra', times=times, values=values, xs=xs, scores=scores,
-         traj=traj, truth=truth, unit_times=tu, unit_values=vu,
+         traj=traj, truth=truth, truth_scores=truth_scores, unit_times=tu, unit_values=vu,
          unit_y0=np.array([3.0, 5.0]), unit_x=np.array([1, 2, 2, 0.5]),
          small_times=ts, small_values=vs, small_scores=ss)
 
@@ -218,6 +233,8 @@ def golden_sir():
         y0 = np.array([int(x[2]), 1.0, 0.0])
         return odeint(model._rhs, y0, times, (x[0], x[1]), **TRUTH)[:, 1:]
     truth = np.array([truth_one(x) for x in xs[:8]])
+    truth_scores = np.array([gauss_ll_from(truth_one(x), values, x[3:])
+                             for x in xs])
     # float y0 (no truncation) and the reference unit test
     # (pints/tests/test_toy_sir_model.py:48-60)
     mf = pints.toy.SIRModel([100, 10, 1])
@@ -229,7 +246,7 @@ def golden_sir():
     gls = pints.GaussianLogLikelihood(pints.MultiOutputProblem(model, ts, vs))
     ss = np.array(pints.SequentialEvaluator(gls).evaluate(xs[:16]))
     save('sir', times=times, values=values, xs=xs, scores=scores, traj=traj,
-         truth=truth, unit_times=tu, unit_values=vu, unit_values_frac=vf,
+         truth=truth, truth_scores=truth_scores, unit_times=tu, unit_values=vu, unit_values_frac=vf,
          unit_y0=np.array([100.0, 10.0, 1.0]), small_times=ts,
          small_values=vs, small_scores=ss)
 
