@@ -20,28 +20,80 @@
 namespace {
 
 // --------------------------------------------------------------- tableau
-constexpr double A21 = 1.0 / 5.0;
-constexpr double A31 = 3.0 / 40.0, A32 = 9.0 / 40.0;
-constexpr double A41 = 44.0 / 45.0, A42 = -56.0 / 15.0, A43 = 32.0 / 9.0;
-constexpr double A51 = 19372.0 / 6561.0, A52 = -25360.0 / 2187.0,
-                 A53 = 64448.0 / 6561.0, A54 = -212.0 / 729.0;
-constexpr double A61 = 9017.0 / 3168.0, A62 = -355.0 / 33.0,
-                 A63 = 46732.0 / 5247.0, A64 = 49.0 / 176.0,
-                 A65 = -5103.0 / 18656.0;
-constexpr double B1 = 35.0 / 384.0, B3 = 500.0 / 1113.0, B4 = 125.0 / 192.0,
-                 B5 = -2187.0 / 6784.0, B6 = 11.0 / 84.0;
-// error estimate = h * sum E_i k_i  (5th minus 4th order weights)
-constexpr double E1 = 71.0 / 57600.0, E3 = -71.0 / 16695.0, E4 = 71.0 / 1920.0,
-                 E5 = -17253.0 / 339200.0, E6 = 22.0 / 525.0, E7 = -1.0 / 40.0;
-// dense output (Hairer, Norsett & Wanner, contd5)
-constexpr double D1 = -12715105075.0 / 11282082432.0,
-                 D3 = 87487479700.0 / 32700410799.0,
-                 D4 = -10690763975.0 / 1880347072.0,
-                 D5 = 701980252875.0 / 199316789632.0,
-                 D6 = -1453857185.0 / 822651844.0,
-                 D7 = 69997945.0 / 29380423.0;
+// Dormand-Prince 5(4): stage weights A, 5th-order weights B, error weights E
+// (5th minus 4th order), dense-output weights D (Hairer, Norsett & Wanner,
+// contd5).  Kept in __constant__ memory so every DFMA/DMUL takes its coefficient
+// straight from the constant bank instead of re-materialising 64-bit immediates
+// (two UMOVs each) inside the step loop.
+enum { I_A21, I_A31, I_A32, I_A41, I_A42, I_A43, I_A51, I_A52, I_A53, I_A54, I_A61, I_A62, I_A63, I_A64, I_A65, I_B1, I_B3, I_B4, I_B5, I_B6, I_E1, I_E3, I_E4, I_E5, I_E6, I_E7, I_D1, I_D3, I_D4, I_D5, I_D6, I_D7, N_TAB };
+__constant__ double TAB[N_TAB] = {
+    1.0 / 5.0,
+    3.0 / 40.0,
+    9.0 / 40.0,
+    44.0 / 45.0,
+    -56.0 / 15.0,
+    32.0 / 9.0,
+    19372.0 / 6561.0,
+    -25360.0 / 2187.0,
+    64448.0 / 6561.0,
+    -212.0 / 729.0,
+    9017.0 / 3168.0,
+    -355.0 / 33.0,
+    46732.0 / 5247.0,
+    49.0 / 176.0,
+    -5103.0 / 18656.0,
+    35.0 / 384.0,
+    500.0 / 1113.0,
+    125.0 / 192.0,
+    -2187.0 / 6784.0,
+    11.0 / 84.0,
+    71.0 / 57600.0,
+    -71.0 / 16695.0,
+    71.0 / 1920.0,
+    -17253.0 / 339200.0,
+    22.0 / 525.0,
+    -1.0 / 40.0,
+    -12715105075.0 / 11282082432.0,
+    87487479700.0 / 32700410799.0,
+    -10690763975.0 / 1880347072.0,
+    701980252875.0 / 199316789632.0,
+    -1453857185.0 / 822651844.0,
+    69997945.0 / 29380423.0,
+};
+#define A21 TAB[I_A21]
+#define A31 TAB[I_A31]
+#define A32 TAB[I_A32]
+#define A41 TAB[I_A41]
+#define A42 TAB[I_A42]
+#define A43 TAB[I_A43]
+#define A51 TAB[I_A51]
+#define A52 TAB[I_A52]
+#define A53 TAB[I_A53]
+#define A54 TAB[I_A54]
+#define A61 TAB[I_A61]
+#define A62 TAB[I_A62]
+#define A63 TAB[I_A63]
+#define A64 TAB[I_A64]
+#define A65 TAB[I_A65]
+#define B1 TAB[I_B1]
+#define B3 TAB[I_B3]
+#define B4 TAB[I_B4]
+#define B5 TAB[I_B5]
+#define B6 TAB[I_B6]
+#define E1 TAB[I_E1]
+#define E3 TAB[I_E3]
+#define E4 TAB[I_E4]
+#define E5 TAB[I_E5]
+#define E6 TAB[I_E6]
+#define E7 TAB[I_E7]
+#define D1 TAB[I_D1]
+#define D3 TAB[I_D3]
+#define D4 TAB[I_D4]
+#define D5 TAB[I_D5]
+#define D6 TAB[I_D6]
+#define D7 TAB[I_D7]
 
-constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
+constexpr double MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;   // safety 0.9 in step_factor()
 
 // ----------------------------------------------------------------- models
 // Each model: NS states, NO outputs, OUT0 = index of the first output state,
@@ -49,22 +101,27 @@ constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
 // (autonomous) right-hand side.
 struct FhnModel {
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 3;
-    double a, b, c, neg_inv_c;
+    // V' = c (V - V^3/3 + R) = (c - (c/3) V^2) V + c R
+    // R' = -(V - a + b R) / c  = (-1/c) V + (a/c) + (-b/c) R
+    // written with per-vector constants so one evaluation is 6 FP64 ops
+    double c, c3, nic, aoc, nboc;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
                                          double *y, double /*t_first*/,
                                          double *t0) {
-        a = x[0]; b = x[1]; c = x[2];
-        neg_inv_c = -1.0 / c;
+        const double a = x[0], b = x[1];
+        c = x[2];
+        c3 = c * (-1.0 / 3.0);
+        nic = -1.0 / c;
+        aoc = -nic * a;
+        nboc = nic * b;
         y[0] = mc.c[0]; y[1] = mc.c[1];
         *t0 = 0.0;
     }
     __device__ __forceinline__ void rhs(const double *y, double *f) const {
         const double V = y[0], R = y[1];
-        // (V - V^3/3 + R) * c ;  (V - a + b R) / -c
-        const double v2 = V * V;
-        const double cubic = fma(v2 * (-1.0 / 3.0), V, V);
-        f[0] = (cubic + R) * c;
-        f[1] = fma(b, R, V - a) * neg_inv_c;
+        const double u = fma(c3, V * V, c);
+        f[0] = fma(u, V, c * R);
+        f[1] = fma(nboc, R, fma(nic, V, aoc));
     }
 };
 
@@ -79,9 +136,8 @@ struct LvModel {
     }
     __device__ __forceinline__ void rhs(const double *y, double *f) const {
         const double u = y[0], v = y[1];
-        const double uv = u * v;
-        f[0] = fma(a, u, -(b * uv));      // a x - b x y
-        f[1] = fma(d, uv, -(c * v));      // -c y + d x y
+        f[0] = u * fma(-b, v, a);         // a x - b x y
+        f[1] = v * fma(d, u, -c);         // -c y + d x y
     }
 };
 
@@ -100,31 +156,43 @@ struct SirModel {
         *t0 = t_first;                    // initial condition holds at times[0]
     }
     __device__ __forceinline__ void rhs(const double *y, double *f) const {
-        const double gsi = gamma * y[0] * y[1];
+        const double ngsi = (-gamma * y[0]) * y[1];
         const double vi = v * y[1];
-        f[0] = -gsi;
-        f[1] = gsi - vi;
+        f[0] = ngsi;
+        f[1] = -ngsi - vi;
         f[2] = vi;
     }
 };
 
-__device__ __forceinline__ double rcp_approx(double x) {
-    // MUFU.RCP64H seed (>= 20 bits) + one Newton step: ~1e-12 relative, plenty
-    // for the step-size controller (accept/reject never depends on it).
+// MUFU.RCP64H: >= 20 good bits, on the XU pipe (off the FP64 pipe).
+__device__ __forceinline__ double rcp_seed(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+
+// Full-precision reciprocal for normal-range x: seed + two Newton steps
+// (20 -> 40 -> 80 bits); no slow path, four DFMAs.
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r = rcp_seed(x);
+    r = fma(r, fma(-x, r, 1.0), r);
     return fma(r, fma(-x, r, 1.0), r);
 }
 
+// Mean square of err_i / (atol + rtol * (|y_i| + |ynew_i|) / 2).  The scale
+// uses the mean of the two magnitudes (one DADD with |.| modifiers) instead of
+// their max (a DSETP plus a 64-bit select); the 1e-6-accurate reciprocal seed
+// is enough because the result is only compared with 1 and fed to the
+// step-size controller.
 template <int NS>
-__device__ __forceinline__ double err_norm2(const double *err, const double *y,
-                                            const double *yn, double rtol,
-                                            double atol) {
+__device__ __forceinline__ double err_norm2(const double *esum, double h,
+                                            const double *y, const double *yn,
+                                            double half_rtol, double atol) {
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-        const double sc = fma(rtol, fmax(fabs(y[i]), fabs(yn[i])), atol);
-        const double q = err[i] * rcp_approx(sc);
+        const double sc = fma(half_rtol, fabs(y[i]) + fabs(yn[i]), atol);
+        const double q = (esum[i] * h) * rcp_seed(sc);
         s = fma(q, q, s);
     }
     return s * (1.0 / NS);
@@ -139,6 +207,26 @@ __device__ __forceinline__ double step_factor(double norm2) {
     return static_cast<double>(0.9f * f);
 }
 
+// Observed series access.  In shared memory the rows are read with explicit
+// ld.shared through a 32-bit byte address kept in a register (the generic
+// pointer form makes the compiler rebuild the shared-window base on every
+// access); otherwise through the read-only global path.
+template <bool SMEM>
+struct Series {
+    uint32_t sbase;
+    const double *gbase;
+    __device__ __forceinline__ double at(uint32_t byte_off) const {
+        double v;
+        if (SMEM) {
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase + byte_off));
+        } else {
+            v = __ldg(reinterpret_cast<const double *>(
+                reinterpret_cast<const char *>(gbase) + byte_off));
+        }
+        return v;
+    }
+};
+
 template <class M, bool SMEM, bool TRAJ>
 __global__ void __launch_bounds__(128)
 ode_kernel(const __grid_constant__ ProblemDev P,
@@ -147,18 +235,18 @@ ode_kernel(const __grid_constant__ ProblemDev P,
            double *__restrict__ scores, double *__restrict__ traj,
            int32_t *__restrict__ steps_out, const SolverDev S) {
     constexpr int NS = M::NS, NO = M::NO, OUT0 = M::OUT0;
-    constexpr int ROW = 1 + NO;
+    constexpr uint32_t ROWB = (1 + NO) * 8;          // bytes per series row
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
 
-    const double *series;
+    Series<SMEM> series;
+    series.gbase = P.series;
+    series.sbase = 0;
     if (SMEM) {
         const uint32_t bytes =
-            static_cast<uint32_t>((static_cast<int64_t>(P.n_times) * ROW * 8 + 15) & ~15ll);
+            static_cast<uint32_t>((static_cast<int64_t>(P.n_times) * ROWB + 15) & ~15ll);
         stage_series(smem, P.series, bytes, &bar);
-        series = smem;
-    } else {
-        series = P.series;
+        series.sbase = smem_u32(smem);
     }
 
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -182,29 +270,36 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 
     M model;
     double y[NS], t;
-    model.load(x, mc, y, nt > 0 ? series[0] : 0.0, &t);
+    model.load(x, mc, y, nt > 0 ? series.at(0) : 0.0, &t);
 
     double ss[NO];
 #pragma unroll
     for (int o = 0; o < NO; ++o) ss[o] = 0.0;
 
-    int idx = 0;
+    // `off` is the byte offset of the next observation row, `t_out` its time
+    // (+inf once the series is exhausted): one register compare per step
+    // decides whether any interpolation is needed.
+    const uint32_t end = static_cast<uint32_t>(nt) * ROWB;
+    uint32_t off = 0;
+    double t_out = nt > 0 ? series.at(0) : INFINITY;
     double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * NO : nullptr;
 
     // observations at (or before) the initial time see the initial state
-    while (idx < nt && series[idx * ROW] <= t) {
+    while (t_out <= t) {
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
-            if (TRAJ) my_traj[idx * NO + o] = y[OUT0 + o];
-            const double r = series[idx * ROW + 1 + o] - y[OUT0 + o];
+            if (TRAJ) my_traj[o] = y[OUT0 + o];
+            const double r = series.at(off + 8 + 8 * o) - y[OUT0 + o];
             ss[o] = fma(r, r, ss[o]);
         }
-        ++idx;
+        if (TRAJ) my_traj += NO;
+        off += ROWB;
+        t_out = off < end ? series.at(off) : INFINITY;
     }
 
-    const double rtol = S.rtol, atol = S.atol;
+    const double half_rtol = 0.5 * S.rtol, atol = S.atol;
     double k1[NS], k2[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS];
-    double yn[NS], w[NS], err[NS];
+    double yn[NS], w[NS], esum[NS];
     model.rhs(y, k1);
 
     // ---- first step (Hairer's hinit, as scipy's select_initial_step) ----
@@ -213,7 +308,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            const double sc = fma(rtol, fabs(y[j]), atol);
+            const double sc = fma(S.rtol, fabs(y[j]), atol);
             const double a0 = y[j] / sc, a1 = k1[j] / sc;
             d0 = fma(a0, a0, d0);
             d1 = fma(a1, a1, d1);
@@ -227,7 +322,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         double d2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            const double sc = fma(rtol, fabs(y[j]), atol);
+            const double sc = fma(S.rtol, fabs(y[j]), atol);
             const double a2 = (k2[j] - k1[j]) / sc;
             d2 = fma(a2, a2, d2);
         }
@@ -243,13 +338,13 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     bool after_reject = false;
     const int max_steps = S.max_steps;
 
-    while (idx < nt) {
+    while (off < end) {
         if (attempts >= max_steps || !(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) {
             failed = true;
             break;
         }
         ++attempts;
-        // ---- six stages ----
+        // ---- six stages (k1 is f(y): first-same-as-last) ----
 #pragma unroll
         for (int j = 0; j < NS; ++j) w[j] = fma(h, A21 * k1[j], y[j]);
         model.rhs(w, k2);
@@ -273,17 +368,17 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         for (int j = 0; j < NS; ++j)
             yn[j] = fma(h, fma(B6, k6[j], fma(B5, k5[j], fma(B4, k4[j], fma(B3, k3[j], B1 * k1[j])))), y[j]);
         model.rhs(yn, k7);
-        // ---- embedded error ----
+        // ---- embedded error estimate (to be scaled by h) ----
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            err[j] = h * fma(E7, k7[j], fma(E6, k6[j], fma(E5, k5[j], fma(E4, k4[j], fma(E3, k3[j], E1 * k1[j])))));
-        const double n2 = err_norm2<NS>(err, y, yn, rtol, atol);
+            esum[j] = fma(E7, k7[j], fma(E6, k6[j], fma(E5, k5[j], fma(E4, k4[j], fma(E3, k3[j], E1 * k1[j])))));
+        const double n2 = err_norm2<NS>(esum, h, y, yn, half_rtol, atol);
 
         if (n2 <= 1.0) {
             // ---- accepted: interpolate at the observation times inside ----
             const double t_new = t + h;
-            if (series[idx * ROW] <= t_new) {
-                const double inv_h = 1.0 / h;
+            if (t_out <= t_new) {
+                const double inv_h = rcp_newton(h);
                 double r2[NS], r3[NS], r4[NS], r5[NS];
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
@@ -294,18 +389,20 @@ ode_kernel(const __grid_constant__ ProblemDev P,
                     r5[j] = h * fma(D7, k7[j], fma(D6, k6[j], fma(D5, k5[j], fma(D4, k4[j], fma(D3, k3[j], D1 * k1[j])))));
                 }
                 do {
-                    const double th = (series[idx * ROW] - t) * inv_h;
+                    const double th = (t_out - t) * inv_h;
                     const double th1 = 1.0 - th;
 #pragma unroll
                     for (int o = 0; o < NO; ++o) {
                         const int j = OUT0 + o;
                         const double v = fma(th, fma(th1, fma(th, fma(th1, r5[j], r4[j]), r3[j]), r2[j]), y[j]);
-                        if (TRAJ) my_traj[idx * NO + o] = v;
-                        const double r = series[idx * ROW + 1 + o] - v;
+                        if (TRAJ) my_traj[o] = v;
+                        const double r = series.at(off + 8 + 8 * o) - v;
                         ss[o] = fma(r, r, ss[o]);
                     }
-                    ++idx;
-                } while (idx < nt && series[idx * ROW] <= t_new);
+                    if (TRAJ) my_traj += NO;
+                    off += ROWB;
+                    t_out = off < end ? series.at(off) : INFINITY;
+                } while (t_out <= t_new);
             }
             t = t_new;
 #pragma unroll
@@ -326,8 +423,10 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 
     if (steps_out) steps_out[i] = attempts;
     if (TRAJ) {
-        if (failed)
-            for (int q = idx * NO; q < nt * NO; ++q) my_traj[q] = NAN;
+        if (failed) {
+            const int64_t rest = (static_cast<int64_t>(end) - off) / ROWB * NO;
+            for (int64_t q = 0; q < rest; ++q) my_traj[q] = NAN;
+        }
     } else {
         scores[i] = failed ? NAN : objective_finish(P, ss, x);
     }
