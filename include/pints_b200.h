@@ -93,7 +93,8 @@ int64_t pb200_series_len(int32_t n_times, int32_t n_outputs);
  * (pints/_core.py:102-327, pints/_log_pdfs.py:134-241).
  *
  * d_series   device buffer of pb200_series_len() doubles, 16-byte aligned:
- *            n_times rows of [t_j, v_j0 .. v_j(n_outputs-1)], zero padded.
+ *            n_times rows of [t_j, v_j0 .. v_j(n_outputs-1)], then one
+ *            sentinel row whose time is +infinity (values 0), zero padded.
  *            Times must be non-negative and non-decreasing
  *            (pints/_core.py:129-133, :238-242); the caller checks that.
  * model_consts (host)

@@ -12,6 +12,9 @@ reference's own interfaces for that path:
   toy.LotkaVolterraModel, toy.SIRModel, toy.ConstantModel
   SumOfSquaresError, GaussianKnownSigmaLogLikelihood, GaussianLogLikelihood,
   ProbabilityBasedError, LogPosterior, UniformLogPrior, RectangularBoundaries
+  HaarioBardenetACMC, DifferentialEvolutionMCMC   device-resident samplers
+  XNES (vectorised), CudaOptimisationController, CudaMCMCController,
+  cuda_evaluators()                   run the reference's own controllers on GPU
 
 Host code is Python; compute is hand-written CUDA behind the C ABI of
 ``include/pints_b200.h`` (bound with ctypes in ``_lib``); PyTorch supplies
@@ -36,6 +39,11 @@ _LAZY = {
     'Evaluator': '_evaluation', 'CudaEvaluator': '_evaluation',
     'DeviceProblem': '_engine', 'fp64_probe': '_engine',
     'require_cuda': '_engine',
+    'HaarioBardenetACMC': '_samplers',
+    'DifferentialEvolutionMCMC': '_samplers',
+    'XNES': '_controllers', 'cuda_evaluators': '_controllers',
+    'CudaOptimisationController': '_controllers',
+    'CudaMCMCController': '_controllers',
 }
 
 

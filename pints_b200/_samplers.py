@@ -1,0 +1,423 @@
+"""
+Device-resident MCMC samplers: the companion kernels of the evaluation path.
+
+  HaarioBardenetACMC          all chains of pints.HaarioBardenetACMC at once
+                              (pints/_mcmc/_adaptive_covariance.py:109-131,
+                              :236-303; pints/_mcmc/_haario_bardenet_ac.py:59-73)
+  DifferentialEvolutionMCMC   pints.DifferentialEvolutionMCMC
+                              (pints/_mcmc/_differential_evolution.py:89-124,
+                              :146-192, :283-332)
+
+Both keep the reference's ask/tell protocol, but for *all* chains in one call and
+with the state living in HBM: ``ask()`` returns the ``(n_chains, d)`` proposals as
+a device tensor, ``tell(fx)`` takes the ``(n_chains,)`` log-pdfs as a device
+tensor.  The accept/reject rule and the adaptation arithmetic are bit-exact with
+the reference given the same proposals, scores and uniforms (``replay`` inputs;
+see tests/test_gpu_samplers.py).  With ``rng='philox'`` proposals and uniforms
+come from a counter-based generator on the device; the Haario-Bardenet proposal
+then uses a Cholesky factor where NumPy uses an SVD, which is a different but
+equally distributed draw (statistical parity only).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._engine import _ptr, _stream_ptr, require_cuda
+
+
+def _f64(x, device):
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device)
+
+
+class _DeviceOps(object):
+    """Thin wrappers of the sampler entry points of the C ABI."""
+
+    def __init__(self, device):
+        self.device = require_cuda(device)
+        self.lib = _lib.load()
+
+    def _call(self, fn, *args):
+        with torch.cuda.device(self.device):
+            _lib.check(fn(*args, _stream_ptr(self.device)))
+
+    def mh_accept(self, cur, cur_f, prop, fx, log_u, accepted, require_finite):
+        n, d = cur.shape
+        self._call(self.lib.pb200_mh_accept, _ptr(cur), _ptr(cur_f), _ptr(prop),
+                   _ptr(fx), _ptr(log_u), _ptr(accepted), n, d,
+                   1 if require_finite else 0)
+
+    def hbac_adapt(self, cur, accepted, mu, sigma, log_lambda, gamma, target):
+        n, d = cur.shape
+        self._call(self.lib.pb200_hbac_adapt, _ptr(cur), _ptr(accepted),
+                   _ptr(mu), _ptr(sigma), _ptr(log_lambda), n, d,
+                   float(gamma), float(target))
+
+    def hbac_propose(self, cur, sigma, log_lambda, z, prop):
+        n, d = cur.shape
+        self._call(self.lib.pb200_hbac_propose, _ptr(cur), _ptr(sigma),
+                   _ptr(log_lambda), _ptr(z), _ptr(prop), n, d)
+
+    def de_propose(self, cur_all, first, eps, r1, r2, prop, gamma):
+        n, d = prop.shape
+        self._call(self.lib.pb200_de_propose, _ptr(cur_all), int(first),
+                   _ptr(eps), _ptr(r1), _ptr(r2), _ptr(prop), n, d,
+                   float(gamma))
+
+    def normal(self, out, seed, offset):
+        self._call(self.lib.pb200_philox_normal, _ptr(out), out.numel(),
+                   ctypes.c_uint64(seed), ctypes.c_uint64(offset))
+
+    def uniform(self, out, seed, offset):
+        self._call(self.lib.pb200_philox_uniform, _ptr(out), out.numel(),
+                   ctypes.c_uint64(seed), ctypes.c_uint64(offset))
+
+    def pairs(self, r1, r2, first, n_total, seed, offset):
+        self._call(self.lib.pb200_philox_pairs, _ptr(r1), _ptr(r2),
+                   r1.numel(), int(first), int(n_total),
+                   ctypes.c_uint64(seed), ctypes.c_uint64(offset))
+
+
+class _Philox(object):
+    """Bookkeeping of the counter space: every draw gets a fresh offset."""
+
+    def __init__(self, seed):
+        self.seed = int(seed) & (2**64 - 1)
+        self.offset = 0
+
+    def take(self, n):
+        off = self.offset
+        self.offset += (int(n) + 1) // 2 + 1
+        return off
+
+
+class HaarioBardenetACMC(object):
+    """All chains of the Haario-Bardenet adaptive covariance sampler.
+
+    Parameters
+    ----------
+    x0 : (n_chains, d) starting points
+    sigma0 : None, (d,), (d, d) or (n_chains, d, d)
+        Initial proposal covariance; ``None`` gives the reference's default
+        ``diag(0.01 |x0|)`` per chain (zeros replaced by one,
+        pints/_mcmc/__init__.py:84-91).
+    rng : 'philox' (device draws) or 'replay' (the caller supplies proposals
+        and log-uniforms to ``ask``/``tell``; used for bit-exact parity tests
+        and for reproducing a NumPy-seeded reference run).
+    """
+
+    def __init__(self, x0, sigma0=None, device=None, rng='philox', seed=0,
+                 eta=0.6, target_acceptance=0.234):
+        x0 = np.array(x0, dtype=np.float64, copy=True)
+        if x0.ndim != 2:
+            raise ValueError('x0 must have shape (n_chains, n_parameters).')
+        self._n, self._d = x0.shape
+        if self._d > _lib.MAX_PARAMS:
+            raise ValueError('At most %d parameters are supported.'
+                             % _lib.MAX_PARAMS)
+        if rng not in ('philox', 'replay'):
+            raise ValueError("rng must be 'philox' or 'replay'")
+        self._ops = _DeviceOps(device)
+        dev = self._ops.device
+        self._rng_mode = rng
+        self._rng = _Philox(seed)
+        n, d = self._n, self._d
+        if sigma0 is None:
+            s = np.abs(x0)
+            s[s == 0] = 1
+            sigma = np.zeros((n, d, d))
+            sigma[:, np.arange(d), np.arange(d)] = 0.01 * s
+        else:
+            s = np.array(sigma0, dtype=np.float64)
+            if s.shape == (n, d, d):
+                sigma = s.copy()
+            elif s.size == d:
+                sigma = np.tile(np.diag(s.reshape(d)), (n, 1, 1))
+            else:
+                sigma = np.tile(s.reshape((d, d)), (n, 1, 1))
+        self._x0 = _f64(x0, dev)
+        self._sigma = _f64(sigma, dev)
+        self._mu = self._x0.clone()
+        self._log_lambda = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._current = torch.empty_like(self._x0)
+        self._current_f = torch.empty(n, dtype=torch.float64, device=dev)
+        self._proposed = torch.empty_like(self._x0)
+        self._z = torch.empty_like(self._x0)
+        self._log_u = torch.empty(n, dtype=torch.float64, device=dev)
+        self._accepted = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._eta = float(eta)
+        self._target = float(target_acceptance)
+        self._adaptive = False
+        self._adaptations = 1
+        self._gamma = 1.0
+        self._iterations = 0
+        self._acceptance_count = torch.zeros(n, dtype=torch.int64, device=dev)
+        self._started = False
+        self._have_current = False
+        self._asked = False
+
+    # -- reference-shaped accessors -----------------------------------
+    def n_chains(self):
+        return self._n
+
+    def n_parameters(self):
+        return self._d
+
+    def needs_initial_phase(self):
+        return True
+
+    def in_initial_phase(self):
+        return not self._adaptive
+
+    def set_initial_phase(self, initial_phase):
+        self._adaptive = not bool(initial_phase)
+
+    def eta(self):
+        return self._eta
+
+    def set_eta(self, eta):
+        if eta <= 0:
+            raise ValueError('eta should be greater than zero')
+        self._eta = float(eta)
+
+    def target_acceptance_rate(self):
+        return self._target
+
+    def set_target_acceptance_rate(self, rate=0.234):
+        rate = float(rate)
+        if rate <= 0:
+            raise ValueError('Target acceptance rate must be greater than 0.')
+        if rate > 1:
+            raise ValueError('Target acceptance rate cannot exceed 1.')
+        self._target = rate
+
+    def acceptance_rate(self):
+        """Per-chain measured acceptance rate (host array)."""
+        if self._iterations == 0:
+            return np.zeros(self._n)
+        return self._acceptance_count.cpu().numpy() / float(self._iterations)
+
+    def current(self):
+        return self._current
+
+    def current_log_pdfs(self):
+        return self._current_f
+
+    def state(self):
+        """Host copies of (mu, sigma, log_lambda), for tests and diagnostics."""
+        return (self._mu.cpu().numpy(), self._sigma.cpu().numpy(),
+                self._log_lambda.cpu().numpy())
+
+    @classmethod
+    def name(cls):
+        return 'Haario-Bardenet adaptive covariance MCMC'
+
+    # -- ask / tell -----------------------------------------------------
+    def ask(self, proposed=None):
+        """Proposals for all chains (device tensor ``(n_chains, d)``).  In
+        replay mode pass the proposals drawn elsewhere."""
+        if not self._started:
+            self._started = True
+            self._proposed.copy_(self._x0)
+        elif not self._asked:
+            if proposed is not None:
+                self._proposed.copy_(torch.as_tensor(proposed).to(
+                    self._proposed.device))
+            elif self._rng_mode == 'replay':
+                raise RuntimeError('replay mode: ask() needs the proposals')
+            else:
+                off = self._rng.take(self._z.numel())
+                self._ops.normal(self._z, self._rng.seed, off)
+                self._ops.hbac_propose(self._current, self._sigma,
+                                       self._log_lambda, self._z,
+                                       self._proposed)
+        self._asked = True
+        return self._proposed
+
+    def tell(self, fx, log_u=None):
+        """Accept/reject and adapt.  ``fx`` holds the log-pdfs of the proposals
+        (device tensor or array).  Returns ``(current, current_log_pdfs,
+        accepted)`` as device tensors."""
+        if not self._asked:
+            raise RuntimeError('Tell called before proposal was set.')
+        self._asked = False
+        fx = torch.as_tensor(fx)
+        if fx.device != self._current.device or fx.dtype != torch.float64:
+            fx = fx.to(device=self._current.device, dtype=torch.float64)
+        self._iterations += 1
+        if not self._have_current:
+            if not bool(torch.isfinite(fx).all()):
+                raise ValueError(
+                    'Initial point for MCMC must have finite logpdf.')
+            self._current.copy_(self._proposed)
+            self._current_f.copy_(fx)
+            self._accepted.fill_(1)
+            self._have_current = True
+            return self._current, self._current_f, self._accepted
+        if log_u is not None:
+            self._log_u.copy_(torch.as_tensor(log_u).to(self._log_u.device))
+        elif self._rng_mode == 'replay':
+            raise RuntimeError('replay mode: tell() needs log_u')
+        else:
+            off = self._rng.take(self._n)
+            self._ops.uniform(self._log_u, self._rng.seed, off)
+            torch.log_(self._log_u)
+        self._ops.mh_accept(self._current, self._current_f, self._proposed, fx,
+                            self._log_u, self._accepted, True)
+        self._acceptance_count += self._accepted
+        if self._adaptive:
+            # gamma is the same for every chain: computed on the host exactly as
+            # the reference does (pints/_mcmc/_adaptive_covariance.py:289)
+            self._gamma = (self._adaptations + 1) ** -self._eta
+            self._adaptations += 1
+            self._ops.hbac_adapt(self._current, self._accepted, self._mu,
+                                 self._sigma, self._log_lambda, self._gamma,
+                                 self._target)
+        return self._current, self._current_f, self._accepted
+
+
+class DifferentialEvolutionMCMC(object):
+    """Differential-evolution MCMC with the reference's default settings
+    (Gaussian error, relative scaling, ``gamma = 2.38 / sqrt(2 d)`` and
+    ``gamma = 1`` on every tenth proposal round).
+
+    ``first`` / ``n_total`` describe a shard of a larger chain set: this object
+    owns chains ``[first, first + n)`` of ``n_total``; ``ask`` then needs the
+    positions of all chains (``all_current``), which the caller all-gathers.
+    """
+
+    def __init__(self, chains, x0, device=None, rng='philox', seed=0,
+                 first=0, n_total=None, x0_mean=None):
+        x0 = np.array(x0, dtype=np.float64, copy=True)
+        if x0.ndim != 2 or x0.shape[0] != int(chains):
+            raise ValueError(
+                'Number of initial positions must be equal to number of'
+                ' chains.')
+        self._n, self._d = x0.shape
+        self._first = int(first)
+        self._n_total = int(n_total) if n_total is not None else self._n
+        if self._n_total < 3:
+            raise ValueError('Need at least 3 chains.')
+        if rng not in ('philox', 'replay'):
+            raise ValueError("rng must be 'philox' or 'replay'")
+        self._ops = _DeviceOps(device)
+        dev = self._ops.device
+        self._rng_mode = rng
+        self._rng = _Philox(seed)
+        self._gamma_default = 2.38 / np.sqrt(2 * self._d)
+        self._gamma_switch_rate = 10
+        self._b = 0.001
+        # scale of the error process: |mean(x0) * b| over ALL chains
+        mean = np.mean(x0, axis=0) if x0_mean is None else np.asarray(x0_mean)
+        self._b_star = np.abs(mean * self._b)
+        self._d_b_star = _f64(self._b_star, dev)
+        self._x0 = _f64(x0, dev)
+        n, d = self._n, self._d
+        self._current = torch.empty_like(self._x0)
+        self._current_f = torch.empty(n, dtype=torch.float64, device=dev)
+        self._proposed = torch.empty_like(self._x0)
+        self._eps = torch.empty_like(self._x0)
+        self._r1 = torch.empty(n, dtype=torch.int32, device=dev)
+        self._r2 = torch.empty(n, dtype=torch.int32, device=dev)
+        self._log_u = torch.empty(n, dtype=torch.float64, device=dev)
+        self._accepted = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._iter_count = 0
+        self._started = False
+        self._have_current = False
+        self._asked = False
+
+    def n_chains(self):
+        return self._n
+
+    def n_parameters(self):
+        return self._d
+
+    def needs_initial_phase(self):
+        return False
+
+    def gamma(self):
+        return self._gamma_default
+
+    def b_star(self):
+        return self._b_star
+
+    def current(self):
+        return self._current
+
+    def current_log_pdfs(self):
+        return self._current_f
+
+    @classmethod
+    def name(cls):
+        return 'Differential Evolution MCMC'
+
+    def next_gamma(self):
+        """The gamma the coming proposal round uses
+        (pints/_mcmc/_differential_evolution.py:98-101,118)."""
+        if self._iter_count % self._gamma_switch_rate == 0:
+            return 1.0
+        return float(self._gamma_default)
+
+    def ask(self, eps=None, r1=None, r2=None, all_current=None):
+        """Proposals ``x_j + gamma (x_r1 - x_r2) + eps_j`` for the owned chains.
+        Replay mode: pass ``eps`` (n, d) and ``r1``/``r2`` (n,) drawn elsewhere.
+        Sharded: pass ``all_current`` (n_total, d), the gathered positions."""
+        if not self._started:
+            self._started = True
+            self._proposed.copy_(self._x0)
+            self._asked = True
+            return self._proposed
+        if not self._asked:
+            gamma = self.next_gamma()
+            self._iter_count += 1
+            dev = self._current.device
+            if eps is not None:
+                self._eps.copy_(torch.as_tensor(eps).to(dev))
+                self._r1.copy_(torch.as_tensor(np.asarray(r1, np.int32)).to(dev))
+                self._r2.copy_(torch.as_tensor(np.asarray(r2, np.int32)).to(dev))
+            elif self._rng_mode == 'replay':
+                raise RuntimeError('replay mode: ask() needs eps, r1 and r2')
+            else:
+                off = self._rng.take(self._eps.numel())
+                self._ops.normal(self._eps, self._rng.seed, off)
+                self._eps.mul_(self._d_b_star)
+                off = self._rng.take(2 * self._n)
+                self._ops.pairs(self._r1, self._r2, self._first,
+                                self._n_total, self._rng.seed, off)
+            pool = self._current if all_current is None else all_current
+            if pool.shape[0] != self._n_total:
+                raise ValueError('all_current must hold all %d chains'
+                                 % self._n_total)
+            self._ops.de_propose(pool, self._first, self._eps, self._r1,
+                                 self._r2, self._proposed, gamma)
+        self._asked = True
+        return self._proposed
+
+    def tell(self, fx, log_u=None):
+        if not self._asked:
+            raise RuntimeError('Tell called before proposal was set.')
+        self._asked = False
+        fx = torch.as_tensor(fx)
+        if fx.device != self._current.device or fx.dtype != torch.float64:
+            fx = fx.to(device=self._current.device, dtype=torch.float64)
+        if not self._have_current:
+            if not bool(torch.isfinite(fx).all()):
+                raise ValueError(
+                    'Initial points for MCMC must have finite logpdf.')
+            self._current.copy_(self._proposed)
+            self._current_f.copy_(fx)
+            self._accepted.fill_(1)
+            self._have_current = True
+            return self._current, self._current_f, self._accepted
+        if log_u is not None:
+            self._log_u.copy_(torch.as_tensor(log_u).to(self._log_u.device))
+        elif self._rng_mode == 'replay':
+            raise RuntimeError('replay mode: tell() needs log_u')
+        else:
+            off = self._rng.take(self._n)
+            self._ops.uniform(self._log_u, self._rng.seed, off)
+            torch.log_(self._log_u)
+        self._ops.mh_accept(self._current, self._current_f, self._proposed, fx,
+                            self._log_u, self._accepted, False)
+        return self._current, self._current_f, self._accepted

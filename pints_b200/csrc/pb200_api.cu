@@ -58,6 +58,10 @@ int check_batch(const pb200_problem *p, const void *d_params, int64_t n, int64_t
     if (n < 0) { pb200_set_error("%s: n = %lld < 0", who, (long long)n); return PB200_EINVAL; }
     if (n == 0) return PB200_OK;
     if (!d_params || !d_out) { pb200_set_error("%s: NULL device pointer", who); return PB200_EINVAL; }
+    if (!p->dev.series) {
+        pb200_set_error("%s: the problem was created without a series buffer", who);
+        return PB200_EINVAL;
+    }
     const int need = model_only ? p->dev.n_model_params : p->dev.n_params;
     if (ld < need) {
         pb200_set_error("%s: row stride %lld is shorter than the %d parameters of this problem",
@@ -77,8 +81,9 @@ const char *pb200_last_error(void) { return g_error; }
 
 int64_t pb200_series_len(int32_t n_times, int32_t n_outputs) {
     if (n_times < 0 || n_outputs < 1) return -1;
-    const int64_t len = static_cast<int64_t>(n_times) * (1 + n_outputs);
-    return (len + 1) & ~1ll;            // whole 16-byte units for the bulk copy
+    // n_times rows plus one sentinel row (time = +inf), in whole 16-byte units
+    const int64_t len = (static_cast<int64_t>(n_times) + 1) * (1 + n_outputs);
+    return (len + 1) & ~1ll;
 }
 
 int pb200_problem_create(int32_t model, int32_t objective, int32_t n_times,

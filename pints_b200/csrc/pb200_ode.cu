@@ -93,7 +93,6 @@ __constant__ double TAB[N_TAB] = {
 #define D6 TAB[I_D6]
 #define D7 TAB[I_D7]
 
-constexpr double MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;   // safety 0.9 in step_factor()
 
 // ----------------------------------------------------------------- models
 // Each model: NS states, NO outputs, OUT0 = index of the first output state,
@@ -198,13 +197,16 @@ __device__ __forceinline__ double err_norm2(const double *esum, double h,
     return s * (1.0 / NS);
 }
 
-// factor = SAFETY * norm^(-1/5) from norm^2, through the SFU in fp32: the
-// controller only needs a few digits.
-__device__ __forceinline__ double step_factor(double norm2) {
+// Step-size factor 0.9 * norm^(-1/5), clamped to [0.2, 10], from norm^2.  It
+// runs on the SFU in fp32 (lg2/ex2 approximations): the controller needs a few
+// digits only, and accept/reject is decided in fp64 on norm^2 <= 1, never on
+// this value.  norm2 = 0 -> 10, norm2 = inf or NaN -> 0.2.
+__device__ __forceinline__ float step_factor(double norm2) {
     const float n2 = static_cast<float>(norm2);
-    // norm^(-0.2) = (norm2)^(-0.1)
-    const float f = exp2f(-0.1f * __log2f(n2));
-    return static_cast<double>(0.9f * f);
+    float l, f;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(n2));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(-0.1f * l));
+    return fminf(fmaxf(0.9f * f, 0.2f), 10.0f);
 }
 
 // Observed series access.  In shared memory the rows are read with explicit
@@ -228,7 +230,10 @@ struct Series {
 };
 
 template <class M, bool SMEM, bool TRAJ>
-__global__ void __launch_bounds__(128)
+#ifndef PB200_MAXTHREADS
+#define PB200_MAXTHREADS 128
+#endif
+__global__ void __launch_bounds__(PB200_MAXTHREADS)
 ode_kernel(const __grid_constant__ ProblemDev P,
            const __grid_constant__ ModelConsts mc,
            const double *__restrict__ params, int64_t n, int64_t ld,
@@ -243,8 +248,8 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     series.gbase = P.series;
     series.sbase = 0;
     if (SMEM) {
-        const uint32_t bytes =
-            static_cast<uint32_t>((static_cast<int64_t>(P.n_times) * ROWB + 15) & ~15ll);
+        const uint32_t bytes = static_cast<uint32_t>(
+            ((static_cast<int64_t>(P.n_times) + 1) * ROWB + 15) & ~15ll);
         stage_series(smem, P.series, bytes, &bar);
         series.sbase = smem_u32(smem);
     }
@@ -271,17 +276,19 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     M model;
     double y[NS], t;
     model.load(x, mc, y, nt > 0 ? series.at(0) : 0.0, &t);
+    if (nt == 0) t = 0.0;
 
     double ss[NO];
 #pragma unroll
     for (int o = 0; o < NO; ++o) ss[o] = 0.0;
 
-    // `off` is the byte offset of the next observation row, `t_out` its time
-    // (+inf once the series is exhausted): one register compare per step
-    // decides whether any interpolation is needed.
+    // `off` is the byte offset of the next observation row, `t_out` its time.
+    // The packed series ends with a sentinel row whose time is +inf, so the
+    // interpolation loop needs no bounds check and one register compare per
+    // step decides whether any interpolation is needed.
     const uint32_t end = static_cast<uint32_t>(nt) * ROWB;
     uint32_t off = 0;
-    double t_out = nt > 0 ? series.at(0) : INFINITY;
+    double t_out = series.at(0);
     double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * NO : nullptr;
 
     // observations at (or before) the initial time see the initial state
@@ -294,7 +301,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         }
         if (TRAJ) my_traj += NO;
         off += ROWB;
-        t_out = off < end ? series.at(off) : INFINITY;
+        t_out = series.at(off);
     }
 
     const double half_rtol = 0.5 * S.rtol, atol = S.atol;
@@ -333,13 +340,85 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         h = fmin(100.0 * h_a, h_b);
     }
 
+#ifdef PB200_REGTAB
+    // experiment: pin the 32 tableau entries in registers (opaque moves stop
+    // the compiler from re-loading them from the constant bank every step)
+    double RT[N_TAB];
+#pragma unroll
+    for (int q = 0; q < N_TAB; ++q)
+        asm volatile("mov.f64 %0, %1;" : "=d"(RT[q]) : "d"(TAB[q]));
+#undef A21
+#undef A31
+#undef A32
+#undef A41
+#undef A42
+#undef A43
+#undef A51
+#undef A52
+#undef A53
+#undef A54
+#undef A61
+#undef A62
+#undef A63
+#undef A64
+#undef A65
+#undef B1
+#undef B3
+#undef B4
+#undef B5
+#undef B6
+#undef E1
+#undef E3
+#undef E4
+#undef E5
+#undef E6
+#undef E7
+#undef D1
+#undef D3
+#undef D4
+#undef D5
+#undef D6
+#undef D7
+#define A21 RT[I_A21]
+#define A31 RT[I_A31]
+#define A32 RT[I_A32]
+#define A41 RT[I_A41]
+#define A42 RT[I_A42]
+#define A43 RT[I_A43]
+#define A51 RT[I_A51]
+#define A52 RT[I_A52]
+#define A53 RT[I_A53]
+#define A54 RT[I_A54]
+#define A61 RT[I_A61]
+#define A62 RT[I_A62]
+#define A63 RT[I_A63]
+#define A64 RT[I_A64]
+#define A65 RT[I_A65]
+#define B1 RT[I_B1]
+#define B3 RT[I_B3]
+#define B4 RT[I_B4]
+#define B5 RT[I_B5]
+#define B6 RT[I_B6]
+#define E1 RT[I_E1]
+#define E3 RT[I_E3]
+#define E4 RT[I_E4]
+#define E5 RT[I_E5]
+#define E6 RT[I_E6]
+#define E7 RT[I_E7]
+#define D1 RT[I_D1]
+#define D3 RT[I_D3]
+#define D4 RT[I_D4]
+#define D5 RT[I_D5]
+#define D6 RT[I_D6]
+#define D7 RT[I_D7]
+#endif
     int attempts = 0;
     bool failed = false;
     bool after_reject = false;
     const int max_steps = S.max_steps;
 
     while (off < end) {
-        if (attempts >= max_steps || !(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) {
+        if (attempts >= max_steps) {
             failed = true;
             break;
         }
@@ -373,6 +452,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         for (int j = 0; j < NS; ++j)
             esum[j] = fma(E7, k7[j], fma(E6, k6[j], fma(E5, k5[j], fma(E4, k4[j], fma(E3, k3[j], E1 * k1[j])))));
         const double n2 = err_norm2<NS>(esum, h, y, yn, half_rtol, atol);
+        float fac = step_factor(n2);
 
         if (n2 <= 1.0) {
             // ---- accepted: interpolate at the observation times inside ----
@@ -401,24 +481,26 @@ ode_kernel(const __grid_constant__ ProblemDev P,
                     }
                     if (TRAJ) my_traj += NO;
                     off += ROWB;
-                    t_out = off < end ? series.at(off) : INFINITY;
+                    t_out = series.at(off);
                 } while (t_out <= t_new);
             }
             t = t_new;
 #pragma unroll
             for (int j = 0; j < NS; ++j) { y[j] = yn[j]; k1[j] = k7[j]; }
-            double fac = (n2 < 1e-20) ? MAX_FACTOR
-                                      : fmin(MAX_FACTOR, step_factor(n2));
-            if (after_reject) fac = fmin(fac, 1.0);
-            h *= fac;
+            // no growth on the step right after a rejection
+            if (after_reject) fac = fminf(fac, 1.0f);
             after_reject = false;
         } else {
-            // rejected (also when the norm is NaN): shrink and retry
-            const double fac = (n2 > 1.0) ? fmax(MIN_FACTOR, step_factor(n2))
-                                          : MIN_FACTOR;
-            h *= fac;
+            // rejected (also when the norm is NaN, which gives fac = 0.2)
+            fac = fminf(fac, 1.0f);
             after_reject = true;
+            // step size underflow: give up on this vector (score NaN)
+            if (!(fabs(h) * 0.2 > 1e-14 * fmax(fabs(t), 1.0))) {
+                failed = true;
+                break;
+            }
         }
+        h *= static_cast<double>(fac);
     }
 
     if (steps_out) steps_out[i] = attempts;
@@ -437,7 +519,8 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
                  int64_t ld, double *d_scores, double *d_traj,
                  int32_t *d_steps, const SolverDev &s, int block,
                  cudaStream_t st) {
-    const int64_t bytes = (static_cast<int64_t>(p->dev.n_times) * (1 + M::NO) * 8 + 15) & ~15ll;
+    // series rows + the +inf sentinel row, in whole 16-byte units
+    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + 1) * (1 + M::NO) * 8 + 15) & ~15ll;
     const bool use_smem = bytes <= 96 * 1024;   // keeps >= 2 blocks per SM
     const bool traj = d_traj != nullptr;
     if (block <= 0) block = 64;

@@ -1,0 +1,85 @@
+"""
+world_size-2 checks of the multi-process path on the CPU (gloo): the block
+partition, the padded all-gather of scores, and that every rank ends up with
+the full, correctly ordered result.  The device launch is replaced by the CPU
+oracle here (test-only); the NCCL version of the same code runs in bench.py
+and tests/test_gpu_multi.py.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def test_shard_bounds():
+    from pints_b200._dist import shard_bounds
+    for n in (0, 1, 2, 7, 8, 9, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi, per = shard_bounds(n, world, r)
+                assert 0 <= lo <= hi <= n and hi - lo <= per
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+
+
+def _worker(rank, world, port, n, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import pints_b200 as pb
+        from pints_b200._dist import ShardedEvaluator
+        from oracle import pints_oracle as po
+
+        rng = np.random.RandomState(1)
+        times = np.linspace(0, 100, 40)
+        values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 1, 40)
+        spec = po.Spec('logistic', times, values, 'sse')
+        f = pb.SumOfSquaresError(pb.SingleOutputProblem(
+            pb.toy.LogisticModel(), times, values))
+
+        class CpuSharded(ShardedEvaluator):
+            # test-only: oracle instead of the CUDA launch, CPU tensors
+            def _width(self):
+                return 2
+
+            def _collective_device(self):
+                return torch.device('cpu')
+
+            def _local_scores(self, xs, out):
+                out[:xs.shape[0]] = torch.from_numpy(po.scores(spec, xs))
+
+        ev = CpuSharded(f)
+        xs = np.array([0.1, 50]) * (1 + 0.1 * rng.randn(n, 2))
+        got = ev.evaluate(xs)
+        want = po.scores(spec, xs)
+        ok = isinstance(got, list) and len(got) == n and \
+            np.array_equal(np.array(got), want)
+        # list-of-arrays input and an empty batch
+        ok = ok and ev.evaluate([x for x in xs]) == got
+        ok = ok and ev.evaluate([]) == []
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n', [1, 7, 64])
+def test_sharded_evaluator_world_size_2(n):
+    port = 29500 + (os.getpid() % 2000) + n
+    out = mp.get_context('spawn').Array('i', [0, 0])
+    procs = [mp.get_context('spawn').Process(
+        target=_worker, args=(r, 2, port, n, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1, 1]

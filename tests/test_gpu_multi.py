@@ -1,0 +1,79 @@
+"""
+Multi-GPU checks (need >= 2 GPUs; skipped otherwise): a CudaEvaluator over
+several devices and the one-process-per-GPU ShardedEvaluator over NCCL return
+exactly what one device returns.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import pints_oracle as po
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+def n_gpus():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def build_function(pb):
+    spec = po.headline_fhn_spec()
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    return pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason='needs 2 GPUs')
+def test_multi_device_evaluator_equals_single():
+    import pints_b200 as pb
+    f = build_function(pb)
+    xs = po.headline_fhn_points(10001)
+    one = pb.CudaEvaluator(f, devices='cuda:0', as_list=False).evaluate(xs)
+    g = n_gpus()
+    many = pb.CudaEvaluator(f, devices=list(range(g)),
+                            as_list=False).evaluate(xs)
+    assert np.array_equal(one, many)
+    few = pb.CudaEvaluator(f, devices=[0, 1], as_list=False).evaluate(xs[:3])
+    assert np.array_equal(few, one[:3])
+
+
+def _nccl_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        import pints_b200 as pb
+        from pints_b200._dist import ShardedEvaluator
+        f = build_function(pb)
+        xs = po.headline_fhn_points(4099)
+        got = ShardedEvaluator(f, as_list=False).evaluate(xs)
+        want = pb.CudaEvaluator(f, devices='cuda:%d' % rank,
+                                as_list=False).evaluate(xs)
+        out[rank] = 1 if np.array_equal(got, want) else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason='needs 2 GPUs')
+def test_sharded_evaluator_nccl():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context('spawn')
+    out = ctx.Array('i', [0] * world)
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world

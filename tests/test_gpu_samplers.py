@@ -1,0 +1,251 @@
+"""
+Sampler kernels on the GPU (through the C ABI):
+
+* bit-exact replay of the reference's HaarioBardenetACMC and
+  DifferentialEvolutionMCMC: fed the proposals / draws / scores recorded from
+  the real reference (tests/golden/*_replay.npz), the device reproduces every
+  accept/reject decision, every next position and the adapted mu / sigma /
+  log-lambda exactly (==, not approximately);
+* the counter-based device RNG and the Cholesky proposal are statistically
+  right;
+* whole chains run on the device recover the posterior.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pints_oracle as po
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+@pytest.fixture(scope='module')
+def pb():
+    import pints_b200
+    pints_b200.require_cuda()
+    return pints_b200
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def test_hbac_replay_is_bit_exact(pb):
+    g = load_golden('hbac_replay')
+    n_iter, n, d = g['proposed'].shape
+    s = pb.HaarioBardenetACMC(g['x0'], rng='replay')
+    assert np.array_equal(s.state()[1], g['sigma0'])
+    decisions = 0
+    for it in range(n_iter):
+        if it == int(g['warm']):
+            s.set_initial_phase(False)
+        xs = s.ask(proposed=g['proposed'][it] if it > 0 else None)
+        assert np.array_equal(host(xs), g['proposed'][it])
+        cur, cur_f, acc = s.tell(g['fx'][it], log_u=g['log_u'][it])
+        assert np.array_equal(host(acc), g['accepted'][it]), it
+        assert np.array_equal(host(cur), g['current'][it]), it
+        assert np.array_equal(host(cur_f), g['current_f'][it]), it
+        mu, sigma, log_lambda = s.state()
+        assert np.array_equal(mu, g['mu'][it]), it
+        assert np.array_equal(sigma, g['sigma'][it]), it
+        assert np.array_equal(log_lambda, g['log_lambda'][it]), it
+        if it >= int(g['warm']):
+            assert s._gamma == g['gamma'][it]
+        decisions += n
+    # the fixture exercises both outcomes and the non-finite rule
+    assert 0.05 < g['accepted'][1:].mean() < 0.95
+    assert g['accepted'][7, 2] == 0 and g['accepted'][9, 4] == 0
+    assert decisions == n_iter * n
+    rate = s.acceptance_rate()
+    # the first point is accepted without counting (reference :249-262)
+    assert np.allclose(rate, g['accepted'][1:].sum(0) / n_iter)
+
+
+def test_hbac_first_point_must_be_finite(pb):
+    s = pb.HaarioBardenetACMC(np.ones((4, 2)), rng='replay')
+    s.ask()
+    with pytest.raises(ValueError):
+        s.tell(np.array([0.0, -np.inf, 0.0, 0.0]))
+    s2 = pb.HaarioBardenetACMC(np.ones((4, 2)), rng='replay')
+    with pytest.raises(RuntimeError):
+        s2.tell(np.zeros(4))
+
+
+def test_de_replay_is_bit_exact(pb):
+    g = load_golden('de_replay')
+    n_iter, n, d = g['proposed'].shape
+    s = pb.DifferentialEvolutionMCMC(n, g['x0'], rng='replay')
+    assert np.array_equal(s.b_star(), g['b_star'])
+    for it in range(n_iter):
+        if it == 0:
+            xs = s.ask()
+        else:
+            assert s.next_gamma() == g['gamma'][it]
+            xs = s.ask(eps=g['eps'][it], r1=g['r1'][it], r2=g['r2'][it])
+        assert np.array_equal(host(xs), g['proposed'][it]), it
+        cur, cur_f, acc = s.tell(g['fx'][it],
+                                 log_u=g['log_u'][it] if it > 0 else None)
+        assert np.array_equal(host(acc), g['accepted'][it]), it
+        assert np.array_equal(host(cur), g['current'][it]), it
+        assert np.array_equal(host(cur_f), g['current_f'][it]), it
+    assert g['accepted'][5, 1] == 0 and g['accepted'][6, 3] == 0   # NaN, -inf
+
+
+def test_de_sharded_equals_whole(pb):
+    """Two shards that see the all-gathered positions propose exactly what one
+    sampler owning all chains proposes."""
+    g = load_golden('de_replay')
+    n_iter, n, d = g['proposed'].shape
+    h = n // 2
+    mean = g['x0'].mean(axis=0)
+    a = pb.DifferentialEvolutionMCMC(h, g['x0'][:h], rng='replay', first=0,
+                                     n_total=n, x0_mean=mean)
+    b = pb.DifferentialEvolutionMCMC(n - h, g['x0'][h:], rng='replay', first=h,
+                                     n_total=n, x0_mean=mean)
+    for it in range(12):
+        if it == 0:
+            xa, xb = a.ask(), b.ask()
+        else:
+            pool = torch.cat([a.current(), b.current()])
+            xa = a.ask(eps=g['eps'][it][:h], r1=g['r1'][it][:h],
+                       r2=g['r2'][it][:h], all_current=pool)
+            xb = b.ask(eps=g['eps'][it][h:], r1=g['r1'][it][h:],
+                       r2=g['r2'][it][h:], all_current=pool)
+        both = np.vstack([host(xa), host(xb)])
+        assert np.array_equal(both, g['proposed'][it]), it
+        lu = g['log_u'][it] if it > 0 else np.zeros(n)
+        a.tell(g['fx'][it][:h], log_u=lu[:h] if it > 0 else None)
+        b.tell(g['fx'][it][h:], log_u=lu[h:] if it > 0 else None)
+        assert np.array_equal(
+            np.vstack([host(a.current()), host(b.current())]),
+            g['current'][it])
+
+
+def test_philox_streams(pb):
+    from pints_b200._samplers import _DeviceOps
+    ops = _DeviceOps(None)
+    n = 1 << 20
+    z = torch.empty(n, dtype=torch.float64, device=ops.device)
+    u = torch.empty(n, dtype=torch.float64, device=ops.device)
+    ops.normal(z, 1234, 0)
+    ops.uniform(u, 1234, 0)
+    z, u = host(z), host(u)
+    assert abs(z.mean()) < 4e-3 and abs(z.std() - 1) < 4e-3
+    assert abs((z**3).mean()) < 2e-2 and abs((z**4).mean() - 3) < 5e-2
+    assert 0 < u.min() and u.max() < 1
+    assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 5e-3
+    # reproducible, and different for another seed / offset
+    z2 = torch.empty(n, dtype=torch.float64, device=ops.device)
+    ops.normal(z2, 1234, 0)
+    assert np.array_equal(host(z2), z)
+    ops.normal(z2, 1235, 0)
+    assert not np.array_equal(host(z2), z)
+    ops.normal(z2, 1234, 7)
+    assert np.array_equal(host(z2)[:100], z[14:114])
+    # pairs: distinct, never the chain itself, uniform over the others
+    m, total, first = 30000, 10, 3
+    r1 = torch.empty(m, dtype=torch.int32, device=ops.device)
+    r2 = torch.empty(m, dtype=torch.int32, device=ops.device)
+    total_big = m + first
+    ops.pairs(r1, r2, first, total_big, 99, 0)
+    a, b = host(r1), host(r2)
+    me = first + np.arange(m)
+    assert np.all(a != b) and np.all(a != me) and np.all(b != me)
+    assert a.min() >= 0 and a.max() < total_big and b.max() < total_big
+    r1s = torch.empty(7, dtype=torch.int32, device=ops.device)
+    r2s = torch.empty(7, dtype=torch.int32, device=ops.device)
+    counts = np.zeros((total, total))
+    for rep in range(300):
+        ops.pairs(r1s, r2s, first, total, 5, rep * 16)
+        for j, (p, q) in enumerate(zip(host(r1s), host(r2s))):
+            assert p != q and p != first + j and q != first + j
+            assert 0 <= p < total and 0 <= q < total
+            counts[first + j, p] += 1
+    row = counts[first]
+    assert row[first] == 0 and row.sum() == 300
+    assert np.all(row[np.arange(total) != first] > 10)
+
+
+def test_hbac_device_proposals_have_the_right_covariance(pb):
+    rng = np.random.RandomState(0)
+    d, n = 4, 200000
+    a = rng.randn(d, d)
+    cov = a @ a.T + 0.1 * np.eye(d)
+    x0 = np.tile(rng.randn(d), (n, 1))
+    s = pb.HaarioBardenetACMC(x0, sigma0=cov, rng='philox', seed=11)
+    s.ask()
+    s.tell(np.zeros(n))
+    s._log_lambda.fill_(0.3)
+    xs = host(s.ask())
+    emp = np.cov((xs - x0).T)
+    want = cov * np.exp(0.3)
+    assert np.allclose(emp, want, rtol=0.03, atol=0.03 * np.abs(want).max())
+    assert np.allclose((xs - x0).mean(0), 0, atol=0.02 * np.sqrt(want.max()))
+
+
+def logistic_posterior(pb, n_times=200):
+    rng = np.random.RandomState(3)
+    times = np.linspace(0, 100, n_times)
+    values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 2, n_times)
+    problem = pb.SingleOutputProblem(pb.toy.LogisticModel(), times, values)
+    post = pb.LogPosterior(pb.GaussianLogLikelihood(problem),
+                           pb.UniformLogPrior([0, 10, 0.1], [1, 100, 20]))
+    return post
+
+
+@pytest.mark.parametrize('method', ['hbac', 'de'])
+def test_device_mcmc_recovers_the_posterior(pb, method):
+    post = logistic_posterior(pb)
+    n_chains, n_iter = 256, 1500
+    rng = np.random.RandomState(4)
+    x0 = np.array([0.1, 50, 2]) * (1 + 0.05 * rng.randn(n_chains, 3))
+    cls = pb.HaarioBardenetACMC if method == 'hbac' \
+        else pb.DifferentialEvolutionMCMC
+    mc = pb.CudaMCMCController(post, n_chains, x0, method=cls, seed=7)
+    mc.set_max_iterations(n_iter)
+    chains = mc.run()
+    assert chains.shape == (n_chains, n_iter, 3)
+    assert np.all(np.isfinite(chains))
+    assert np.array_equal(chains[:, 0], x0)            # first sample is x0
+    tail = chains[:, n_iter // 2:].reshape(-1, 3)
+    mean, sd = tail.mean(0), tail.std(0)
+    assert abs(mean[0] - 0.1) < 0.01 and abs(mean[1] - 50) < 1.5
+    assert abs(mean[2] - 2) < 0.4
+    assert np.all(sd > 0)
+    # chains really move, and stay inside the prior box
+    moved = (np.diff(chains[:, :, 0], axis=1) != 0).mean()
+    assert 0.05 < moved < 0.9
+    assert tail[:, 0].min() >= 0 and tail[:, 1].max() < 100
+    if method == 'hbac':
+        rate = mc.sampler().acceptance_rate()
+        assert 0.1 < rate.mean() < 0.5
+    assert mc.n_evaluations() == n_chains * n_iter and mc.time() > 0
+    with pytest.raises(RuntimeError):
+        mc.run()
+
+
+def test_cuda_optimisation_controller_with_vectorised_xnes(pb):
+    rng = np.random.RandomState(8)
+    times = np.linspace(0, 100, 300)
+    values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 1, 300)
+    problem = pb.SingleOutputProblem(pb.toy.LogisticModel(), times, values)
+    np.random.seed(1)
+    opt = pb.CudaOptimisationController(
+        pb.SumOfSquaresError(problem), [0.3, 20],
+        boundaries=pb.RectangularBoundaries([0, 1], [1, 200]), method=pb.XNES)
+    opt.optimiser().set_population_size(512)
+    opt.set_max_iterations(60)
+    x, f = opt.run()
+    assert abs(x[0] - 0.1) < 5e-3 and abs(x[1] - 50) < 0.5
+    assert f < 1.2 * 300
+    # maximising a log-likelihood finds the same point
+    np.random.seed(1)
+    opt = pb.CudaOptimisationController(
+        pb.GaussianKnownSigmaLogLikelihood(problem, 1.0), [0.3, 20],
+        boundaries=pb.RectangularBoundaries([0, 1], [1, 200]))
+    opt.optimiser().set_population_size(512)
+    opt.set_max_iterations(60)
+    x2, f2 = opt.run()
+    assert np.allclose(x2, x, rtol=1e-3) and f2 < 0
