@@ -65,6 +65,7 @@ extern "C" {
 #define PB200_MAX_OUTPUTS   8
 #define PB200_MAX_PARAMS    16      /* model parameters + sigma parameters  */
 #define PB200_MAX_EVENTS    64      /* HH-IK protocol events                */
+#define PB200_SENTINEL_ROWS 4       /* +inf rows that end the packed series */
 
 typedef struct pb200_problem pb200_problem;
 
@@ -93,8 +94,9 @@ int64_t pb200_series_len(int32_t n_times, int32_t n_outputs);
  * (pints/_core.py:102-327, pints/_log_pdfs.py:134-241).
  *
  * d_series   device buffer of pb200_series_len() doubles, 16-byte aligned:
- *            n_times rows of [t_j, v_j0 .. v_j(n_outputs-1)], then one
- *            sentinel row whose time is +infinity (values 0), zero padded.
+ *            n_times rows of [t_j, v_j0 .. v_j(n_outputs-1)], then
+ *            PB200_SENTINEL_ROWS rows whose time is +infinity (values 0), zero
+ *            padded: the kernels read a few rows ahead without bounds checks.
  *            Times must be non-negative and non-decreasing
  *            (pints/_core.py:129-133, :238-242); the caller checks that.
  * model_consts (host)

@@ -20,6 +20,7 @@ MODEL_LOGISTIC, MODEL_HH_IK, MODEL_CONSTANT = 0, 1, 2
 MODEL_FHN, MODEL_LOTKA_VOLTERRA, MODEL_SIR = 3, 4, 5
 OBJ_SSE, OBJ_GAUSSIAN_KNOWN_SIGMA, OBJ_GAUSSIAN = 0, 1, 2
 MAX_OUTPUTS, MAX_PARAMS, MAX_EVENTS = 8, 16, 64
+SENTINEL_ROWS = 4
 
 MODEL_NAMES = {MODEL_LOGISTIC: 'logistic', MODEL_HH_IK: 'hh_ik',
                MODEL_CONSTANT: 'constant', MODEL_FHN: 'fhn',

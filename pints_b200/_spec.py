@@ -78,16 +78,17 @@ class ProblemSpec(object):
                               _lib.MODEL_SIR)
 
     def packed_series(self):
-        """Rows ``[t_j, v_j0 ..]``, then a sentinel row with time ``+inf``,
-        padded to whole 16-byte units: the layout ``pb200_problem_create``
-        expects in device memory."""
+        """Rows ``[t_j, v_j0 ..]``, then ``SENTINEL_ROWS`` rows with time
+        ``+inf``, padded to whole 16-byte units: the layout
+        ``pb200_problem_create`` expects in device memory."""
         row = 1 + self.n_outputs
-        n = (self.n_times + 1) * row
+        nt, extra = self.n_times, _lib.SENTINEL_ROWS
+        n = (nt + extra) * row
         out = np.zeros((n + 1) & ~1, dtype=np.float64)
-        block = out[:n].reshape((self.n_times + 1, row))
-        block[:-1, 0] = self.times
-        block[:-1, 1:] = self.values
-        block[-1, 0] = np.inf
+        block = out[:n].reshape((nt + extra, row))
+        block[:nt, 0] = self.times
+        block[:nt, 1:] = self.values
+        block[nt:, 0] = np.inf
         return out
 
     def flops_per_eval(self, steps):

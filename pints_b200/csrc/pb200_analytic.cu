@@ -146,7 +146,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
     const double *series;
     if (SMEM) {
         const uint32_t bytes = static_cast<uint32_t>(
-            ((static_cast<int64_t>(nt) + 1) * row * 8 + 15) & ~15ll);
+            ((static_cast<int64_t>(nt) + PB200_SENTINEL_ROWS) * row * 8 + 15) & ~15ll);
         stage_series(smem, P.series, bytes, &bar);
         series = smem;
     } else {
@@ -206,7 +206,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
 template <class E>
 int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
                 int64_t ld, double *d_scores, double *d_traj, cudaStream_t st) {
-    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + 1) * p->dev.row * 8 + 15) & ~15ll;
+    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * p->dev.row * 8 + 15) & ~15ll;
     const bool use_smem = bytes <= 100 * 1024;
     const bool traj = d_traj != nullptr;
     int dev = 0, sms = 148;

@@ -46,6 +46,7 @@ SolverDev resolve_opts(const pb200_solver_opts *o, int *block) {
     SolverDev s;
     s.rtol = (o && o->rtol > 0) ? o->rtol : 1.49012e-8;
     s.atol = (o && o->atol > 0) ? o->atol : 1.49012e-8;
+    s.half_rtol = 0.5 * s.rtol;
     s.h0 = (o && o->h0 > 0) ? o->h0 : 0.0;
     s.max_steps = (o && o->max_steps > 0) ? o->max_steps : 1000000;
     *block = (o && o->block > 0) ? o->block : 0;
@@ -81,8 +82,8 @@ const char *pb200_last_error(void) { return g_error; }
 
 int64_t pb200_series_len(int32_t n_times, int32_t n_outputs) {
     if (n_times < 0 || n_outputs < 1) return -1;
-    // n_times rows plus one sentinel row (time = +inf), in whole 16-byte units
-    const int64_t len = (static_cast<int64_t>(n_times) + 1) * (1 + n_outputs);
+    // n_times rows plus the sentinel rows (time = +inf), in whole 16-byte units
+    const int64_t len = (static_cast<int64_t>(n_times) + PB200_SENTINEL_ROWS) * (1 + n_outputs);
     return (len + 1) & ~1ll;
 }
 

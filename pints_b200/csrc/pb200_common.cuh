@@ -46,6 +46,7 @@ struct pb200_problem {
 
 struct SolverDev {
     double rtol, atol, h0;
+    double half_rtol;             // 0.5 * rtol, used every step
     int32_t max_steps;
 };
 

@@ -230,6 +230,9 @@ struct Series {
 };
 
 template <class M, bool SMEM, bool TRAJ>
+#ifndef PB200_PIPE_U
+#define PB200_PIPE_U 2          // deferred interpolation slots per step attempt
+#endif
 #ifndef PB200_MAXTHREADS
 #define PB200_MAXTHREADS 128
 #endif
@@ -249,7 +252,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     series.sbase = 0;
     if (SMEM) {
         const uint32_t bytes = static_cast<uint32_t>(
-            ((static_cast<int64_t>(P.n_times) + 1) * ROWB + 15) & ~15ll);
+            ((static_cast<int64_t>(P.n_times) + PB200_SENTINEL_ROWS) * ROWB + 15) & ~15ll);
         stage_series(smem, P.series, bytes, &bar);
         series.sbase = smem_u32(smem);
     }
@@ -304,7 +307,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         t_out = series.at(off);
     }
 
-    const double half_rtol = 0.5 * S.rtol, atol = S.atol;
+    const double half_rtol = S.half_rtol, atol = S.atol;
     double k1[NS], k2[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS];
     double yn[NS], w[NS], esum[NS];
     model.rhs(y, k1);
@@ -340,89 +343,78 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         h = fmin(100.0 * h_a, h_b);
     }
 
-#ifdef PB200_REGTAB
-    // experiment: pin the 32 tableau entries in registers (opaque moves stop
-    // the compiler from re-loading them from the constant bank every step)
-    double RT[N_TAB];
-#pragma unroll
-    for (int q = 0; q < N_TAB; ++q)
-        asm volatile("mov.f64 %0, %1;" : "=d"(RT[q]) : "d"(TAB[q]));
-#undef A21
-#undef A31
-#undef A32
-#undef A41
-#undef A42
-#undef A43
-#undef A51
-#undef A52
-#undef A53
-#undef A54
-#undef A61
-#undef A62
-#undef A63
-#undef A64
-#undef A65
-#undef B1
-#undef B3
-#undef B4
-#undef B5
-#undef B6
-#undef E1
-#undef E3
-#undef E4
-#undef E5
-#undef E6
-#undef E7
-#undef D1
-#undef D3
-#undef D4
-#undef D5
-#undef D6
-#undef D7
-#define A21 RT[I_A21]
-#define A31 RT[I_A31]
-#define A32 RT[I_A32]
-#define A41 RT[I_A41]
-#define A42 RT[I_A42]
-#define A43 RT[I_A43]
-#define A51 RT[I_A51]
-#define A52 RT[I_A52]
-#define A53 RT[I_A53]
-#define A54 RT[I_A54]
-#define A61 RT[I_A61]
-#define A62 RT[I_A62]
-#define A63 RT[I_A63]
-#define A64 RT[I_A64]
-#define A65 RT[I_A65]
-#define B1 RT[I_B1]
-#define B3 RT[I_B3]
-#define B4 RT[I_B4]
-#define B5 RT[I_B5]
-#define B6 RT[I_B6]
-#define E1 RT[I_E1]
-#define E3 RT[I_E3]
-#define E4 RT[I_E4]
-#define E5 RT[I_E5]
-#define E6 RT[I_E6]
-#define E7 RT[I_E7]
-#define D1 RT[I_D1]
-#define D3 RT[I_D3]
-#define D4 RT[I_D4]
-#define D5 RT[I_D5]
-#define D6 RT[I_D6]
-#define D7 RT[I_D7]
-#endif
     int attempts = 0;
     bool failed = false;
     bool after_reject = false;
     const int max_steps = S.max_steps;
 
+    // The observations inside an accepted step are NOT interpolated right away:
+    // the step's dense-output coefficients are parked ("pending interval") and
+    // consumed during the NEXT attempt, where U branch-free interpolation slots
+    // sit in the same basic block as the six stages.  The slots are independent
+    // of the stage arithmetic, so they fill the issue slots that the serial
+    // RHS -> stage -> RHS dependency chain (9-cycle DFMA latency) leaves empty;
+    // with only ~3.5 warps per scheduler at population 65 536 that is where the
+    // FP64 pipe was idling.  Steps that contain more than U observations drain
+    // the rest in a (divergent) loop before the coefficients are overwritten.
+    constexpr int U = PB200_PIPE_U;
+    double p_t = 0.0, p_end = -INFINITY, p_invh = 0.0;
+    double p_y[NO], p_r2[NO], p_r3[NO], p_r4[NO], p_r5[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) p_y[o] = p_r2[o] = p_r3[o] = p_r4[o] = p_r5[o] = 0.0;
+    const double t_last = nt > 0 ? series.at(end - ROWB) : -INFINITY;
+
+    // one interpolation of the pending interval at time tq against row `row`
+    auto interpolate = [&](double tq, uint32_t row, bool valid) {
+        const double th = (tq - p_t) * p_invh;
+        const double th1 = 1.0 - th;
+        const double thq = th * th1;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            // y + th ((r2 + th1 r3) + (th th1)(r4 + th1 r5))
+            const double v = fma(th, fma(thq, fma(th1, p_r5[o], p_r4[o]),
+                                         fma(th1, p_r3[o], p_r2[o])), p_y[o]);
+            if (TRAJ) { if (valid) my_traj[(row - off) / ROWB * NO + o] = v; }
+            const double r = valid ? series.at(row + 8 + 8 * o) - v : 0.0;
+            ss[o] = fma(r, r, ss[o]);
+        }
+    };
+    auto drain = [&]() {
+        while (t_out <= p_end) {
+            interpolate(t_out, off, true);
+            if (TRAJ) my_traj += NO;
+            off += ROWB;
+            t_out = series.at(off);
+        }
+    };
+
     while (off < end) {
+        if (p_end >= t_last) {          // every remaining observation is pending
+            drain();
+            break;
+        }
         if (attempts >= max_steps) {
             failed = true;
             break;
         }
         ++attempts;
+        const double inv_h = rcp_newton(h);
+        // ---- U deferred interpolation slots (branch free) ----
+        if (U > 0) {
+            double tq[U > 0 ? U : 1];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int k = 0; k < U; ++k) tq[k] = series.at(off + k * ROWB);
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const bool valid = tq[k] <= p_end;     // monotone in k
+                interpolate(tq[k], off + k * ROWB, valid);
+                cnt += valid ? 1u : 0u;
+            }
+            if (TRAJ) my_traj += cnt * NO;
+            off += cnt * ROWB;
+            t_out = series.at(off);
+        }
         // ---- six stages (k1 is f(y): first-same-as-last) ----
 #pragma unroll
         for (int j = 0; j < NS; ++j) w[j] = fma(h, A21 * k1[j], y[j]);
@@ -453,37 +445,26 @@ ode_kernel(const __grid_constant__ ProblemDev P,
             esum[j] = fma(E7, k7[j], fma(E6, k6[j], fma(E5, k5[j], fma(E4, k4[j], fma(E3, k3[j], E1 * k1[j])))));
         const double n2 = err_norm2<NS>(esum, h, y, yn, half_rtol, atol);
         float fac = step_factor(n2);
+        // observations of the pending interval beyond the U slots
+        drain();
 
         if (n2 <= 1.0) {
-            // ---- accepted: interpolate at the observation times inside ----
+            // ---- accepted: park the dense-output coefficients ----
             const double t_new = t + h;
-            if (t_out <= t_new) {
-                const double inv_h = rcp_newton(h);
-                double r2[NS], r3[NS], r4[NS], r5[NS];
 #pragma unroll
-                for (int o = 0; o < NO; ++o) {
-                    const int j = OUT0 + o;
-                    r2[j] = yn[j] - y[j];
-                    r3[j] = fma(h, k1[j], -r2[j]);
-                    r4[j] = (r2[j] - h * k7[j]) - r3[j];
-                    r5[j] = h * fma(D7, k7[j], fma(D6, k6[j], fma(D5, k5[j], fma(D4, k4[j], fma(D3, k3[j], D1 * k1[j])))));
-                }
-                do {
-                    const double th = (t_out - t) * inv_h;
-                    const double th1 = 1.0 - th;
-#pragma unroll
-                    for (int o = 0; o < NO; ++o) {
-                        const int j = OUT0 + o;
-                        const double v = fma(th, fma(th1, fma(th, fma(th1, r5[j], r4[j]), r3[j]), r2[j]), y[j]);
-                        if (TRAJ) my_traj[o] = v;
-                        const double r = series.at(off + 8 + 8 * o) - v;
-                        ss[o] = fma(r, r, ss[o]);
-                    }
-                    if (TRAJ) my_traj += NO;
-                    off += ROWB;
-                    t_out = series.at(off);
-                } while (t_out <= t_new);
+            for (int o = 0; o < NO; ++o) {
+                const int j = OUT0 + o;
+                const double d = yn[j] - y[j];
+                const double b = fma(h, k1[j], -d);
+                p_y[o] = y[j];
+                p_r2[o] = d;
+                p_r3[o] = b;
+                p_r4[o] = (d - h * k7[j]) - b;
+                p_r5[o] = h * fma(D7, k7[j], fma(D6, k6[j], fma(D5, k5[j], fma(D4, k4[j], fma(D3, k3[j], D1 * k1[j])))));
             }
+            p_t = t;
+            p_end = t_new;
+            p_invh = inv_h;
             t = t_new;
 #pragma unroll
             for (int j = 0; j < NS; ++j) { y[j] = yn[j]; k1[j] = k7[j]; }
@@ -519,9 +500,13 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
                  int64_t ld, double *d_scores, double *d_traj,
                  int32_t *d_steps, const SolverDev &s, int block,
                  cudaStream_t st) {
-    // series rows + the +inf sentinel row, in whole 16-byte units
-    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + 1) * (1 + M::NO) * 8 + 15) & ~15ll;
+    // series rows + the +inf sentinel rows, in whole 16-byte units
+    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * (1 + M::NO) * 8 + 15) & ~15ll;
+#ifdef PB200_NO_SMEM
+    const bool use_smem = false;
+#else
     const bool use_smem = bytes <= 96 * 1024;   // keeps >= 2 blocks per SM
+#endif
     const bool traj = d_traj != nullptr;
     if (block <= 0) block = 64;
     const int64_t grid = (n + block - 1) / block;

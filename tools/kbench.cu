@@ -32,7 +32,7 @@ int main(int argc, char **argv) {
     long slen = pb200_series_len(nt, no);
     std::vector<double> series(slen, 0.0);
     for (int j = 0; j < nt; ++j) series[3 * j] = 20.0 * j / (nt - 1);
-    series[3 * nt] = INFINITY;          // sentinel row
+    for (int k = 0; k < PB200_SENTINEL_ROWS; ++k) series[3 * (nt + k)] = INFINITY;   // sentinel rows
     double *d_series; CK(cudaMalloc(&d_series, slen * 8));
     CK(cudaMemcpy(d_series, series.data(), slen * 8, cudaMemcpyHostToDevice));
     double mc[2] = {-1.0, 1.0};
