@@ -127,45 +127,82 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------ clocks
 
 class ClockSampler(threading.Thread):
-    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
-    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap']
+    """SM clock and throttle reasons sampled DURING the timed region, through
+    NVML in-process (a `nvidia-smi` call takes longer than the whole region);
+    falls back to nvidia-smi if NVML cannot be loaded."""
+    REASONS = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4,
+               'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+               'hw_power_brake_slowdown': 0x80}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index = index
+        self.period = period
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = 'nvml'
         self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(
+                self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+            self.source = 'nvidia-smi'
+            self.period = 0.1
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h,
+                                                           n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        out = subprocess.run(
+            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+             '--format=csv,noheader,nounits'], stdout=subprocess.PIPE,
+            stderr=subprocess.DEVNULL, text=True,
+            timeout=5).stdout.strip().split(',')
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for name, flag in zip(names, out[2:]):
+            if flag.strip().lower().startswith('active'):
+                self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(
-                    ['nvidia-smi', '-i', str(self.index),
-                     '--query-gpu=' + self.QUERY,
-                     '--format=csv,noheader,nounits'],
-                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                    text=True, timeout=5).stdout.strip().split(',')
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for name, flag in zip(self.NAMES, out[2:]):
-                    if flag.strip().lower().startswith('active'):
-                        self.reasons.add(name)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(self.period)
 
     def finish(self):
         self._stop_evt.set()
         self.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz,
-                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+                'reasons': sorted(self.reasons), 'samples': len(self.samples),
+                'source': self.source}
 
 
 # ----------------------------------------------------------------- our arm
@@ -284,12 +321,22 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.finish()
+    # the same with the reference's return type (a Python list of floats):
+    # the boxing of 65 536 floats alone costs about as much as the solve
+    ev_list = pb.CudaEvaluator(ll, devices=device)
+    ev_list.evaluate(xs)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = ev_list.evaluate(xs)
+    barrier()
+    e2e_list_s = time.perf_counter() - t0
 
     if world > 1:
-        t = torch.tensor([step_ms, kern_ms, e2e_s], dtype=torch.float64,
-                         device=device)
+        t = torch.tensor([step_ms, kern_ms, e2e_s, e2e_list_s],
+                         dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, kern_ms, e2e_s = t.tolist()
+        step_ms, kern_ms, e2e_s, e2e_list_s = t.tolist()
 
     if rank == 0:
         total = pop * world * args.steps
@@ -319,7 +366,12 @@ def run_ours(args):
             'e2e': {'value': total / e2e_s, 'unit': UNIT,
                     'h2d_bytes_per_step': int(xs.nbytes) * world,
                     'd2h_bytes_per_step': int(pop * 8) * world,
-                    'api': 'CudaEvaluator.evaluate(ndarray) -> ndarray'},
+                    'api': 'CudaEvaluator(f, as_list=False).evaluate(ndarray) '
+                           '-> ndarray; pageable host array in, staged through '
+                           'pinned memory in 4 chunks on 4 streams',
+                    'value_as_list': total / e2e_list_s,
+                    'api_as_list': 'CudaEvaluator(f).evaluate(ndarray) -> list '
+                                   '(the reference\'s return type)'},
             'gpu_launches': args.steps * world,
             'clocks': clocks,
             'wall_s_timed_region': wall,

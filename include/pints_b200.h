@@ -149,6 +149,22 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n,
                const pb200_solver_opts *opts, void *stream);
 
 /*
+ * The same through HOST buffers, for callers that hold their positions in host
+ * memory (which is what the reference's evaluators receive): enqueues the
+ * host->device copy of the parameters, the fused kernel and the device->host
+ * copy of the scores on `stream`, then returns; the caller synchronises the
+ * stream before reading h_scores.  h_params / h_scores should be page-locked
+ * (pinned) for the copies to be asynchronous.  d_params_ws (n*ld doubles) and
+ * d_scores_ws (n doubles) are device workspaces owned by the caller; h_steps /
+ * d_steps_ws are optional (both NULL or both given).
+ */
+int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n,
+                    int64_t ld, double *h_scores, int32_t *h_steps,
+                    double *d_params_ws, double *d_scores_ws,
+                    int32_t *d_steps_ws, const pb200_solver_opts *opts,
+                    void *stream);
+
+/*
  * Batched ForwardModel.simulate / Problem.evaluate
  * (pints/_core.py:147-153, :257-265): writes the n trajectories
  * d_traj[n][n_times][n_outputs].  Also the first half of the unfused baseline.

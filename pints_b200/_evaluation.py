@@ -3,6 +3,8 @@
 ``pints.ParallelEvaluator`` (pints/_evaluation.py:63-123, :126-413, :457-482)
 that scores the whole batch of positions in one fused CUDA launch.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -59,18 +61,25 @@ class _SpecFunction(object):
 
 
 class _Lane(object):
-    """Per-device state of a CudaEvaluator: problem handle + staging."""
+    """Per-device state of a CudaEvaluator: problem handle, a stream, pinned
+    host staging buffers and device workspaces (grown geometrically)."""
+
+    N_STREAMS = 4
 
     def __init__(self, spec, device, opts):
         self.device = device
         self.problem = DeviceProblem(spec, device, **opts)
-        self.stream = torch.cuda.Stream(device=device)
+        self.streams = [torch.cuda.Stream(device=device)
+                        for _ in range(self.N_STREAMS)]
+        self.stream_ptrs = [ctypes.c_void_p(s.cuda_stream)
+                            for s in self.streams]
+        self.used = 0
         self.capacity = 0
-        self.h_in = self.h_out = self.d_in = self.d_out = self.d_steps = None
+        self.width = 0
         self.h_steps = None
 
     def reserve(self, n, d, want_steps):
-        if n > self.capacity:
+        if n > self.capacity or d != self.width:
             cap = max(n, int(self.capacity * 1.5), 1024)
             self.h_in = torch.empty((cap, d), dtype=torch.float64,
                                     pin_memory=True)
@@ -79,13 +88,51 @@ class _Lane(object):
                                     device=self.device)
             self.d_out = torch.empty(cap, dtype=torch.float64,
                                      device=self.device)
-            self.d_steps = self.h_steps = None
-            self.capacity = cap
-        if want_steps and self.d_steps is None:
+            # numpy views and raw pointers, so a call does no tensor slicing
+            self.h_in_np = self.h_in.numpy()
+            self.h_out_np = self.h_out.numpy()
+            self.a_h_in, self.a_h_out = self.h_in.data_ptr(), self.h_out.data_ptr()
+            self.a_d_in, self.a_d_out = self.d_in.data_ptr(), self.d_out.data_ptr()
+            self.h_steps = None
+            self.capacity, self.width = cap, d
+        if want_steps and self.h_steps is None:
             self.d_steps = torch.zeros(self.capacity, dtype=torch.int32,
                                        device=self.device)
             self.h_steps = torch.zeros(self.capacity, dtype=torch.int32,
                                        pin_memory=True)
+            self.h_steps_np = self.h_steps.numpy()
+            self.a_h_steps = self.h_steps.data_ptr()
+            self.a_d_steps = self.d_steps.data_ptr()
+
+    def launch(self, lib, xs, want_steps, chunk_rows):
+        """Stage `xs` into pinned memory and enqueue copy-in, kernel and
+        copy-out (one pb200_eval_host call per chunk).  Chunks go to different
+        streams: while the host stages chunk k+1, the GPU already integrates
+        chunk k, and the chunks' kernels share the SMs."""
+        m, d = xs.shape
+        self.reserve(m, d, want_steps)
+        V = ctypes.c_void_p
+        n_chunks = max(1, min(len(self.streams), -(-m // chunk_rows)))
+        rows = -(-m // n_chunks)
+        self.used = 0
+        with torch.cuda.device(self.device):
+            for c in range(n_chunks):
+                lo, hi = c * rows, min(m, (c + 1) * rows)
+                if hi <= lo:
+                    break
+                np.copyto(self.h_in_np[lo:hi], xs[lo:hi])
+                _lib.check(lib.pb200_eval_host(
+                    self.problem._handle, V(self.a_h_in + lo * d * 8), hi - lo,
+                    d, V(self.a_h_out + lo * 8),
+                    V(self.a_h_steps + lo * 4) if want_steps else None,
+                    V(self.a_d_in + lo * d * 8), V(self.a_d_out + lo * 8),
+                    V(self.a_d_steps + lo * 4) if want_steps else None,
+                    ctypes.byref(self.problem.opts), self.stream_ptrs[c]))
+                self.used = c + 1
+
+    def wait(self):
+        for s in self.streams[:self.used]:
+            s.synchronize()
 
 
 class CudaEvaluator(Evaluator):
@@ -118,6 +165,9 @@ class CudaEvaluator(Evaluator):
     as_list
         Return a Python list like the reference (default) or, if ``False``, a
         float64 ndarray (every consumer in the reference accepts either).
+    chunk_rows
+        Host batches larger than this are staged and launched in up to four
+        chunks on separate streams, so that staging overlaps with compute.
 
     Unlike ``ParallelEvaluator`` (pints/_evaluation.py:310) this evaluator never
     draws from ``numpy.random``, so controller trajectories equal those of a
@@ -125,7 +175,8 @@ class CudaEvaluator(Evaluator):
     """
 
     def __init__(self, function, args=None, devices=None, rtol=None, atol=None,
-                 max_steps=None, h0=None, block=None, as_list=True):
+                 max_steps=None, h0=None, block=None, as_list=True,
+                 chunk_rows=16384):
         if isinstance(function, ProblemSpec):
             spec = function
             function = _SpecFunction(spec)
@@ -135,11 +186,12 @@ class CudaEvaluator(Evaluator):
         if len(self._args) != 0:
             raise ValueError(
                 'CudaEvaluator does not support extra function arguments.')
-        _lib.load()                            # fail now if the library is absent
+        self._lib = _lib.load()                # fails now if the library is absent
         self._spec = spec if spec is not None else describe(function)
         self._opts = dict(rtol=rtol, atol=atol, max_steps=max_steps, h0=h0,
                           block=block)
         self._as_list = bool(as_list)
+        self._chunk_rows = max(1, int(chunk_rows))
         if devices is None or isinstance(devices, (int, str, torch.device)):
             devices = [devices]
         self._device_args = list(devices)
@@ -188,22 +240,14 @@ class CudaEvaluator(Evaluator):
             lo, hi = k * per, min(n, (k + 1) * per)
             if hi <= lo:
                 continue
+            lane.launch(self._lib, xs[lo:hi], return_steps, self._chunk_rows)
+            work.append((lane, lo, hi))
+        for lane, lo, hi in work:
+            lane.wait()
             m = hi - lo
-            lane.reserve(m, d, return_steps)
-            lane.h_in[:m].numpy()[...] = xs[lo:hi]
-            with torch.cuda.device(lane.device), torch.cuda.stream(lane.stream):
-                lane.d_in[:m].copy_(lane.h_in[:m], non_blocking=True)
-                lane.problem.eval(lane.d_in[:m], out=lane.d_out[:m],
-                                  steps=lane.d_steps if return_steps else None)
-                lane.h_out[:m].copy_(lane.d_out[:m], non_blocking=True)
-                if return_steps:
-                    lane.h_steps[:m].copy_(lane.d_steps[:m], non_blocking=True)
-            work.append((lane, lo, hi, m))
-        for lane, lo, hi, m in work:
-            lane.stream.synchronize()
-            scores[lo:hi] = lane.h_out[:m].numpy()
+            scores[lo:hi] = lane.h_out_np[:m]
             if return_steps:
-                steps[lo:hi] = lane.h_steps[:m].numpy()
+                steps[lo:hi] = lane.h_steps_np[:m]
         if return_steps:
             self.last_steps = steps
             return scores, steps

@@ -201,6 +201,31 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_
     return launch_analytic(p, d_params, n, ld, d_scores, nullptr, st);
 }
 
+int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n, int64_t ld,
+                    double *h_scores, int32_t *h_steps, double *d_params_ws,
+                    double *d_scores_ws, int32_t *d_steps_ws, const pb200_solver_opts *opts,
+                    void *stream) {
+    int rc = check_batch(p, h_params, n, ld, h_scores, "pb200_eval_host");
+    if (rc || n == 0) return rc;
+    if (!d_params_ws || !d_scores_ws || ((h_steps == nullptr) != (d_steps_ws == nullptr))) {
+        pb200_set_error("pb200_eval_host: missing device workspace");
+        return PB200_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = pb200_check_cuda(cudaMemcpyAsync(d_params_ws, h_params, static_cast<size_t>(n) * ld * 8,
+                                          cudaMemcpyHostToDevice, st), "copy of parameters");
+    if (rc) return rc;
+    rc = pb200_eval(p, d_params_ws, n, ld, d_scores_ws, d_steps_ws, opts, stream);
+    if (rc) return rc;
+    rc = pb200_check_cuda(cudaMemcpyAsync(h_scores, d_scores_ws, static_cast<size_t>(n) * 8,
+                                          cudaMemcpyDeviceToHost, st), "copy of scores");
+    if (rc) return rc;
+    if (h_steps)
+        rc = pb200_check_cuda(cudaMemcpyAsync(h_steps, d_steps_ws, static_cast<size_t>(n) * 4,
+                                              cudaMemcpyDeviceToHost, st), "copy of steps");
+    return rc;
+}
+
 int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
                    double *d_traj, int32_t *d_steps, const pb200_solver_opts *opts,
                    void *stream) {
