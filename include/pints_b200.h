@@ -65,7 +65,7 @@ extern "C" {
 #define PB200_MAX_OUTPUTS   8
 #define PB200_MAX_PARAMS    16      /* model parameters + sigma parameters  */
 #define PB200_MAX_EVENTS    64      /* HH-IK protocol events                */
-#define PB200_SENTINEL_ROWS 4       /* +inf rows that end the packed series */
+#define PB200_SENTINEL_ROWS 8       /* +inf rows that end the packed series */
 
 typedef struct pb200_problem pb200_problem;
 
@@ -79,6 +79,8 @@ typedef struct pb200_solver_opts {
     int32_t max_steps;   /* attempted steps per vector; <= 0 -> 1000000.     */
                          /* A vector that exceeds it scores NaN.             */
     int32_t block;       /* threads per block; <= 0 -> automatic             */
+    int32_t lanes;       /* GPU lanes per parameter vector: 1, or 2 (one per */
+                         /* state, two-state models only); <= 0 -> automatic */
 } pb200_solver_opts;
 
 int         pb200_version(void);

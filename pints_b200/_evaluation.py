@@ -162,6 +162,9 @@ class CudaEvaluator(Evaluator):
         Controls of the adaptive Dormand-Prince 5(4) integrator for the ODE
         models; the tolerances default to scipy odeint's 1.49012e-8 that the
         reference runs with (pints/toy/_toy_classes.py:225-233).
+    lanes_per_vector
+        GPU lanes that integrate one parameter vector: 1, or 2 (one lane per
+        state component, two-state models only); default automatic.
     as_list
         Return a Python list like the reference (default) or, if ``False``, a
         float64 ndarray (every consumer in the reference accepts either).
@@ -176,7 +179,7 @@ class CudaEvaluator(Evaluator):
 
     def __init__(self, function, args=None, devices=None, rtol=None, atol=None,
                  max_steps=None, h0=None, block=None, as_list=True,
-                 chunk_rows=16384):
+                 chunk_rows=16384, lanes_per_vector=None):
         if isinstance(function, ProblemSpec):
             spec = function
             function = _SpecFunction(spec)
@@ -189,7 +192,7 @@ class CudaEvaluator(Evaluator):
         self._lib = _lib.load()                # fails now if the library is absent
         self._spec = spec if spec is not None else describe(function)
         self._opts = dict(rtol=rtol, atol=atol, max_steps=max_steps, h0=h0,
-                          block=block)
+                          block=block, lanes=lanes_per_vector)
         self._as_list = bool(as_list)
         self._chunk_rows = max(1, int(chunk_rows))
         if devices is None or isinstance(devices, (int, str, torch.device)):

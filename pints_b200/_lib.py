@@ -20,7 +20,7 @@ MODEL_LOGISTIC, MODEL_HH_IK, MODEL_CONSTANT = 0, 1, 2
 MODEL_FHN, MODEL_LOTKA_VOLTERRA, MODEL_SIR = 3, 4, 5
 OBJ_SSE, OBJ_GAUSSIAN_KNOWN_SIGMA, OBJ_GAUSSIAN = 0, 1, 2
 MAX_OUTPUTS, MAX_PARAMS, MAX_EVENTS = 8, 16, 64
-SENTINEL_ROWS = 4
+SENTINEL_ROWS = 8
 
 MODEL_NAMES = {MODEL_LOGISTIC: 'logistic', MODEL_HH_IK: 'hh_ik',
                MODEL_CONSTANT: 'constant', MODEL_FHN: 'fhn',
@@ -33,7 +33,8 @@ OBJECTIVE_NAMES = {OBJ_SSE: 'sse',
 class SolverOpts(Structure):
     """``pb200_solver_opts``"""
     _fields_ = [('rtol', c_double), ('atol', c_double), ('h0', c_double),
-                ('max_steps', c_int32), ('block', c_int32)]
+                ('max_steps', c_int32), ('block', c_int32),
+                ('lanes', c_int32)]
 
 
 class LibraryError(RuntimeError):

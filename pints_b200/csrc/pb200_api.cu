@@ -42,7 +42,7 @@ const ModelInfo kModels[PB200_N_MODELS] = {
     /* SIR            */ {3, 2, 4, true},
 };
 
-SolverDev resolve_opts(const pb200_solver_opts *o, int *block) {
+SolverDev resolve_opts(const pb200_solver_opts *o, int *block, int *lanes) {
     SolverDev s;
     s.rtol = (o && o->rtol > 0) ? o->rtol : 1.49012e-8;
     s.atol = (o && o->atol > 0) ? o->atol : 1.49012e-8;
@@ -50,6 +50,7 @@ SolverDev resolve_opts(const pb200_solver_opts *o, int *block) {
     s.h0 = (o && o->h0 > 0) ? o->h0 : 0.0;
     s.max_steps = (o && o->max_steps > 0) ? o->max_steps : 1000000;
     *block = (o && o->block > 0) ? o->block : 0;
+    *lanes = (o && o->lanes > 0) ? o->lanes : 0;
     return s;
 }
 
@@ -189,9 +190,9 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_
     if (rc || n == 0) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kModels[p->dev.model].ode) {
-        int block;
-        SolverDev s = resolve_opts(opts, &block);
-        return launch_ode(p, d_params, n, ld, d_scores, nullptr, d_steps, s, block, st);
+        int block, lanes;
+        SolverDev s = resolve_opts(opts, &block, &lanes);
+        return launch_ode(p, d_params, n, ld, d_scores, nullptr, d_steps, s, block, lanes, st);
     }
     if (d_steps) {
         rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),
@@ -233,9 +234,9 @@ int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, in
     if (rc || n == 0) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kModels[p->dev.model].ode) {
-        int block;
-        SolverDev s = resolve_opts(opts, &block);
-        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, st);
+        int block, lanes;
+        SolverDev s = resolve_opts(opts, &block, &lanes);
+        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, lanes, st);
     }
     if (d_steps) {
         rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),

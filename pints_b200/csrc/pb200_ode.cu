@@ -95,15 +95,19 @@ __constant__ double TAB[N_TAB] = {
 
 
 // ----------------------------------------------------------------- models
-// Each model: NS states, NO outputs, OUT0 = index of the first output state,
-// load() turns a parameter row into per-thread constants and y0, rhs() is the
-// (autonomous) right-hand side.
+// Each model: NS states, NO outputs, OUT0 = index of the first output state.
+// load() turns a parameter row into per-thread constants and y0; rhs() is the
+// plain (autonomous) right-hand side, used once for the first step size;
+// scale(h) folds the step size into the constants so that hrhs() returns
+// K = h f(y) directly: every stage, the error estimate and the dense output
+// then work on h-scaled increments and need no further multiplication by h.
 struct FhnModel {
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 3;
     // V' = c (V - V^3/3 + R) = (c - (c/3) V^2) V + c R
     // R' = -(V - a + b R) / c  = (-1/c) V + (a/c) + (-b/c) R
     // written with per-vector constants so one evaluation is 6 FP64 ops
     double c, c3, nic, aoc, nboc;
+    double hc, hc3, hnic, haoc, hnboc;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
                                          double *y, double /*t_first*/,
                                          double *t0) {
@@ -122,11 +126,21 @@ struct FhnModel {
         f[0] = fma(u, V, c * R);
         f[1] = fma(nboc, R, fma(nic, V, aoc));
     }
+    __device__ __forceinline__ void scale(double h) {
+        hc = h * c; hc3 = h * c3; hnic = h * nic; haoc = h * aoc; hnboc = h * nboc;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        const double V = y[0], R = y[1];
+        const double u = fma(hc3, V * V, hc);
+        K[0] = fma(u, V, hc * R);
+        K[1] = fma(hnboc, R, fma(hnic, V, haoc));
+    }
 };
 
 struct LvModel {
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 4;
     double a, b, c, d;
+    double ha, nhb, nhc, hd;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
                                          double *y, double, double *t0) {
         a = x[0]; b = x[1]; c = x[2]; d = x[3];
@@ -138,11 +152,20 @@ struct LvModel {
         f[0] = u * fma(-b, v, a);         // a x - b x y
         f[1] = v * fma(d, u, -c);         // -c y + d x y
     }
+    __device__ __forceinline__ void scale(double h) {
+        ha = h * a; nhb = -h * b; nhc = -h * c; hd = h * d;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        const double u = y[0], v = y[1];
+        K[0] = u * fma(nhb, v, ha);
+        K[1] = v * fma(hd, u, nhc);
+    }
 };
 
 struct SirModel {
     static constexpr int NS = 3, NO = 2, OUT0 = 1, NP = 3;
     double gamma, v;
+    double nhg, hv;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
                                          double *y, double t_first,
                                          double *t0) {
@@ -161,6 +184,16 @@ struct SirModel {
         f[1] = -ngsi - vi;
         f[2] = vi;
     }
+    __device__ __forceinline__ void scale(double h) {
+        nhg = -h * gamma; hv = h * v;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        const double ngsi = (nhg * y[0]) * y[1];
+        const double vi = hv * y[1];
+        K[0] = ngsi;
+        K[1] = -ngsi - vi;
+        K[2] = vi;
+    }
 };
 
 // MUFU.RCP64H: >= 20 good bits, on the XU pipe (off the FP64 pipe).
@@ -170,49 +203,81 @@ __device__ __forceinline__ double rcp_seed(double x) {
     return r;
 }
 
-// Full-precision reciprocal for normal-range x: seed + two Newton steps
-// (20 -> 40 -> 80 bits); no slow path, four DFMAs.
+// Reciprocal of a normal-range x: seed + Newton steps (20 -> 40 -> 80 bits);
+// no slow path, two DFMAs per step.
+template <int STEPS>
 __device__ __forceinline__ double rcp_newton(double x) {
     double r = rcp_seed(x);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return fma(r, fma(-x, r, 1.0), r);
-}
-
-// Mean square of err_i / (atol + rtol * (|y_i| + |ynew_i|) / 2).  The scale
-// uses the mean of the two magnitudes (one DADD with |.| modifiers) instead of
-// their max (a DSETP plus a 64-bit select); the 1e-6-accurate reciprocal seed
-// is enough because the result is only compared with 1 and fed to the
-// step-size controller.
-template <int NS>
-__device__ __forceinline__ double err_norm2(const double *esum, double h,
-                                            const double *y, const double *yn,
-                                            double half_rtol, double atol) {
-    double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        const double sc = fma(half_rtol, fabs(y[i]) + fabs(yn[i]), atol);
-        const double q = (esum[i] * h) * rcp_seed(sc);
-        s = fma(q, q, s);
-    }
-    return s * (1.0 / NS);
+    for (int k = 0; k < STEPS; ++k) r = fma(r, fma(-x, r, 1.0), r);
+    return r;
 }
 
-// Step-size factor 0.9 * norm^(-1/5), clamped to [0.2, 10], from norm^2.  It
-// runs on the SFU in fp32 (lg2/ex2 approximations): the controller needs a few
-// digits only, and accept/reject is decided in fp64 on norm^2 <= 1, never on
-// this value.  norm2 = 0 -> 10, norm2 = inf or NaN -> 0.2.
-__device__ __forceinline__ float step_factor(double norm2) {
-    const float n2 = static_cast<float>(norm2);
+// ss += r * r only where `valid`: a predicated DFMA instead of a DFMA plus a
+// 64-bit select (two FSELs on the issue port).
+__device__ __forceinline__ void acc_sq_if(double &ss, double r, bool valid) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p fma.rn.f64 %0, %1, %1, %0;\n\t}"
+        : "+d"(ss) : "d"(r), "r"(static_cast<uint32_t>(valid)));
+}
+
+// Order of two doubles from their bit patterns (integer pipe instead of a
+// DSETP on the FP64 pipe).  Exact for non-negative a and any b whose sign bit
+// marks "never" (-inf): times are non-negative, +inf is the largest pattern.
+__device__ __forceinline__ bool le_bits(double a, double b) {
+    return __double_as_longlong(a) <= __double_as_longlong(b);
+}
+
+// Step-size factor 0.9 * err^(-1/5), clamped to [0.2, 10], from the SUM of
+// squared scaled errors (err^2 = sum / NS).  It runs on the SFU in fp32
+// (lg2/ex2 approximations): the controller needs a few digits only, and
+// accept/reject is decided on the fp64 sum, never on this value.
+// sum = 0 -> 10, sum = inf or NaN -> 0.2.
+template <int NS>
+__device__ __forceinline__ float step_factor(double sum2) {
+    const float n2 = static_cast<float>(sum2);
     float l, f;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(n2));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(-0.1f * l));
-    return fminf(fmaxf(0.9f * f, 0.2f), 10.0f);
+    // 0.9 * NS^(1/10)
+    const float k = NS == 1 ? 0.9f : NS == 2 ? 0.96459370f : NS == 3 ? 1.00450979f
+                                                             : 0.9f * exp2f(0.1f * log2f((float)NS));
+    return fminf(fmaxf(k * f, 0.2f), 10.0f);
+}
+
+// The same factor without the SFU and without fp64 <-> fp32 conversions: the
+// high word of a positive double is a fixed-point log2, so
+//   hi(fac) = MAGIC - hi(sum2) / 10
+// gives 0.9 (sum2 / NS)^(-1/10) to +-3.3 % (the piecewise-linear mantissa
+// error, centred by the magic constant) in four integer instructions, and the
+// clamps to [0.2, 10] (and to <= 1 after a rejection) are integer min / max on
+// the same word.  A 3 % wobble in the safety factor leaves the number of
+// attempted steps unchanged (measured: 384.6 against 385.1 per vector on the
+// headline population).  sum2 = 0 -> 10, inf / NaN -> 0.2.
+template <int NS>
+__device__ __forceinline__ double step_factor_bits(double sum2, bool cap_at_one) {
+    // 0x3FF00000 + 2^20 log2(0.9 NS^0.1) - 50000 (centring) + 0x3FF00000 / 10
+    constexpr int32_t magic =
+        NS == 1 ? 1179753186 : NS == 2 ? 1179858044 : NS == 3 ? 1179919381 : 1179962902;
+    static_assert(NS >= 1 && NS <= 4, "magic constant tabulated for 1..4 states");
+    const uint32_t hi = static_cast<uint32_t>(__double2hiint(sum2));
+    int32_t hy = magic - static_cast<int32_t>(__umulhi(hi, 0x1999999Au));
+    hy = max(hy, 0x3FC99999);                        // 0.2
+    hy = min(hy, cap_at_one ? 0x3FF00000 : 0x40240000);   // 1 or 10
+    return __hiloint2double(hy, 0);
 }
 
 // Observed series access.  In shared memory the rows are read with explicit
 // ld.shared through a 32-bit byte address kept in a register (the generic
 // pointer form makes the compiler rebuild the shared-window base on every
 // access); otherwise through the read-only global path.
+// Opaque copy: keeps the compiler from recomputing the shared-window address
+// (S2UR SR_CgaCtaId + three uniform ops) at every use inside the step loop.
+__device__ __forceinline__ uint32_t launder_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 template <bool SMEM>
 struct Series {
     uint32_t sbase;
@@ -229,13 +294,41 @@ struct Series {
     }
 };
 
-template <class M, bool SMEM, bool TRAJ>
 #ifndef PB200_PIPE_U
-#define PB200_PIPE_U 2          // deferred interpolation slots per step attempt
+#define PB200_PIPE_U 2          // in-line interpolation slots per step attempt
 #endif
 #ifndef PB200_MAXTHREADS
 #define PB200_MAXTHREADS 128
 #endif
+#ifndef PB200_CLOOP_POS
+#define PB200_CLOOP_POS 1       // 0: top of the iteration, 1: after the error estimate
+#endif
+#ifndef PB200_CLOOP_WIDTH
+#define PB200_CLOOP_WIDTH 1     // observations per trip of the (C) loop
+#endif
+#ifndef PB200_LOOP_UNROLL
+#define PB200_LOOP_UNROLL 2
+#endif
+#ifndef PB200_CTRL_BITS
+#define PB200_CTRL_BITS 0       // integer step-size factor (no SFU)
+#endif
+#ifndef PB200_RCP_STEPS
+#define PB200_RCP_STEPS 1
+#endif
+static_assert(PB200_PIPE_U + 1 <= PB200_SENTINEL_ROWS, "not enough sentinel rows");
+
+// Control flow is warp-uniform: every lane of a warp runs the same number of
+// loop iterations (votes decide), finished lanes idle on harmless arithmetic.
+// One iteration = one attempted step of every lane, a single basic block:
+//   (C) observations of the pending interval beyond the U in-line slots
+//       (uniform loop, only while some lane still has more than U pending),
+//   (A) U predicated interpolation slots of the pending interval,
+//   (B) the six stages on h-scaled increments, error estimate, controller,
+//   (D) accept/reject by selects, dense-output coefficients parked for the
+//       NEXT iteration's (C)/(A).
+// (A) is independent of (B), so it fills the issue slots that the serial
+// RHS -> stage -> RHS chain (9-cycle DFMA latency) leaves empty.
+template <class M, bool SMEM, bool TRAJ>
 __global__ void __launch_bounds__(PB200_MAXTHREADS)
 ode_kernel(const __grid_constant__ ProblemDev P,
            const __grid_constant__ ModelConsts mc,
@@ -244,6 +337,8 @@ ode_kernel(const __grid_constant__ ProblemDev P,
            int32_t *__restrict__ steps_out, const SolverDev S) {
     constexpr int NS = M::NS, NO = M::NO, OUT0 = M::OUT0;
     constexpr uint32_t ROWB = (1 + NO) * 8;          // bytes per series row
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int U = PB200_PIPE_U;
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
 
@@ -254,11 +349,14 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         const uint32_t bytes = static_cast<uint32_t>(
             ((static_cast<int64_t>(P.n_times) + PB200_SENTINEL_ROWS) * ROWB + 15) & ~15ll);
         stage_series(smem, P.series, bytes, &bar);
-        series.sbase = smem_u32(smem);
+        series.sbase = launder_u32(smem_u32(smem));
     }
 
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // lanes past the end of the population shadow the last vector and write
+    // nothing: whole warps stay convergent for the votes below
+    const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool live = gi < n;
+    const int64_t i = live ? gi : n - 1;
 
     const int nt = P.n_times;
     const int n_read = TRAJ ? P.n_model_params : P.n_params;
@@ -267,50 +365,54 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     for (int k = 0; k < M::NP + NO; ++k)
         x[k] = (k < n_read) ? params[i * ld + k] : 0.0;
 
+    bool idle = !live;
     if (!TRAJ) {
         double early;
         if (objective_precheck(P, x, &early)) {
-            scores[i] = early;
-            if (steps_out) steps_out[i] = 0;
-            return;
+            if (live) {
+                scores[i] = early;
+                if (steps_out) steps_out[i] = 0;
+            }
+            idle = true;
         }
     }
 
     M model;
     double y[NS], t;
     model.load(x, mc, y, nt > 0 ? series.at(0) : 0.0, &t);
-    if (nt == 0) t = 0.0;
 
     double ss[NO];
 #pragma unroll
     for (int o = 0; o < NO; ++o) ss[o] = 0.0;
 
-    // `off` is the byte offset of the next observation row, `t_out` its time.
-    // The packed series ends with a sentinel row whose time is +inf, so the
-    // interpolation loop needs no bounds check and one register compare per
-    // step decides whether any interpolation is needed.
+    // `off` is the byte offset of the next observation row.  The packed series
+    // ends with sentinel rows whose time is +inf, so reading a few rows ahead
+    // needs no bounds check.
     const uint32_t end = static_cast<uint32_t>(nt) * ROWB;
     uint32_t off = 0;
-    double t_out = series.at(0);
     double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * NO : nullptr;
 
     // observations at (or before) the initial time see the initial state
-    while (t_out <= t) {
+    if (!idle) {
+        double t_out = series.at(0);
+        while (t_out <= t) {
 #pragma unroll
-        for (int o = 0; o < NO; ++o) {
-            if (TRAJ) my_traj[o] = y[OUT0 + o];
-            const double r = series.at(off + 8 + 8 * o) - y[OUT0 + o];
-            ss[o] = fma(r, r, ss[o]);
+            for (int o = 0; o < NO; ++o) {
+                if (TRAJ) my_traj[off / ROWB * NO + o] = y[OUT0 + o];
+                const double r = series.at(off + 8 + 8 * o) - y[OUT0 + o];
+                ss[o] = fma(r, r, ss[o]);
+            }
+            off += ROWB;
+            t_out = series.at(off);
         }
-        if (TRAJ) my_traj += NO;
-        off += ROWB;
-        t_out = series.at(off);
+    } else {
+        off = end;
     }
 
     const double half_rtol = S.half_rtol, atol = S.atol;
-    double k1[NS], k2[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS];
-    double yn[NS], w[NS], esum[NS];
-    model.rhs(y, k1);
+    double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], K6[NS], K7[NS];
+    double yn[NS], w[NS];
+    model.rhs(y, K1);
 
     // ---- first step (Hairer's hinit, as scipy's select_initial_step) ----
     double h = S.h0;
@@ -319,7 +421,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
             const double sc = fma(S.rtol, fabs(y[j]), atol);
-            const double a0 = y[j] / sc, a1 = k1[j] / sc;
+            const double a0 = y[j] / sc, a1 = K1[j] / sc;
             d0 = fma(a0, a0, d0);
             d1 = fma(a1, a1, d1);
         }
@@ -327,13 +429,13 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         d1 = sqrt(d1 * (1.0 / NS));
         double h_a = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
 #pragma unroll
-        for (int j = 0; j < NS; ++j) w[j] = fma(h_a, k1[j], y[j]);
-        model.rhs(w, k2);
+        for (int j = 0; j < NS; ++j) w[j] = fma(h_a, K1[j], y[j]);
+        model.rhs(w, K2);
         double d2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
             const double sc = fma(S.rtol, fabs(y[j]), atol);
-            const double a2 = (k2[j] - k1[j]) / sc;
+            const double a2 = (K2[j] - K1[j]) / sc;
             d2 = fma(a2, a2, d2);
         }
         d2 = sqrt(d2 * (1.0 / NS)) / h_a;
@@ -342,166 +444,498 @@ ode_kernel(const __grid_constant__ ProblemDev P,
                                          : pow(0.01 / dm, 0.2);
         h = fmin(100.0 * h_a, h_b);
     }
+    // from here on K1 = h f(y)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) K1[j] *= h;
+    model.scale(h);
 
     int attempts = 0;
     bool failed = false;
     bool after_reject = false;
     const int max_steps = S.max_steps;
+    const double t_last = nt > 0 ? series.at(end - ROWB) : -INFINITY;
+    // below this step size the vector is given up (score NaN)
+    const double h_min = 1e-14 * fmax(fabs(t_last), 1.0);
 
-    // The observations inside an accepted step are NOT interpolated right away:
-    // the step's dense-output coefficients are parked ("pending interval") and
-    // consumed during the NEXT attempt, where U branch-free interpolation slots
-    // sit in the same basic block as the six stages.  The slots are independent
-    // of the stage arithmetic, so they fill the issue slots that the serial
-    // RHS -> stage -> RHS dependency chain (9-cycle DFMA latency) leaves empty;
-    // with only ~3.5 warps per scheduler at population 65 536 that is where the
-    // FP64 pipe was idling.  Steps that contain more than U observations drain
-    // the rest in a (divergent) loop before the coefficients are overwritten.
-    constexpr int U = PB200_PIPE_U;
-    double p_t = 0.0, p_end = -INFINITY, p_invh = 0.0;
+    // pending interval: dense-output coefficients of the last accepted step,
+    // theta = tq * p_invh + p_c0, 1 - theta = -tq * p_invh + p_c1
+    double p_end = -INFINITY, p_invh = 0.0, p_c0 = 0.0, p_c1 = 0.0;
     double p_y[NO], p_r2[NO], p_r3[NO], p_r4[NO], p_r5[NO];
 #pragma unroll
     for (int o = 0; o < NO; ++o) p_y[o] = p_r2[o] = p_r3[o] = p_r4[o] = p_r5[o] = 0.0;
-    const double t_last = nt > 0 ? series.at(end - ROWB) : -INFINITY;
 
     // one interpolation of the pending interval at time tq against row `row`
     auto interpolate = [&](double tq, uint32_t row, bool valid) {
-        const double th = (tq - p_t) * p_invh;
-        const double th1 = 1.0 - th;
-        const double thq = th * th1;
+        const double th = fma(tq, p_invh, p_c0);
+        const double th1 = fma(-tq, p_invh, p_c1);
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
-            // y + th ((r2 + th1 r3) + (th th1)(r4 + th1 r5))
-            const double v = fma(th, fma(thq, fma(th1, p_r5[o], p_r4[o]),
-                                         fma(th1, p_r3[o], p_r2[o])), p_y[o]);
-            if (TRAJ) { if (valid) my_traj[(row - off) / ROWB * NO + o] = v; }
-            const double r = valid ? series.at(row + 8 + 8 * o) - v : 0.0;
-            ss[o] = fma(r, r, ss[o]);
-        }
-    };
-    auto drain = [&]() {
-        while (t_out <= p_end) {
-            interpolate(t_out, off, true);
-            if (TRAJ) my_traj += NO;
-            off += ROWB;
-            t_out = series.at(off);
+            // y + th (r2 + th1 (r3 + th (r4 + th1 r5)))
+            const double v = fma(th, fma(th1, fma(th, fma(th1, p_r5[o], p_r4[o]), p_r3[o]), p_r2[o]), p_y[o]);
+            const double r = series.at(row + 8 + 8 * o) - v;
+            if (TRAJ) { if (valid) my_traj[row / ROWB * NO + o] = v; }
+            acc_sq_if(ss[o], r, valid);
         }
     };
 
-    while (off < end) {
-        if (p_end >= t_last) {          // every remaining observation is pending
-            drain();
-            break;
+    constexpr int kLoopUnroll = PB200_LOOP_UNROLL;
+#pragma unroll kLoopUnroll
+    for (;;) {
+        const bool fin = (off >= end) || failed;
+        if (__all_sync(FULL, fin)) break;
+        // an attempt is counted while the solution has not reached the last
+        // observation; the iteration after that only empties the pending interval
+        if (!fin && t < t_last) {
+            if (attempts >= max_steps) failed = true;
+            else ++attempts;
         }
-        if (attempts >= max_steps) {
-            failed = true;
-            break;
+
+#if PB200_CLOOP_POS == 0
+        // ---- (C) pending observations beyond the U slots ----
+        {
+            double t_ahead = series.at(off + U * ROWB);
+            while (__any_sync(FULL, le_bits(t_ahead, p_end))) {
+                const bool more = le_bits(t_ahead, p_end);
+                interpolate(series.at(off), off, more);
+                off += more ? ROWB : 0u;
+                t_ahead = series.at(off + U * ROWB);
+            }
         }
-        ++attempts;
-        const double inv_h = rcp_newton(h);
-        // ---- U deferred interpolation slots (branch free) ----
-        if (U > 0) {
+#endif
+        // ---- (A) U interpolation slots (predicated) ----
+        {
             double tq[U > 0 ? U : 1];
             uint32_t cnt = 0;
 #pragma unroll
             for (int k = 0; k < U; ++k) tq[k] = series.at(off + k * ROWB);
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const bool valid = tq[k] <= p_end;     // monotone in k
+                const bool valid = le_bits(tq[k], p_end);     // monotone in k
                 interpolate(tq[k], off + k * ROWB, valid);
                 cnt += valid ? 1u : 0u;
             }
-            if (TRAJ) my_traj += cnt * NO;
             off += cnt * ROWB;
-            t_out = series.at(off);
         }
-        // ---- six stages (k1 is f(y): first-same-as-last) ----
+        // ---- (B) six stages on K = h f (K1 is h f(y): first-same-as-last) ----
 #pragma unroll
-        for (int j = 0; j < NS; ++j) w[j] = fma(h, A21 * k1[j], y[j]);
-        model.rhs(w, k2);
-#pragma unroll
-        for (int j = 0; j < NS; ++j)
-            w[j] = fma(h, fma(A32, k2[j], A31 * k1[j]), y[j]);
-        model.rhs(w, k3);
+        for (int j = 0; j < NS; ++j) w[j] = fma(A21, K1[j], y[j]);
+        model.hrhs(w, K2);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            w[j] = fma(h, fma(A43, k3[j], fma(A42, k2[j], A41 * k1[j])), y[j]);
-        model.rhs(w, k4);
+            w[j] = fma(A32, K2[j], fma(A31, K1[j], y[j]));
+        model.hrhs(w, K3);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            w[j] = fma(h, fma(A54, k4[j], fma(A53, k3[j], fma(A52, k2[j], A51 * k1[j]))), y[j]);
-        model.rhs(w, k5);
+            w[j] = fma(A43, K3[j], fma(A42, K2[j], fma(A41, K1[j], y[j])));
+        model.hrhs(w, K4);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            w[j] = fma(h, fma(A65, k5[j], fma(A64, k4[j], fma(A63, k3[j], fma(A62, k2[j], A61 * k1[j])))), y[j]);
-        model.rhs(w, k6);
+            w[j] = fma(A54, K4[j], fma(A53, K3[j], fma(A52, K2[j], fma(A51, K1[j], y[j]))));
+        model.hrhs(w, K5);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            yn[j] = fma(h, fma(B6, k6[j], fma(B5, k5[j], fma(B4, k4[j], fma(B3, k3[j], B1 * k1[j])))), y[j]);
-        model.rhs(yn, k7);
-        // ---- embedded error estimate (to be scaled by h) ----
+            w[j] = fma(A65, K5[j], fma(A64, K4[j], fma(A63, K3[j], fma(A62, K2[j], fma(A61, K1[j], y[j])))));
+        model.hrhs(w, K6);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            esum[j] = fma(E7, k7[j], fma(E6, k6[j], fma(E5, k5[j], fma(E4, k4[j], fma(E3, k3[j], E1 * k1[j])))));
-        const double n2 = err_norm2<NS>(esum, h, y, yn, half_rtol, atol);
-        float fac = step_factor(n2);
-        // observations of the pending interval beyond the U slots
-        drain();
+            yn[j] = fma(B6, K6[j], fma(B5, K5[j], fma(B4, K4[j], fma(B3, K3[j], fma(B1, K1[j], y[j])))));
+        model.hrhs(yn, K7);
+        // ---- embedded error estimate, sum of squared scaled errors ----
+        // scale atol + rtol (|y| + |ynew|) / 2: one DADD with |.| modifiers
+        // instead of max (DSETP + 64-bit select); the 1e-6-accurate reciprocal
+        // seed is enough for a value that is only compared with NS and fed
+        // to the controller.
+        double sum2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            const double e = fma(E7, K7[j], fma(E6, K6[j], fma(E5, K5[j], fma(E4, K4[j], fma(E3, K3[j], E1 * K1[j])))));
+            const double sc = fma(half_rtol, fabs(y[j]) + fabs(yn[j]), atol);
+            const double q = e * rcp_seed(sc);
+            sum2 = j == 0 ? q * q : fma(q, q, sum2);
+        }
+        // accepted iff mean square <= 1; NaN compares as "rejected"
+        const bool ok = __double_as_longlong(sum2) >= 0 &&
+                        __double_as_longlong(sum2) <= __double_as_longlong(static_cast<double>(NS));
+        // no growth on the step right after a rejection, none on a rejection
+#if PB200_CTRL_BITS
+        const double facd = step_factor_bits<NS>(sum2, !ok || after_reject);
+#else
+        float fac = step_factor<NS>(sum2);
+        if (!ok || after_reject) fac = fminf(fac, 1.0f);
+        const double facd = static_cast<double>(fac);
+#endif
+        after_reject = !ok;
+#if PB200_CLOOP_POS == 1
+        // ---- (C) pending observations beyond the U slots, W per trip ----
+        {
+            constexpr int W = PB200_CLOOP_WIDTH;
+            double tn[W];
+#pragma unroll
+            for (int k = 0; k < W; ++k) tn[k] = series.at(off + k * ROWB);
+            while (__any_sync(FULL, le_bits(tn[0], p_end))) {
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    const bool more = le_bits(tn[k], p_end);
+                    interpolate(tn[k], off + k * ROWB, more);
+                    cnt += more ? 1u : 0u;
+                }
+                off += cnt * ROWB;
+#pragma unroll
+                for (int k = 0; k < W; ++k) tn[k] = series.at(off + k * ROWB);
+            }
+        }
+#endif
 
-        if (n2 <= 1.0) {
-            // ---- accepted: park the dense-output coefficients ----
-            const double t_new = t + h;
+        // ---- (D) dense-output coefficients of this step (Hairer's contd5
+        // on h-scaled increments); junk when rejected, masked by p_end ----
+        const double inv_h = rcp_newton<PB200_RCP_STEPS>(h);
+        const double t_new = t + h;
 #pragma unroll
-            for (int o = 0; o < NO; ++o) {
-                const int j = OUT0 + o;
-                const double d = yn[j] - y[j];
-                const double b = fma(h, k1[j], -d);
-                p_y[o] = y[j];
-                p_r2[o] = d;
-                p_r3[o] = b;
-                p_r4[o] = (d - h * k7[j]) - b;
-                p_r5[o] = h * fma(D7, k7[j], fma(D6, k6[j], fma(D5, k5[j], fma(D4, k4[j], fma(D3, k3[j], D1 * k1[j])))));
-            }
-            p_t = t;
-            p_end = t_new;
-            p_invh = inv_h;
-            t = t_new;
-#pragma unroll
-            for (int j = 0; j < NS; ++j) { y[j] = yn[j]; k1[j] = k7[j]; }
-            // no growth on the step right after a rejection
-            if (after_reject) fac = fminf(fac, 1.0f);
-            after_reject = false;
-        } else {
-            // rejected (also when the norm is NaN, which gives fac = 0.2)
-            fac = fminf(fac, 1.0f);
-            after_reject = true;
-            // step size underflow: give up on this vector (score NaN)
-            if (!(fabs(h) * 0.2 > 1e-14 * fmax(fabs(t), 1.0))) {
-                failed = true;
-                break;
-            }
+        for (int o = 0; o < NO; ++o) {
+            const int j = OUT0 + o;
+            const double d = yn[j] - y[j];
+            const double b = K1[j] - d;
+            p_y[o] = y[j];
+            p_r2[o] = d;
+            p_r3[o] = b;
+            p_r4[o] = (d - K7[j]) - b;
+            p_r5[o] = fma(D7, K7[j], fma(D6, K6[j], fma(D5, K5[j], fma(D4, K4[j], fma(D3, K3[j], D1 * K1[j])))));
         }
-        h *= static_cast<double>(fac);
+        p_invh = inv_h;
+        p_c0 = -t * inv_h;
+        p_c1 = t_new * inv_h;
+        p_end = ok ? t_new : -INFINITY;
+        t = ok ? t_new : t;
+        h *= facd;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            y[j] = ok ? yn[j] : y[j];
+            K1[j] = (ok ? K7[j] : K1[j]) * facd;     // h_new f(y)
+        }
+        model.scale(h);
+        // step size underflow: give up on this vector
+        if (!ok && __double_as_longlong(h) < __double_as_longlong(h_min)) failed = true;
     }
 
+    if (idle) return;
     if (steps_out) steps_out[i] = attempts;
     if (TRAJ) {
         if (failed) {
-            const int64_t rest = (static_cast<int64_t>(end) - off) / ROWB * NO;
-            for (int64_t q = 0; q < rest; ++q) my_traj[q] = NAN;
+            const int64_t first = static_cast<int64_t>(off / ROWB) * NO;
+            const int64_t total = static_cast<int64_t>(nt) * NO;
+            for (int64_t q = first; q < total; ++q) my_traj[q] = NAN;
         }
     } else {
         scores[i] = failed ? NAN : objective_finish(P, ss, x);
     }
 }
 
+// ======================================================================
+// Pair kernel: TWO lanes per parameter vector, one per state component
+// (FitzHugh-Nagumo, Lotka-Volterra: NS = NO = 2).  A population of 65 536 on
+// one B200 is only 2048 one-lane warps = 3.5 per scheduler, too few to cover
+// the 9-cycle dependent-DFMA latency of the serial stage chain.  Splitting a
+// vector over a lane pair doubles the warps (6.9 per scheduler, one wave of
+// 7 blocks x 128 threads per SM) and halves every warp's instruction stream:
+// stage sums, error term, dense-output coefficients and interpolation are
+// per component anyway; only the right-hand side needs the partner's stage
+// value (one 64-bit lane exchange per stage) and the error norm one more.
+// Controller arithmetic is duplicated in both lanes and bitwise identical.
+// ======================================================================
+__device__ __forceinline__ double pair_other(double v) {
+    return __shfl_xor_sync(0xffffffffu, v, 1);
+}
+
+// Lane view of a two-state model: lane s integrates component s with
+// K_s = hrhs(w_s, w_other); the constants hold the step size and are updated
+// multiplicatively (hC *= h_new / h) together with the FSAL slope.
+struct FhnLane {
+    static constexpr int NP = 3, NC = 4;
+    // s = 0 (V): f = (c3 V^2 + c) V + c R        C = {c3, c, c, 0}
+    // s = 1 (R): f = (-b/c) R + ((-1/c) V + a/c)  C = {0, -b/c, -1/c, a/c}
+    __device__ __forceinline__ static void load(const double *x, int s, double *C) {
+        const double a = x[0], b = x[1], c = x[2];
+        const double nic = -1.0 / c;
+        C[0] = s ? 0.0 : c * (-1.0 / 3.0);
+        C[1] = s ? nic * b : c;
+        C[2] = s ? nic : c;
+        C[3] = s ? -nic * a : 0.0;
+    }
+    __device__ __forceinline__ static double hrhs(const double *C, double ws, double wo) {
+        return fma(fma(C[0], ws * ws, C[1]), ws, fma(C[2], wo, C[3]));
+    }
+};
+
+struct LvLane {
+    static constexpr int NP = 4, NC = 2;
+    // s = 0 (x): f = x (a - b y)     C = {-b, a}
+    // s = 1 (y): f = y (d x - c)     C = {d, -c}
+    __device__ __forceinline__ static void load(const double *x, int s, double *C) {
+        C[0] = s ? x[3] : -x[1];
+        C[1] = s ? -x[2] : x[0];
+    }
+    __device__ __forceinline__ static double hrhs(const double *C, double ws, double wo) {
+        return ws * fma(C[0], wo, C[1]);
+    }
+};
+
+#ifndef PB200_PAIR_U
+#define PB200_PAIR_U 3
+#endif
+#ifndef PB200_PAIR_THREADS
+#define PB200_PAIR_THREADS 128
+#endif
+#ifndef PB200_PAIR_MINBLOCKS
+#define PB200_PAIR_MINBLOCKS 7
+#endif
+static_assert(PB200_PAIR_U + 1 <= PB200_SENTINEL_ROWS, "not enough sentinel rows");
+
+template <class L, bool SMEM, bool TRAJ>
+__global__ void __launch_bounds__(PB200_PAIR_THREADS, PB200_PAIR_MINBLOCKS)
+ode_pair_kernel(const __grid_constant__ ProblemDev P,
+                const __grid_constant__ ModelConsts mc,
+                const double *__restrict__ params, int64_t n, int64_t ld,
+                double *__restrict__ scores, double *__restrict__ traj,
+                int32_t *__restrict__ steps_out, const SolverDev S) {
+    constexpr int NO = 2, NC = L::NC;
+    constexpr uint32_t ROWB = (1 + NO) * 8;
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int U = PB200_PAIR_U;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    Series<SMEM> series;
+    series.gbase = P.series;
+    series.sbase = 0;
+    if (SMEM) {
+        const uint32_t bytes = static_cast<uint32_t>(
+            ((static_cast<int64_t>(P.n_times) + PB200_SENTINEL_ROWS) * ROWB + 15) & ~15ll);
+        stage_series(smem, P.series, bytes, &bar);
+        series.sbase = launder_u32(smem_u32(smem));
+    }
+
+    const int64_t gt = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int s = static_cast<int>(gt & 1);          // my state component
+    const bool live = (gt >> 1) < n;
+    const int64_t i = live ? (gt >> 1) : n - 1;
+
+    const int nt = P.n_times;
+    const int n_read = TRAJ ? P.n_model_params : P.n_params;
+    double x[PB200_MAX_PARAMS];
+#pragma unroll
+    for (int k = 0; k < L::NP + NO; ++k)
+        x[k] = (k < n_read) ? params[i * ld + k] : 0.0;
+
+    bool idle = !live;
+    if (!TRAJ) {
+        double early;
+        if (objective_precheck(P, x, &early)) {
+            if (live && s == 0) {
+                scores[i] = early;
+                if (steps_out) steps_out[i] = 0;
+            }
+            idle = true;
+        }
+    }
+
+    double C[NC];                       // step-scaled constants (h = 1 for now)
+    L::load(x, s, C);
+    double y = s ? mc.c[1] : mc.c[0];
+    double t = 0.0;
+    double ss = 0.0;
+
+    const uint32_t vofs = 8 + 8 * s;    // my observed value inside a row
+    const uint32_t end = static_cast<uint32_t>(nt) * ROWB;
+    uint32_t off = 0;
+    double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * NO + s : nullptr;
+
+    if (!idle) {
+        double t_out = series.at(0);
+        while (t_out <= t) {
+            if (TRAJ) my_traj[off / ROWB * NO] = y;
+            const double r = series.at(off + vofs) - y;
+            ss = fma(r, r, ss);
+            off += ROWB;
+            t_out = series.at(off);
+        }
+    } else {
+        off = end;
+    }
+
+    const double half_rtol = S.half_rtol, atol = S.atol;
+    double K1 = L::hrhs(C, y, pair_other(y));            // f(y), h = 1
+
+    // ---- first step (Hairer's hinit, as scipy's select_initial_step) ----
+    double h = S.h0;
+    if (!(h > 0.0)) {
+        const double sc = fma(S.rtol, fabs(y), atol);
+        const double a0 = y / sc, a1 = K1 / sc;
+        double d0 = a0 * a0, d1 = a1 * a1;
+        d0 = sqrt((d0 + pair_other(d0)) * 0.5);
+        d1 = sqrt((d1 + pair_other(d1)) * 0.5);
+        const double h_a = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        const double w = fma(h_a, K1, y);
+        const double k2 = L::hrhs(C, w, pair_other(w));
+        const double a2 = (k2 - K1) / sc;
+        double d2 = a2 * a2;
+        d2 = sqrt((d2 + pair_other(d2)) * 0.5) / h_a;
+        const double dm = fmax(d1, d2);
+        const double h_b = (dm <= 1e-15) ? fmax(1e-6, h_a * 1e-3)
+                                         : pow(0.01 / dm, 0.2);
+        h = fmin(100.0 * h_a, h_b);
+    }
+    K1 *= h;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) C[k] *= h;
+
+    int attempts = 0;
+    bool failed = false;
+    bool after_reject = false;
+    const int max_steps = S.max_steps;
+    const double t_last = nt > 0 ? series.at(end - ROWB) : -INFINITY;
+    const double h_min = 1e-14 * fmax(fabs(t_last), 1.0);
+
+    double p_end = -INFINITY, p_invh = 0.0, p_c0 = 0.0, p_c1 = 0.0;
+    double p_y = 0.0, p_r2 = 0.0, p_r3 = 0.0, p_r4 = 0.0, p_r5 = 0.0;
+
+    auto interpolate = [&](double tq, uint32_t row, bool valid) {
+        const double th = fma(tq, p_invh, p_c0);
+        const double th1 = fma(-tq, p_invh, p_c1);
+        const double v = fma(th, fma(th1, fma(th, fma(th1, p_r5, p_r4), p_r3), p_r2), p_y);
+        const double r = series.at(row + vofs) - v;
+        if (TRAJ) { if (valid) my_traj[row / ROWB * NO] = v; }
+        acc_sq_if(ss, r, valid);
+    };
+
+    constexpr int kLoopUnroll = PB200_LOOP_UNROLL;
+#pragma unroll kLoopUnroll
+    for (;;) {
+        const bool fin = (off >= end) || failed;
+        if (__all_sync(FULL, fin)) break;
+        if (!fin && t < t_last) {
+            if (attempts >= max_steps) failed = true;
+            else ++attempts;
+        }
+        // ---- (C) pending observations beyond the U slots ----
+        {
+            double t_ahead = series.at(off + U * ROWB);
+            while (__any_sync(FULL, le_bits(t_ahead, p_end))) {
+                const bool more = le_bits(t_ahead, p_end);
+                interpolate(series.at(off), off, more);
+                off += more ? ROWB : 0u;
+                t_ahead = series.at(off + U * ROWB);
+            }
+        }
+        // ---- (A) U interpolation slots (predicated) ----
+        {
+            double tq[U > 0 ? U : 1];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int k = 0; k < U; ++k) tq[k] = series.at(off + k * ROWB);
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const bool valid = le_bits(tq[k], p_end);
+                interpolate(tq[k], off + k * ROWB, valid);
+                cnt += valid ? 1u : 0u;
+            }
+            off += cnt * ROWB;
+        }
+        // ---- (B) six stages, my component; partner's stage value by shuffle ----
+        double w = fma(A21, K1, y);
+        const double K2 = L::hrhs(C, w, pair_other(w));
+        w = fma(A32, K2, fma(A31, K1, y));
+        const double K3 = L::hrhs(C, w, pair_other(w));
+        w = fma(A43, K3, fma(A42, K2, fma(A41, K1, y)));
+        const double K4 = L::hrhs(C, w, pair_other(w));
+        w = fma(A54, K4, fma(A53, K3, fma(A52, K2, fma(A51, K1, y))));
+        const double K5 = L::hrhs(C, w, pair_other(w));
+        w = fma(A65, K5, fma(A64, K4, fma(A63, K3, fma(A62, K2, fma(A61, K1, y)))));
+        const double K6 = L::hrhs(C, w, pair_other(w));
+        const double yn = fma(B6, K6, fma(B5, K5, fma(B4, K4, fma(B3, K3, fma(B1, K1, y)))));
+        const double K7 = L::hrhs(C, yn, pair_other(yn));
+        // ---- error: my squared scaled component + the partner's ----
+        const double e = fma(E7, K7, fma(E6, K6, fma(E5, K5, fma(E4, K4, fma(E3, K3, E1 * K1)))));
+        const double sc = fma(half_rtol, fabs(y) + fabs(yn), atol);
+        const double q = e * rcp_seed(sc);
+        const double q2 = q * q;
+        const double sum2 = q2 + pair_other(q2);          // commutative: same bits in both lanes
+        const bool ok = __double_as_longlong(sum2) >= 0 &&
+                        __double_as_longlong(sum2) <= __double_as_longlong(2.0);
+#if PB200_CTRL_BITS
+        const double facd = step_factor_bits<2>(sum2, !ok || after_reject);
+#else
+        float fac = step_factor<2>(sum2);
+        if (!ok || after_reject) fac = fminf(fac, 1.0f);
+        const double facd = static_cast<double>(fac);
+#endif
+        after_reject = !ok;
+        // ---- (D) dense-output coefficients, accept / reject by selects ----
+        const double inv_h = rcp_newton<PB200_RCP_STEPS>(h);
+        const double t_new = t + h;
+        {
+            const double d = yn - y;
+            const double b = K1 - d;
+            p_y = y;
+            p_r2 = d;
+            p_r3 = b;
+            p_r4 = (d - K7) - b;
+            p_r5 = fma(D7, K7, fma(D6, K6, fma(D5, K5, fma(D4, K4, fma(D3, K3, D1 * K1)))));
+        }
+        p_invh = inv_h;
+        p_c0 = -t * inv_h;
+        p_c1 = t_new * inv_h;
+        p_end = ok ? t_new : -INFINITY;
+        t = ok ? t_new : t;
+        h *= facd;
+        y = ok ? yn : y;
+        K1 = (ok ? K7 : K1) * facd;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) C[k] *= facd;
+        if (!ok && __double_as_longlong(h) < __double_as_longlong(h_min)) failed = true;
+    }
+
+    const double ss_other = pair_other(ss);
+    if (idle) return;
+    if (TRAJ) {
+        if (failed) {
+            for (uint32_t row = off; row < end; row += ROWB) my_traj[row / ROWB * NO] = NAN;
+        }
+        if (s == 0 && steps_out) steps_out[i] = attempts;
+    } else if (s == 0) {
+        if (steps_out) steps_out[i] = attempts;
+        const double both[2] = {ss, ss_other};
+        scores[i] = failed ? NAN : objective_finish(P, both, x);
+    }
+}
+
+// series rows + the +inf sentinel rows, in whole 16-byte units
+static int64_t staged_bytes(const pb200_problem *p, int no) {
+    return ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * (1 + no) * 8 + 15) & ~15ll;
+}
+
+#define PB200_LAUNCH(KERN, GRID, BLOCK, DYN)                                             \
+    do {                                                                                 \
+        auto kern = KERN;                                                                \
+        const size_t dyn_ = (DYN);                                                       \
+        if (dyn_ > 48 * 1024) {                                                          \
+            int rc = pb200_check_cuda(                                                   \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     static_cast<int>(dyn_)),                            \
+                "cudaFuncSetAttribute");                                                 \
+            if (rc) return rc;                                                           \
+        }                                                                                \
+        kern<<<static_cast<unsigned>(GRID), BLOCK, dyn_, st>>>(                          \
+            p->dev, p->mc, d_params, n, ld, d_scores, d_traj, d_steps, s);               \
+    } while (0)
+
+// one lane per parameter vector (any model)
 template <class M>
 int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
                  int64_t ld, double *d_scores, double *d_traj,
                  int32_t *d_steps, const SolverDev &s, int block,
                  cudaStream_t st) {
-    // series rows + the +inf sentinel rows, in whole 16-byte units
-    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * (1 + M::NO) * 8 + 15) & ~15ll;
+    const int64_t bytes = staged_bytes(p, M::NO);
 #ifdef PB200_NO_SMEM
     const bool use_smem = false;
 #else
@@ -509,46 +943,85 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
 #endif
     const bool traj = d_traj != nullptr;
     if (block <= 0) block = 64;
+    if (block > PB200_MAXTHREADS) block = PB200_MAXTHREADS;
+    block = (block + 31) & ~31;                 // whole warps: the kernel votes
     const int64_t grid = (n + block - 1) / block;
     if (grid <= 0) return PB200_OK;
     if (grid > 2147483647ll) {
         pb200_set_error("too many parameter vectors for one launch: %lld", (long long)n);
         return PB200_EINVAL;
     }
-#define PB200_LAUNCH(SM, TR)                                                             \
-    do {                                                                                 \
-        auto kern = ode_kernel<M, SM, TR>;                                               \
-        size_t dyn = SM ? static_cast<size_t>(bytes) : 0;                                \
-        if (dyn > 48 * 1024) {                                                           \
-            int rc = pb200_check_cuda(                                                   \
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     static_cast<int>(dyn)),                             \
-                "cudaFuncSetAttribute");                                                 \
-            if (rc) return rc;                                                           \
-        }                                                                                \
-        kern<<<static_cast<unsigned>(grid), block, dyn, st>>>(                           \
-            p->dev, p->mc, d_params, n, ld, d_scores, d_traj, d_steps, s);               \
-    } while (0)
+    const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
     if (use_smem) {
-        if (traj) PB200_LAUNCH(true, true); else PB200_LAUNCH(true, false);
+        if (traj) PB200_LAUNCH((ode_kernel<M, true, true>), grid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, true, false>), grid, block, dyn);
     } else {
-        if (traj) PB200_LAUNCH(false, true); else PB200_LAUNCH(false, false);
+        if (traj) PB200_LAUNCH((ode_kernel<M, false, true>), grid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, false, false>), grid, block, dyn);
     }
-#undef PB200_LAUNCH
     return pb200_check_cuda(cudaGetLastError(), "ode_kernel launch");
 }
 
+// two lanes per parameter vector (two-state models)
+template <class L>
+int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
+                int64_t ld, double *d_scores, double *d_traj,
+                int32_t *d_steps, const SolverDev &s, int block,
+                cudaStream_t st) {
+    const int64_t bytes = staged_bytes(p, 2);
+#ifdef PB200_NO_SMEM
+    const bool use_smem = false;
+#else
+    // one wave of PB200_PAIR_MINBLOCKS blocks per SM must fit in 227 KB
+    const bool use_smem = bytes <= (227 * 1024) / PB200_PAIR_MINBLOCKS - 1024;
+#endif
+    const bool traj = d_traj != nullptr;
+    if (block <= 0) block = PB200_PAIR_THREADS;
+    if (block > PB200_PAIR_THREADS) block = PB200_PAIR_THREADS;
+    block = (block + 31) & ~31;
+    const int64_t threads = 2 * n;
+    const int64_t grid = (threads + block - 1) / block;
+    if (grid <= 0) return PB200_OK;
+    if (grid > 2147483647ll) {
+        pb200_set_error("too many parameter vectors for one launch: %lld", (long long)n);
+        return PB200_EINVAL;
+    }
+    const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
+    if (use_smem) {
+        if (traj) PB200_LAUNCH((ode_pair_kernel<L, true, true>), grid, block, dyn);
+        else PB200_LAUNCH((ode_pair_kernel<L, true, false>), grid, block, dyn);
+    } else {
+        if (traj) PB200_LAUNCH((ode_pair_kernel<L, false, true>), grid, block, dyn);
+        else PB200_LAUNCH((ode_pair_kernel<L, false, false>), grid, block, dyn);
+    }
+    return pb200_check_cuda(cudaGetLastError(), "ode_pair_kernel launch");
+}
+#undef PB200_LAUNCH
+
 }  // namespace
+
+#ifndef PB200_DEFAULT_LANES
+#define PB200_DEFAULT_LANES 1
+#endif
 
 int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
                int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
-               const SolverDev &s, int block, cudaStream_t st) {
+               const SolverDev &s, int block, int lanes, cudaStream_t st) {
+    if (lanes <= 0) lanes = PB200_DEFAULT_LANES;
+    if (lanes != 1 && lanes != 2) {
+        pb200_set_error("lanes per vector must be 0 (automatic), 1 or 2, got %d", lanes);
+        return PB200_EINVAL;
+    }
     switch (p->dev.model) {
         case PB200_MODEL_FHN:
+            if (lanes == 2)
+                return launch_pair<FhnLane>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, st);
             return launch_model<FhnModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, st);
         case PB200_MODEL_LOTKA_VOLTERRA:
+            if (lanes == 2)
+                return launch_pair<LvLane>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, st);
             return launch_model<LvModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, st);
-        case PB200_MODEL_SIR:
+        case PB200_MODEL_SIR:           // three states: always one lane per vector
             return launch_model<SirModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, st);
     }
     pb200_set_error("model %d is not an ODE model", p->dev.model);

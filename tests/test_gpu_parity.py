@@ -306,6 +306,34 @@ def test_sir(pb):
 
 # ------------------------------------------- live oracle, seeded random inputs
 
+def test_two_lanes_per_vector(pb):
+    """The pair kernel (one lane per state component) solves the same problem:
+    same parity bars, and agreement with the one-lane kernel far inside them."""
+    g = load_golden('fhn')
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), g['times'],
+                                    g['values'])
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, float(g['sigma']))
+    one = evaluate(pb, ll, g['xs'], lanes_per_vector=1)
+    two = evaluate(pb, ll, g['xs'], lanes_per_vector=2)
+    assert np.max(rel_err(two, g['scores'])) < ODE_SCORE_RTOL
+    check_ode_scores(two, g['scores'], g['truth_scores'])
+    assert np.max(rel_err(two, one)) < 1e-7
+    wide = evaluate(pb, ll, g['xs_wide'], lanes_per_vector=2)
+    assert np.max(rel_err(wide, g['truth_scores_wide'])) < ODE_SCORE_RTOL
+    g = load_golden('lotka_volterra')
+    problem = pb.MultiOutputProblem(pb.toy.LotkaVolterraModel(), g['times'],
+                                    g['values'])
+    f = pb.GaussianLogLikelihood(problem)
+    two = evaluate(pb, f, g['xs'], lanes_per_vector=2, rtol=5e-9, atol=5e-9)
+    check_ode_scores(two, g['scores'], g['truth_scores'])
+    # three-state model: the option is ignored, not an error
+    g = load_golden('sir')
+    problem = pb.MultiOutputProblem(pb.toy.SIRModel(), g['times'], g['values'])
+    f = pb.GaussianLogLikelihood(problem)
+    assert np.array_equal(evaluate(pb, f, g['xs'], lanes_per_vector=2),
+                          evaluate(pb, f, g['xs'], lanes_per_vector=1))
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)

@@ -34,8 +34,9 @@ def test_library_builds_loads_and_exports_the_header():
         assert hasattr(lib, name), name + ' is declared but not exported'
     assert sorted(_lib.SIGNATURES) == declared
     assert lib.pb200_version() == 100
-    assert lib.pb200_series_len(1000, 2) == 3012     # + 4 sentinel rows
-    assert lib.pb200_series_len(3, 2) == 22          # 21 padded to 16-byte units
+    assert lib.pb200_series_len(1000, 2) == 3 * (1000 + _lib.SENTINEL_ROWS)
+    # (3 + 8) rows * 3 doubles = 33, padded to whole 16-byte units
+    assert lib.pb200_series_len(3, 2) == 34
 
 
 def test_library_is_sm100a_only():
@@ -97,7 +98,7 @@ def test_describe_mirror_objects():
     off = -0.5 * 1000 * np.log(2 * np.pi) - 1000 * np.log(0.5)
     assert s.obj_consts == [off, off, -2.0, -2.0]
     packed = s.packed_series()
-    assert packed.shape == (3012,)
+    assert packed.shape == (3 * (1000 + _lib.SENTINEL_ROWS),)
     assert np.array_equal(packed[:3000].reshape(1000, 3)[:, 0], g['times'])
     assert np.array_equal(packed[:3000].reshape(1000, 3)[:, 1:], g['values'])
     assert np.all(packed[3000::3] == np.inf) and not packed[3001::3].any()

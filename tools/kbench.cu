@@ -59,7 +59,8 @@ int main(int argc, char **argv) {
     double *d_x, *d_s; int *d_steps;
     CK(cudaMalloc(&d_x, xs.size() * 8)); CK(cudaMalloc(&d_s, n * 8)); CK(cudaMalloc(&d_steps, n * 4));
     CK(cudaMemcpy(d_x, xs.data(), xs.size() * 8, cudaMemcpyHostToDevice));
-    pb200_solver_opts opts = {0, 0, 0, 0, block};
+    int lanes = argc > 6 ? atoi(argv[6]) : 0;
+    pb200_solver_opts opts = {0, 0, 0, 0, block, lanes};
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int w = 0; w < 3; ++w) PB(pb200_eval(p, d_x, n, 3, d_s, d_steps, &opts, nullptr));
     CK(cudaDeviceSynchronize());
@@ -78,7 +79,7 @@ int main(int argc, char **argv) {
     for (long i = 0; i < n; ++i) { if (std::isfinite(s[i])) sum += s[i]; else ++bad; steps += st[i]; }
     double flops = 234.0 * steps + 24.0 * nt * (double)n;
     double med = ms[reps / 2];
-    printf("n=%ld block=%d spread=%g nt=%d  median %.4f ms  min %.4f ms  %.3e evals/s  %.2f TFLOP/s  mean_steps %.1f  checksum %.10e  nonfinite %ld\n",
-           n, block, spread, nt, med, ms[0], n / (med * 1e-3), flops / (med * 1e-3) / 1e12, steps / n, sum / (n - bad), bad);
+    printf("lanes=%d n=%ld block=%d spread=%g nt=%d  median %.4f ms  min %.4f ms  %.3e evals/s  %.2f TFLOP/s  mean_steps %.1f  checksum %.10e  nonfinite %ld\n",
+           lanes, n, block, spread, nt, med, ms[0], n / (med * 1e-3), flops / (med * 1e-3) / 1e12, steps / n, sum / (n - bad), bad);
     return 0;
 }
