@@ -151,6 +151,21 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n,
                const pb200_solver_opts *opts, void *stream);
 
 /*
+ * The same with cost-coherent scheduling (ODE models; ignored for closed-form
+ * models): a counting sort on |f(y0)|^2 groups vectors with similar dynamics
+ * into the same warps before the fused launch, so that lock-stepped lanes take
+ * similar step sequences.  Scores and step counts are written at the original
+ * row positions and do not depend on the grouping.  d_sort_ws is a 16-byte
+ * aligned device workspace of pb200_sort_workspace_bytes(n) bytes owned by the
+ * caller (NULL = no sorting, i.e. pb200_eval).
+ */
+int64_t pb200_sort_workspace_bytes(int64_t n);
+int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
+                      int64_t ld, double *d_scores, int32_t *d_steps,
+                      const pb200_solver_opts *opts, void *d_sort_ws,
+                      int64_t sort_ws_bytes, void *stream);
+
+/*
  * The same through HOST buffers, for callers that hold their positions in host
  * memory (which is what the reference's evaluators receive): enqueues the
  * host->device copy of the parameters, the fused kernel and the device->host
@@ -158,13 +173,14 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n,
  * stream before reading h_scores.  h_params / h_scores should be page-locked
  * (pinned) for the copies to be asynchronous.  d_params_ws (n*ld doubles) and
  * d_scores_ws (n doubles) are device workspaces owned by the caller; h_steps /
- * d_steps_ws are optional (both NULL or both given).
+ * d_steps_ws are optional (both NULL or both given); d_sort_ws as in
+ * pb200_eval_sorted (NULL = no sorting).
  */
 int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n,
                     int64_t ld, double *h_scores, int32_t *h_steps,
                     double *d_params_ws, double *d_scores_ws,
-                    int32_t *d_steps_ws, const pb200_solver_opts *opts,
-                    void *stream);
+                    int32_t *d_steps_ws, void *d_sort_ws, int64_t sort_ws_bytes,
+                    const pb200_solver_opts *opts, void *stream);
 
 /*
  * Batched ForwardModel.simulate / Problem.evaluate

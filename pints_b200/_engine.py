@@ -52,13 +52,19 @@ def solver_opts(rtol=None, atol=None, h0=None, max_steps=None, block=None,
 class DeviceProblem(object):
     """A ``ProblemSpec`` resident on one GPU."""
 
-    def __init__(self, spec, device=None, **opts):
+    #: populations at least this large are sorted by cost before the launch
+    SORT_MIN_ROWS = 1024
+
+    def __init__(self, spec, device=None, sort=None, **opts):
         if not isinstance(spec, ProblemSpec):
             raise TypeError('spec must be a ProblemSpec')
         self.spec = spec
         self.device = require_cuda(device)
         self._lib = _lib.load()
         self.opts = solver_opts(**opts)
+        # cost-coherent scheduling (pb200_eval_sorted): None = automatic
+        self.sort = sort
+        self._sort_ws = {}
         with torch.cuda.device(self.device):
             self._series = torch.from_numpy(spec.packed_series()).to(
                 self.device)
@@ -102,6 +108,25 @@ class DeviceProblem(object):
             d_params = d_params.contiguous()
         return d_params
 
+    def wants_sort(self, n):
+        """Whether a batch of ``n`` rows is scheduled through the cost sort."""
+        if not self.spec.is_ode():
+            return False
+        if self.sort is None:
+            return n >= self.SORT_MIN_ROWS
+        return bool(self.sort)
+
+    def sort_workspace(self, n, key=0):
+        """Device workspace of ``pb200_sort_workspace_bytes(n)`` bytes, cached
+        per ``key`` (one per stream that may run concurrently)."""
+        need = int(self._lib.pb200_sort_workspace_bytes(n))
+        ws = self._sort_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, int(1.5 * need) if ws is not None else need),
+                             dtype=torch.uint8, device=self.device)
+            self._sort_ws[key] = ws
+        return ws
+
     def eval(self, d_params, out=None, steps=None):
         """Scores of the rows of ``d_params`` (device tensor ``(n, d)``);
         asynchronous on the current stream.  Returns a device tensor."""
@@ -110,10 +135,15 @@ class DeviceProblem(object):
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.pb200_eval(
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            ws, ws_bytes = None, 0
+            if self.wants_sort(n):
+                t = self.sort_workspace(n, stream)
+                ws, ws_bytes = ctypes.c_void_p(t.data_ptr()), t.numel()
+            _lib.check(self._lib.pb200_eval_sorted(
                 self._handle, _ptr(d_params), n, d_params.stride(0),
                 _ptr(out), _ptr(steps), ctypes.byref(self.opts),
-                _stream_ptr(self.device)))
+                ws, ws_bytes, ctypes.c_void_p(stream)))
         return out
 
     def simulate(self, d_params, out=None, steps=None):

@@ -66,9 +66,9 @@ class _Lane(object):
 
     N_STREAMS = 4
 
-    def __init__(self, spec, device, opts):
+    def __init__(self, spec, device, opts, sort=None):
         self.device = device
-        self.problem = DeviceProblem(spec, device, **opts)
+        self.problem = DeviceProblem(spec, device, sort=sort, **opts)
         self.streams = [torch.cuda.Stream(device=device)
                         for _ in range(self.N_STREAMS)]
         self.stream_ptrs = [ctypes.c_void_p(s.cuda_stream)
@@ -121,12 +121,17 @@ class _Lane(object):
                 if hi <= lo:
                     break
                 np.copyto(self.h_in_np[lo:hi], xs[lo:hi])
+                ws, ws_bytes = None, 0
+                if self.problem.wants_sort(hi - lo):
+                    t = self.problem.sort_workspace(rows, ('chunk', c))
+                    ws, ws_bytes = V(t.data_ptr()), t.numel()
                 _lib.check(lib.pb200_eval_host(
                     self.problem._handle, V(self.a_h_in + lo * d * 8), hi - lo,
                     d, V(self.a_h_out + lo * 8),
                     V(self.a_h_steps + lo * 4) if want_steps else None,
                     V(self.a_d_in + lo * d * 8), V(self.a_d_out + lo * 8),
                     V(self.a_d_steps + lo * 4) if want_steps else None,
+                    ws, ws_bytes,
                     ctypes.byref(self.problem.opts), self.stream_ptrs[c]))
                 self.used = c + 1
 
@@ -165,6 +170,10 @@ class CudaEvaluator(Evaluator):
     lanes_per_vector
         GPU lanes that integrate one parameter vector: 1, or 2 (one lane per
         state component, two-state models only); default automatic.
+    sort
+        Cost-coherent scheduling of the ODE models (vectors with similar
+        dynamics share a warp; results do not depend on it): ``True``,
+        ``False`` or ``None`` = automatic (on for batches of 1024 rows or more).
     as_list
         Return a Python list like the reference (default) or, if ``False``, a
         float64 ndarray (every consumer in the reference accepts either).
@@ -179,7 +188,7 @@ class CudaEvaluator(Evaluator):
 
     def __init__(self, function, args=None, devices=None, rtol=None, atol=None,
                  max_steps=None, h0=None, block=None, as_list=True,
-                 chunk_rows=16384, lanes_per_vector=None):
+                 chunk_rows=16384, lanes_per_vector=None, sort=None):
         if isinstance(function, ProblemSpec):
             spec = function
             function = _SpecFunction(spec)
@@ -193,6 +202,7 @@ class CudaEvaluator(Evaluator):
         self._spec = spec if spec is not None else describe(function)
         self._opts = dict(rtol=rtol, atol=atol, max_steps=max_steps, h0=h0,
                           block=block, lanes=lanes_per_vector)
+        self._sort = sort
         self._as_list = bool(as_list)
         self._chunk_rows = max(1, int(chunk_rows))
         if devices is None or isinstance(devices, (int, str, torch.device)):
@@ -212,7 +222,8 @@ class CudaEvaluator(Evaluator):
     def _setup(self):
         if self._lanes is None:
             devs = [require_cuda(d) for d in self._device_args]
-            self._lanes = [_Lane(self._spec, d, self._opts) for d in devs]
+            self._lanes = [_Lane(self._spec, d, self._opts, self._sort)
+                           for d in devs]
         return self._lanes
 
     def device_problem(self, index=0):

@@ -56,8 +56,11 @@ SIGNATURES = {
     'pb200_problem_n_parameters': (c_int32, [_P]),
     'pb200_eval': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                              POINTER(SolverOpts), _P]),
+    'pb200_sort_workspace_bytes': (c_int64, [c_int64]),
+    'pb200_eval_sorted': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
+                                    POINTER(SolverOpts), _P, c_int64, _P]),
     'pb200_eval_host': (c_int32, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P,
-                                  POINTER(SolverOpts), _P]),
+                                  _P, c_int64, POINTER(SolverOpts), _P]),
     'pb200_simulate': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                                  POINTER(SolverOpts), _P]),
     'pb200_score_trajectories': (c_int32, [_P, _P, _P, c_int64, c_int64, _P,

@@ -183,16 +183,29 @@ int32_t pb200_problem_n_parameters(const pb200_problem *p) {
     return p ? p->dev.n_params : -1;
 }
 
-int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
-               double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
-               void *stream) {
+int64_t pb200_sort_workspace_bytes(int64_t n) { return ode_sort_workspace_bytes(n); }
+
+int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+                      double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
+                      void *d_sort_ws, int64_t sort_ws_bytes, void *stream) {
     int rc = check_batch(p, d_params, n, ld, d_scores, "pb200_eval");
     if (rc || n == 0) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kModels[p->dev.model].ode) {
         int block, lanes;
         SolverDev s = resolve_opts(opts, &block, &lanes);
-        return launch_ode(p, d_params, n, ld, d_scores, nullptr, d_steps, s, block, lanes, st);
+        if (d_sort_ws) {
+            if (sort_ws_bytes < ode_sort_workspace_bytes(n) ||
+                (reinterpret_cast<uintptr_t>(d_sort_ws) & 15) != 0) {
+                pb200_set_error("pb200_eval_sorted: workspace of %lld bytes (16-byte aligned) "
+                                "needed, got %lld", (long long)ode_sort_workspace_bytes(n),
+                                (long long)sort_ws_bytes);
+                return PB200_EINVAL;
+            }
+            if (n > 2147483647ll) d_sort_ws = nullptr;       // int32 permutation
+        }
+        return launch_ode(p, d_params, n, ld, d_scores, nullptr, d_steps, s, block, lanes,
+                          d_sort_ws, st);
     }
     if (d_steps) {
         rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),
@@ -202,10 +215,16 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_
     return launch_analytic(p, d_params, n, ld, d_scores, nullptr, st);
 }
 
+int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+               double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
+               void *stream) {
+    return pb200_eval_sorted(p, d_params, n, ld, d_scores, d_steps, opts, nullptr, 0, stream);
+}
+
 int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n, int64_t ld,
                     double *h_scores, int32_t *h_steps, double *d_params_ws,
-                    double *d_scores_ws, int32_t *d_steps_ws, const pb200_solver_opts *opts,
-                    void *stream) {
+                    double *d_scores_ws, int32_t *d_steps_ws, void *d_sort_ws,
+                    int64_t sort_ws_bytes, const pb200_solver_opts *opts, void *stream) {
     int rc = check_batch(p, h_params, n, ld, h_scores, "pb200_eval_host");
     if (rc || n == 0) return rc;
     if (!d_params_ws || !d_scores_ws || ((h_steps == nullptr) != (d_steps_ws == nullptr))) {
@@ -216,7 +235,8 @@ int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n, i
     rc = pb200_check_cuda(cudaMemcpyAsync(d_params_ws, h_params, static_cast<size_t>(n) * ld * 8,
                                           cudaMemcpyHostToDevice, st), "copy of parameters");
     if (rc) return rc;
-    rc = pb200_eval(p, d_params_ws, n, ld, d_scores_ws, d_steps_ws, opts, stream);
+    rc = pb200_eval_sorted(p, d_params_ws, n, ld, d_scores_ws, d_steps_ws, opts, d_sort_ws,
+                           sort_ws_bytes, stream);
     if (rc) return rc;
     rc = pb200_check_cuda(cudaMemcpyAsync(h_scores, d_scores_ws, static_cast<size_t>(n) * 8,
                                           cudaMemcpyDeviceToHost, st), "copy of scores");
@@ -236,7 +256,7 @@ int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, in
     if (kModels[p->dev.model].ode) {
         int block, lanes;
         SolverDev s = resolve_opts(opts, &block, &lanes);
-        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, lanes, st);
+        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, lanes, nullptr, st);
     }
     if (d_steps) {
         rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),

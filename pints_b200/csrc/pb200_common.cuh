@@ -172,7 +172,9 @@ __device__ __forceinline__ bool objective_precheck(const ProblemDev &P,
 // host-side launchers implemented in the kernel translation units
 int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
                int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
-               const SolverDev &s, int block, int lanes, cudaStream_t st);
+               const SolverDev &s, int block, int lanes, void *sort_ws,
+               cudaStream_t st);
+int64_t ode_sort_workspace_bytes(int64_t n);
 int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
                     int64_t ld, double *d_scores, double *d_traj,
                     cudaStream_t st);

@@ -334,6 +334,50 @@ def test_two_lanes_per_vector(pb):
                           evaluate(pb, f, g['xs'], lanes_per_vector=1))
 
 
+def test_cost_sorted_scheduling_changes_nothing(pb):
+    """pb200_eval_sorted groups similar vectors into warps; scores and step
+    counts are per vector and must not depend on the grouping, bit for bit."""
+    spec = po.headline_fhn_spec()
+    xs = np.concatenate([po.headline_fhn_points(3000),
+                         np.random.RandomState(3).uniform(
+                             [0, 0, 1], [1, 1, 5], (1100, 3))])
+    xs[17, 2] = -1.0                               # sigma-free, but c < 0: NaN path
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    a, sa = pb.CudaEvaluator(ll, sort=False).evaluate_array(xs, True)
+    b, sb = pb.CudaEvaluator(ll, sort=True).evaluate_array(xs, True)
+    assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(sa, sb)
+    c = pb.CudaEvaluator(ll, sort=True, lanes_per_vector=2,
+                         chunk_rows=1 << 30).evaluate_array(xs)
+    assert np.nanmax(rel_err(c, a)) < 1e-7
+    # device-resident path, odd sizes, prior box deciding some rows early
+    import torch
+    prior = pb.UniformLogPrior([0, 0, 1.5], [1, 1, 4.5])
+    post = pb.LogPosterior(ll, prior)
+    for n in (1, 31, 1025, 4100):
+        dp_s = pb.CudaEvaluator(post, sort=True).device_problem()
+        dp_u = pb.CudaEvaluator(post, sort=False).device_problem()
+        d_x = torch.from_numpy(np.ascontiguousarray(xs[:n])).cuda()
+        u = dp_u.eval(d_x).cpu().numpy()
+        v = dp_s.eval(d_x).cpu().numpy()
+        assert np.array_equal(u, v, equal_nan=True), n
+        assert np.isneginf(u).any() or n < 3001
+    # other models take the generic key
+    g = load_golden('sir')
+    problem = pb.MultiOutputProblem(pb.toy.SIRModel(), g['times'], g['values'])
+    f = pb.GaussianLogLikelihood(problem)
+    assert np.array_equal(evaluate(pb, f, g['xs'], sort=True),
+                          evaluate(pb, f, g['xs'], sort=False))
+    g = load_golden('lotka_volterra')
+    problem = pb.MultiOutputProblem(pb.toy.LotkaVolterraModel(), g['times'],
+                                    g['values'])
+    f = pb.GaussianLogLikelihood(problem)
+    assert np.array_equal(evaluate(pb, f, g['xs'], sort=True),
+                          evaluate(pb, f, g['xs'], sort=False))
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)

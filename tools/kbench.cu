@@ -56,18 +56,29 @@ int main(int argc, char **argv) {
         if (spread > 0) for (int k = 0; k < 3; ++k) xs[i * 3 + k] = truth[k] * (1 + spread * nrand());
         else { xs[i * 3] = urand(); xs[i * 3 + 1] = urand(); xs[i * 3 + 2] = 1.0 + 4.0 * urand(); }   // wide box
     }
+    int presort = argc > 7 ? atoi(argv[7]) : 0;     // 1: host-side sort by c (what a device sort would achieve)
+    if (presort) {
+        std::vector<long> idx(n); for (long i = 0; i < n; ++i) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](long a, long b) { return xs[a * 3 + 2] < xs[b * 3 + 2]; });
+        std::vector<double> ys(xs.size());
+        for (long i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) ys[i * 3 + k] = xs[idx[i] * 3 + k];
+        xs.swap(ys);
+    }
+    int devsort = argc > 8 ? atoi(argv[8]) : 0;     // 1: pb200_eval_sorted
+    void *d_ws = nullptr; long ws_bytes = 0;
+    if (devsort) { ws_bytes = pb200_sort_workspace_bytes(n); CK(cudaMalloc(&d_ws, ws_bytes)); }
     double *d_x, *d_s; int *d_steps;
     CK(cudaMalloc(&d_x, xs.size() * 8)); CK(cudaMalloc(&d_s, n * 8)); CK(cudaMalloc(&d_steps, n * 4));
     CK(cudaMemcpy(d_x, xs.data(), xs.size() * 8, cudaMemcpyHostToDevice));
     int lanes = argc > 6 ? atoi(argv[6]) : 0;
     pb200_solver_opts opts = {0, 0, 0, 0, block, lanes};
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int w = 0; w < 3; ++w) PB(pb200_eval(p, d_x, n, 3, d_s, d_steps, &opts, nullptr));
+    for (int w = 0; w < 3; ++w) PB(pb200_eval_sorted(p, d_x, n, 3, d_s, d_steps, &opts, d_ws, ws_bytes, nullptr));
     CK(cudaDeviceSynchronize());
     std::vector<float> ms(reps);
     for (int r = 0; r < reps; ++r) {
         CK(cudaEventRecord(e0));
-        PB(pb200_eval(p, d_x, n, 3, d_s, nullptr, &opts, nullptr));
+        PB(pb200_eval_sorted(p, d_x, n, 3, d_s, nullptr, &opts, d_ws, ws_bytes, nullptr));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms[r], e0, e1));
     }
@@ -79,7 +90,7 @@ int main(int argc, char **argv) {
     for (long i = 0; i < n; ++i) { if (std::isfinite(s[i])) sum += s[i]; else ++bad; steps += st[i]; }
     double flops = 234.0 * steps + 24.0 * nt * (double)n;
     double med = ms[reps / 2];
-    printf("lanes=%d n=%ld block=%d spread=%g nt=%d  median %.4f ms  min %.4f ms  %.3e evals/s  %.2f TFLOP/s  mean_steps %.1f  checksum %.10e  nonfinite %ld\n",
-           lanes, n, block, spread, nt, med, ms[0], n / (med * 1e-3), flops / (med * 1e-3) / 1e12, steps / n, sum / (n - bad), bad);
+    printf("sort=%d%d lanes=%d n=%ld block=%d spread=%g nt=%d  median %.4f ms  min %.4f ms  %.3e evals/s  %.2f TFLOP/s  mean_steps %.1f  checksum %.10e  nonfinite %ld\n",
+           presort, devsort, lanes, n, block, spread, nt, med, ms[0], n / (med * 1e-3), flops / (med * 1e-3) / 1e12, steps / n, sum / (n - bad), bad);
     return 0;
 }
