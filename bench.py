@@ -36,6 +36,13 @@ WORKLOAD = ('FitzhughNagumoModel (3 params, 1000 times on [0,20]) + '
             '[0.1,0.5,3]*(1+0.05*randn) seed 2')
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one ode_kernel launch at this
+# workload, from the `ncu --set full` capture summarised in
+# profiles/r01e_ode_kernel_summary.md (algorithmic HBM traffic: 32 B per
+# evaluation = 2.1 MB per launch; the path is FP64-bound, not HBM-bound)
+TRAFFIC_BYTES_PER_LAUNCH = 1902336
+
+
 # ------------------------------------------------------------ CPU baseline
 
 _worker_spec = None
@@ -357,7 +364,7 @@ def run_ours(args):
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops,
                 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
-                'traffic': None,
+                'traffic': TRAFFIC_BYTES_PER_LAUNCH,
                 'peak_source': 'measured live by pb200_fp64_probe (FMA chains);'
                                ' MEASURED_PEAKS.json has no FP64 entry; '
                                'nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2',
@@ -372,7 +379,8 @@ def run_ours(args):
                     'value_as_list': total / e2e_list_s,
                     'api_as_list': 'CudaEvaluator(f).evaluate(ndarray) -> list '
                                    '(the reference\'s return type)'},
-            'gpu_launches': args.steps * world,
+            # per step and rank: three counting-sort kernels + the fused ODE kernel
+            'gpu_launches': args.steps * world * 4,
             'clocks': clocks,
             'wall_s_timed_region': wall,
         }

@@ -16,6 +16,7 @@
 // this kernel uses DP5(4) at the same tolerances, see DESIGN.md for the
 // measured agreement.
 #include "pb200_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -341,20 +342,49 @@ static_assert(PB200_PIPE_U + 1 <= PB200_SENTINEL_ROWS, "not enough sentinel rows
 //       NEXT iteration's (C)/(A).
 // (A) is independent of (B), so it fills the issue slots that the serial
 // RHS -> stage -> RHS chain (9-cycle DFMA latency) leaves empty.
-template <class M, bool SMEM, bool TRAJ>
-__global__ void __launch_bounds__(PB200_MAXTHREADS)
+// ---------------------------------------------------------------------------
+// Warp migration between the four schedulers of an SM (MIG = true).
+// A warp stays on the scheduler (SM sub-partition) it was created on, and a
+// single-wave launch takes as long as the BUSIEST scheduler: a population of
+// 65 536 is 13.84 warps per SM, i.e. 4+4+3+3 per scheduler, and runs exactly
+// as long as 16 warps per SM would (measured: 0.327 ms for 9..12 warps per SM,
+// 0.425 ms for 13..16).  With one block per SM the placement is known (warp w
+// sits on scheduler w mod 4), so the block is laid out as
+//     warps 0 .. q4-1        workers                  (q4 a multiple of 4)
+//     warps q4 .. q4+r-1     the r extra workers, on schedulers 0 .. r-1
+//     warps q4+2 .. q4+1+r   receivers, parked on a named barrier on
+//                            schedulers 2 .. 1+r    (r = 1 or 2)
+// and about half way through the series each extra worker writes its state
+// (y, h f(y), t, h, sums of squares, counters: 2.7 KB) to shared memory and
+// retires; the receiver picks it up.  The busy schedulers drop from q+1 to q
+// warps when the idle ones go from q to q+1: every scheduler carries about
+// q + r/4 + ... warps on average instead of q+1 on the critical ones.
+// Results are bit-identical to the plain layout (the state moves verbatim).
+// ---------------------------------------------------------------------------
+struct MigDev {
+    int32_t q4;          // workers that never move
+    int32_t r;           // extra workers that hand over to a receiver (0 = no migration)
+    uint32_t off_mid;    // series byte offset at which they do
+    uint32_t buf_off;    // byte offset of the hand-over area in dynamic shared memory
+};
+
+template <class M, bool SMEM, bool TRAJ, bool MIG>
+__global__ void __launch_bounds__(MIG ? 512 : PB200_MAXTHREADS)
 ode_kernel(const __grid_constant__ ProblemDev P,
            const __grid_constant__ ModelConsts mc,
            const double *__restrict__ params, int64_t n, int64_t ld,
            double *__restrict__ scores, double *__restrict__ traj,
            int32_t *__restrict__ steps_out, const int32_t *__restrict__ perm,
-           const SolverDev S) {
+           const SolverDev S, const MigDev mig) {
     constexpr int NS = M::NS, NO = M::NO, OUT0 = M::OUT0;
     constexpr uint32_t ROWB = (1 + NO) * 8;          // bytes per series row
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr int U = PB200_PIPE_U;
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
+    // role of this warp in the migrating layout
+    enum { WORKER = 0, SOURCE = 1, RECEIVER = 2 };
+    int role = WORKER, mig_j = 0;
 
     Series<SMEM> series;
     series.gbase = P.series;
@@ -368,11 +398,29 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 
     // lanes past the end of the population shadow the last vector and write
     // nothing: whole warps stay convergent for the votes below
-    const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool live = gi < n;
+    int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool filler = false;
+    if (MIG) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        int vw = warp;                                // warp whose vectors I hold
+        if (warp >= mig.q4 + 2 && warp < mig.q4 + 2 + mig.r) {
+            role = RECEIVER; mig_j = warp - mig.q4 - 2; vw = mig.q4 + mig_j;
+        } else if (warp >= mig.q4 + mig.r) {
+            filler = true; vw = 0;                    // filler warp (r = 1): idles
+        } else if (warp >= mig.q4) {
+            role = SOURCE; mig_j = warp - mig.q4;
+        }
+        gi = (static_cast<int64_t>(blockIdx.x) * (mig.q4 + mig.r) + vw) * 32 + lane;
+    }
+    // the role is the same for a whole warp; taking it from a vote tells the
+    // compiler so (branches on it stay uniform, constants stay in uniform
+    // registers)
+    const bool is_source = MIG && __all_sync(FULL, role == SOURCE);
+    const bool is_receiver = MIG && __all_sync(FULL, role == RECEIVER);
+    const bool live = gi < n && !filler;
     // `perm` (optional) lists the vectors in order of a cost key, so that the
     // lanes of a warp integrate similar dynamics (see sort_* below)
-    const int64_t slot = live ? gi : n - 1;
+    const int64_t slot = gi < n ? gi : n - 1;
     const int64_t i = perm ? perm[slot] : slot;
 
     const int nt = P.n_times;
@@ -386,7 +434,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     if (!TRAJ) {
         double early;
         if (objective_precheck(P, x, &early)) {
-            if (live) {
+            if (live && !is_receiver) {
                 scores[i] = early;
                 if (steps_out) steps_out[i] = 0;
             }
@@ -497,11 +545,39 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         }
     };
 
+    // hand-over area of extra worker j: MIG_ND rows of 32 doubles, then 4 rows
+    // of 32 words (off, attempts, flags, spare)
+    constexpr int MIG_ND = 2 * NS + 2 + NO;
+    double *mig_d = nullptr;
+    uint32_t *mig_w = nullptr;
+    if (is_source || is_receiver) {
+        mig_d = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + mig.buf_off) +
+                mig_j * (MIG_ND + 2) * 32 + (threadIdx.x & 31);
+        mig_w = reinterpret_cast<uint32_t *>(mig_d - (threadIdx.x & 31) + MIG_ND * 32) +
+                (threadIdx.x & 31);
+    }
+    if (is_receiver) {
+        // parked until the extra worker has written its state
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + mig_j) : "memory");
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { y[j] = mig_d[j * 32]; K1[j] = mig_d[(NS + j) * 32]; }
+        t = mig_d[2 * NS * 32];
+        h = mig_d[(2 * NS + 1) * 32];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) ss[o] = mig_d[(2 * NS + 2 + o) * 32];
+        off = mig_w[0];
+        attempts = static_cast<int>(mig_w[32]);
+        failed = (mig_w[64] & 1u) != 0;
+        after_reject = (mig_w[64] & 2u) != 0;
+        model.scale(h);
+    }
+
     constexpr int kLoopUnroll = PB200_LOOP_UNROLL;
 #pragma unroll kLoopUnroll
     for (;;) {
         const bool fin = (off >= end) || failed;
         if (__all_sync(FULL, fin)) break;
+        if (is_source && __any_sync(FULL, off >= mig.off_mid)) break;
         // an attempt is counted while the solution has not reached the last
         // observation; the iteration after that only empties the pending interval
         if (!fin && t < t_last) {
@@ -634,6 +710,30 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         model.scale(h);
         // step size underflow: give up on this vector
         if (!ok && __double2hiint(h) < __double2hiint(h_min)) failed = true;
+    }
+
+    if (is_source) {
+        // empty the pending interval (its coefficients do not travel), then
+        // hand the state to the receiver and retire
+        double t_next = series.at(off);
+        while (__any_sync(FULL, le_bits(t_next, t))) {
+            const bool more = le_bits(t_next, t);
+            interpolate(t_next, off, more);
+            off += more ? ROWB : 0u;
+            t_next = series.at(off);
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { mig_d[j * 32] = y[j]; mig_d[(NS + j) * 32] = K1[j]; }
+        mig_d[2 * NS * 32] = t;
+        mig_d[(2 * NS + 1) * 32] = h;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) mig_d[(2 * NS + 2 + o) * 32] = ss[o];
+        mig_w[0] = off;
+        mig_w[32] = static_cast<uint32_t>(attempts);
+        mig_w[64] = (failed ? 1u : 0u) | (after_reject ? 2u : 0u);
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 64;" ::"r"(1 + mig_j) : "memory");
+        return;
     }
 
     if (idle) return;
@@ -1068,6 +1168,35 @@ int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
     return pb200_check_cuda(cudaGetLastError(), "sort kernels launch");
 }
 
+// device facts and tuning knobs of the migrating layout
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 148;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+static bool mig_enabled() {
+    static const int on = [] {
+        const char *e = getenv("PB200_MIGRATE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+static double mig_alpha() {
+    static const double a = [] {
+        const char *e = getenv("PB200_MIGRATE_AT");
+        const double v = e ? atof(e) : 0.0;
+        return (v > 0.0 && v < 1.0) ? v : 0.55;
+    }();
+    return a;
+}
+
 // series rows + the +inf sentinel rows, in whole 16-byte units
 static int64_t staged_bytes(const pb200_problem *p, int no) {
     return ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * (1 + no) * 8 + 15) & ~15ll;
@@ -1085,7 +1214,7 @@ static int64_t staged_bytes(const pb200_problem *p, int no) {
             if (rc) return rc;                                                           \
         }                                                                                \
         kern<<<static_cast<unsigned>(GRID), BLOCK, dyn_, st>>>(                          \
-            p->dev, p->mc, d_params, n, ld, d_scores, d_traj, d_steps, perm, s);         \
+            p->dev, p->mc, d_params, n, ld, d_scores, d_traj, d_steps, perm, s PB200_XARG); \
     } while (0)
 
 // one lane per parameter vector (any model)
@@ -1116,13 +1245,39 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
         return PB200_EINVAL;
     }
     const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
-    if (use_smem) {
-        if (traj) PB200_LAUNCH((ode_kernel<M, true, true>), grid, block, dyn);
-        else PB200_LAUNCH((ode_kernel<M, true, false>), grid, block, dyn);
-    } else {
-        if (traj) PB200_LAUNCH((ode_kernel<M, false, true>), grid, block, dyn);
-        else PB200_LAUNCH((ode_kernel<M, false, false>), grid, block, dyn);
+    // single-wave populations with one or two warps per SM more than a
+    // multiple of four: migrating layout, one block per SM (see MigDev)
+    MigDev mig = {0, 0, 0, 0};
+    if (use_smem && !traj && mig_enabled()) {
+        const int64_t warps = (n + 31) / 32;
+        const int sms = sm_count();
+        const int64_t per_sm = (warps + sms - 1) / sms;
+        const int r = static_cast<int>(per_sm % 4);
+        if (per_sm >= 5 && per_sm <= 14 && (r == 1 || r == 2)) {
+            mig.q4 = static_cast<int32_t>(per_sm - r);
+            mig.r = r;
+            const int64_t row = (1 + M::NO) * 8;
+            int64_t mid = static_cast<int64_t>(mig_alpha() * p->dev.n_times);
+            mid = mid < 1 ? 1 : mid;
+            mig.off_mid = static_cast<uint32_t>(mid * row);
+            mig.buf_off = static_cast<uint32_t>(bytes);
+        }
     }
+#define PB200_XARG , mig
+    if (mig.r) {
+        const int mblock = (mig.q4 + 2 + mig.r) * 32;
+        const int64_t per_block = static_cast<int64_t>(mig.q4 + mig.r) * 32;
+        const int64_t mgrid = (n + per_block - 1) / per_block;
+        const size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
+        PB200_LAUNCH((ode_kernel<M, true, false, true>), mgrid, mblock, mdyn);
+    } else if (use_smem) {
+        if (traj) PB200_LAUNCH((ode_kernel<M, true, true, false>), grid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, true, false, false>), grid, block, dyn);
+    } else {
+        if (traj) PB200_LAUNCH((ode_kernel<M, false, true, false>), grid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, false, false, false>), grid, block, dyn);
+    }
+#undef PB200_XARG
     return pb200_check_cuda(cudaGetLastError(), "ode_kernel launch");
 }
 
@@ -1156,6 +1311,7 @@ int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
         return PB200_EINVAL;
     }
     const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
+#define PB200_XARG
     if (use_smem) {
         if (traj) PB200_LAUNCH((ode_pair_kernel<L, true, true>), grid, block, dyn);
         else PB200_LAUNCH((ode_pair_kernel<L, true, false>), grid, block, dyn);
@@ -1163,6 +1319,7 @@ int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
         if (traj) PB200_LAUNCH((ode_pair_kernel<L, false, true>), grid, block, dyn);
         else PB200_LAUNCH((ode_pair_kernel<L, false, false>), grid, block, dyn);
     }
+#undef PB200_XARG
     return pb200_check_cuda(cudaGetLastError(), "ode_pair_kernel launch");
 }
 #undef PB200_LAUNCH

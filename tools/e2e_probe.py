@@ -9,14 +9,16 @@ s = po.headline_fhn_spec()
 ll = pb.GaussianKnownSigmaLogLikelihood(pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), s.times, s.values), 0.5)
 xs = po.headline_fhn_points(65536)
 ref = None
-for chunk in (1 << 30, 32768, 16384, 8192):
-    ev = pb.CudaEvaluator(ll, as_list=False, chunk_rows=chunk)
+for chunk, sort in ((1 << 30, True), (32768, True), (16384, True), (8192, True),
+                    (1 << 30, False), (16384, False)):
+    ev = pb.CudaEvaluator(ll, as_list=False, chunk_rows=chunk, sort=sort)
     for _ in range(5): out = ev.evaluate(xs)
     if ref is None: ref = out
     assert np.array_equal(out, ref)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(50): ev.evaluate(xs)
     dt = (time.perf_counter() - t0) / 50
+    print('sort=%s ' % sort, end='')
     print('chunk_rows=%d: %.3f ms per evaluate, %.3e evals/s' % (chunk, dt * 1e3, 65536 / dt))
 ev = pb.CudaEvaluator(ll)   # list output
 for _ in range(5): ev.evaluate(xs)
