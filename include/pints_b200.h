@@ -183,6 +183,19 @@ int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n,
                     const pb200_solver_opts *opts, void *stream);
 
 /*
+ * Building block of the pipelined host path: one asynchronous copy on `stream`
+ * between a page-locked host buffer and a device buffer (to_device = 1: host to
+ * device, 0: device to host).  CudaEvaluator stages a batch into pinned memory
+ * in slices and sends each slice while it stages the next, then launches ONE
+ * fused kernel over the whole batch.
+ */
+int pb200_copy_async(void *dst, const void *src, int64_t bytes,
+                     int32_t to_device, void *stream);
+/* 1 if `ptr` points into page-locked host memory (then a batch can be sent
+ * from where it lies, without staging), else 0. */
+int pb200_host_is_pinned(const void *ptr);
+
+/*
  * Batched ForwardModel.simulate / Problem.evaluate
  * (pints/_core.py:147-153, :257-265): writes the n trajectories
  * d_traj[n][n_times][n_outputs].  Also the first half of the unfused baseline.

@@ -37,6 +37,7 @@ __version__ = '0.1.0'
 
 _LAZY = {
     'Evaluator': '_evaluation', 'CudaEvaluator': '_evaluation',
+    'pinned_empty': '_evaluation',
     'DeviceProblem': '_engine', 'fp64_probe': '_engine',
     'require_cuda': '_engine',
     'HaarioBardenetACMC': '_samplers',

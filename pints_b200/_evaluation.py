@@ -104,40 +104,72 @@ class _Lane(object):
             self.a_h_steps = self.h_steps.data_ptr()
             self.a_d_steps = self.d_steps.data_ptr()
 
+    #: rows staged into pinned memory (and sent) per slice
+    STAGE_ROWS = 16384
+
     def launch(self, lib, xs, want_steps, chunk_rows):
         """Stage `xs` into pinned memory and enqueue copy-in, kernel and
-        copy-out (one pb200_eval_host call per chunk).  Chunks go to different
-        streams: while the host stages chunk k+1, the GPU already integrates
-        chunk k, and the chunks' kernels share the SMs."""
+        copy-out.  The batch is cut into at most N_STREAMS compute chunks of
+        `chunk_rows` rows or more, one fused launch each on its own stream; a
+        chunk is staged in slices of STAGE_ROWS rows, and each slice is on its
+        way to the device while the host stages the next one."""
         m, d = xs.shape
         self.reserve(m, d, want_steps)
         V = ctypes.c_void_p
-        n_chunks = max(1, min(len(self.streams), -(-m // chunk_rows)))
+        n_chunks = max(1, min(len(self.streams), m // max(1, chunk_rows)))
         rows = -(-m // n_chunks)
         self.used = 0
+        handle, opts = self.problem._handle, ctypes.byref(self.problem.opts)
+        pinned = bool(xs.flags['C_CONTIGUOUS'] and m * d >= 4096 and
+                      lib.pb200_host_is_pinned(V(xs.ctypes.data)))
         with torch.cuda.device(self.device):
             for c in range(n_chunks):
                 lo, hi = c * rows, min(m, (c + 1) * rows)
                 if hi <= lo:
                     break
-                np.copyto(self.h_in_np[lo:hi], xs[lo:hi])
+                st = self.stream_ptrs[c]
+                if pinned:
+                    # page-locked input: sent from where it lies
+                    _lib.check(lib.pb200_copy_async(
+                        V(self.a_d_in + lo * d * 8),
+                        V(xs.ctypes.data + lo * d * 8), (hi - lo) * d * 8, 1, st))
+                else:
+                    for a in range(lo, hi, self.STAGE_ROWS):
+                        b = min(hi, a + self.STAGE_ROWS)
+                        np.copyto(self.h_in_np[a:b], xs[a:b])
+                        _lib.check(lib.pb200_copy_async(
+                            V(self.a_d_in + a * d * 8),
+                            V(self.a_h_in + a * d * 8), (b - a) * d * 8, 1, st))
                 ws, ws_bytes = None, 0
                 if self.problem.wants_sort(hi - lo):
                     t = self.problem.sort_workspace(rows, ('chunk', c))
                     ws, ws_bytes = V(t.data_ptr()), t.numel()
-                _lib.check(lib.pb200_eval_host(
-                    self.problem._handle, V(self.a_h_in + lo * d * 8), hi - lo,
-                    d, V(self.a_h_out + lo * 8),
-                    V(self.a_h_steps + lo * 4) if want_steps else None,
-                    V(self.a_d_in + lo * d * 8), V(self.a_d_out + lo * 8),
+                _lib.check(lib.pb200_eval_sorted(
+                    handle, V(self.a_d_in + lo * d * 8), hi - lo, d,
+                    V(self.a_d_out + lo * 8),
                     V(self.a_d_steps + lo * 4) if want_steps else None,
-                    ws, ws_bytes,
-                    ctypes.byref(self.problem.opts), self.stream_ptrs[c]))
+                    opts, ws, ws_bytes, st))
+                _lib.check(lib.pb200_copy_async(
+                    V(self.a_h_out + lo * 8), V(self.a_d_out + lo * 8),
+                    (hi - lo) * 8, 0, st))
+                if want_steps:
+                    _lib.check(lib.pb200_copy_async(
+                        V(self.a_h_steps + lo * 4), V(self.a_d_steps + lo * 4),
+                        (hi - lo) * 4, 0, st))
                 self.used = c + 1
 
     def wait(self):
         for s in self.streams[:self.used]:
             s.synchronize()
+
+
+def pinned_empty(shape):
+    """A float64 ndarray in page-locked host memory.  Positions written into
+    such an array (e.g. by a vectorised ``ask()``) are sent to the GPU by
+    :class:`CudaEvaluator` from where they lie, without the staging copy that
+    ordinary (pageable) arrays need."""
+    t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    return t.numpy()
 
 
 class CudaEvaluator(Evaluator):
@@ -178,8 +210,10 @@ class CudaEvaluator(Evaluator):
         Return a Python list like the reference (default) or, if ``False``, a
         float64 ndarray (every consumer in the reference accepts either).
     chunk_rows
-        Host batches larger than this are staged and launched in up to four
-        chunks on separate streams, so that staging overlaps with compute.
+        Host batches of several times this many rows are cut into up to four
+        compute chunks (one fused launch each, on separate streams), so that
+        staging of a later chunk overlaps with the solve of an earlier one.
+        Within a chunk the rows are staged and sent in slices of 16384.
 
     Unlike ``ParallelEvaluator`` (pints/_evaluation.py:310) this evaluator never
     draws from ``numpy.random``, so controller trajectories equal those of a
@@ -188,7 +222,7 @@ class CudaEvaluator(Evaluator):
 
     def __init__(self, function, args=None, devices=None, rtol=None, atol=None,
                  max_steps=None, h0=None, block=None, as_list=True,
-                 chunk_rows=16384, lanes_per_vector=None, sort=None):
+                 chunk_rows=65536, lanes_per_vector=None, sort=None):
         if isinstance(function, ProblemSpec):
             spec = function
             function = _SpecFunction(spec)

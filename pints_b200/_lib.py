@@ -61,6 +61,8 @@ SIGNATURES = {
                                     POINTER(SolverOpts), _P, c_int64, _P]),
     'pb200_eval_host': (c_int32, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P,
                                   _P, c_int64, POINTER(SolverOpts), _P]),
+    'pb200_copy_async': (c_int32, [_P, _P, c_int64, c_int32, _P]),
+    'pb200_host_is_pinned': (c_int32, [_P]),
     'pb200_simulate': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                                  POINTER(SolverOpts), _P]),
     'pb200_score_trajectories': (c_int32, [_P, _P, _P, c_int64, c_int64, _P,

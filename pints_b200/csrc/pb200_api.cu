@@ -247,6 +247,30 @@ int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n, i
     return rc;
 }
 
+int pb200_host_is_pinned(const void *ptr) {
+    if (!ptr) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();                      // plain pageable memory on old drivers
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+int pb200_copy_async(void *dst, const void *src, int64_t bytes, int32_t to_device,
+                     void *stream) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) {
+        pb200_set_error("pb200_copy_async: bad arguments");
+        return PB200_EINVAL;
+    }
+    if (bytes == 0) return PB200_OK;
+    return pb200_check_cuda(
+        cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes),
+                        to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                        static_cast<cudaStream_t>(stream)),
+        "pb200_copy_async");
+}
+
 int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
                    double *d_traj, int32_t *d_steps, const pb200_solver_opts *opts,
                    void *stream) {

@@ -17,6 +17,8 @@
 // measured agreement.
 #include "pb200_common.cuh"
 #include <cstdlib>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -1039,84 +1041,107 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
 // comes from the model (cost_key): the time-scale parameter c for
 // FitzHugh-Nagumo, |f(y0)|^2 (the initial rate of change) otherwise.  A counting
 // sort over SORT_BINS linear bins between the smallest and the largest key is
-// enough (no order is needed inside a bin) and costs three small launches.
+// enough (no order is needed inside a bin) and is one cooperative launch.
 // ======================================================================
+static int sm_count();
 constexpr int SORT_BINS = 1024;
 constexpr int SORT_THREADS = 256;
+constexpr int SORT_MAX_BLOCKS = 1024;
 
 struct SortHeader {
-    uint32_t max_bits;        // max over keys of bits(key)        (keys >= 0)
-    uint32_t max_neg_bits;    // max over keys of ~bits(key), i.e. ~min
-    uint32_t pad[2];
     uint32_t hist[SORT_BINS];
     uint32_t cursor[SORT_BINS];
+    uint32_t block_max[SORT_MAX_BLOCKS];      // per block: max of bits(key)   (keys >= 0)
+    uint32_t block_negmax[SORT_MAX_BLOCKS];   // per block: max of ~bits(key), i.e. ~min
 };
 
+// One cooperative launch, three phases separated by grid-wide barriers:
+//   A  keys (and each block's key range); clear the histogram
+//   B  bin index per vector, histogram (shared-memory atomics, then global)
+//   C  every block scans the 1024-bin histogram for itself, reserves its range
+//      in every bin it touches and scatters its vectors' indices
 template <class M>
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_keys_kernel(const __grid_constant__ ProblemDev P,
-                 const __grid_constant__ ModelConsts mc,
-                 const double *__restrict__ params, int64_t n, int64_t ld,
-                 const double *__restrict__ series, float *__restrict__ keys,
-                 SortHeader *__restrict__ hdr) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    float key = 0.0f;
-    bool have = false;
-    if (i < n) {
+sort_kernel(const __grid_constant__ ProblemDev P,
+            const __grid_constant__ ModelConsts mc,
+            const double *__restrict__ params, int64_t n, int64_t ld,
+            float *__restrict__ keys, SortHeader *__restrict__ hdr,
+            int32_t *__restrict__ perm) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t sh_a[SORT_BINS];      // B: histogram      C: scan of the histogram
+    __shared__ uint32_t sh_b[SORT_BINS];      // C: this block's count per bin, then its start
+    __shared__ uint32_t sh_w[2 * SORT_THREADS / 32];
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- A ----
+    uint32_t hi = 0u, lo = 0u;
+    for (int64_t i = first; i < n; i += stride) {
         double x[PB200_MAX_PARAMS];
 #pragma unroll
         for (int k = 0; k < M::NP + M::NO; ++k)
             x[k] = (k < P.n_params) ? params[i * ld + k] : 0.0;
+        float key = 0.0f;
         double early;
         if (!objective_precheck(P, x, &early)) {      // decided vectors keep key 0
             M model;
             double y[M::NS], t0;
-            model.load(x, mc, y, P.n_times > 0 ? series[0] : 0.0, &t0);
+            model.load(x, mc, y, P.n_times > 0 ? P.series[0] : 0.0, &t0);
             key = static_cast<float>(model.cost_key(y));
             if (!(key >= 0.0f)) key = 0.0f;            // NaN
             key = fminf(key, 3.0e38f);
         }
         keys[i] = key;
-        have = true;
+        hi = max(hi, __float_as_uint(key));
+        lo = max(lo, ~__float_as_uint(key));
     }
-    uint32_t hi = have ? __float_as_uint(key) : 0u;
-    uint32_t lo = have ? ~__float_as_uint(key) : 0u;
     hi = __reduce_max_sync(0xffffffffu, hi);
     lo = __reduce_max_sync(0xffffffffu, lo);
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&hdr->max_bits, hi);
-        atomicMax(&hdr->max_neg_bits, lo);
-    }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(float *__restrict__ keys, int64_t n, SortHeader *__restrict__ hdr) {
-    __shared__ uint32_t sh[SORT_BINS];
-    for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x) sh[b] = 0;
+    if (lane == 0) { sh_w[warp] = hi; sh_w[SORT_THREADS / 32 + warp] = lo; }
     __syncthreads();
-    const float lo = __uint_as_float(~hdr->max_neg_bits);
-    const float hi = __uint_as_float(hdr->max_bits);
-    const float scale = hi > lo ? static_cast<float>(SORT_BINS) / (hi - lo) : 0.0f;
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) {
-        int bin = static_cast<int>((keys[i] - lo) * scale);
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SORT_THREADS / 32; ++w) {
+            hi = max(hi, sh_w[w]);
+            lo = max(lo, sh_w[SORT_THREADS / 32 + w]);
+        }
+        hdr->block_max[blockIdx.x] = hi;
+        hdr->block_negmax[blockIdx.x] = lo;
+    }
+    for (int64_t b = first; b < 2 * SORT_BINS; b += stride) hdr->hist[b] = 0;   // hist + cursor
+    grid.sync();
+
+    // ---- B ----
+    hi = 0u; lo = 0u;
+    for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x) {
+        hi = max(hi, hdr->block_max[b]);
+        lo = max(lo, hdr->block_negmax[b]);
+    }
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    lo = __reduce_max_sync(0xffffffffu, lo);
+    if (lane == 0) { sh_w[warp] = hi; sh_w[SORT_THREADS / 32 + warp] = lo; }
+    for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x) sh_a[b] = 0;
+    __syncthreads();
+    for (int w = 0; w < SORT_THREADS / 32; ++w) {
+        hi = max(hi, sh_w[w]);
+        lo = max(lo, sh_w[SORT_THREADS / 32 + w]);
+    }
+    const float kmin = __uint_as_float(~lo), kmax = __uint_as_float(hi);
+    const float scale = kmax > kmin ? static_cast<float>(SORT_BINS) / (kmax - kmin) : 0.0f;
+    uint32_t *bins = reinterpret_cast<uint32_t *>(keys);
+    for (int64_t i = first; i < n; i += stride) {
+        int bin = static_cast<int>((keys[i] - kmin) * scale);
         bin = min(max(bin, 0), SORT_BINS - 1);
-        atomicAdd(&sh[bin], 1u);
-        reinterpret_cast<uint32_t *>(keys)[i] = static_cast<uint32_t>(bin);
+        atomicAdd(&sh_a[bin], 1u);
+        bins[i] = static_cast<uint32_t>(bin);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x)
-        if (sh[b]) atomicAdd(&hdr->hist[b], sh[b]);
-}
+        if (sh_a[b]) atomicAdd(&hdr->hist[b], sh_a[b]);
+    grid.sync();
 
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_scatter_kernel(const uint32_t *__restrict__ bins, int64_t n,
-                    SortHeader *__restrict__ hdr, int32_t *__restrict__ perm) {
-    __shared__ uint32_t base[SORT_BINS];      // exclusive scan of the histogram
-    __shared__ uint32_t cnt[SORT_BINS];       // this block's count per bin, then its start
-    __shared__ uint32_t warp_tot[SORT_THREADS / 32];
+    // ---- C ----
     constexpr int PER = SORT_BINS / SORT_THREADS;
-    // every block scans the (small) global histogram for itself
     uint32_t v[PER], run = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) { v[k] = hdr->hist[threadIdx.x * PER + k]; run += v[k]; }
@@ -1124,27 +1149,33 @@ sort_scatter_kernel(const uint32_t *__restrict__ bins, int64_t n,
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if ((threadIdx.x & 31) >= d) inc += o;
+        if (lane >= d) inc += o;
     }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
-    for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x) cnt[b] = 0;
+    __syncthreads();                      // sh_w and sh_a are reused
+    if (lane == 31) sh_w[warp] = inc;
+    for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x) sh_b[b] = 0;
     __syncthreads();
     uint32_t before = inc - run;
-    for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_tot[w];
+    for (int w = 0; w < warp; ++w) before += sh_w[w];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) { base[threadIdx.x * PER + k] = before; before += v[k]; }
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    uint32_t bin = 0, rank = 0;
-    if (i < n) {
-        bin = bins[i];
-        rank = atomicAdd(&cnt[bin], 1u);
+    for (int k = 0; k < PER; ++k) { sh_a[threadIdx.x * PER + k] = before; before += v[k]; }
+    // ranks inside this block (one round of the grid-stride loop at a time)
+    for (int64_t base_i = static_cast<int64_t>(blockIdx.x) * blockDim.x; base_i < n; base_i += stride) {
+        const int64_t i = base_i + threadIdx.x;
+        uint32_t bin = 0, rank = 0;
+        if (i < n) {
+            bin = bins[i];
+            rank = atomicAdd(&sh_b[bin], 1u);
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x)
+            if (sh_b[b]) sh_b[b] = atomicAdd(&hdr->cursor[b], sh_b[b]);
+        __syncthreads();
+        if (i < n) perm[sh_a[bin] + sh_b[bin] + rank] = static_cast<int32_t>(i);
+        __syncthreads();
+        for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x) sh_b[b] = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    // reserve this block's range in every bin it touches
-    for (int b = threadIdx.x; b < SORT_BINS; b += blockDim.x)
-        if (cnt[b]) cnt[b] = atomicAdd(&hdr->cursor[b], cnt[b]);
-    __syncthreads();
-    if (i < n) perm[base[bin] + cnt[bin] + rank] = static_cast<int32_t>(i);
 }
 
 // Builds the permutation in `ws` (pb200_sort_workspace_bytes(n) bytes);
@@ -1155,17 +1186,20 @@ int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
     SortHeader *hdr = static_cast<SortHeader *>(ws);
     float *keys = reinterpret_cast<float *>(hdr + 1);
     int32_t *out = reinterpret_cast<int32_t *>(keys + n);
-    int rc = pb200_check_cuda(cudaMemsetAsync(hdr, 0, sizeof(SortHeader), st),
-                              "cudaMemsetAsync(sort header)");
-    if (rc) return rc;
-    const unsigned grid = static_cast<unsigned>((n + SORT_THREADS - 1) / SORT_THREADS);
-    sort_keys_kernel<M><<<grid, SORT_THREADS, 0, st>>>(p->dev, p->mc, d_params, n, ld,
-                                                        p->dev.series, keys, hdr);
-    sort_hist_kernel<<<grid, SORT_THREADS, 0, st>>>(keys, n, hdr);
-    sort_scatter_kernel<<<grid, SORT_THREADS, 0, st>>>(reinterpret_cast<uint32_t *>(keys), n,
-                                                        hdr, out);
+    // co-resident blocks only (grid-wide barriers): at most 4 per SM
+    int64_t grid = (n + SORT_THREADS - 1) / SORT_THREADS;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+    if (grid > cap) grid = cap;
+    if (grid > SORT_MAX_BLOCKS) grid = SORT_MAX_BLOCKS;
+    void *args[] = {const_cast<ProblemDev *>(&p->dev), const_cast<ModelConsts *>(&p->mc),
+                    &d_params, &n, &ld, &keys, &hdr, &out};
+    int rc = pb200_check_cuda(
+        cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sort_kernel<M>),
+                                    dim3(static_cast<unsigned>(grid)), dim3(SORT_THREADS),
+                                    args, 0, st),
+        "cooperative launch of the sort kernel");
     *perm = out;
-    return pb200_check_cuda(cudaGetLastError(), "sort kernels launch");
+    return rc;
 }
 
 // device facts and tuning knobs of the migrating layout
