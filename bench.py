@@ -241,6 +241,9 @@ def run_ours(args):
 
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    # stdout carries exactly one JSON line: keep NCCL's version banner off it
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
 
