@@ -60,7 +60,10 @@ extern "C" {
 #define PB200_OBJ_SSE                   0  /* pints/_error_measures.py:373-376     */
 #define PB200_OBJ_GAUSSIAN_KNOWN_SIGMA  1  /* pints/_log_likelihoods.py:1012-1041  */
 #define PB200_OBJ_GAUSSIAN              2  /* pints/_log_likelihoods.py:1110-1129  */
-#define PB200_N_OBJECTIVES              3
+#define PB200_OBJ_MSE                   3  /* pints/_error_measures.py:74-114      */
+#define PB200_OBJ_RMSE                  4  /* pints/_error_measures.py:135-161 (normalised)
+                                              and :201-229 (plain, norm = 1)       */
+#define PB200_N_OBJECTIVES              5
 
 #define PB200_MAX_OUTPUTS   8
 #define PB200_MAX_PARAMS    16      /* model parameters + sigma parameters  */
@@ -113,6 +116,10 @@ int64_t pb200_series_len(int32_t n_times, int32_t n_outputs);
  *   SSE                   weights[n_outputs]
  *   GAUSSIAN_KNOWN_SIGMA  offset[n_outputs], multip[n_outputs]
  *   GAUSSIAN              [0.5 * n_times * log(2 pi)]
+ *   MSE                   weights[n_outputs], 1 / (n_times * n_outputs)
+ *   RMSE                  [1 / n_times, norm]   single output; norm = 1 for
+ *                         RootMeanSquaredError, 1 / sqrt(mean(values^2)) for
+ *                         NormalisedRootMeanSquaredError
  * sign       +1, or -1 for ProbabilityBasedError
  *            (pints/_error_measures.py:183-184)
  * prior_lower/upper (host, n_prior entries or NULL/0): box of a
@@ -224,6 +231,38 @@ int pb200_mh_accept(double *d_current, double *d_current_f,
                     const double *d_log_u, uint8_t *d_accepted,
                     int64_t n, int32_t d, int32_t require_finite,
                     void *stream);
+
+/* The same, also writing log_ratio_j = fx_j - cur_f_j (taken BEFORE the update;
+ * the adaptive samplers below use it whatever the decision was). */
+int pb200_mh_accept_ratio(double *d_current, double *d_current_f,
+                          const double *d_proposed, const double *d_fx,
+                          const double *d_log_u, uint8_t *d_accepted,
+                          double *d_log_ratio, int64_t n, int32_t d,
+                          int32_t require_finite, void *stream);
+
+/*
+ * Adaptation step of the adaptive-covariance family
+ * (pints/_mcmc/_adaptive_covariance.py:88-107, :286-300):
+ *   HAARIO_BARDENET  pints/_mcmc/_haario_bardenet_ac.py:65-68 (= pb200_hbac_adapt)
+ *   HAARIO           pints/_mcmc/_haario_ac.py:63-66: log lambda moves with the
+ *                    acceptance PROBABILITY min(1, exp(log_ratio))
+ *   RAO_BLACKWELL    pints/_mcmc/_rao_blackwell_ac.py:58-74: sigma is updated with
+ *                    p * proposed + (1 - p) * previous instead of the new point;
+ *                    needs d_previous (the points before the accept step) and
+ *                    d_proposed; d_log_lambda is not touched
+ * Products and sums are rounded one by one as NumPy does; exp() may differ from
+ * NumPy's in the last place, so HAARIO / RAO_BLACKWELL states agree with the
+ * reference to ~1e-15 relative (decisions are taken elsewhere and are exact).
+ */
+#define PB200_AC_HAARIO_BARDENET 0
+#define PB200_AC_HAARIO          1
+#define PB200_AC_RAO_BLACKWELL   2
+int pb200_ac_adapt(int32_t variant, const double *d_current,
+                   const double *d_previous, const double *d_proposed,
+                   const uint8_t *d_accepted, const double *d_log_ratio,
+                   double *d_mu, double *d_sigma, double *d_log_lambda,
+                   int64_t n, int32_t d, double gamma, double target,
+                   void *stream);
 
 /*
  * Haario-Bardenet adaptation after the accept step

@@ -291,6 +291,21 @@ def sum_of_squares_error(sim, values, weights):
     return np.sum((np.sum(((sim - values)**2), axis=0) * weights), axis=0)
 
 
+def mean_squared_error(sim, values, weights):
+    """pints/_error_measures.py:100-113."""
+    ninv = 1.0 / np.prod(values.shape)
+    return ninv * np.sum(weights * np.sum((sim - values)**2, axis=0), axis=0)
+
+
+def root_mean_squared_error(sim, values, normalised=False):
+    """pints/_error_measures.py:201-229, and :135-161 when normalised
+    (single-output problems)."""
+    ninv = 1.0 / len(values)
+    norm = 1.0 / np.sqrt(ninv * np.sum(values**2)) if normalised else None
+    f = np.sqrt(ninv * np.sum((sim - values)**2))
+    return norm * f if normalised else f
+
+
 def gaussian_known_sigma_consts(n_times, n_outputs, sigma):
     """Pre-computed parts (pints/_log_likelihoods.py:1012-1035)."""
     if np.isscalar(sigma):
@@ -329,8 +344,9 @@ class Spec(object):
     consts       model constants (dict)
     times        (n_t,)
     values       (n_t,) for single-output problems, (n_t, n_o) for multi
-    objective    'sse' | 'gaussian_known_sigma' | 'gaussian'
-    obj          'sse': weights (n_o,); 'gaussian_known_sigma': sigma
+    objective    'sse' | 'mse' | 'rmse' | 'nrmse' | 'gaussian_known_sigma' |
+                 'gaussian'
+    obj          'sse', 'mse': weights (n_o,); 'gaussian_known_sigma': sigma
     sign         +1, or -1 when wrapped in ProbabilityBasedError
                  (pints/_error_measures.py:183-184)
     prior_box    optional (lower, upper) of a UniformLogPrior combined through
@@ -352,9 +368,13 @@ class Spec(object):
         self.sign = sign
         self.prior_box = prior_box
         self.tol = dict(tol or {})
-        if objective == 'sse':
+        if objective in ('sse', 'mse'):
             w = [1] * self.n_outputs if obj is None else obj
             self.weights = np.asarray([float(v) for v in w])
+        elif objective in ('rmse', 'nrmse'):
+            if self.multi_output:
+                raise ValueError('This measure is only defined for single '
+                                 'output problems.')
         elif objective == 'gaussian_known_sigma':
             self.offset, self.multip = gaussian_known_sigma_consts(
                 self.n_times, self.n_outputs, obj)
@@ -397,6 +417,11 @@ class Spec(object):
             sim = self.trajectory(x, **tol)
             if self.objective == 'sse':
                 f = sum_of_squares_error(sim, self.values, self.weights)
+            elif self.objective == 'mse':
+                f = mean_squared_error(sim, self.values, self.weights)
+            elif self.objective in ('rmse', 'nrmse'):
+                f = root_mean_squared_error(sim, self.values,
+                                            self.objective == 'nrmse')
             else:
                 f = gaussian_known_sigma_ll(sim, self.values, self.offset,
                                             self.multip)

@@ -26,7 +26,10 @@ from ._spec import ProblemSpec, describe, describe_model             # noqa
 from ._core import (ForwardModel, SingleOutputProblem,               # noqa
                     MultiOutputProblem)
 from ._objectives import (ErrorMeasure, ProblemErrorMeasure,         # noqa
-                          SumOfSquaresError, ProbabilityBasedError, LogPDF,
+                          SumOfSquaresError, MeanSquaredError,
+                          RootMeanSquaredError,
+                          NormalisedRootMeanSquaredError,
+                          ProbabilityBasedError, LogPDF,
                           LogPrior, LogLikelihood, ProblemLogLikelihood,
                           GaussianKnownSigmaLogLikelihood,
                           GaussianLogLikelihood, RectangularBoundaries,
@@ -40,7 +43,9 @@ _LAZY = {
     'pinned_empty': '_evaluation',
     'DeviceProblem': '_engine', 'fp64_probe': '_engine',
     'require_cuda': '_engine',
-    'HaarioBardenetACMC': '_samplers',
+    'HaarioBardenetACMC': '_samplers', 'HaarioACMC': '_samplers',
+    'RaoBlackwellACMC': '_samplers',
+    'MetropolisRandomWalkMCMC': '_samplers',
     'DifferentialEvolutionMCMC': '_samplers',
     'XNES': '_controllers', 'cuda_evaluators': '_controllers',
     'CudaOptimisationController': '_controllers',

@@ -356,7 +356,8 @@ class CudaMCMCController(object):
 
     Parameters follow the reference: ``log_pdf`` (a supported LogPDF, see
     ``CudaEvaluator``), ``chains``, ``x0`` (``chains`` starting points),
-    ``sigma0``, ``method`` (``HaarioBardenetACMC`` (default) or
+    ``sigma0``, ``method`` (``HaarioBardenetACMC`` (default), ``HaarioACMC``,
+    ``RaoBlackwellACMC``, ``MetropolisRandomWalkMCMC`` or
     ``DifferentialEvolutionMCMC`` from this package).
     """
 
@@ -380,14 +381,18 @@ class CudaMCMCController(object):
                 'All initial positions must have the same dimension as the'
                 ' given LogPDF.')
         method = HaarioBardenetACMC if method is None else method
-        if method is HaarioBardenetACMC:
+        if isinstance(method, type) and issubclass(method, HaarioBardenetACMC):
+            # the single-chain family: HaarioBardenetACMC, HaarioACMC,
+            # RaoBlackwellACMC, MetropolisRandomWalkMCMC (all chains at once)
             self._sampler = method(x0, sigma0, device=device, seed=seed)
         elif method is DifferentialEvolutionMCMC:
             self._sampler = method(self._n_chains, x0, device=device,
                                    seed=seed)
         else:
-            raise ValueError('method must be HaarioBardenetACMC or '
-                             'DifferentialEvolutionMCMC from pints_b200')
+            raise ValueError(
+                'method must be one of the device samplers of pints_b200: '
+                'HaarioBardenetACMC, HaarioACMC, RaoBlackwellACMC, '
+                'MetropolisRandomWalkMCMC or DifferentialEvolutionMCMC')
         self._max_iterations = 10000
         self._initial_phase_iterations = 200 \
             if self._sampler.needs_initial_phase() else None

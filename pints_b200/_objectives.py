@@ -68,6 +68,9 @@ class ProblemErrorMeasure(ErrorMeasure):
     def problem(self):
         return self._problem
 
+    def _problem_is_multi_output(self):
+        return np.ndim(self._values) == 2
+
 
 class SumOfSquaresError(_DeviceCallable, ProblemErrorMeasure):
     """``sum_o w_o sum_t (sim - data)^2`` (pints/_error_measures.py:338-385)."""
@@ -80,6 +83,46 @@ class SumOfSquaresError(_DeviceCallable, ProblemErrorMeasure):
             raise ValueError(
                 'Number of weights must match number of problem outputs.')
         self._weights = np.asarray([float(w) for w in weights])
+
+
+class MeanSquaredError(_DeviceCallable, ProblemErrorMeasure):
+    """``sum_o w_o sum_t (sim - data)^2 / (n_t n_o)``
+    (pints/_error_measures.py:74-114)."""
+
+    def __init__(self, problem, weights=None):
+        super().__init__(problem)
+        self._ninv = 1.0 / np.prod(self._values.shape)
+        if weights is None:
+            weights = [1] * self._n_outputs
+        elif self._n_outputs != len(weights):
+            raise ValueError(
+                'Number of weights must match number of problem outputs.')
+        self._weights = np.asarray([float(w) for w in weights])
+
+
+class RootMeanSquaredError(_DeviceCallable, ProblemErrorMeasure):
+    """``sqrt(sum_t (sim - data)^2 / n_t)``, single-output problems only
+    (pints/_error_measures.py:201-229)."""
+
+    def __init__(self, problem):
+        super().__init__(problem)
+        if self._problem_is_multi_output():
+            raise ValueError(
+                'This measure is only defined for single output problems.')
+        self._ninv = 1.0 / len(self._values)
+
+
+class NormalisedRootMeanSquaredError(_DeviceCallable, ProblemErrorMeasure):
+    """``sqrt(mean((sim - data)^2)) / sqrt(mean(data^2))``
+    (pints/_error_measures.py:135-161)."""
+
+    def __init__(self, problem):
+        super().__init__(problem)
+        if self._problem_is_multi_output():
+            raise ValueError(
+                'This measure is only defined for single output problems.')
+        self._ninv = 1.0 / len(self._values)
+        self._norm = 1.0 / np.sqrt(self._ninv * np.sum(self._values**2))
 
 
 class ProbabilityBasedError(_DeviceCallable, ErrorMeasure):

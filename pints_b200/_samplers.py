@@ -48,6 +48,21 @@ class _DeviceOps(object):
                    _ptr(fx), _ptr(log_u), _ptr(accepted), n, d,
                    1 if require_finite else 0)
 
+    def mh_accept_ratio(self, cur, cur_f, prop, fx, log_u, accepted, log_ratio,
+                        require_finite):
+        n, d = cur.shape
+        self._call(self.lib.pb200_mh_accept_ratio, _ptr(cur), _ptr(cur_f),
+                   _ptr(prop), _ptr(fx), _ptr(log_u), _ptr(accepted),
+                   _ptr(log_ratio), n, d, 1 if require_finite else 0)
+
+    def ac_adapt(self, variant, cur, prev, prop, accepted, log_ratio, mu, sigma,
+                 log_lambda, gamma, target):
+        n, d = cur.shape
+        self._call(self.lib.pb200_ac_adapt, int(variant), _ptr(cur),
+                   _ptr(prev), _ptr(prop), _ptr(accepted), _ptr(log_ratio),
+                   _ptr(mu), _ptr(sigma), _ptr(log_lambda), n, d, float(gamma),
+                   float(target))
+
     def hbac_adapt(self, cur, accepted, mu, sigma, log_lambda, gamma, target):
         n, d = cur.shape
         self._call(self.lib.pb200_hbac_adapt, _ptr(cur), _ptr(accepted),
@@ -93,7 +108,8 @@ class _Philox(object):
 
 
 class HaarioBardenetACMC(object):
-    """All chains of the Haario-Bardenet adaptive covariance sampler.
+    """All chains of the Haario-Bardenet adaptive covariance sampler
+    (pints/_mcmc/_haario_bardenet_ac.py).
 
     Parameters
     ----------
@@ -106,6 +122,8 @@ class HaarioBardenetACMC(object):
         and log-uniforms to ``ask``/``tell``; used for bit-exact parity tests
         and for reproducing a NumPy-seeded reference run).
     """
+
+    _VARIANT = _lib.AC_HAARIO_BARDENET
 
     def __init__(self, x0, sigma0=None, device=None, rng='philox', seed=0,
                  eta=0.6, target_acceptance=0.234):
@@ -145,6 +163,8 @@ class HaarioBardenetACMC(object):
         self._proposed = torch.empty_like(self._x0)
         self._z = torch.empty_like(self._x0)
         self._log_u = torch.empty(n, dtype=torch.float64, device=dev)
+        self._log_ratio = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._previous = torch.empty_like(self._x0)
         self._accepted = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._eta = float(eta)
         self._target = float(target_acceptance)
@@ -263,18 +283,93 @@ class HaarioBardenetACMC(object):
             off = self._rng.take(self._n)
             self._ops.uniform(self._log_u, self._rng.seed, off)
             torch.log_(self._log_u)
-        self._ops.mh_accept(self._current, self._current_f, self._proposed, fx,
-                            self._log_u, self._accepted, True)
+        v = self._VARIANT
+        if v == _lib.AC_HAARIO_BARDENET or v is None:
+            self._ops.mh_accept(self._current, self._current_f, self._proposed,
+                                fx, self._log_u, self._accepted, True)
+        else:
+            if v == _lib.AC_RAO_BLACKWELL:
+                self._previous.copy_(self._current)
+            self._ops.mh_accept_ratio(
+                self._current, self._current_f, self._proposed, fx,
+                self._log_u, self._accepted, self._log_ratio, True)
         self._acceptance_count += self._accepted
-        if self._adaptive:
+        if self._adaptive and v is not None:
             # gamma is the same for every chain: computed on the host exactly as
             # the reference does (pints/_mcmc/_adaptive_covariance.py:289)
             self._gamma = (self._adaptations + 1) ** -self._eta
             self._adaptations += 1
-            self._ops.hbac_adapt(self._current, self._accepted, self._mu,
-                                 self._sigma, self._log_lambda, self._gamma,
-                                 self._target)
+            if v == _lib.AC_HAARIO_BARDENET:
+                self._ops.hbac_adapt(self._current, self._accepted, self._mu,
+                                     self._sigma, self._log_lambda,
+                                     self._gamma, self._target)
+            else:
+                self._ops.ac_adapt(
+                    v, self._current, self._previous, self._proposed,
+                    self._accepted, self._log_ratio, self._mu, self._sigma,
+                    self._log_lambda, self._gamma, self._target)
         return self._current, self._current_f, self._accepted
+
+
+class HaarioACMC(HaarioBardenetACMC):
+    """All chains of the Haario adaptive covariance sampler
+    (pints/_mcmc/_haario_ac.py): as Haario-Bardenet, but log lambda moves with
+    the acceptance probability ``min(1, exp(log_ratio))`` instead of the 0/1
+    outcome."""
+    _VARIANT = _lib.AC_HAARIO
+
+    @classmethod
+    def name(cls):
+        return 'Haario adaptive covariance MCMC'
+
+
+class RaoBlackwellACMC(HaarioBardenetACMC):
+    """All chains of the Rao-Blackwell adaptive covariance sampler
+    (pints/_mcmc/_rao_blackwell_ac.py): proposals from ``lambda sigma`` with the
+    fixed ``lambda = 2.38^2 / d``; sigma adapts towards
+    ``p * proposed + (1 - p) * previous``."""
+    _VARIANT = _lib.AC_RAO_BLACKWELL
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        # device proposals take exp(log lambda) * sigma: a constant here
+        self._lambda = (2.38 ** 2) / self._d
+        self._log_lambda.fill_(float(np.log(self._lambda)))
+
+    def state(self):
+        mu, sigma, _ = super().state()
+        return mu, sigma, np.zeros(self._n)
+
+    @classmethod
+    def name(cls):
+        return 'Rao-Blackwell adaptive covariance MCMC'
+
+
+class MetropolisRandomWalkMCMC(HaarioBardenetACMC):
+    """All chains of the Metropolis random-walk sampler
+    (pints/_mcmc/_metropolis.py): proposals from the fixed ``sigma0``, the same
+    accept rule, no adaptation and no initial phase."""
+    _VARIANT = None
+
+    def needs_initial_phase(self):
+        return False
+
+    def in_initial_phase(self):
+        return False
+
+    def set_initial_phase(self, initial_phase):
+        raise NotImplementedError
+
+    def acceptance_rate(self):
+        # the reference counts from the second tell on
+        # (pints/_mcmc/_metropolis.py:146-180)
+        if self._iterations <= 1:
+            return np.zeros(self._n)
+        return self._acceptance_count.cpu().numpy() / float(self._iterations - 1)
+
+    @classmethod
+    def name(cls):
+        return 'Metropolis random walk MCMC'
 
 
 class DifferentialEvolutionMCMC(object):

@@ -171,10 +171,13 @@ def describe(function):
         else:
             break
     kind = _kind(f)
-    if kind not in ('SumOfSquaresError', 'GaussianKnownSigmaLogLikelihood',
+    if kind not in ('SumOfSquaresError', 'MeanSquaredError',
+                    'RootMeanSquaredError', 'NormalisedRootMeanSquaredError',
+                    'GaussianKnownSigmaLogLikelihood',
                     'GaussianLogLikelihood'):
         raise TypeError(
-            'CudaEvaluator supports SumOfSquaresError, '
+            'CudaEvaluator supports SumOfSquaresError, MeanSquaredError, '
+            '(Normalised)RootMeanSquaredError, '
             'GaussianKnownSigmaLogLikelihood and GaussianLogLikelihood '
             '(optionally inside LogPosterior with a UniformLogPrior and/or '
             'ProbabilityBasedError); got %s.%s (no CPU fallback).'
@@ -192,6 +195,15 @@ def describe(function):
     if kind == 'SumOfSquaresError':
         objective = _lib.OBJ_SSE
         obj_consts = list(np.asarray(f._weights, dtype=float))
+    elif kind == 'MeanSquaredError':
+        objective = _lib.OBJ_MSE
+        obj_consts = list(np.asarray(f._weights, dtype=float)) + \
+            [float(f._ninv)]
+    elif kind in ('RootMeanSquaredError', 'NormalisedRootMeanSquaredError'):
+        if multi:
+            raise TypeError('%s needs a SingleOutputProblem' % kind)
+        objective = _lib.OBJ_RMSE
+        obj_consts = [float(f._ninv), float(getattr(f, '_norm', 1.0))]
     elif kind == 'GaussianKnownSigmaLogLikelihood':
         objective = _lib.OBJ_GAUSSIAN_KNOWN_SIGMA
         offset = np.ones(n_outputs) * np.asarray(f._offset, dtype=float)

@@ -131,7 +131,13 @@ int pb200_problem_create(int32_t model, int32_t objective, int32_t n_times,
         }
     }
     const int want_obj = objective == PB200_OBJ_SSE ? n_outputs
-                         : objective == PB200_OBJ_GAUSSIAN_KNOWN_SIGMA ? 2 * n_outputs : 1;
+                         : objective == PB200_OBJ_GAUSSIAN_KNOWN_SIGMA ? 2 * n_outputs
+                         : objective == PB200_OBJ_MSE ? n_outputs + 1
+                         : objective == PB200_OBJ_RMSE ? 2 : 1;
+    if (objective == PB200_OBJ_RMSE && n_outputs != 1) {
+        pb200_set_error("the root-mean-squared errors are defined for single-output problems");
+        return PB200_EINVAL;
+    }
     if (n_obj_consts != want_obj || !obj_consts) {
         pb200_set_error("objective %d needs %d constants, got %d", objective, want_obj,
                         n_obj_consts);

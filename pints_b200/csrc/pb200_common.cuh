@@ -107,6 +107,7 @@ __device__ __forceinline__ void stage_series(double *dst, const double *src,
 //          (pints/_log_likelihoods.py:1039-1041)
 //   GAUSS  np.sum(-logn - nt*log(sigma) - np.sum(error**2, axis=0)/(2 sigma**2))
 //          (pints/_log_likelihoods.py:1123-1129)
+//   MSE    (pints/_error_measures.py:111-113), RMSE / NRMSE (:159-161, :227-229)
 // then LogPosterior adds the prior constant (pints/_log_pdfs.py:207-212) and
 // ProbabilityBasedError flips the sign (pints/_error_measures.py:183-184).
 // ---------------------------------------------------------------------------
@@ -120,6 +121,16 @@ __device__ __forceinline__ double objective_finish(const ProblemDev &P,
             double term = __dmul_rn(ss[o], P.oc[o]);
             acc = (o == 0) ? term : __dadd_rn(acc, term);
         }
+    } else if (P.objective == PB200_OBJ_MSE) {
+        //   ninv * np.sum(weights * np.sum((sim - data)**2, axis=0), axis=0)
+        for (int o = 0; o < no; ++o) {
+            double term = __dmul_rn(P.oc[o], ss[o]);
+            acc = (o == 0) ? term : __dadd_rn(acc, term);
+        }
+        acc = __dmul_rn(P.oc[no], acc);
+    } else if (P.objective == PB200_OBJ_RMSE) {
+        //   norm * np.sqrt(ninv * np.sum((sim - data)**2))
+        acc = __dmul_rn(P.oc[1], __dsqrt_rn(__dmul_rn(P.oc[0], ss[0])));
     } else if (P.objective == PB200_OBJ_GAUSSIAN_KNOWN_SIGMA) {
         for (int o = 0; o < no; ++o) {
             double term = __dadd_rn(P.oc[o], __dmul_rn(P.oc[no + o], ss[o]));

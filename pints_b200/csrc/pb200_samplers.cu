@@ -24,12 +24,14 @@ __global__ void mh_accept_kernel(double *__restrict__ cur, double *__restrict__ 
                                  const double *__restrict__ prop,
                                  const double *__restrict__ fx,
                                  const double *__restrict__ log_u,
-                                 uint8_t *__restrict__ accepted, int64_t n, int d,
+                                 uint8_t *__restrict__ accepted,
+                                 double *__restrict__ log_ratio, int64_t n, int d,
                                  int require_finite) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const double f_new = fx[j];
     const double ratio = __dsub_rn(f_new, cur_f[j]);
+    if (log_ratio) log_ratio[j] = ratio;
     bool acc = log_u[j] < ratio;                 // NaN compares false
     if (require_finite) acc = acc && isfinite(f_new);
     if (acc) {
@@ -66,6 +68,58 @@ __global__ void hbac_adapt_kernel(const double *__restrict__ cur,
     // log lambda += gamma (accepted - target)
     const double p = accepted[j] ? 1.0 : 0.0;
     log_lambda[j] = __dadd_rn(log_lambda[j], __dmul_rn(gamma, __dsub_rn(p, target)));
+}
+
+// Adaptation step of the three adaptive-covariance samplers.  They share
+//   mu    <- (1 - gamma) mu + gamma x                       (x = new current)
+//   sigma <- (1 - gamma) sigma + gamma v v^T
+// and differ in v and in the scale:
+//   HAARIO_BARDENET  v = x - mu,  log lambda += gamma (accepted - target)
+//                    pints/_mcmc/_haario_bardenet_ac.py:65-68
+//   HAARIO           v = x - mu,  log lambda += gamma (p - target),
+//                    p = exp(log_ratio) if log_ratio < 0 else 1
+//                    pints/_mcmc/_haario_ac.py:63-66
+//   RAO_BLACKWELL    v = (p Y + (1 - p) X) - mu, Y the proposal, X the
+//                    previous point; fixed scale
+//                    pints/_mcmc/_rao_blackwell_ac.py:58-74
+// (mu is the updated one in every case).  `log_ratio < 0` is false for NaN, so a
+// NaN score gives p = 1 exactly as in the reference.
+__global__ void ac_adapt_kernel(int variant, const double *__restrict__ cur,
+                                const double *__restrict__ prev,
+                                const double *__restrict__ prop,
+                                const uint8_t *__restrict__ accepted,
+                                const double *__restrict__ log_ratio,
+                                double *__restrict__ mu, double *__restrict__ sigma,
+                                double *__restrict__ log_lambda, int64_t n, int d,
+                                double gamma, double target) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double keep = __dsub_rn(1.0, gamma);
+    double p = accepted[j] ? 1.0 : 0.0;
+    if (variant != PB200_AC_HAARIO_BARDENET) {
+        const double lr = log_ratio[j];
+        p = lr < 0.0 ? exp(lr) : 1.0;
+    }
+    double dev[PB200_MAX_PARAMS];
+    for (int k = 0; k < d; ++k) {
+        const double x = cur[j * d + k];
+        const double m = __dadd_rn(__dmul_rn(keep, mu[j * d + k]), __dmul_rn(gamma, x));
+        mu[j * d + k] = m;
+        double v = x;
+        if (variant == PB200_AC_RAO_BLACKWELL)
+            v = __dadd_rn(__dmul_rn(p, prop[j * d + k]),
+                          __dmul_rn(__dsub_rn(1.0, p), prev[j * d + k]));
+        dev[k] = __dsub_rn(v, m);
+    }
+    double *sg = sigma + j * static_cast<int64_t>(d) * d;
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+            const double outer = __dmul_rn(dev[a], dev[b]);
+            sg[a * d + b] = __dadd_rn(__dmul_rn(keep, sg[a * d + b]),
+                                      __dmul_rn(gamma, outer));
+        }
+    if (variant != PB200_AC_RAO_BLACKWELL)
+        log_lambda[j] = __dadd_rn(log_lambda[j], __dmul_rn(gamma, __dsub_rn(p, target)));
 }
 
 __global__ void hbac_propose_kernel(const double *__restrict__ cur,
@@ -199,17 +253,53 @@ inline unsigned blocks_for(int64_t n, int block) {
 
 extern "C" {
 
-int pb200_mh_accept(double *d_current, double *d_current_f, const double *d_proposed,
-                    const double *d_fx, const double *d_log_u, uint8_t *d_accepted,
-                    int64_t n, int32_t d, int32_t require_finite, void *stream) {
+int pb200_mh_accept_ratio(double *d_current, double *d_current_f, const double *d_proposed,
+                          const double *d_fx, const double *d_log_u, uint8_t *d_accepted,
+                          double *d_log_ratio, int64_t n, int32_t d, int32_t require_finite,
+                          void *stream) {
     if (n < 0 || d < 1 || d > PB200_MAX_PARAMS) {
         pb200_set_error("pb200_mh_accept: bad n=%lld or d=%d", (long long)n, d);
         return PB200_EINVAL;
     }
     if (n == 0) return PB200_OK;
     mh_accept_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_current, d_current_f, d_proposed, d_fx, d_log_u, d_accepted, n, d, require_finite);
+        d_current, d_current_f, d_proposed, d_fx, d_log_u, d_accepted, d_log_ratio, n, d,
+        require_finite);
     return pb200_check_cuda(cudaGetLastError(), "mh_accept_kernel launch");
+}
+
+int pb200_mh_accept(double *d_current, double *d_current_f, const double *d_proposed,
+                    const double *d_fx, const double *d_log_u, uint8_t *d_accepted,
+                    int64_t n, int32_t d, int32_t require_finite, void *stream) {
+    return pb200_mh_accept_ratio(d_current, d_current_f, d_proposed, d_fx, d_log_u, d_accepted,
+                                 nullptr, n, d, require_finite, stream);
+}
+
+int pb200_ac_adapt(int32_t variant, const double *d_current, const double *d_previous,
+                   const double *d_proposed, const uint8_t *d_accepted,
+                   const double *d_log_ratio, double *d_mu, double *d_sigma,
+                   double *d_log_lambda, int64_t n, int32_t d, double gamma, double target,
+                   void *stream) {
+    if (n < 0 || d < 1 || d > PB200_MAX_PARAMS) {
+        pb200_set_error("pb200_ac_adapt: bad n=%lld or d=%d", (long long)n, d);
+        return PB200_EINVAL;
+    }
+    if (variant < PB200_AC_HAARIO_BARDENET || variant > PB200_AC_RAO_BLACKWELL) {
+        pb200_set_error("pb200_ac_adapt: unknown variant %d", variant);
+        return PB200_EUNSUPPORTED;
+    }
+    if (n == 0) return PB200_OK;
+    if (!d_current || !d_accepted || !d_mu || !d_sigma ||
+        (variant != PB200_AC_RAO_BLACKWELL && !d_log_lambda) ||
+        (variant != PB200_AC_HAARIO_BARDENET && !d_log_ratio) ||
+        (variant == PB200_AC_RAO_BLACKWELL && (!d_previous || !d_proposed))) {
+        pb200_set_error("pb200_ac_adapt: a buffer this variant needs is NULL");
+        return PB200_EINVAL;
+    }
+    ac_adapt_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        variant, d_current, d_previous, d_proposed, d_accepted, d_log_ratio, d_mu, d_sigma,
+        d_log_lambda, n, d, gamma, target);
+    return pb200_check_cuda(cudaGetLastError(), "ac_adapt_kernel launch");
 }
 
 int pb200_hbac_adapt(const double *d_current, const uint8_t *d_accepted, double *d_mu,

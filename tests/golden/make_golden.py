@@ -287,6 +287,41 @@ def golden_constant():
 # sampler replays: every draw and decision of the reference, step by step
 # --------------------------------------------------------------------------
 
+def golden_error_measures():
+    """MeanSquaredError / RootMeanSquaredError / NormalisedRootMeanSquaredError
+    of the reference on the logistic, FHN and HH-IK problems."""
+    model = pints.toy.LogisticModel()
+    times = np.linspace(0, 100, 1000)
+    np.random.seed(1)
+    values = model.simulate([0.1, 50], times) + np.random.normal(0, 1, 1000)
+    problem = pints.SingleOutputProblem(model, times, values)
+    rng = np.random.RandomState(14)
+    xs = np.array([0.1, 50]) * (1 + 0.2 * rng.randn(48, 2))
+    ev = pints.SequentialEvaluator
+    out = dict(times=times, values=values, xs=xs)
+    out['mse'] = np.array(ev(pints.MeanSquaredError(problem)).evaluate(xs))
+    out['mse_w'] = np.array(
+        ev(pints.MeanSquaredError(problem, [2.5])).evaluate(xs))
+    out['rmse'] = np.array(
+        ev(pints.RootMeanSquaredError(problem)).evaluate(xs))
+    out['nrmse'] = np.array(
+        ev(pints.NormalisedRootMeanSquaredError(problem)).evaluate(xs))
+    # multi-output, weighted, on the ODE model
+    fmodel, ftimes, fvalues, fproblem = fhn_problem()
+    fx = np.array([0.1, 0.5, 3]) * (1 + 0.05 * rng.randn(24, 3))
+    out['fhn_xs'] = fx
+    out['fhn_mse'] = np.array(
+        ev(pints.MeanSquaredError(fproblem, [1.0, 0.25])).evaluate(fx))
+    truth = np.array([odeint(fmodel._rhs, fmodel._y0, ftimes, (x,), **TRUTH)
+                      for x in fx])
+    ninv = 1.0 / np.prod(fvalues.shape)
+    out['fhn_mse_truth'] = np.array(
+        [ninv * np.sum(np.array([1.0, 0.25])
+                       * np.sum((t - fvalues)**2, axis=0), axis=0)
+         for t in truth])
+    save('error_measures', **out)
+
+
 def _logistic_posterior():
     model = pints.toy.LogisticModel()
     times = np.linspace(0, 100, 50)
@@ -296,16 +331,19 @@ def _logistic_posterior():
     return pints.GaussianLogLikelihood(problem), times, values
 
 
-def golden_hbac():
-    """HaarioBardenetACMC, several independent chains driven exactly as
-    MCMCController does (pints/_mcmc/__init__.py:706-788): all asks, then all
-    tells; adaptation switched on after `warm` iterations."""
+def _golden_adaptive(cls, name, seed, n_iter=160, warm=40):
+    """A single-chain sampler class of the reference, several independent
+    chains driven exactly as MCMCController does
+    (pints/_mcmc/__init__.py:706-788): all asks, then all tells; adaptation
+    (where the class has an initial phase) switched on after `warm` iterations.
+    """
     ll, times, values = _logistic_posterior()
-    n_chains, n_iter, warm, d = 6, 160, 40, 3
+    n_chains, d = 6, 3
     rng = np.random.RandomState(21)
     x0 = np.array([0.1, 50, 2]) * (1 + 0.02 * rng.randn(n_chains, d))
-    np.random.seed(12)
-    samplers = [pints.HaarioBardenetACMC(x) for x in x0]
+    np.random.seed(seed)
+    samplers = [cls(x) for x in x0]
+    adaptive_class = samplers[0].needs_initial_phase()
     rec = dict(
         proposed=np.zeros((n_iter, n_chains, d)),
         fx=np.zeros((n_iter, n_chains)),
@@ -321,10 +359,10 @@ def golden_hbac():
         z=np.full((n_iter, n_chains, d), np.nan),
     )
     for it in range(n_iter):
-        if it == warm:
+        if it == warm and adaptive_class:
             for s in samplers:
                 s.set_initial_phase(False)
-        rec['adaptive'][it] = it >= warm
+        rec['adaptive'][it] = it >= warm and adaptive_class
         # ask: record the standard normals each multivariate_normal consumes
         xs = []
         for c, s in enumerate(samplers):
@@ -350,12 +388,34 @@ def golden_hbac():
             rec['accepted'][it, c] = acc
             rec['current'][it, c] = cur
             rec['current_f'][it, c] = cur_f
-            rec['mu'][it, c] = s._mu
-            rec['sigma'][it, c] = s._sigma
-            rec['log_lambda'][it, c] = s._log_lambda
-        rec['gamma'][it] = samplers[0]._gamma
-    save('hbac_replay', x0=x0, times=times, values=values, warm=np.array(warm),
+            if adaptive_class:
+                rec['mu'][it, c] = s._mu
+                rec['sigma'][it, c] = s._sigma
+                rec['log_lambda'][it, c] = getattr(s, '_log_lambda', 0.0)
+        rec['gamma'][it] = getattr(samplers[0], '_gamma', 0.0)
+    save(name, x0=x0, times=times, values=values, warm=np.array(warm),
          sigma0=np.array([s._sigma0 for s in samplers]), **rec)
+
+
+def golden_hbac():
+    """HaarioBardenetACMC (pints/_mcmc/_haario_bardenet_ac.py)."""
+    _golden_adaptive(pints.HaarioBardenetACMC, 'hbac_replay', 12)
+
+
+def golden_haario():
+    """HaarioACMC (pints/_mcmc/_haario_ac.py)."""
+    _golden_adaptive(pints.HaarioACMC, 'haario_replay', 14)
+
+
+def golden_rao_blackwell():
+    """RaoBlackwellACMC (pints/_mcmc/_rao_blackwell_ac.py)."""
+    _golden_adaptive(pints.RaoBlackwellACMC, 'rao_blackwell_replay', 15)
+
+
+def golden_metropolis():
+    """MetropolisRandomWalkMCMC (pints/_mcmc/_metropolis.py)."""
+    _golden_adaptive(pints.MetropolisRandomWalkMCMC, 'metropolis_replay', 16,
+                     n_iter=120)
 
 
 def golden_de():
@@ -408,6 +468,11 @@ def golden_de():
 
 if __name__ == '__main__':
     print('reference:', pints.__file__, pints.__version__)
+    only = sys.argv[1:]
+    if only:
+        for name in only:
+            globals()['golden_' + name]()
+        sys.exit(0)
     golden_fhn()
     golden_fhn_unit_test()
     golden_logistic()
@@ -415,5 +480,9 @@ if __name__ == '__main__':
     golden_lv()
     golden_sir()
     golden_constant()
+    golden_error_measures()
     golden_hbac()
+    golden_haario()
+    golden_rao_blackwell()
+    golden_metropolis()
     golden_de()

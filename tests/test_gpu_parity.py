@@ -378,6 +378,35 @@ def test_cost_sorted_scheduling_changes_nothing(pb):
                           evaluate(pb, f, g['xs'], sort=False))
 
 
+def test_mean_squared_and_root_mean_squared_errors(pb):
+    """(f) row 3: MeanSquaredError / RootMeanSquaredError /
+    NormalisedRootMeanSquaredError epilogues (pints/_error_measures.py:74-161,
+    :201-229) against the reference's own numbers."""
+    g = load_golden('error_measures')
+    problem = pb.SingleOutputProblem(pb.toy.LogisticModel(), g['times'],
+                                     g['values'])
+    for f, key in ((pb.MeanSquaredError(problem), 'mse'),
+                   (pb.MeanSquaredError(problem, [2.5]), 'mse_w'),
+                   (pb.RootMeanSquaredError(problem), 'rmse'),
+                   (pb.NormalisedRootMeanSquaredError(problem), 'nrmse')):
+        got = evaluate(pb, f, g['xs'])
+        assert np.max(rel_err(got, g[key])) < ANALYTIC_RTOL, key
+    spec = po.headline_fhn_spec()
+    fproblem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                     spec.values)
+    got = evaluate(pb, pb.MeanSquaredError(fproblem, [1.0, 0.25]), g['fhn_xs'])
+    check_ode_scores(got, g['fhn_mse'], g['fhn_mse_truth'])
+    with pytest.raises(ValueError):
+        pb.RootMeanSquaredError(fproblem)
+    with pytest.raises(ValueError):
+        pb.MeanSquaredError(fproblem, [1.0])
+    # inside ProbabilityBasedError-free minimisation they are plain errors:
+    # the sign stays +1 and the evaluator returns them as they are
+    ev = pb.CudaEvaluator(pb.RootMeanSquaredError(problem), as_list=True)
+    out = ev.evaluate(g['xs'][:4])
+    assert isinstance(out, list) and np.allclose(out, g['rmse'][:4], rtol=1e-12)
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)

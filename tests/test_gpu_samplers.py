@@ -62,6 +62,49 @@ def test_hbac_replay_is_bit_exact(pb):
     assert np.allclose(rate, g['accepted'][1:].sum(0) / n_iter)
 
 
+@pytest.mark.parametrize('name,fixture', [
+    ('HaarioACMC', 'haario_replay'),
+    ('RaoBlackwellACMC', 'rao_blackwell_replay'),
+    ('MetropolisRandomWalkMCMC', 'metropolis_replay')])
+def test_adaptive_family_replay(pb, name, fixture):
+    """(f) row 4: the other samplers that share the accept rule.  Fed the
+    reference's recorded proposals, scores and log-uniforms, every decision and
+    every next position is identical; the adapted state matches to ~1e-15
+    (HaarioACMC and RaoBlackwellACMC use exp(log_ratio), where CUDA's exp and
+    NumPy's may differ in the last place -- the difference is then carried
+    along, hence 1e-12 over 120 adaptation steps)."""
+    g = load_golden(fixture)
+    n_iter, n, d = g['proposed'].shape
+    s = getattr(pb, name)(g['x0'], rng='replay')
+    adaptive_class = s.needs_initial_phase()
+    for it in range(n_iter):
+        if adaptive_class and it == int(g['warm']):
+            s.set_initial_phase(False)
+        xs = s.ask(proposed=g['proposed'][it] if it > 0 else None)
+        assert np.array_equal(host(xs), g['proposed'][it])
+        cur, cur_f, acc = s.tell(g['fx'][it], log_u=g['log_u'][it])
+        assert np.array_equal(host(acc), g['accepted'][it]), it
+        assert np.array_equal(host(cur), g['current'][it]), it
+        assert np.array_equal(host(cur_f), g['current_f'][it]), it
+        if adaptive_class:
+            mu, sigma, log_lambda = s.state()
+            assert np.array_equal(mu, g['mu'][it]), it        # no exp in mu
+            scale = np.abs(g['sigma'][it]).max(axis=(1, 2), keepdims=True)
+            assert np.all(np.abs(sigma - g['sigma'][it]) <= 1e-12 * scale), it
+            assert np.allclose(log_lambda, g['log_lambda'][it], rtol=1e-12,
+                               atol=1e-14), it
+    assert g['accepted'][7, 2] == 0 and g['accepted'][9, 4] == 0
+    if name == 'MetropolisRandomWalkMCMC':
+        with pytest.raises(NotImplementedError):
+            s.set_initial_phase(True)
+        assert np.allclose(s.acceptance_rate(),
+                           g['accepted'][1:].sum(0) / (n_iter - 1.0))
+    else:
+        assert g['accepted'][1:].mean() > 0.1
+        assert np.allclose(s.acceptance_rate(),
+                           g['accepted'][1:].sum(0) / n_iter)
+
+
 def test_hbac_first_point_must_be_finite(pb):
     s = pb.HaarioBardenetACMC(np.ones((4, 2)), rng='replay')
     s.ask()
@@ -195,14 +238,14 @@ def logistic_posterior(pb, n_times=200):
     return post
 
 
-@pytest.mark.parametrize('method', ['hbac', 'de'])
+@pytest.mark.parametrize('method', ['hbac', 'de', 'haario', 'rao_blackwell'])
 def test_device_mcmc_recovers_the_posterior(pb, method):
     post = logistic_posterior(pb)
     n_chains, n_iter = 256, 1500
     rng = np.random.RandomState(4)
     x0 = np.array([0.1, 50, 2]) * (1 + 0.05 * rng.randn(n_chains, 3))
-    cls = pb.HaarioBardenetACMC if method == 'hbac' \
-        else pb.DifferentialEvolutionMCMC
+    cls = {'hbac': pb.HaarioBardenetACMC, 'de': pb.DifferentialEvolutionMCMC,
+           'haario': pb.HaarioACMC, 'rao_blackwell': pb.RaoBlackwellACMC}[method]
     mc = pb.CudaMCMCController(post, n_chains, x0, method=cls, seed=7)
     mc.set_max_iterations(n_iter)
     chains = mc.run()
@@ -218,9 +261,9 @@ def test_device_mcmc_recovers_the_posterior(pb, method):
     moved = (np.diff(chains[:, :, 0], axis=1) != 0).mean()
     assert 0.05 < moved < 0.9
     assert tail[:, 0].min() >= 0 and tail[:, 1].max() < 100
-    if method == 'hbac':
+    if method != 'de':
         rate = mc.sampler().acceptance_rate()
-        assert 0.1 < rate.mean() < 0.5
+        assert 0.1 < rate.mean() < 0.6
     assert mc.n_evaluations() == n_chains * n_iter and mc.time() > 0
     with pytest.raises(RuntimeError):
         mc.run()

@@ -278,7 +278,11 @@ def test_cuda_evaluator_is_a_pints_evaluator(pints_ref):
     pints.LogPosterior(mll, pints.UniformLogPrior([0, 0, 0], [1, 1, 10]))
     # unsupported reference objects are refused, not evaluated on the CPU
     with pytest.raises(TypeError):
-        pb.CudaEvaluator(pints.MeanSquaredError(p))
+        pb.CudaEvaluator(pints.StudentTLogLikelihood(p))
+    # ... while the mean-squared family of the reference is on the path
+    spec = pb.describe(pints.MeanSquaredError(p, [1.0, 0.5]))
+    assert spec.objective == _lib.OBJ_MSE
+    assert spec.obj_consts == [1.0, 0.5, 1.0 / 2000]
     with pytest.raises(TypeError):
         pb.CudaEvaluator(pints.toy.RosenbrockError())
     with pytest.raises(TypeError):

@@ -397,3 +397,31 @@ def test_oracle_equals_live_reference(pints_ref):
     for x in np.array([0.01, 10, 10, 0.125, 80]) * (1 + 0.2 * rng.randn(5, 5)):
         assert np.array_equal(m.simulate(x, th),
                               po.hh_ik_simulate(x, th, n0=0.4))
+
+
+def test_error_measures_golden():
+    """MeanSquaredError, RootMeanSquaredError, NormalisedRootMeanSquaredError
+    (pints/_error_measures.py:74-161, :201-229): the oracle reproduces the
+    reference exactly; known answers from pints/tests/test_error_measures.py."""
+    g = load_golden('error_measures')
+    for objective, obj, key in (('mse', None, 'mse'), ('mse', [2.5], 'mse_w'),
+                                ('rmse', None, 'rmse'),
+                                ('nrmse', None, 'nrmse')):
+        s = po.Spec('logistic', g['times'], g['values'], objective, obj)
+        assert np.array_equal(po.scores(s, g['xs']), g[key]), key
+    s = po.Spec('fhn', np.linspace(0, 20, 1000), po.headline_fhn_spec().values,
+                'mse', [1.0, 0.25])
+    assert np.array_equal(po.scores(s, g['fhn_xs']), g['fhn_mse'])
+    # reference unit tests on ConstantModel (multi-output: output o = p_o (o+1))
+    # pints/tests/test_error_measures.py MeanSquaredError: values all ones...
+    times = np.array([1.0, 2.0, 3.0])
+    values = np.array([[1.0, 4.0], [1.0, 4.0], [1.0, 4.0]])
+    s = po.Spec('constant', times, values, 'mse')
+    assert po.scores(s, [[1.0, 2.0]])[0] == 0.0
+    assert po.scores(s, [[2.0, 2.0]])[0] == 0.5          # (1^2 * 3) / 6
+    s1 = po.Spec('constant', times, values[:, 0], 'rmse')
+    assert po.scores(s1, [[3.0]])[0] == 2.0
+    s1 = po.Spec('constant', times, values[:, 0], 'nrmse')
+    assert po.scores(s1, [[3.0]])[0] == 2.0
+    with pytest.raises(ValueError):
+        po.Spec('constant', times, values, 'rmse')
