@@ -47,7 +47,8 @@ _LAZY = {
     'RaoBlackwellACMC': '_samplers',
     'MetropolisRandomWalkMCMC': '_samplers',
     'DifferentialEvolutionMCMC': '_samplers',
-    'XNES': '_controllers', 'cuda_evaluators': '_controllers',
+    'XNES': '_controllers', 'SNES': '_controllers', 'PSO': '_controllers',
+    'BareCMAES': '_controllers', 'cuda_evaluators': '_controllers',
     'CudaOptimisationController': '_controllers',
     'CudaMCMCController': '_controllers',
 }

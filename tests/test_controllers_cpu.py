@@ -90,6 +90,54 @@ def test_vectorised_xnes_matches_reference(pints_ref):
     assert new._suggested_population_size() == ref._suggested_population_size()
 
 
+@pytest.mark.parametrize('name', ['SNES', 'PSO', 'BareCMAES'])
+def test_vectorised_optimisers_match_reference(pints_ref, name):
+    """(f) row 1: vectorised host ask()/tell() of the other population-based
+    optimisers.  Same trajectories as the reference classes (to rounding: BLAS
+    products replace per-sample loops) and IDENTICAL consumption of the global
+    numpy.random stream, generation by generation."""
+    pints = pints_ref
+    target = np.array([1.0, -2.0, 0.5])
+    f = lambda x: float(np.sum((np.asarray(x) - target)**2))  # noqa
+    for bounded in (False, True):
+        b_ref = pints.RectangularBoundaries([-5, -5, -5], [5, 5, 5]) \
+            if bounded else None
+        b_new = pb.RectangularBoundaries([-5, -5, -5], [5, 5, 5]) \
+            if bounded else None
+        np.random.seed(5)
+        ref = getattr(pints, name)([0.5, 0.5, 0.5], 2.0, b_ref)
+        ref.set_population_size(24)
+        trace = []
+        for _ in range(25):
+            xs = ref.ask()
+            ref.tell([f(x) for x in xs])
+            trace.append((np.array(xs), np.array(ref.x_best()), ref.f_best(),
+                          np.random.get_state()[1].copy()))
+        np.random.seed(5)
+        new = getattr(pb, name)([0.5, 0.5, 0.5], 2.0, b_new)
+        new.set_population_size(24)
+        for k in range(25):
+            xs = new.ask()
+            assert xs.shape == trace[k][0].shape, (name, bounded, k)
+            assert np.allclose(xs, trace[k][0], rtol=1e-8, atol=1e-10), k
+            new.tell(np.array([f(x) for x in xs]))
+            assert np.allclose(new.x_best(), trace[k][1], rtol=1e-8, atol=1e-10)
+            assert np.isclose(new.f_best(), trace[k][2], rtol=1e-8, atol=1e-12)
+            assert np.array_equal(np.random.get_state()[1], trace[k][3]), k
+        assert new.name() == ref.name()
+        assert new.population_size() == ref.population_size()
+        assert not new.needs_sensitivities()
+    # the optimisers do converge
+    assert new.f_best() < (0.5 if name == 'PSO' else 1e-2)
+    if name == 'BareCMAES':
+        assert np.allclose(new.cov(), ref.cov(), rtol=1e-6, atol=1e-12)
+        assert new.stop() is False
+    if name == 'PSO':
+        with pytest.raises(ValueError):
+            new2 = pb.PSO([1, 2])
+            new2.set_local_global_balance(1.5)
+
+
 def test_xnes_argument_checks():
     with pytest.raises(ValueError):
         pb.XNES([])

@@ -292,3 +292,21 @@ def test_cuda_optimisation_controller_with_vectorised_xnes(pb):
     opt.set_max_iterations(60)
     x2, f2 = opt.run()
     assert np.allclose(x2, x, rtol=1e-3) and f2 < 0
+
+
+@pytest.mark.parametrize('name', ['SNES', 'PSO', 'BareCMAES'])
+def test_cuda_optimisation_controller_with_other_vectorised_optimisers(pb, name):
+    rng = np.random.RandomState(8)
+    times = np.linspace(0, 100, 300)
+    values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 1, 300)
+    problem = pb.SingleOutputProblem(pb.toy.LogisticModel(), times, values)
+    np.random.seed(2)
+    opt = pb.CudaOptimisationController(
+        pb.MeanSquaredError(problem), [0.3, 20],
+        boundaries=pb.RectangularBoundaries([0, 1], [1, 200]),
+        method=getattr(pb, name))
+    opt.optimiser().set_population_size(2048)
+    opt.set_max_iterations(80)
+    x, f = opt.run()
+    assert abs(x[0] - 0.1) < 1e-2 and abs(x[1] - 50) < 1.0, (x, f)
+    assert f < 1.3
