@@ -54,7 +54,10 @@ extern "C" {
 #define PB200_MODEL_FHN             3   /* _fitzhugh_nagumo_model.py:111-117   */
 #define PB200_MODEL_LOTKA_VOLTERRA  4   /* _lotka_volterra_model.py:91-97      */
 #define PB200_MODEL_SIR             5   /* _sir_model.py:96-111                */
-#define PB200_N_MODELS              6
+#define PB200_MODEL_GOODWIN         6   /* _goodwin_oscillator_model.py:101-107 */
+#define PB200_MODEL_HES1            7   /* _hes1_michaelis_menten.py:129-140   */
+#define PB200_MODEL_REPRESSILATOR   8   /* _repressilator_model.py:91-108      */
+#define PB200_N_MODELS              9
 
 /* objectives */
 #define PB200_OBJ_SSE                   0  /* pints/_error_measures.py:373-376     */
@@ -112,6 +115,9 @@ int64_t pb200_series_len(int32_t n_times, int32_t n_outputs);
  *   FHN             [y0_V, y0_R]
  *   LOTKA_VOLTERRA  [y0_x, y0_y]
  *   SIR             [y0_S (unused), y0_I, y0_R, truncate_S0 (0|1)]
+ *   GOODWIN         [y0_x, y0_y, y0_z]
+ *   HES1            [m0, p1_0, p2_0, k_deg]          (output: m)
+ *   REPRESSILATOR   [y0 (6 values)]                  (outputs: m1, m2, m3)
  * obj_consts (host)
  *   SSE                   weights[n_outputs]
  *   GAUSSIAN_KNOWN_SIGMA  offset[n_outputs], multip[n_outputs]

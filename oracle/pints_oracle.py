@@ -240,6 +240,66 @@ def sir_simulate(parameters, times, y0=None, **tol):
     return sol[:, 1:]
 
 
+def goodwin_rhs(state, time, parameters):
+    """pints/toy/_goodwin_oscillator_model.py:101-107."""
+    x, y, z = state
+    k2, k3, m1, m2, m3 = parameters
+    dxdt = 1 / (1 + z**10) - m1 * x
+    dydt = k2 * x - m2 * y
+    dzdt = k3 * y - m3 * z
+    return dxdt, dydt, dzdt
+
+
+GOODWIN_Y0 = (0.0054, 0.053, 1.93)
+
+
+def goodwin_simulate(parameters, times, y0=None, **tol):
+    """pints/toy/_goodwin_oscillator_model.py:19-20 (y0) through the shared
+    driver (three states, all of them outputs)."""
+    y0 = list(GOODWIN_Y0 if y0 is None else y0)
+    return _toy_ode_simulate(goodwin_rhs, y0, parameters, times, 3, **tol)
+
+
+def hes1_simulate(parameters, times, m0=2, fixed=(5., 3., 0.03), **tol):
+    """pints/toy/_hes1_michaelis_menten.py:129-159: states (m, p1, p2), only m
+    is returned; ``fixed = (p1_0, p2_0, k_deg)``."""
+    kdeg = fixed[2]
+
+    def rhs(state, time, parameters):
+        m, p1, p2 = state
+        P0, v, k1, h = parameters
+        return np.array([
+            - kdeg * m + 1. / (1. + (p2 / P0)**h),
+            - kdeg * p1 + v * m - k1 * p1,
+            - kdeg * p2 + k1 * p1])
+    y0 = [m0, fixed[0], fixed[1]]
+    return _toy_ode_simulate(rhs, y0, parameters, times, 1, **tol)
+
+
+def repressilator_rhs(y, t, alpha_0, alpha, beta, n):
+    """pints/toy/_repressilator_model.py:91-103."""
+    dy = np.zeros(6)
+    dy[0] = -y[0] + alpha / (1 + y[5]**n) + alpha_0
+    dy[1] = -y[1] + alpha / (1 + y[3]**n) + alpha_0
+    dy[2] = -y[2] + alpha / (1 + y[4]**n) + alpha_0
+    dy[3] = -beta * (y[3] - y[0])
+    dy[4] = -beta * (y[4] - y[1])
+    dy[5] = -beta * (y[5] - y[2])
+    return dy
+
+
+def repressilator_simulate(parameters, times, y0=None, **tol):
+    """pints/toy/_repressilator_model.py:105-108: integrated from ``times[0]``
+    (no ``t = 0`` is inserted), the three mRNA states are returned; default
+    y0 = [0, 0, 0, 2, 1, 3] (:68-70)."""
+    alpha_0, alpha, beta, n = parameters
+    start = np.array([0, 0, 0, 2, 1, 3]) if y0 is None \
+        else np.array(y0, dtype=float)
+    y = odeint(repressilator_rhs, start, times, (alpha_0, alpha, beta, n),
+               **tol)
+    return y[:, :3]
+
+
 TRUTH_TOL = dict(rtol=1e-13, atol=1e-13, mxstep=100000)
 
 
@@ -247,7 +307,8 @@ TRUTH_TOL = dict(rtol=1e-13, atol=1e-13, mxstep=100000)
 # model registry used by the spec-driven entry points below
 # --------------------------------------------------------------------------
 
-MODELS = ('logistic', 'hh_ik', 'constant', 'fhn', 'lotka_volterra', 'sir')
+MODELS = ('logistic', 'hh_ik', 'constant', 'fhn', 'lotka_volterra', 'sir',
+          'goodwin', 'hes1', 'repressilator')
 
 
 def simulate(model, consts, parameters, times, **tol):
@@ -268,6 +329,14 @@ def simulate(model, consts, parameters, times, **tol):
         return lv_simulate(parameters, times, consts.get('y0'), **tol)
     if model == 'sir':
         return sir_simulate(parameters, times, consts.get('y0'), **tol)
+    if model == 'goodwin':
+        return goodwin_simulate(parameters, times, consts.get('y0'), **tol)
+    if model == 'hes1':
+        return hes1_simulate(parameters, times, consts.get('m0', 2),
+                             consts.get('fixed', (5., 3., 0.03)), **tol)
+    if model == 'repressilator':
+        return repressilator_simulate(parameters, times, consts.get('y0'),
+                                      **tol)
     raise ValueError('unknown model ' + str(model))
 
 
@@ -383,7 +452,8 @@ class Spec(object):
 
     def n_model_parameters(self):
         return {'logistic': 2, 'hh_ik': 5, 'fhn': 3, 'lotka_volterra': 4,
-                'sir': 3}.get(self.model, self.n_outputs)
+                'sir': 3, 'goodwin': 5, 'hes1': 4,
+                'repressilator': 4}.get(self.model, self.n_outputs)
 
     def n_parameters(self):
         extra = self.n_outputs if self.objective == 'gaussian' else 0

@@ -66,7 +66,8 @@ class ProblemSpec(object):
     def n_model_parameters(self):
         fixed = {_lib.MODEL_LOGISTIC: 2, _lib.MODEL_HH_IK: 5,
                  _lib.MODEL_FHN: 3, _lib.MODEL_LOTKA_VOLTERRA: 4,
-                 _lib.MODEL_SIR: 3}
+                 _lib.MODEL_SIR: 3, _lib.MODEL_GOODWIN: 5,
+                 _lib.MODEL_HES1: 4, _lib.MODEL_REPRESSILATOR: 4}
         return fixed.get(self.model, self.n_outputs)
 
     def n_parameters(self):
@@ -75,7 +76,8 @@ class ProblemSpec(object):
 
     def is_ode(self):
         return self.model in (_lib.MODEL_FHN, _lib.MODEL_LOTKA_VOLTERRA,
-                              _lib.MODEL_SIR)
+                              _lib.MODEL_SIR, _lib.MODEL_GOODWIN,
+                              _lib.MODEL_HES1, _lib.MODEL_REPRESSILATOR)
 
     def packed_series(self):
         """Rows ``[t_j, v_j0 ..]``, then ``SENTINEL_ROWS`` rows with time
@@ -103,6 +105,16 @@ class ProblemSpec(object):
             return 222.0 * steps + 24.0 * nt
         if self.model == _lib.MODEL_SIR:
             return 298.0 * steps + 32.0 * nt
+        # same accounting for the other ODE models: 64 per state and step for
+        # the stage sums, error estimate and norm; 6 right-hand sides (pow and
+        # division count 1); 10 for the controller; 18 per state for the dense
+        # output; per observation 2 + 11 per output
+        if self.model == _lib.MODEL_GOODWIN:
+            return (3 * 64 + 6 * 16 + 10 + 54) * steps + 35.0 * nt
+        if self.model == _lib.MODEL_HES1:
+            return (3 * 64 + 6 * 14 + 10 + 54) * steps + 13.0 * nt
+        if self.model == _lib.MODEL_REPRESSILATOR:
+            return (6 * 64 + 6 * 27 + 10 + 108) * steps + 35.0 * nt
         if self.model == _lib.MODEL_HH_IK:
             return 0.0 * steps + 12.0 * nt + 750.0
         return 0.0 * steps + 8.0 * nt * self.n_outputs
@@ -145,10 +157,20 @@ def describe_model(model):
         truncate = 1.0 if y0.dtype.kind in 'iu' else 0.0
         return _lib.MODEL_SIR, [float(y0[0]), float(y0[1]), float(y0[2]),
                                 truncate]
+    if kind == 'GoodwinOscillatorModel':
+        y0 = np.asarray(model._y0, dtype=float)
+        return _lib.MODEL_GOODWIN, [y0[0], y0[1], y0[2]]
+    if kind == 'Hes1Model':
+        y0 = np.asarray(model._y0, dtype=float)
+        return _lib.MODEL_HES1, [y0[0], y0[1], y0[2], float(model._kdeg)]
+    if kind == 'RepressilatorModel':
+        y0 = np.asarray(model._y0, dtype=float)
+        return _lib.MODEL_REPRESSILATOR, list(y0)
     raise TypeError(
         'CudaEvaluator supports the toy models LogisticModel, '
         'HodgkinHuxleyIKModel, ConstantModel, FitzhughNagumoModel, '
-        'LotkaVolterraModel and SIRModel; got %s.%s (no CPU fallback).'
+        'LotkaVolterraModel, SIRModel, GoodwinOscillatorModel, Hes1Model and '
+        'RepressilatorModel; got %s.%s (no CPU fallback).'
         % (type(model).__module__, type(model).__name__))
 
 

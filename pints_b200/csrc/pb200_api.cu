@@ -40,6 +40,9 @@ const ModelInfo kModels[PB200_N_MODELS] = {
     /* FHN            */ {3, 2, 2, true},
     /* LOTKA_VOLTERRA */ {4, 2, 2, true},
     /* SIR            */ {3, 2, 4, true},
+    /* GOODWIN        */ {5, 3, 3, true},
+    /* HES1           */ {4, 1, 4, true},
+    /* REPRESSILATOR  */ {4, 3, 6, true},
 };
 
 SolverDev resolve_opts(const pb200_solver_opts *o, int *block, int *lanes) {

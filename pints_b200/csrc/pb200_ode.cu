@@ -105,6 +105,7 @@ __constant__ double TAB[N_TAB] = {
 // K = h f(y) directly: every stage, the error estimate and the dense output
 // then work on h-scaled increments and need no further multiplication by h.
 struct FhnModel {
+    static constexpr bool MIGRATES = true;
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 3;
     // V' = c (V - V^3/3 + R) = (c - (c/3) V^2) V + c R
     // R' = -(V - a + b R) / c  = (-1/c) V + (a/c) + (-b/c) R
@@ -144,6 +145,7 @@ struct FhnModel {
 };
 
 struct LvModel {
+    static constexpr bool MIGRATES = true;
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 4;
     double a, b, c, d;
     double ha, nhb, nhc, hd;
@@ -174,6 +176,7 @@ struct LvModel {
 };
 
 struct SirModel {
+    static constexpr bool MIGRATES = true;
     static constexpr int NS = 3, NO = 2, OUT0 = 1, NP = 3;
     double gamma, v;
     double nhg, hv;
@@ -209,6 +212,123 @@ struct SirModel {
         K[0] = ngsi;
         K[1] = -ngsi - vi;
         K[2] = vi;
+    }
+};
+
+// Goodwin oscillator (pints/toy/_goodwin_oscillator_model.py:101-107):
+//   x' = 1 / (1 + z^10) - m1 x,  y' = k2 x - m2 y,  z' = k3 y - m3 z
+struct GoodwinModel {
+    static constexpr int NS = 3, NO = 3, OUT0 = 0, NP = 5;
+    static constexpr bool MIGRATES = false;     // needs 146 registers
+    double k2, k3, m1, m2, m3;
+    double h_, hk2, hk3, nhm1, nhm2, nhm3;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double, double *t0) {
+        k2 = x[0]; k3 = x[1]; m1 = x[2]; m2 = x[3]; m3 = x[4];
+        y[0] = mc.c[0]; y[1] = mc.c[1]; y[2] = mc.c[2];
+        *t0 = 0.0;
+    }
+    __device__ __forceinline__ static double pow10(double z) {
+        const double z2 = z * z, z4 = z2 * z2;
+        return (z4 * z4) * z2;
+    }
+    __device__ __forceinline__ void rhs(const double *y, double *f) const {
+        f[0] = 1.0 / (1.0 + pow10(y[2])) - m1 * y[0];
+        f[1] = k2 * y[0] - m2 * y[1];
+        f[2] = k3 * y[1] - m3 * y[2];
+    }
+    __device__ __forceinline__ void scale(double h) {
+        h_ = h; hk2 = h * k2; hk3 = h * k3; nhm1 = -h * m1; nhm2 = -h * m2; nhm3 = -h * m3;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        K[0] = fma(nhm1, y[0], h_ / (1.0 + pow10(y[2])));
+        K[1] = fma(hk2, y[0], nhm2 * y[1]);
+        K[2] = fma(hk3, y[1], nhm3 * y[2]);
+    }
+    __device__ __forceinline__ double cost_key(const double *y) const {
+        double f[NS];
+        rhs(y, f);
+        return fma(f[0], f[0], fma(f[1], f[1], f[2] * f[2]));
+    }
+};
+
+// Hes1 Michaelis-Menten model (pints/toy/_hes1_michaelis_menten.py:129-140),
+// output = m; constants [m0, p1_0, p2_0, k_deg]:
+//   m'  = -k_deg m + 1 / (1 + (p2 / P0)^h)
+//   p1' = -k_deg p1 + v m - k1 p1,   p2' = -k_deg p2 + k1 p1
+struct Hes1Model {
+    static constexpr int NS = 3, NO = 1, OUT0 = 0, NP = 4;
+    static constexpr bool MIGRATES = false;     // pow() needs > 128 registers
+    double iP0, v, k1, hh, kdeg;
+    double h_, hv, hk1, nhkd;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double, double *t0) {
+        iP0 = 1.0 / x[0]; v = x[1]; k1 = x[2]; hh = x[3];
+        y[0] = mc.c[0]; y[1] = mc.c[1]; y[2] = mc.c[2];
+        kdeg = mc.c[3];
+        *t0 = 0.0;
+    }
+    __device__ __forceinline__ void rhs(const double *y, double *f) const {
+        f[0] = -kdeg * y[0] + 1.0 / (1.0 + pow(y[2] * iP0, hh));
+        f[1] = -kdeg * y[1] + v * y[0] - k1 * y[1];
+        f[2] = -kdeg * y[2] + k1 * y[1];
+    }
+    __device__ __forceinline__ void scale(double h) {
+        h_ = h; hv = h * v; hk1 = h * k1; nhkd = -h * kdeg;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        K[0] = fma(nhkd, y[0], h_ / (1.0 + pow(y[2] * iP0, hh)));
+        K[1] = fma(hv, y[0], (nhkd - hk1) * y[1]);
+        K[2] = fma(hk1, y[1], nhkd * y[2]);
+    }
+    __device__ __forceinline__ double cost_key(const double *y) const {
+        double f[NS];
+        rhs(y, f);
+        return fma(f[0], f[0], fma(f[1], f[1], f[2] * f[2]));
+    }
+};
+
+// Repressilator (pints/toy/_repressilator_model.py:91-108), six states, the
+// three mRNA levels are the outputs; like SIR it is integrated from times[0]:
+//   m_i' = -m_i + alpha / (1 + p_j^n) + alpha_0,   p_i' = -beta (p_i - m_i)
+// with (i, j) = (0, 2), (1, 0), (2, 1) (protein j represses gene i).
+struct RepressilatorModel {
+    static constexpr int NS = 6, NO = 3, OUT0 = 0, NP = 4;
+    static constexpr bool MIGRATES = false;     // 6 states need > 128 registers
+    double a0, al, be, nn;
+    double h_, ha0, hal, hbe;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double t_first, double *t0) {
+        a0 = x[0]; al = x[1]; be = x[2]; nn = x[3];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) y[k] = mc.c[k];
+        *t0 = t_first;
+    }
+    __device__ __forceinline__ void rhs(const double *y, double *f) const {
+        f[0] = -y[0] + al / (1.0 + pow(y[5], nn)) + a0;
+        f[1] = -y[1] + al / (1.0 + pow(y[3], nn)) + a0;
+        f[2] = -y[2] + al / (1.0 + pow(y[4], nn)) + a0;
+        f[3] = -be * (y[3] - y[0]);
+        f[4] = -be * (y[4] - y[1]);
+        f[5] = -be * (y[5] - y[2]);
+    }
+    __device__ __forceinline__ void scale(double h) {
+        h_ = h; ha0 = h * a0; hal = h * al; hbe = h * be;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        K[0] = fma(-h_, y[0], hal / (1.0 + pow(y[5], nn))) + ha0;
+        K[1] = fma(-h_, y[1], hal / (1.0 + pow(y[3], nn))) + ha0;
+        K[2] = fma(-h_, y[2], hal / (1.0 + pow(y[4], nn))) + ha0;
+        K[3] = hbe * (y[0] - y[3]);
+        K[4] = hbe * (y[1] - y[4]);
+        K[5] = hbe * (y[2] - y[5]);
+    }
+    __device__ __forceinline__ double cost_key(const double *y) const {
+        double f[NS], s2 = 0.0;
+        rhs(y, f);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) s2 = fma(f[k], f[k], s2);
+        return s2;
     }
 };
 
@@ -256,6 +376,7 @@ __device__ __forceinline__ float step_factor(double sum2) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(-0.1f * l));
     // 0.9 * NS^(1/10)
     const float k = NS == 1 ? 0.9f : NS == 2 ? 0.96459370f : NS == 3 ? 1.00450979f
+                  : NS == 4 ? 1.03382570f : NS == 5 ? 1.05715438f : NS == 6 ? 1.07660593f
                                                              : 0.9f * exp2f(0.1f * log2f((float)NS));
     return fminf(fmaxf(k * f, 0.2f), 10.0f);
 }
@@ -273,8 +394,9 @@ template <int NS>
 __device__ __forceinline__ double step_factor_bits(double sum2, bool cap_at_one) {
     // 0x3FF00000 + 2^20 log2(0.9 NS^0.1) - 50000 (centring) + 0x3FF00000 / 10
     constexpr int32_t magic =
-        NS == 1 ? 1179753186 : NS == 2 ? 1179858044 : NS == 3 ? 1179919381 : 1179962902;
-    static_assert(NS >= 1 && NS <= 4, "magic constant tabulated for 1..4 states");
+        NS == 1 ? 1179753186 : NS == 2 ? 1179858044 : NS == 3 ? 1179919381
+        : NS == 4 ? 1179962902 : NS == 5 ? 1179996658 : 1180024239;
+    static_assert(NS >= 1 && NS <= 6, "magic constant tabulated for 1..6 states");
     const uint32_t hi = static_cast<uint32_t>(__double2hiint(sum2));
     int32_t hy = magic - static_cast<int32_t>(__umulhi(hi, 0x1999999Au));
     hy = max(hy, 0x3FC99999);                        // 0.2
@@ -1282,7 +1404,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     // single-wave populations with one or two warps per SM more than a
     // multiple of four: migrating layout, one block per SM (see MigDev)
     MigDev mig = {0, 0, 0, 0};
-    if (use_smem && !traj && mig_enabled()) {
+    if (M::MIGRATES && use_smem && !traj && mig_enabled()) {
         const int64_t warps = (n + 31) / 32;
         const int sms = sm_count();
         const int64_t per_sm = (warps + sms - 1) / sms;
@@ -1299,11 +1421,13 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     }
 #define PB200_XARG , mig
     if (mig.r) {
+        if constexpr (M::MIGRATES) {
         const int mblock = (mig.q4 + 2 + mig.r) * 32;
         const int64_t per_block = static_cast<int64_t>(mig.q4 + mig.r) * 32;
         const int64_t mgrid = (n + per_block - 1) / per_block;
         const size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
         PB200_LAUNCH((ode_kernel<M, true, false, true>), mgrid, mblock, mdyn);
+        }
     } else if (use_smem) {
         if (traj) PB200_LAUNCH((ode_kernel<M, true, true, false>), grid, block, dyn);
         else PB200_LAUNCH((ode_kernel<M, true, false, false>), grid, block, dyn);
@@ -1384,6 +1508,12 @@ int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
             return launch_model<LvModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
         case PB200_MODEL_SIR:           // three states: always one lane per vector
             return launch_model<SirModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+        case PB200_MODEL_GOODWIN:
+            return launch_model<GoodwinModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+        case PB200_MODEL_HES1:
+            return launch_model<Hes1Model>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+        case PB200_MODEL_REPRESSILATOR:
+            return launch_model<RepressilatorModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
     }
     pb200_set_error("model %d is not an ODE model", p->dev.model);
     return PB200_EUNSUPPORTED;

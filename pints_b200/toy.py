@@ -339,3 +339,118 @@ class SIRModel(_ToyODE):
         recovered = [0, 0, 0, 0, 5, 7, 8, 13, 13, 16, 17, 24, 30, 31, 33, 34,
                      36, 36, 36, 36, 37]
         return np.column_stack((infected, recovered))
+
+
+class GoodwinOscillatorModel(_ToyODE):
+    """Goodwin oscillator: ``x' = 1/(1 + z^10) - m1 x``, ``y' = k2 x - m2 y``,
+    ``z' = k3 y - m3 z``; parameters ``(k2, k3, m1, m2, m3)``, three outputs
+    (pints/toy/_goodwin_oscillator_model.py:14-115)."""
+
+    def __init__(self):
+        super().__init__()
+        self._y0 = [0.0054, 0.053, 1.93]
+
+    def set_initial_conditions(self, y0):
+        self._y0 = y0
+        self._sim_cache = None
+
+    def n_outputs(self):
+        return 3
+
+    def n_parameters(self):
+        return 5
+
+    def suggested_parameters(self):
+        return np.array([2, 4, 0.12, 0.08, 0.1])
+
+    def suggested_times(self):
+        return np.linspace(0, 100, 200)
+
+
+class Hes1Model(_ToyODE):
+    """HES1 Michaelis-Menten model: states ``(m, p1, p2)``, only ``m`` is
+    observed; parameters ``(P0, v, k1, h)``; ``m0`` and the fixed parameters
+    ``(p1_0, p2_0, k_deg)`` as in the reference
+    (pints/toy/_hes1_michaelis_menten.py:14-190)."""
+
+    def __init__(self, m0=None, fixed_parameters=None):
+        super().__init__()
+        self.set_fixed_parameters([5., 3., 0.03] if fixed_parameters is None
+                                  else fixed_parameters)
+        self.set_m0(2 if m0 is None else m0)
+
+    def m0(self):
+        return self._y0[0]
+
+    def fixed_parameters(self):
+        return [self._p0[0], self._p0[1], self._kdeg]
+
+    def set_m0(self, m0):
+        if m0 < 0:
+            raise ValueError('Initial condition cannot be negative.')
+        self._y0 = [m0, self._p0[0], self._p0[1]]
+        self._sim_cache = None
+
+    def set_fixed_parameters(self, k):
+        a, b, c = k
+        if a < 0 or b < 0 or c < 0:
+            raise ValueError('Implicit parameters cannot be negative.')
+        self._p0 = [a, b]
+        self._kdeg = c
+        self._sim_cache = None
+
+    def n_states(self):
+        return 3
+
+    def n_outputs(self):
+        return 1
+
+    def n_parameters(self):
+        return 4
+
+    def suggested_parameters(self):
+        return np.array([2.4, 0.025, 0.11, 6.9])
+
+    def suggested_times(self):
+        return np.arange(0, 270, 30)
+
+    def suggested_values(self):
+        return np.array([2, 1.20, 5.90, 4.58, 2.64, 5.38, 6.42, 5.60, 4.48])
+
+
+class RepressilatorModel(_ToyODE):
+    """Repressilator: three mRNA and three protein levels, the mRNA levels are
+    the outputs; parameters ``(alpha_0, alpha, beta, n)``; like ``SIRModel`` it
+    is integrated from ``times[0]`` (pints/toy/_repressilator_model.py:14-125).
+    """
+
+    def __init__(self, y0=None):
+        super().__init__()
+        if y0 is None:
+            self._y0 = np.array([0, 0, 0, 2, 1, 3])
+        else:
+            self._y0 = np.array(y0, dtype=float)
+            if len(self._y0) != 6:
+                raise ValueError('Initial value must have size 6.')
+            if np.any(self._y0 < 0):
+                raise ValueError('Initial states can not be negative.')
+
+    def n_states(self):
+        return 6
+
+    def n_outputs(self):
+        return 3
+
+    def n_parameters(self):
+        return 4
+
+    def simulate(self, parameters, times):
+        times = np.asarray(times, dtype=float).reshape(-1)
+        out, batch = self._simulate_device(parameters, times)
+        return out if batch else out[0]
+
+    def suggested_parameters(self):
+        return np.array([1, 1000, 5, 2])
+
+    def suggested_times(self):
+        return np.linspace(0, 40, 400)

@@ -287,6 +287,59 @@ def golden_constant():
 # sampler replays: every draw and decision of the reference, step by step
 # --------------------------------------------------------------------------
 
+def _golden_ode(name, model, times, true_x, sigma, spread, truth_one, seed):
+    """Trajectories and GaussianLogLikelihood scores of one more ODE toy
+    model, with tight-tolerance counterparts."""
+    rng = np.random.RandomState(seed)
+    clean = np.asarray(model.simulate(true_x, times))
+    noisy = clean + rng.normal(0, sigma, clean.shape)
+    multi = clean.ndim == 2
+    problem = (pints.MultiOutputProblem if multi
+               else pints.SingleOutputProblem)(model, times, noisy)
+    ll = pints.GaussianLogLikelihood(problem)
+    no = problem.n_outputs()
+    n = 48
+    xs = np.array(true_x, dtype=float) * (1 + spread * rng.randn(n, len(true_x)))
+    xg = np.hstack([xs, sigma * (1 + 0.1 * rng.rand(n, no))])
+    scores = np.array(pints.SequentialEvaluator(ll).evaluate(xg))
+    traj = np.array([model.simulate(x, times) for x in xs[:8]])
+    truth = np.array([truth_one(x) for x in xs])
+    truth_scores = np.array([
+        gauss_ll_from(t, noisy, xg[k, -no:]) for k, t in enumerate(truth)])
+    save(name, times=times, values=noisy, xs=xg, scores=scores, traj=traj,
+         truth=truth[:8], truth_scores=truth_scores)
+
+
+def golden_goodwin():
+    model = pints.toy.GoodwinOscillatorModel()
+    times = np.linspace(0, 100, 400)
+
+    def truth_one(x):
+        return odeint(model._rhs, model._y0, times, (x,), **TRUTH)
+    _golden_ode('goodwin', model, times, model.suggested_parameters(), 0.02,
+                0.02, truth_one, 31)
+
+
+def golden_hes1():
+    model = pints.toy.Hes1Model()
+    times = np.linspace(0, 270, 300)
+
+    def truth_one(x):
+        return odeint(model._rhs, model._y0, times, (x,), **TRUTH)[:, 0]
+    _golden_ode('hes1', model, times, model.suggested_parameters(), 0.2, 0.03,
+                truth_one, 32)
+
+
+def golden_repressilator():
+    model = pints.toy.RepressilatorModel()
+    times = np.linspace(0, 40, 400)
+
+    def truth_one(x):
+        return odeint(model._rhs, model._y0, times, tuple(x), **TRUTH)[:, :3]
+    _golden_ode('repressilator', model, times, [1, 1000, 5, 2], 2.0, 0.02,
+                truth_one, 33)
+
+
 def golden_error_measures():
     """MeanSquaredError / RootMeanSquaredError / NormalisedRootMeanSquaredError
     of the reference on the logistic, FHN and HH-IK problems."""
@@ -480,6 +533,9 @@ if __name__ == '__main__':
     golden_lv()
     golden_sir()
     golden_constant()
+    golden_goodwin()
+    golden_hes1()
+    golden_repressilator()
     golden_error_measures()
     golden_hbac()
     golden_haario()

@@ -286,6 +286,19 @@ def test_cuda_evaluator_is_a_pints_evaluator(pints_ref):
     with pytest.raises(TypeError):
         pb.CudaEvaluator(pints.toy.RosenbrockError())
     with pytest.raises(TypeError):
-        pb.CudaEvaluator(pints.GaussianLogLikelihood(pints.MultiOutputProblem(
-            pints.toy.GoodwinOscillatorModel(), g['times'],
-            np.zeros((1000, 3)))))
+        pb.CudaEvaluator(pints.GaussianLogLikelihood(pints.SingleOutputProblem(
+            pints.toy.SimpleHarmonicOscillatorModel(), g['times'],
+            np.zeros(1000))))
+    # ... while the further ODE toy models of the reference are on the path
+    spec = pb.describe(pints.GaussianLogLikelihood(pints.MultiOutputProblem(
+        pints.toy.GoodwinOscillatorModel(), g['times'], np.zeros((1000, 3)))))
+    assert spec.model == _lib.MODEL_GOODWIN and spec.n_parameters() == 8
+    assert spec.model_consts == [0.0054, 0.053, 1.93]
+    spec = pb.describe(pints.SumOfSquaresError(pints.SingleOutputProblem(
+        pints.toy.Hes1Model(), g['times'], np.zeros(1000))))
+    assert spec.model == _lib.MODEL_HES1
+    assert spec.model_consts == [2.0, 5.0, 3.0, 0.03]
+    spec = pb.describe(pints.SumOfSquaresError(pints.MultiOutputProblem(
+        pints.toy.RepressilatorModel(), g['times'], np.zeros((1000, 3)))))
+    assert spec.model == _lib.MODEL_REPRESSILATOR
+    assert spec.model_consts == [0, 0, 0, 2, 1, 3]

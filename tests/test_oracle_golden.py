@@ -425,3 +425,30 @@ def test_error_measures_golden():
     assert po.scores(s1, [[3.0]])[0] == 2.0
     with pytest.raises(ValueError):
         po.Spec('constant', times, values, 'rmse')
+
+
+@pytest.mark.parametrize('name', ['goodwin', 'hes1', 'repressilator'])
+def test_more_ode_models_golden(name):
+    """(f) row 4: Goodwin, Hes1 and Repressilator restated in the oracle are
+    bit-identical to the reference (same odeint call, same right-hand side)."""
+    g = load_golden(name)
+    s = po.Spec(name, g['times'], g['values'], 'gaussian')
+    assert np.array_equal(po.scores(s, g['xs'][:12]), g['scores'][:12])
+    no = s.n_outputs
+    for x, ref in zip(g['xs'][:3], g['traj']):
+        sim = s.trajectory(x[:-no])
+        assert np.array_equal(np.asarray(sim).reshape(ref.shape), ref)
+
+
+def test_more_ode_models_reference_unit_tests():
+    # pints/tests/test_toy_goodwin_oscillator_model.py: suggested run, shapes
+    t = np.linspace(0, 100, 200)
+    v = po.goodwin_simulate([2, 4, 0.12, 0.08, 0.1], t)
+    assert v.shape == (200, 3) and np.all(v[0] == po.GOODWIN_Y0)
+    # pints/tests/test_toy_hes1_michaelis_menten_model.py:27-32 values at the
+    # suggested times start from m0 = 2
+    v = po.hes1_simulate([2.4, 0.025, 0.11, 6.9], np.arange(0, 270, 30))
+    assert v.shape == (9,) and v[0] == 2
+    # pints/tests/test_toy_repressilator_model.py: starts at y0[:3]
+    v = po.repressilator_simulate([1, 1000, 5, 2], np.linspace(0, 40, 400))
+    assert v.shape == (400, 3) and np.all(v[0] == 0)
