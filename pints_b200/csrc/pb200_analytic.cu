@@ -27,10 +27,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---- per-vector model state (warp-uniform unless noted) -------------------
 struct LogisticEval {
+    static constexpr bool POINT_AUX = false;
     double r, k, c;
     bool zero;
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
-                                            double *, int) {
+                                            double *, int, bool) {
         r = x[0]; k = x[1];
         const double p0 = mc.c[0];
         zero = (p0 == 0.0) || (k < 0.0);
@@ -45,9 +46,10 @@ struct LogisticEval {
 };
 
 struct ConstantEval {
+    static constexpr bool POINT_AUX = false;
     double p[PB200_MAX_OUTPUTS];
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &,
-                                            double *, int no) {
+                                            double *, int no, bool) {
         for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
             p[o] = (o < no) ? __dmul_rn(x[o], static_cast<double>(o + 1)) : 0.0;
     }
@@ -61,12 +63,22 @@ struct ConstantEval {
 // over the whole segment; one lane then chains the gate value across events
 // (n_next = inf - (inf - n_start) * decay).  Records go to a per-warp table in
 // shared memory: [inf, n_start, t_start, -1/tau].
+//
+// Which segment a time point lies in, and how far into it, depends on the
+// protocol only, not on the parameters: when the series is staged in shared
+// memory each block works that out ONCE (prepare_points: the row's time is
+// replaced by t - t_start and the segment index goes to a byte array), so the
+// per-point work of every vector is one multiply, one exp and the polynomial
+// instead of a binary search over the events and an IEEE division as well.
 struct HhEval {
+    static constexpr bool POINT_AUX = true;
     double g_max, e_k;
     int n_ev;
     const double *events;     // in the kernel parameter (constant bank)
+    // record of segment s: [inf, n_start, t_start, tau], or for the staged
+    // (fast) path [inf, inf - n_start, -1/tau, v - E_k]
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
-                                            double *table, int) {
+                                            double *table, int, bool fast) {
         const int lane = threadIdx.x & 31;
         const double n0 = mc.c[0];
         g_max = mc.c[1]; e_k = mc.c[2];
@@ -93,8 +105,8 @@ struct HhEval {
                 decay = exp(__ddiv_rn(-__dsub_rn(events[s], t_start), tau));
             table[s * SEG_STRIDE + 0] = inf;
             table[s * SEG_STRIDE + 1] = decay;      // replaced by n_start below
-            table[s * SEG_STRIDE + 2] = t_start;
-            table[s * SEG_STRIDE + 3] = tau;
+            table[s * SEG_STRIDE + 2] = fast ? -1.0 / tau : t_start;
+            table[s * SEG_STRIDE + 3] = fast ? __dsub_rn(v, e_k) : tau;
         }
         __syncwarp();
         if (lane == 0) {
@@ -102,7 +114,7 @@ struct HhEval {
             for (int s = 0; s <= n_ev; ++s) {
                 const double inf = table[s * SEG_STRIDE + 0];
                 const double decay = table[s * SEG_STRIDE + 1];
-                table[s * SEG_STRIDE + 1] = n_start;
+                table[s * SEG_STRIDE + 1] = fast ? __dsub_rn(inf, n_start) : n_start;
                 n_start = __dsub_rn(inf, __dmul_rn(__dsub_rn(inf, n_start), decay));
             }
         }
@@ -128,38 +140,91 @@ struct HhEval {
         const double n4 = __dmul_rn(n2, n2);
         return __dmul_rn(__dmul_rn(g_max, n4), __dsub_rn(volt, e_k));
     }
+    // once per block: segment index and time into the segment of every point
+    __device__ static void prepare_points(double *series, int nt, int row,
+                                          const ModelConsts &mc, uint8_t *seg) {
+        const int n_ev = static_cast<int>(mc.c[4]);
+        const double *events = &mc.c[5];
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+            const double t = series[j * row];
+            int lo = 0, hi = n_ev;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (events[mid] <= t) lo = mid + 1; else hi = mid;
+            }
+            seg[j] = static_cast<uint8_t>(lo);
+            series[j * row] = __dsub_rn(t, lo == 0 ? 0.0 : events[lo - 1]);
+        }
+    }
+    // n = inf - (inf - n_start) exp(-(t - t_start) / tau), with the division by
+    // tau as a multiplication by -1/tau (argument error <= 2 ulp, i.e. a
+    // relative 1e-14 on the exponential at most)
+    __device__ __forceinline__ double value_at(double dt, int s, const double *table) const {
+        const double *rec = table + s * SEG_STRIDE;
+        const double e = exp(__dmul_rn(dt, rec[2]));
+        const double nn = __dsub_rn(rec[0], __dmul_rn(rec[1], e));
+        const double n2 = __dmul_rn(nn, nn);
+        const double n4 = __dmul_rn(n2, n2);
+        return __dmul_rn(__dmul_rn(g_max, n4), rec[3]);
+    }
     double mc_vhold;
     const double *mc_volts;
 };
 
-template <class E, bool SMEM, bool TRAJ>
-__global__ void __launch_bounds__(WARPS * 32)
+// dispatch on the per-point auxiliary data (HH-IK with a staged series)
+template <class E>
+__device__ __forceinline__ void point_aux(double *series, int nt, int row,
+                                          const ModelConsts &mc, uint8_t *seg) {
+    if constexpr (E::POINT_AUX) E::prepare_points(series, nt, row, mc, seg);
+}
+template <class E, bool SMEM>
+__device__ __forceinline__ double point_value(const E &ev, double t, int o,
+                                              const double *table, const uint8_t *seg,
+                                              int j) {
+    if constexpr (E::POINT_AUX && SMEM) return ev.value_at(t, seg[j], table);
+    else return ev.value(t, o, table);
+}
+
+// Dynamic shared memory: [staged series][segment index per point (HH-IK)]
+// [one segment table per warp, `table_doubles` each]; the block size is chosen
+// at launch (8 warps for short series, 32 when the series fills most of an SM's
+// shared memory and only one block fits).
+template <class E, bool SMEM, bool TRAJ, bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : 256)
 analytic_kernel(const __grid_constant__ ProblemDev P,
                 const __grid_constant__ ModelConsts mc,
                 const double *__restrict__ params, int64_t n, int64_t ld,
-                double *__restrict__ scores, double *__restrict__ traj) {
+                double *__restrict__ scores, double *__restrict__ traj,
+                uint32_t table_off, uint32_t table_doubles) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ double seg_table[WARPS][(PB200_MAX_EVENTS + 1) * SEG_STRIDE];
+    const int warps = blockDim.x >> 5;
 
     const int row = P.row, no = P.n_outputs, nt = P.n_times;
     const double *series;
+    uint8_t *seg_of = nullptr;
     if (SMEM) {
         const uint32_t bytes = static_cast<uint32_t>(
             ((static_cast<int64_t>(nt) + PB200_SENTINEL_ROWS) * row * 8 + 15) & ~15ll);
         stage_series(smem, P.series, bytes, &bar);
         series = smem;
+        if (E::POINT_AUX) {
+            seg_of = reinterpret_cast<uint8_t *>(smem) + bytes;
+            point_aux<E>(smem, nt, row, mc, seg_of);
+            __syncthreads();
+        }
     } else {
         series = P.series;
     }
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    double *table = seg_table[warp];
-    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * WARPS;
+    double *table = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + table_off) +
+                    static_cast<size_t>(warp) * table_doubles;
+    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * warps;
     const int n_read = TRAJ ? P.n_model_params : P.n_params;
 
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * WARPS + warp; i < n;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * warps + warp; i < n;
          i += warps_total) {
         double x[PB200_MAX_PARAMS];
 #pragma unroll
@@ -174,7 +239,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
             }
         }
         E ev;
-        ev.prepare(x, mc, table, no);
+        ev.prepare(x, mc, table, no, SMEM && E::POINT_AUX);
 
         double ss[PB200_MAX_OUTPUTS];
 #pragma unroll
@@ -186,7 +251,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
 #pragma unroll
             for (int o = 0; o < PB200_MAX_OUTPUTS; ++o) {
                 if (o < no) {
-                    const double v = ev.value(t, o, table);
+                    const double v = point_value<E, SMEM>(ev, t, o, table, seg_of, j);
                     if (TRAJ) my_traj[j * no + o] = v;
                     const double r = __dsub_rn(series[j * row + 1 + o], v);
                     ss[o] = __dadd_rn(ss[o], __dmul_rn(r, r));
@@ -207,19 +272,27 @@ template <class E>
 int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
                 int64_t ld, double *d_scores, double *d_traj, cudaStream_t st) {
     const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * p->dev.row * 8 + 15) & ~15ll;
+    const size_t aux_bytes = E::POINT_AUX ? (static_cast<size_t>(p->dev.n_times) + 15) & ~size_t(15) : 0;
+    // per-warp segment table (HH-IK only): n_events + 1 records
+    const uint32_t table_doubles = E::POINT_AUX
+        ? static_cast<uint32_t>((static_cast<int>(p->mc.c[4]) + 1) * SEG_STRIDE) : 0;
     const bool use_smem = bytes <= 100 * 1024;
     const bool traj = d_traj != nullptr;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t grid = (n + WARPS - 1) / WARPS;
-    const int64_t cap = static_cast<int64_t>(sms) * 4;   // persistent: 4 blocks/SM
+    // a long staged series leaves room for one block per SM: make it a big one
+    const size_t staged = use_smem ? static_cast<size_t>(bytes) + aux_bytes : 0;
+    const int warps = staged > 48 * 1024 ? 32 : 8;
+    const int per_sm = staged > 48 * 1024 ? 1 : 4;
+    const size_t dyn = staged + static_cast<size_t>(warps) * table_doubles * 8;
+    int64_t grid = (n + warps - 1) / warps;
+    const int64_t cap = static_cast<int64_t>(sms) * per_sm;      // persistent grid
     if (grid > cap) grid = cap;
     if (grid <= 0) return PB200_OK;
-#define PB200_LAUNCH(SM, TR)                                                             \
+#define PB200_LAUNCH(SM, TR, BG)                                                         \
     do {                                                                                 \
-        auto kern = analytic_kernel<E, SM, TR>;                                          \
-        size_t dyn = SM ? static_cast<size_t>(bytes) : 0;                                \
+        auto kern = analytic_kernel<E, SM, TR, BG>;                                      \
         if (dyn > 32 * 1024) {                                                           \
             int rc = pb200_check_cuda(                                                   \
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -227,13 +300,16 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
                 "cudaFuncSetAttribute");                                                 \
             if (rc) return rc;                                                           \
         }                                                                                \
-        kern<<<static_cast<unsigned>(grid), WARPS * 32, dyn, st>>>(                      \
-            p->dev, p->mc, d_params, n, ld, d_scores, d_traj);                           \
+        kern<<<static_cast<unsigned>(grid), warps * 32, dyn, st>>>(                      \
+            p->dev, p->mc, d_params, n, ld, d_scores, d_traj,                            \
+            static_cast<uint32_t>(staged), table_doubles);                               \
     } while (0)
-    if (use_smem) {
-        if (traj) PB200_LAUNCH(true, true); else PB200_LAUNCH(true, false);
+    if (warps == 32) {                       // implies use_smem
+        if (traj) PB200_LAUNCH(true, true, true); else PB200_LAUNCH(true, false, true);
+    } else if (use_smem) {
+        if (traj) PB200_LAUNCH(true, true, false); else PB200_LAUNCH(true, false, false);
     } else {
-        if (traj) PB200_LAUNCH(false, true); else PB200_LAUNCH(false, false);
+        if (traj) PB200_LAUNCH(false, true, false); else PB200_LAUNCH(false, false, false);
     }
 #undef PB200_LAUNCH
     return pb200_check_cuda(cudaGetLastError(), "analytic_kernel launch");
