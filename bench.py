@@ -265,7 +265,10 @@ def run_ours(args):
     xs = np.ascontiguousarray(xs_all[rank * pop:(rank + 1) * pop])
     d_x = torch.from_numpy(xs).to(device)
     d_scores = torch.empty(pop, dtype=torch.float64, device=device)
-    d_all = torch.empty(pop * world, dtype=torch.float64, device=device)
+    exchange = None
+    if world > 1:
+        from pints_b200._dist import ScoreExchange
+        exchange = ScoreExchange(pop, device, fused=not args.nccl_allgather)
     d_steps = dp.new_steps(pop)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
@@ -275,9 +278,13 @@ def run_ours(args):
         torch.cuda.synchronize(device)
 
     def step(steps_buf=None):
-        dp.eval(d_x, out=d_scores, steps=steps_buf)
+        # N = 1: sort + fused solve.  N > 1: the same, and the exchange step
+        # (every rank ends up with all scores): fused into the kernel over
+        # NVLink peer memory + a device barrier, or solve + NCCL all-gather
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_scores)
+            exchange.run(dp, d_x, steps=steps_buf)
+        else:
+            dp.eval(d_x, out=d_scores, steps=steps_buf)
 
     # parity spot-check against the CPU oracle numbers produced above
     dp.eval(d_x, out=d_scores, steps=d_steps)
@@ -311,10 +318,8 @@ def run_ours(args):
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         e0[i].record()
-        dp.eval(d_x, out=d_scores)
+        step()
         k0[i].record()
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_scores)
         e1[i].record()
     barrier()
     wall = time.perf_counter() - wall0
@@ -377,7 +382,11 @@ def run_ours(args):
                        'solver': 'DP5(4) rtol=atol=1.49012e-8',
                        'mean_rk_steps': mean_steps,
                        'l2': 'flushed between steps (256 MiB fill)',
-                       'parallelism': 'dp%d' % world},
+                       'parallelism': 'dp%d' % world,
+                       'exchange': 'none (one GPU)' if world == 1 else (
+                           'fused: kernel stores scores into every rank\'s '
+                           'array over NVLink (symmetric memory) + barrier'
+                           if exchange.fused else 'NCCL all-gather')},
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops,
                 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
@@ -422,6 +431,9 @@ def main():
                     help='parameter vectors per GPU per step')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--nccl-allgather', action='store_true',
+                    help='N > 1: exchange the scores with an NCCL all-gather '
+                         'after the kernel instead of the fused peer stores')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

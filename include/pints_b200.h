@@ -71,6 +71,7 @@ extern "C" {
 #define PB200_MAX_OUTPUTS   8
 #define PB200_MAX_PARAMS    16      /* model parameters + sigma parameters  */
 #define PB200_MAX_EVENTS    64      /* HH-IK protocol events                */
+#define PB200_MAX_PEERS     16      /* GPUs of one job (pb200_eval_scatter) */
 #define PB200_SENTINEL_ROWS 8       /* +inf rows that end the packed series */
 
 typedef struct pb200_problem pb200_problem;
@@ -177,6 +178,24 @@ int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
                       int64_t ld, double *d_scores, int32_t *d_steps,
                       const pb200_solver_opts *opts, void *d_sort_ws,
                       int64_t sort_ws_bytes, void *stream);
+
+/*
+ * Multi-GPU variant with the exchange step fused in (the
+ * one collective of the path is the all-gather of the scores, which replaces
+ * the result queue of ParallelEvaluator, pints/_evaluation.py:330-372).
+ * Rank r scores its block of n rows and the kernel stores every score
+ * directly into the gathered array of EVERY rank at row `offset + i`:
+ * peer_scores[q] is the device address, valid in this process, of rank q's
+ * gathered array (its own allocation for q = r, a peer mapping over NVLink
+ * otherwise -- e.g. torch symmetric memory).  No separate all-gather is
+ * needed afterwards, only a barrier before the arrays are read.
+ * d_sort_ws as in pb200_eval_sorted (NULL = no sorting).
+ */
+int pb200_eval_scatter(const pb200_problem *p, const double *d_params, int64_t n,
+                       int64_t ld, int32_t *d_steps,
+                       const pb200_solver_opts *opts, void *d_sort_ws,
+                       int64_t sort_ws_bytes, void *const *peer_scores,
+                       int32_t n_peers, int64_t offset, void *stream);
 
 /*
  * The same through HOST buffers, for callers that hold their positions in host

@@ -146,6 +146,27 @@ class DeviceProblem(object):
                 ws, ws_bytes, ctypes.c_void_p(stream)))
         return out
 
+    def eval_scatter(self, d_params, peer_ptrs, offset, steps=None):
+        """Scores of the rows of ``d_params`` stored straight into the
+        gathered score arrays of all ranks (``peer_ptrs``: device addresses of
+        every rank's array as seen from this process, e.g. the ``buffer_ptrs``
+        of a torch symmetric-memory handle) at rows ``offset + i``:
+        ``pb200_eval_scatter``.  Asynchronous on the current stream; the
+        caller puts a barrier between this and any read of the arrays."""
+        d_params = self._check_params(d_params, self.n_parameters)
+        n = d_params.shape[0]
+        ptrs = (ctypes.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            ws, ws_bytes = None, 0
+            if self.wants_sort(n):
+                t = self.sort_workspace(n, stream)
+                ws, ws_bytes = ctypes.c_void_p(t.data_ptr()), t.numel()
+            _lib.check(self._lib.pb200_eval_scatter(
+                self._handle, _ptr(d_params), n, d_params.stride(0),
+                _ptr(steps), ctypes.byref(self.opts), ws, ws_bytes, ptrs,
+                len(peer_ptrs), int(offset), ctypes.c_void_p(stream)))
+
     def simulate(self, d_params, out=None, steps=None):
         """Trajectories ``(n, n_times, n_outputs)`` of the rows of
         ``d_params`` (only the model parameters are read)."""

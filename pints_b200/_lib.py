@@ -63,6 +63,9 @@ SIGNATURES = {
     'pb200_sort_workspace_bytes': (c_int64, [c_int64]),
     'pb200_eval_sorted': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                                     POINTER(SolverOpts), _P, c_int64, _P]),
+    'pb200_eval_scatter': (c_int32, [_P, _P, c_int64, c_int64, _P,
+                                     POINTER(SolverOpts), _P, c_int64,
+                                     POINTER(c_void_p), c_int32, c_int64, _P]),
     'pb200_eval_host': (c_int32, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P,
                                   _P, c_int64, POINTER(SolverOpts), _P]),
     'pb200_copy_async': (c_int32, [_P, _P, c_int64, c_int32, _P]),

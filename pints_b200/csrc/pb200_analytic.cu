@@ -195,7 +195,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                 const __grid_constant__ ModelConsts mc,
                 const double *__restrict__ params, int64_t n, int64_t ld,
                 double *__restrict__ scores, double *__restrict__ traj,
-                uint32_t table_off, uint32_t table_doubles) {
+                uint32_t table_off, uint32_t table_doubles, const ScatterDev sc) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     const int warps = blockDim.x >> 5;
@@ -234,7 +234,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
         if (!TRAJ) {
             double early;
             if (objective_precheck(P, x, &early)) {     // warp-uniform
-                if (lane == 0) scores[i] = early;
+                if (lane == 0) put_score(sc, scores, i, early);
                 continue;
             }
         }
@@ -262,7 +262,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
 #pragma unroll
             for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
                 if (o < no) ss[o] = warp_sum(ss[o]);
-            if (lane == 0) scores[i] = objective_finish(P, ss, x);
+            if (lane == 0) put_score(sc, scores, i, objective_finish(P, ss, x));
         }
         __syncwarp();
     }
@@ -270,7 +270,8 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
 
 template <class E>
 int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
-                int64_t ld, double *d_scores, double *d_traj, cudaStream_t st) {
+                int64_t ld, double *d_scores, double *d_traj, const ScatterDev &sc,
+                cudaStream_t st) {
     const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * p->dev.row * 8 + 15) & ~15ll;
     const size_t aux_bytes = E::POINT_AUX ? (static_cast<size_t>(p->dev.n_times) + 15) & ~size_t(15) : 0;
     // per-warp segment table (HH-IK only): n_events + 1 records
@@ -302,7 +303,7 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
         }                                                                                \
         kern<<<static_cast<unsigned>(grid), warps * 32, dyn, st>>>(                      \
             p->dev, p->mc, d_params, n, ld, d_scores, d_traj,                            \
-            static_cast<uint32_t>(staged), table_doubles);                               \
+            static_cast<uint32_t>(staged), table_doubles, sc);                           \
     } while (0)
     if (warps == 32) {                       // implies use_smem
         if (traj) PB200_LAUNCH(true, true, true); else PB200_LAUNCH(true, false, true);
@@ -360,14 +361,14 @@ score_traj_kernel(const __grid_constant__ ProblemDev P, const double *__restrict
 
 int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
                     int64_t ld, double *d_scores, double *d_traj,
-                    cudaStream_t st) {
+                    const ScatterDev &sc, cudaStream_t st) {
     switch (p->dev.model) {
         case PB200_MODEL_LOGISTIC:
-            return launch_eval<LogisticEval>(p, d_params, n, ld, d_scores, d_traj, st);
+            return launch_eval<LogisticEval>(p, d_params, n, ld, d_scores, d_traj, sc, st);
         case PB200_MODEL_HH_IK:
-            return launch_eval<HhEval>(p, d_params, n, ld, d_scores, d_traj, st);
+            return launch_eval<HhEval>(p, d_params, n, ld, d_scores, d_traj, sc, st);
         case PB200_MODEL_CONSTANT:
-            return launch_eval<ConstantEval>(p, d_params, n, ld, d_scores, d_traj, st);
+            return launch_eval<ConstantEval>(p, d_params, n, ld, d_scores, d_traj, sc, st);
     }
     pb200_set_error("model %d is not a closed-form model", p->dev.model);
     return PB200_EUNSUPPORTED;

@@ -194,10 +194,13 @@ int32_t pb200_problem_n_parameters(const pb200_problem *p) {
 
 int64_t pb200_sort_workspace_bytes(int64_t n) { return ode_sort_workspace_bytes(n); }
 
-int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
-                      double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
-                      void *d_sort_ws, int64_t sort_ws_bytes, void *stream) {
-    int rc = check_batch(p, d_params, n, ld, d_scores, "pb200_eval");
+namespace {
+int eval_impl(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+              double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
+              void *d_sort_ws, int64_t sort_ws_bytes, const ScatterDev &sc, void *stream,
+              const char *who) {
+    int rc = check_batch(p, d_params, n, ld, sc.n ? static_cast<const void *>(sc.dst[0]) : d_scores,
+                         who);
     if (rc || n == 0) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kModels[p->dev.model].ode) {
@@ -206,22 +209,54 @@ int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
         if (d_sort_ws) {
             if (sort_ws_bytes < ode_sort_workspace_bytes(n) ||
                 (reinterpret_cast<uintptr_t>(d_sort_ws) & 15) != 0) {
-                pb200_set_error("pb200_eval_sorted: workspace of %lld bytes (16-byte aligned) "
-                                "needed, got %lld", (long long)ode_sort_workspace_bytes(n),
+                pb200_set_error("%s: workspace of %lld bytes (16-byte aligned) "
+                                "needed, got %lld", who, (long long)ode_sort_workspace_bytes(n),
                                 (long long)sort_ws_bytes);
                 return PB200_EINVAL;
             }
             if (n > 2147483647ll) d_sort_ws = nullptr;       // int32 permutation
         }
         return launch_ode(p, d_params, n, ld, d_scores, nullptr, d_steps, s, block, lanes,
-                          d_sort_ws, st);
+                          d_sort_ws, sc, st);
     }
     if (d_steps) {
         rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),
                               "cudaMemsetAsync(d_steps)");
         if (rc) return rc;
     }
-    return launch_analytic(p, d_params, n, ld, d_scores, nullptr, st);
+    return launch_analytic(p, d_params, n, ld, d_scores, nullptr, sc, st);
+}
+const ScatterDev kNoScatter = {};
+}  // namespace
+
+int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+                      double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
+                      void *d_sort_ws, int64_t sort_ws_bytes, void *stream) {
+    return eval_impl(p, d_params, n, ld, d_scores, d_steps, opts, d_sort_ws, sort_ws_bytes,
+                     kNoScatter, stream, "pb200_eval");
+}
+
+int pb200_eval_scatter(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+                       int32_t *d_steps, const pb200_solver_opts *opts, void *d_sort_ws,
+                       int64_t sort_ws_bytes, void *const *peer_scores, int32_t n_peers,
+                       int64_t offset, void *stream) {
+    if (!peer_scores || n_peers < 1 || n_peers > PB200_MAX_PEERS || offset < 0) {
+        pb200_set_error("pb200_eval_scatter: 1..%d peer arrays and a non-negative offset needed",
+                        PB200_MAX_PEERS);
+        return PB200_EINVAL;
+    }
+    ScatterDev sc = {};
+    sc.n = n_peers;
+    sc.offset = offset;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_scores[r]) {
+            pb200_set_error("pb200_eval_scatter: peer array %d is NULL", r);
+            return PB200_EINVAL;
+        }
+        sc.dst[r] = static_cast<double *>(peer_scores[r]);
+    }
+    return eval_impl(p, d_params, n, ld, nullptr, d_steps, opts, d_sort_ws, sort_ws_bytes, sc,
+                     stream, "pb200_eval_scatter");
 }
 
 int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
@@ -289,14 +324,15 @@ int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, in
     if (kModels[p->dev.model].ode) {
         int block, lanes;
         SolverDev s = resolve_opts(opts, &block, &lanes);
-        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, lanes, nullptr, st);
+        return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, lanes, nullptr,
+                          ScatterDev{}, st);
     }
     if (d_steps) {
         rc = pb200_check_cuda(cudaMemsetAsync(d_steps, 0, n * sizeof(int32_t), st),
                               "cudaMemsetAsync(d_steps)");
         if (rc) return rc;
     }
-    return launch_analytic(p, d_params, n, ld, nullptr, d_traj, st);
+    return launch_analytic(p, d_params, n, ld, nullptr, d_traj, ScatterDev{}, st);
 }
 
 int pb200_score_trajectories(const pb200_problem *p, const double *d_traj,

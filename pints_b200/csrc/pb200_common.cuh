@@ -44,6 +44,27 @@ struct pb200_problem {
     int64_t series_bytes;         // bytes staged into shared memory
 };
 
+// Where a score goes.  n = 0: the caller's d_scores[i].  n > 0: straight into
+// the gathered score arrays of all ranks of a multi-GPU job (this GPU's own
+// and its peers', mapped over NVLink), at row offset + i of each -- the
+// all-gather of the scores happens inside the kernel, store by store, while
+// other vectors are still being integrated.
+struct ScatterDev {
+    double *dst[PB200_MAX_PEERS];
+    int32_t n;
+    int32_t pad;
+    int64_t offset;
+};
+
+__device__ __forceinline__ void put_score(const ScatterDev &sc, double *scores,
+                                          int64_t i, double v) {
+    if (sc.n == 0) {
+        scores[i] = v;
+    } else {
+        for (int r = 0; r < sc.n; ++r) sc.dst[r][sc.offset + i] = v;
+    }
+}
+
 struct SolverDev {
     double rtol, atol, h0;
     double half_rtol;             // 0.5 * rtol, used every step
@@ -184,11 +205,11 @@ __device__ __forceinline__ bool objective_precheck(const ProblemDev &P,
 int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
                int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
                const SolverDev &s, int block, int lanes, void *sort_ws,
-               cudaStream_t st);
+               const ScatterDev &sc, cudaStream_t st);
 int64_t ode_sort_workspace_bytes(int64_t n);
 int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
                     int64_t ld, double *d_scores, double *d_traj,
-                    cudaStream_t st);
+                    const ScatterDev &sc, cudaStream_t st);
 int launch_score_traj(const pb200_problem *p, const double *d_traj,
                       const double *d_params, int64_t n, int64_t ld,
                       double *d_scores, cudaStream_t st);

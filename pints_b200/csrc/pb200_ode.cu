@@ -499,7 +499,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
            const double *__restrict__ params, int64_t n, int64_t ld,
            double *__restrict__ scores, double *__restrict__ traj,
            int32_t *__restrict__ steps_out, const int32_t *__restrict__ perm,
-           const SolverDev S, const MigDev mig) {
+           const SolverDev S, const MigDev mig, const ScatterDev sc) {
     constexpr int NS = M::NS, NO = M::NO, OUT0 = M::OUT0;
     constexpr uint32_t ROWB = (1 + NO) * 8;          // bytes per series row
     constexpr uint32_t FULL = 0xffffffffu;
@@ -559,7 +559,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         double early;
         if (objective_precheck(P, x, &early)) {
             if (live && !is_receiver) {
-                scores[i] = early;
+                put_score(sc, scores, i, early);
                 if (steps_out) steps_out[i] = 0;
             }
             idle = true;
@@ -869,7 +869,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
             for (int64_t q = first; q < total; ++q) my_traj[q] = NAN;
         }
     } else {
-        scores[i] = failed ? NAN : objective_finish(P, ss, x);
+        put_score(sc, scores, i, failed ? NAN : objective_finish(P, ss, x));
     }
 }
 
@@ -940,7 +940,7 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
                 const double *__restrict__ params, int64_t n, int64_t ld,
                 double *__restrict__ scores, double *__restrict__ traj,
                 int32_t *__restrict__ steps_out, const int32_t *__restrict__ perm,
-                const SolverDev S) {
+                const SolverDev S, const ScatterDev sc) {
     constexpr int NO = 2, NC = L::NC;
     constexpr uint32_t ROWB = (1 + NO) * 8;
     constexpr uint32_t FULL = 0xffffffffu;
@@ -976,7 +976,7 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
         double early;
         if (objective_precheck(P, x, &early)) {
             if (live && s == 0) {
-                scores[i] = early;
+                put_score(sc, scores, i, early);
                 if (steps_out) steps_out[i] = 0;
             }
             idle = true;
@@ -1148,7 +1148,7 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
     } else if (s == 0) {
         if (steps_out) steps_out[i] = attempts;
         const double both[2] = {ss, ss_other};
-        scores[i] = failed ? NAN : objective_finish(P, both, x);
+        put_score(sc, scores, i, failed ? NAN : objective_finish(P, both, x));
     }
 }
 
@@ -1378,7 +1378,7 @@ template <class M>
 int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
                  int64_t ld, double *d_scores, double *d_traj,
                  int32_t *d_steps, const SolverDev &s, int block,
-                 void *sort_ws, cudaStream_t st) {
+                 void *sort_ws, const ScatterDev &sc, cudaStream_t st) {
     const int32_t *perm = nullptr;
     if (sort_ws) {
         int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st);
@@ -1419,7 +1419,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
             mig.buf_off = static_cast<uint32_t>(bytes);
         }
     }
-#define PB200_XARG , mig
+#define PB200_XARG , mig, sc
     if (mig.r) {
         if constexpr (M::MIGRATES) {
         const int mblock = (mig.q4 + 2 + mig.r) * 32;
@@ -1444,7 +1444,7 @@ template <class L, class M>
 int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
                 int64_t ld, double *d_scores, double *d_traj,
                 int32_t *d_steps, const SolverDev &s, int block,
-                void *sort_ws, cudaStream_t st) {
+                void *sort_ws, const ScatterDev &sc, cudaStream_t st) {
     const int32_t *perm = nullptr;
     if (sort_ws) {
         int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st);
@@ -1469,7 +1469,7 @@ int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
         return PB200_EINVAL;
     }
     const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
-#define PB200_XARG
+#define PB200_XARG , sc
     if (use_smem) {
         if (traj) PB200_LAUNCH((ode_pair_kernel<L, true, true>), grid, block, dyn);
         else PB200_LAUNCH((ode_pair_kernel<L, true, false>), grid, block, dyn);
@@ -1491,7 +1491,7 @@ int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
 int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
                int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
                const SolverDev &s, int block, int lanes, void *sort_ws,
-               cudaStream_t st) {
+               const ScatterDev &sc, cudaStream_t st) {
     if (lanes <= 0) lanes = PB200_DEFAULT_LANES;
     if (lanes != 1 && lanes != 2) {
         pb200_set_error("lanes per vector must be 0 (automatic), 1 or 2, got %d", lanes);
@@ -1500,20 +1500,20 @@ int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
     switch (p->dev.model) {
         case PB200_MODEL_FHN:
             if (lanes == 2)
-                return launch_pair<FhnLane, FhnModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
-            return launch_model<FhnModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+                return launch_pair<FhnLane, FhnModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
+            return launch_model<FhnModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_LOTKA_VOLTERRA:
             if (lanes == 2)
-                return launch_pair<LvLane, LvModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
-            return launch_model<LvModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+                return launch_pair<LvLane, LvModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
+            return launch_model<LvModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_SIR:           // three states: always one lane per vector
-            return launch_model<SirModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+            return launch_model<SirModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_GOODWIN:
-            return launch_model<GoodwinModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+            return launch_model<GoodwinModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_HES1:
-            return launch_model<Hes1Model>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+            return launch_model<Hes1Model>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_REPRESSILATOR:
-            return launch_model<RepressilatorModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, st);
+            return launch_model<RepressilatorModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
     }
     pb200_set_error("model %d is not an ODE model", p->dev.model);
     return PB200_EUNSUPPORTED;
