@@ -145,6 +145,24 @@ int pb200_problem_create(int32_t model, int32_t objective,
                          pb200_problem **out);
 void pb200_problem_destroy(pb200_problem *p);
 
+/*
+ * ComposedLogPrior (pints/_log_priors.py:170-219) inside LogPosterior: the box
+ * given to pb200_problem_create holds the supports of all sub-priors (+-inf
+ * where a sub-prior is unbounded) and decides "-inf without simulating"; the
+ * value inside is the sum of n_terms terms added in the sub-priors' order, as
+ * the reference adds them:
+ *   kind 0  constant consts[3k]: a UniformLogPrior's -log(prod(range))
+ *           (pints/_log_priors.py:1315-1320)
+ *   kind 1  GaussianLogPrior on parameter index[k]:
+ *           consts[3k] - consts[3k+1] * (x - consts[3k+2])^2  with
+ *           offset = log(1/sqrt(2 pi sd^2)), factor = 1/(2 sd^2), mean
+ *           (pints/_log_priors.py:463-468)
+ * n_terms = 0 restores the single constant of pb200_problem_create.
+ */
+int pb200_problem_set_prior_terms(pb200_problem *p, int32_t n_terms,
+                                  const int32_t *kinds, const int32_t *index,
+                                  const double *consts);
+
 /* Row length of a parameter vector for this problem
  * (model parameters + n_outputs sigmas for GAUSSIAN). */
 int32_t pb200_problem_n_parameters(const pb200_problem *p);

@@ -406,6 +406,29 @@ def gaussian_ll(sigma, sim, values, n_times):
                   - np.sum(error**2, axis=0) / (2 * sigma**2))
 
 
+def composed_log_prior(parts, x):
+    """``ComposedLogPrior.__call__`` (pints/_log_priors.py:212-219) over
+    ``UniformLogPrior`` (:1315-1320, with ``RectangularBoundaries.check``,
+    pints/_boundaries.py:151-157) and ``GaussianLogPrior`` (:463-468)."""
+    output = 0
+    lo = hi = 0
+    for part in parts:
+        if part[0] == 'uniform':
+            lower, upper = np.asarray(part[1], float), np.asarray(part[2], float)
+            lo, hi = hi, hi + len(lower)
+            xx = x[lo:hi]
+            inside = not (np.any(xx < lower) or np.any(xx >= upper))
+            value = -np.log(np.prod(upper - lower))
+            output += value if inside else -np.inf
+        else:
+            mean, sd = float(part[1]), float(part[2])
+            lo, hi = hi, hi + 1
+            offset = np.log(1 / np.sqrt(2 * np.pi * sd ** 2))
+            factor = 1 / (2 * sd ** 2)
+            output += offset - factor * (x[lo:hi][0] - mean)**2
+    return output
+
+
 class Spec(object):
     """One (model, series, objective) problem, described with plain data.
 
@@ -424,7 +447,7 @@ class Spec(object):
     """
 
     def __init__(self, model, times, values, objective, obj=None, consts=None,
-                 sign=1.0, prior_box=None, tol=None):
+                 sign=1.0, prior_box=None, tol=None, prior_parts=None):
         self.model = model
         self.consts = dict(consts or {})
         self.times = as_vector(times)
@@ -436,6 +459,8 @@ class Spec(object):
         self.objective = objective
         self.sign = sign
         self.prior_box = prior_box
+        # ComposedLogPrior: [('uniform', lower, upper) | ('gaussian', mean, sd)]
+        self.prior_parts = prior_parts
         self.tol = dict(tol or {})
         if objective in ('sse', 'mse'):
             w = [1] * self.n_outputs if obj is None else obj
@@ -468,6 +493,11 @@ class Spec(object):
     def score(self, x, **tol):
         """f(x) exactly as the reference object graph would return it."""
         x = np.asarray(x, dtype=float)
+        if self.prior_parts is not None:
+            log_prior = composed_log_prior(self.prior_parts, x)
+            # LogPosterior.__call__ (pints/_log_pdfs.py:207-212)
+            if log_prior == -np.inf:
+                return self.sign * -np.inf
         if self.prior_box is not None:
             lower, upper = self.prior_box
             # RectangularBoundaries.check: two negative tests, so a NaN
@@ -495,7 +525,7 @@ class Spec(object):
             else:
                 f = gaussian_known_sigma_ll(sim, self.values, self.offset,
                                             self.multip)
-        if self.prior_box is not None:
+        if self.prior_box is not None or self.prior_parts is not None:
             f = log_prior + f
         return self.sign * f
 

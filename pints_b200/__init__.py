@@ -33,7 +33,8 @@ from ._objectives import (ErrorMeasure, ProblemErrorMeasure,         # noqa
                           LogPrior, LogLikelihood, ProblemLogLikelihood,
                           GaussianKnownSigmaLogLikelihood,
                           GaussianLogLikelihood, RectangularBoundaries,
-                          UniformLogPrior, LogPosterior)
+                          UniformLogPrior, GaussianLogPrior,
+                          ComposedLogPrior, LogPosterior)
 from . import toy                                                    # noqa
 
 __version__ = '0.1.0'

@@ -81,6 +81,14 @@ class DeviceProblem(object):
                 _ptr(self._series), mc, n_mc, oc, n_oc, spec.sign, lo, hi,
                 n_prior, spec.log_prior, ctypes.byref(handle)))
         self._handle = handle
+        if spec.prior_terms:
+            n = len(spec.prior_terms)
+            kinds = (ctypes.c_int32 * n)(*[int(t[0]) for t in spec.prior_terms])
+            index = (ctypes.c_int32 * n)(*[int(t[1]) for t in spec.prior_terms])
+            flat = [float(v) for t in spec.prior_terms for v in t[2:5]]
+            consts = (ctypes.c_double * (3 * n))(*flat)
+            _lib.check(self._lib.pb200_problem_set_prior_terms(
+                handle, n, kinds, index, consts))
         self.n_parameters = spec.n_parameters()
         self.n_model_parameters = spec.n_model_parameters()
 

@@ -57,6 +57,9 @@ SIGNATURES = {
         POINTER(c_double), POINTER(c_double), c_int32, c_double,
         POINTER(c_void_p)]),
     'pb200_problem_destroy': (None, [_P]),
+    'pb200_problem_set_prior_terms': (c_int32, [_P, c_int32, POINTER(c_int32),
+                                                POINTER(c_int32),
+                                                POINTER(c_double)]),
     'pb200_problem_n_parameters': (c_int32, [_P]),
     'pb200_eval': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                              POINTER(SolverOpts), _P]),

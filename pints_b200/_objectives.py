@@ -285,6 +285,66 @@ class UniformLogPrior(LogPrior):
         return self._boundaries.sample(n)
 
 
+class GaussianLogPrior(LogPrior):
+    """One-dimensional normal prior (pints/_log_priors.py:441-483)."""
+
+    def __init__(self, mean, sd):
+        self._mean = float(mean)
+        self._sd = float(sd)
+        if self._sd <= 0:
+            raise ValueError('sd parameter must be positive')
+        self._offset = np.log(1 / np.sqrt(2 * np.pi * self._sd ** 2))
+        self._factor = 1 / (2 * self._sd ** 2)
+        self._factor2 = 1 / self._sd**2
+
+    def __call__(self, x):
+        return self._offset - self._factor * (x[0] - self._mean)**2
+
+    def n_parameters(self):
+        return 1
+
+    def mean(self):
+        return self._mean
+
+    def sample(self, n=1):
+        return np.random.normal(self._mean, self._sd, size=(n, 1))
+
+
+class ComposedLogPrior(LogPrior):
+    """Independent sub-priors side by side (pints/_log_priors.py:170-275)."""
+
+    def __init__(self, *priors):
+        if len(priors) < 1:
+            raise ValueError('Must have at least one sub-prior')
+        self._n_parameters = 0
+        for prior in priors:
+            if not isinstance(prior, (LogPrior, base('LogPrior'))):
+                raise ValueError('All sub-priors must extend pints.LogPrior.')
+            self._n_parameters += prior.n_parameters()
+        self._priors = priors
+
+    def __call__(self, x):
+        output = 0
+        lo = hi = 0
+        for prior in self._priors:
+            lo = hi
+            hi += prior.n_parameters()
+            output += prior(x[lo:hi])
+        return output
+
+    def n_parameters(self):
+        return self._n_parameters
+
+    def sample(self, n=1):
+        output = np.zeros((n, self._n_parameters))
+        lo = hi = 0
+        for prior in self._priors:
+            lo = hi
+            hi += prior.n_parameters()
+            output[:, lo:hi] = prior.sample(n)
+        return output
+
+
 class LogPosterior(_DeviceCallable, LogPDF):
     """``log_prior(x) + log_likelihood(x)``; a point outside the prior's
     support is not simulated (pints/_log_pdfs.py:164-241)."""

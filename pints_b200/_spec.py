@@ -38,7 +38,7 @@ class ProblemSpec(object):
 
     def __init__(self, model, model_consts, times, values, objective,
                  obj_consts, sign=1.0, prior_lower=None, prior_upper=None,
-                 log_prior=0.0, multi_output=None):
+                 log_prior=0.0, multi_output=None, prior_terms=None):
         self.model = int(model)
         self.model_consts = [float(v) for v in model_consts]
         self.times = np.ascontiguousarray(times, dtype=np.float64)
@@ -61,6 +61,9 @@ class ProblemSpec(object):
         self.prior_upper = None if prior_upper is None else \
             [float(v) for v in prior_upper]
         self.log_prior = float(log_prior)
+        # composed prior: [(kind, index, c0, c1, c2)] in the sub-priors' order
+        self.prior_terms = [tuple(t) for t in prior_terms] if prior_terms \
+            else None
 
     # ------------------------------------------------------------------
     def n_model_parameters(self):
@@ -174,6 +177,46 @@ def describe_model(model):
         % (type(model).__module__, type(model).__name__))
 
 
+def describe_prior(prior):
+    """(lower, upper, constant, terms) of a supported prior: a UniformLogPrior
+    over RectangularBoundaries, a GaussianLogPrior, or a ComposedLogPrior of
+    those (pints/_log_priors.py:170-219, :441-468, :1264-1320)."""
+    kind = _kind(prior)
+    if kind == 'UniformLogPrior':
+        if _kind(prior._boundaries) != 'RectangularBoundaries':
+            raise TypeError('only UniformLogPrior over RectangularBoundaries '
+                            'is fused into the CUDA path')
+        return (np.asarray(prior._boundaries.lower(), dtype=float),
+                np.asarray(prior._boundaries.upper(), dtype=float),
+                float(prior._value), None)
+    if kind == 'GaussianLogPrior':
+        subs = [prior]
+    elif kind == 'ComposedLogPrior':
+        subs = list(prior._priors)
+    else:
+        raise TypeError(
+            'only UniformLogPrior, GaussianLogPrior and ComposedLogPrior of '
+            'those are fused into the CUDA path; got %s' % type(prior).__name__)
+    lower, upper, terms = [], [], []
+    for sub in subs:
+        k = _kind(sub)
+        if k == 'UniformLogPrior' and \
+                _kind(sub._boundaries) == 'RectangularBoundaries':
+            lower += list(np.asarray(sub._boundaries.lower(), dtype=float))
+            upper += list(np.asarray(sub._boundaries.upper(), dtype=float))
+            terms.append((0, 0, float(sub._value), 0.0, 0.0))
+        elif k == 'GaussianLogPrior':
+            terms.append((1, len(lower), float(sub._offset),
+                          float(sub._factor), float(sub._mean)))
+            lower.append(-np.inf)
+            upper.append(np.inf)
+        else:
+            raise TypeError('unsupported sub-prior %s' % type(sub).__name__)
+    if len(terms) > _lib.MAX_PARAMS:
+        raise TypeError('too many sub-priors')
+    return np.array(lower), np.array(upper), 0.0, terms
+
+
 def describe(function):
     """``ProblemSpec`` of an objective object graph; ``TypeError`` if any part
     of it is outside the supported hot path."""
@@ -238,18 +281,12 @@ def describe(function):
             raise TypeError('inconsistent GaussianLogLikelihood')
     lower = upper = None
     log_prior = 0.0
+    terms = None
     if prior is not None:
-        if _kind(prior) != 'UniformLogPrior' or \
-                _kind(prior._boundaries) != 'RectangularBoundaries':
-            raise TypeError(
-                'only UniformLogPrior over RectangularBoundaries is fused '
-                'into the CUDA path; got %s' % type(prior).__name__)
-        lower = np.asarray(prior._boundaries.lower(), dtype=float)
-        upper = np.asarray(prior._boundaries.upper(), dtype=float)
-        log_prior = float(prior._value)
+        lower, upper, log_prior, terms = describe_prior(prior)
     spec = ProblemSpec(model_id, model_consts, times, values, objective,
                        obj_consts, sign, lower, upper, log_prior,
-                       multi_output=multi)
+                       multi_output=multi, prior_terms=terms)
     if lower is not None and len(lower) != spec.n_parameters():
         raise TypeError('prior and likelihood dimensions differ')
     return spec

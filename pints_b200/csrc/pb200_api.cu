@@ -186,6 +186,33 @@ int pb200_problem_create(int32_t model, int32_t objective, int32_t n_times,
     return PB200_OK;
 }
 
+int pb200_problem_set_prior_terms(pb200_problem *p, int32_t n_terms, const int32_t *kinds,
+                                  const int32_t *index, const double *consts) {
+    if (!p) { pb200_set_error("pb200_problem_set_prior_terms: problem is NULL"); return PB200_EINVAL; }
+    if (n_terms < 0 || n_terms > PB200_MAX_PARAMS || (n_terms > 0 && (!kinds || !index || !consts))) {
+        pb200_set_error("pb200_problem_set_prior_terms: 0..%d terms", PB200_MAX_PARAMS);
+        return PB200_EINVAL;
+    }
+    if (n_terms > 0 && p->dev.n_prior == 0) {
+        pb200_set_error("pb200_problem_set_prior_terms: the problem was created without a prior box");
+        return PB200_EINVAL;
+    }
+    for (int k = 0; k < n_terms; ++k) {
+        if (kinds[k] < 0 || kinds[k] > 1 ||
+            (kinds[k] == 1 && (index[k] < 0 || index[k] >= p->dev.n_params))) {
+            pb200_set_error("pb200_problem_set_prior_terms: bad term %d", k);
+            return PB200_EINVAL;
+        }
+    }
+    p->dev.n_terms = n_terms;
+    for (int k = 0; k < n_terms; ++k) {
+        p->dev.term_kind[k] = kinds[k];
+        p->dev.term_idx[k] = index[k];
+        for (int c = 0; c < 3; ++c) p->dev.term_c[k][c] = consts[3 * k + c];
+    }
+    return PB200_OK;
+}
+
 void pb200_problem_destroy(pb200_problem *p) { delete p; }
 
 int32_t pb200_problem_n_parameters(const pb200_problem *p) {

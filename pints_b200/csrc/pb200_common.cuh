@@ -30,7 +30,31 @@ struct ProblemDev {
     double oc[2 * PB200_MAX_OUTPUTS];      // objective constants
     double lo[PB200_MAX_PARAMS];
     double hi[PB200_MAX_PARAMS];
+    // composed prior (pints/_log_priors.py:212-219): terms added in order;
+    // kind 0 = constant c0, kind 1 = Gaussian c0 - c1 (x[idx] - c2)^2
+    int32_t n_terms;              // 0 = the constant log_prior above
+    int32_t term_kind[PB200_MAX_PARAMS];
+    int32_t term_idx[PB200_MAX_PARAMS];
+    double term_c[PB200_MAX_PARAMS][3];
 };
+
+// log prior of a point inside the box: the constant of a single
+// UniformLogPrior, or the terms of a ComposedLogPrior summed in the reference's
+// order (0 + p_1 + p_2 + ..., each sum rounded).
+__device__ __forceinline__ double log_prior_of(const ProblemDev &P, const double *x) {
+    if (P.n_terms == 0) return P.log_prior;
+    double acc = 0.0;
+    for (int k = 0; k < P.n_terms; ++k) {
+        double term = P.term_c[k][0];
+        if (P.term_kind[k] == 1) {
+            // offset - factor * (x - mean)**2   (pints/_log_priors.py:467-468)
+            const double d = __dsub_rn(x[P.term_idx[k]], P.term_c[k][2]);
+            term = __dsub_rn(term, __dmul_rn(P.term_c[k][1], __dmul_rn(d, d)));
+        }
+        acc = __dadd_rn(acc, term);
+    }
+    return acc;
+}
 
 // Model constants live apart so the ODE kernels do not carry the HH-IK table.
 struct ModelConsts {
@@ -168,7 +192,7 @@ __device__ __forceinline__ double objective_finish(const ProblemDev &P,
             acc = (o == 0) ? term : __dadd_rn(acc, term);
         }
     }
-    if (P.n_prior > 0) acc = __dadd_rn(P.log_prior, acc);
+    if (P.n_prior > 0) acc = __dadd_rn(log_prior_of(P, x), acc);
     return P.sign * acc;
 }
 
@@ -193,7 +217,7 @@ __device__ __forceinline__ bool objective_precheck(const ProblemDev &P,
             bad = bad || (x[P.n_model_params + o] <= 0.0);
         if (bad) {
             double v = -INFINITY;
-            if (P.n_prior > 0) v = P.log_prior + v;
+            if (P.n_prior > 0) v = log_prior_of(P, x) + v;
             *score = P.sign * v;
             return true;
         }

@@ -438,9 +438,6 @@ struct Series {
 #ifndef PB200_MAXTHREADS
 #define PB200_MAXTHREADS 128
 #endif
-#ifndef PB200_CLOOP_POS
-#define PB200_CLOOP_POS 1       // 0: top of the iteration, 1: after the error estimate
-#endif
 #ifndef PB200_CLOOP_WIDTH
 #define PB200_CLOOP_WIDTH 1     // observations per trip of the (C) loop
 #endif
@@ -709,18 +706,6 @@ ode_kernel(const __grid_constant__ ProblemDev P,
             else ++attempts;
         }
 
-#if PB200_CLOOP_POS == 0
-        // ---- (C) pending observations beyond the U slots ----
-        {
-            double t_ahead = series.at(off + U * ROWB);
-            while (__any_sync(FULL, le_bits(t_ahead, t))) {
-                const bool more = le_bits(t_ahead, t);
-                interpolate(series.at(off), off, more);
-                off += more ? ROWB : 0u;
-                t_ahead = series.at(off + U * ROWB);
-            }
-        }
-#endif
         // ---- (A) U interpolation slots (predicated) ----
         {
             double tq[U > 0 ? U : 1];
@@ -784,7 +769,6 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         const double facd = static_cast<double>(fac);
 #endif
         after_reject = !ok;
-#if PB200_CLOOP_POS == 1
         // ---- (C) pending observations beyond the U slots, W per trip ----
         {
             constexpr int W = PB200_CLOOP_WIDTH;
@@ -804,7 +788,6 @@ ode_kernel(const __grid_constant__ ProblemDev P,
                 for (int k = 0; k < W; ++k) tn[k] = series.at(off + k * ROWB);
             }
         }
-#endif
 
         // ---- (D) dense-output coefficients of this step (Hairer's contd5
         // on h-scaled increments); junk when rejected, never read (t stays) ----

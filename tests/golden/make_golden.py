@@ -340,6 +340,39 @@ def golden_repressilator():
                 truth_one, 33)
 
 
+def golden_composed_prior():
+    """LogPosterior with a ComposedLogPrior (uniform box on the first two FHN
+    parameters, Gaussian on the third and on sigma_1, uniform on sigma_2)."""
+    model, times, values, problem = fhn_problem()
+    ll = pints.GaussianLogLikelihood(problem)
+    prior = pints.ComposedLogPrior(
+        pints.UniformLogPrior([0.05, 0.3], [0.15, 0.7]),
+        pints.GaussianLogPrior(3.0, 0.2),
+        pints.GaussianLogPrior(0.5, 0.05),
+        pints.UniformLogPrior([0.4], [0.6]))
+    post = pints.LogPosterior(ll, prior)
+    rng = np.random.RandomState(41)
+    xs = np.array([0.1, 0.5, 3, 0.5, 0.5]) * (1 + 0.05 * rng.randn(40, 5))
+    xs[3, 0] = 0.2          # outside the first box
+    xs[5, 4] = 0.7          # outside the last box
+    xs[7, 3] = -0.1         # sigma <= 0, inside the Gaussian's support
+    scores = np.array(pints.SequentialEvaluator(post).evaluate(xs))
+    priors = np.array([prior(x) for x in xs])
+    # logistic (closed form: 1e-12) with a single Gaussian prior per parameter
+    lmodel = pints.toy.LogisticModel()
+    ltimes = np.linspace(0, 100, 200)
+    lvalues = lmodel.simulate([0.1, 50], ltimes) + rng.normal(0, 1, 200)
+    lproblem = pints.SingleOutputProblem(lmodel, ltimes, lvalues)
+    lpost = pints.LogPosterior(
+        pints.GaussianKnownSigmaLogLikelihood(lproblem, 1.0),
+        pints.ComposedLogPrior(pints.GaussianLogPrior(0.1, 0.02),
+                               pints.GaussianLogPrior(50, 5)))
+    lxs = np.array([0.1, 50]) * (1 + 0.1 * rng.randn(32, 2))
+    lscores = np.array(pints.SequentialEvaluator(lpost).evaluate(lxs))
+    save('composed_prior', xs=xs, scores=scores, priors=priors,
+         ltimes=ltimes, lvalues=lvalues, lxs=lxs, lscores=lscores)
+
+
 def golden_error_measures():
     """MeanSquaredError / RootMeanSquaredError / NormalisedRootMeanSquaredError
     of the reference on the logistic, FHN and HH-IK problems."""
@@ -537,6 +570,7 @@ if __name__ == '__main__':
     golden_hes1()
     golden_repressilator()
     golden_error_measures()
+    golden_composed_prior()
     golden_hbac()
     golden_haario()
     golden_rao_blackwell()

@@ -460,6 +460,54 @@ def test_more_ode_models(pb, name, cls):
     assert np.array_equal(np.asarray(one).reshape(traj[0].shape), traj[0])
 
 
+def test_composed_prior(pb):
+    """(f) row 2: ComposedLogPrior (uniform + Gaussian sub-priors) fused into
+    the epilogue: outside any uniform support, or sigma <= 0, scores -inf
+    without a solve; inside, the terms are added in the reference's order."""
+    g = load_golden('composed_prior')
+    h = po.headline_fhn_spec()
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), h.times,
+                                    h.values)
+    prior = pb.ComposedLogPrior(
+        pb.UniformLogPrior([0.05, 0.3], [0.15, 0.7]),
+        pb.GaussianLogPrior(3.0, 0.2), pb.GaussianLogPrior(0.5, 0.05),
+        pb.UniformLogPrior([0.4], [0.6]))
+    post = pb.LogPosterior(pb.GaussianLogLikelihood(problem), prior)
+    got, steps = pb.CudaEvaluator(post, as_list=False).evaluate_array(
+        g['xs'], True)
+    for k in (3, 5, 7):
+        assert got[k] == -np.inf and steps[k] == 0
+    finite = np.isfinite(g['scores'])
+    assert np.array_equal(np.isfinite(got), finite)
+    assert np.max(rel_err(got[finite], g['scores'][finite])) < ODE_SCORE_RTOL
+    neg = evaluate(pb, pb.ProbabilityBasedError(post), g['xs'])
+    assert np.array_equal(neg, -got)
+    # closed form: 1e-12, two Gaussian sub-priors
+    lproblem = pb.SingleOutputProblem(pb.toy.LogisticModel(), g['ltimes'],
+                                      g['lvalues'])
+    lpost = pb.LogPosterior(
+        pb.GaussianKnownSigmaLogLikelihood(lproblem, 1.0),
+        pb.ComposedLogPrior(pb.GaussianLogPrior(0.1, 0.02),
+                            pb.GaussianLogPrior(50, 5)))
+    got = evaluate(pb, lpost, g['lxs'])
+    assert np.max(rel_err(got, g['lscores'])) < ANALYTIC_RTOL
+    # the mirror priors evaluate like the reference's on the host too
+    for x, want in zip(g['xs'][:6], g['priors'][:6]):
+        assert prior(x) == want
+
+    class OddPrior(pb.LogPrior):           # a user's prior: refused, not guessed
+        def n_parameters(self):
+            return 1
+
+        def __call__(self, x):
+            return 0.0
+
+    with pytest.raises(TypeError):
+        pb.describe(pb.LogPosterior(
+            pb.GaussianKnownSigmaLogLikelihood(lproblem, 1.0),
+            pb.ComposedLogPrior(pb.GaussianLogPrior(0.1, 0.02), OddPrior())))
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)

@@ -452,3 +452,21 @@ def test_more_ode_models_reference_unit_tests():
     # pints/tests/test_toy_repressilator_model.py: starts at y0[:3]
     v = po.repressilator_simulate([1, 1000, 5, 2], np.linspace(0, 40, 400))
     assert v.shape == (400, 3) and np.all(v[0] == 0)
+
+
+def test_composed_prior_golden():
+    """(f) row 2: LogPosterior over a ComposedLogPrior of uniform and Gaussian
+    sub-priors (pints/_log_priors.py:170-219): exact."""
+    g = load_golden('composed_prior')
+    parts = [('uniform', [0.05, 0.3], [0.15, 0.7]), ('gaussian', 3.0, 0.2),
+             ('gaussian', 0.5, 0.05), ('uniform', [0.4], [0.6])]
+    for x, want in zip(g['xs'], g['priors']):
+        assert po.composed_log_prior(parts, x) == want
+    h = po.headline_fhn_spec()
+    s = po.Spec('fhn', h.times, h.values, 'gaussian', prior_parts=parts)
+    assert np.array_equal(po.scores(s, g['xs'][:10]), g['scores'][:10])
+    assert g['scores'][3] == -np.inf and g['scores'][5] == -np.inf
+    assert g['scores'][7] == -np.inf
+    s = po.Spec('logistic', g['ltimes'], g['lvalues'], 'gaussian_known_sigma',
+                1.0, prior_parts=[('gaussian', 0.1, 0.02), ('gaussian', 50, 5)])
+    assert np.array_equal(po.scores(s, g['lxs']), g['lscores'])
