@@ -694,10 +694,33 @@ class CudaMCMCController(object):
     """
 
     def __init__(self, log_pdf, chains, x0, sigma0=None, method=None,
-                 device=None, seed=0, **evaluator_options):
+                 device=None, seed=0, sharded=False, group=None,
+                 **evaluator_options):
         from ._evaluation import CudaEvaluator
         from ._samplers import DifferentialEvolutionMCMC, HaarioBardenetACMC
         self._n_chains = int(chains)
+        # sharded: one process per GPU (torch.distributed); every rank is given
+        # ALL starting points and runs a contiguous block of the chains.  The
+        # adaptive-covariance samplers need no exchange at all; differential
+        # evolution proposes from the positions of two other chains, so the
+        # (n_chains, d) positions are all-gathered once per iteration
+        # (SURVEY.md section 8e).
+        self._sharded = bool(sharded)
+        self._group = group
+        self._first, self._n_local = 0, self._n_chains
+        if self._sharded:
+            import os
+            import torch.distributed as dist
+            from ._dist import shard_bounds
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            if self._n_chains % world != 0:
+                raise ValueError('The number of chains must be a multiple of '
+                                 'the number of ranks.')
+            lo, hi, _ = shard_bounds(self._n_chains, world, rank)
+            self._first, self._n_local = lo, hi - lo
+            seed = int(seed) + 7919 * rank          # distinct device streams
+            if device is None:
+                device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', '0'))
         if self._n_chains < 1:
             raise ValueError('Number of chains must be at least 1.')
         if len(x0) != self._n_chains:
@@ -713,13 +736,22 @@ class CudaMCMCController(object):
                 'All initial positions must have the same dimension as the'
                 ' given LogPDF.')
         method = HaarioBardenetACMC if method is None else method
+        lo, hi = self._first, self._first + self._n_local
+        self._gather_positions = False
         if isinstance(method, type) and issubclass(method, HaarioBardenetACMC):
             # the single-chain family: HaarioBardenetACMC, HaarioACMC,
             # RaoBlackwellACMC, MetropolisRandomWalkMCMC (all chains at once)
-            self._sampler = method(x0, sigma0, device=device, seed=seed)
+            s0 = sigma0
+            if s0 is not None and np.shape(s0) == (self._n_chains,) + \
+                    (self._n_parameters,) * 2:
+                s0 = np.asarray(s0)[lo:hi]
+            self._sampler = method(x0[lo:hi], s0, device=device, seed=seed)
         elif method is DifferentialEvolutionMCMC:
-            self._sampler = method(self._n_chains, x0, device=device,
-                                   seed=seed)
+            self._sampler = method(self._n_local, x0[lo:hi], device=device,
+                                   seed=seed, first=lo,
+                                   n_total=self._n_chains,
+                                   x0_mean=np.mean(x0, axis=0))
+            self._gather_positions = self._sharded
         else:
             raise ValueError(
                 'method must be one of the device samplers of pints_b200: '
@@ -778,20 +810,39 @@ class CudaMCMCController(object):
         n_iter = self._max_iterations
         sampler, problem = self._sampler, self._evaluator.device_problem()
         device = problem.device
-        samples = torch.empty(
-            (self._n_chains, n_iter, self._n_parameters), dtype=torch.float64,
-            device=device)
-        fx = torch.empty(self._n_chains, dtype=torch.float64, device=device)
+        n_local, d = self._n_local, self._n_parameters
+        samples = torch.empty((n_local, n_iter, d), dtype=torch.float64,
+                              device=device)
+        fx = torch.empty(n_local, dtype=torch.float64, device=device)
+        pool = None
+        if self._gather_positions:
+            import torch.distributed as dist
+            pool = torch.empty((self._n_chains, d), dtype=torch.float64,
+                               device=device)
         start = time.perf_counter()
         with torch.cuda.device(device):
             for it in range(n_iter):
                 if self._initial_phase_iterations is not None and \
                         it == self._initial_phase_iterations:
                     sampler.set_initial_phase(False)
-                xs = sampler.ask()
+                if pool is not None and it > 0:
+                    # the one exchange of the sharded DE sampler: everybody's
+                    # current positions (n_chains * d * 8 bytes)
+                    dist.all_gather_into_tensor(
+                        pool, sampler.current().contiguous(),
+                        group=self._group)
+                    xs = sampler.ask(all_current=pool)
+                else:
+                    xs = sampler.ask()
                 problem.eval(xs, out=fx)
                 current, _, _ = sampler.tell(fx)
                 samples[:, it].copy_(current)
+            if self._sharded:
+                import torch.distributed as dist
+                every = torch.empty((self._n_chains, n_iter, d),
+                                    dtype=torch.float64, device=device)
+                dist.all_gather_into_tensor(every, samples, group=self._group)
+                samples = every
             torch.cuda.synchronize(device)
         self._n_evaluations = n_iter * self._n_chains
         self._time = time.perf_counter() - start

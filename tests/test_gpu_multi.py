@@ -86,3 +86,62 @@ def test_sharded_evaluator_nccl():
         assert p.exitcode == 0
     assert [v & 1 for v in out] == [1] * world
     print('fused exchange used:', [bool(v & 2) for v in out])
+
+
+def _mcmc_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        import pints_b200 as pb
+        times = np.linspace(0, 100, 50)
+        rng = np.random.RandomState(11)
+        values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 2, 50)
+        problem = pb.SingleOutputProblem(pb.toy.LogisticModel(), times, values)
+        post = pb.LogPosterior(
+            pb.GaussianLogLikelihood(problem),
+            pb.UniformLogPrior([0, 10, 0.1], [1, 100, 10]))
+        n_chains, n_iter = 256, 1200
+        x0 = np.array([0.1, 50, 2]) * (1 + 0.05 * rng.randn(n_chains, 3))
+        ok = True
+        for method in (pb.DifferentialEvolutionMCMC, pb.HaarioBardenetACMC):
+            mc = pb.CudaMCMCController(post, n_chains, x0, method=method,
+                                       seed=3, sharded=True)
+            mc.set_max_iterations(n_iter)
+            chains = mc.run()
+            ok = ok and chains.shape == (n_chains, n_iter, 3)
+            ok = ok and np.array_equal(chains[:, 0], x0)   # every rank has all
+            tail = chains[:, n_iter // 2:].reshape(-1, 3)
+            mean = tail.mean(0)
+            ok = ok and abs(mean[0] - 0.1) < 0.01 and abs(mean[1] - 50) < 1.5
+            # the two halves were produced by different ranks and both moved
+            half = n_chains // 2
+            for part in (chains[:half], chains[half:]):
+                moved = (np.diff(part[:, :, 0], axis=1) != 0).mean()
+                ok = ok and 0.02 < moved < 0.95
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason='needs 2 GPUs')
+def test_sharded_device_mcmc():
+    """Config 4 of BASELINE.json in small: chains sharded over the GPUs; the
+    differential-evolution sampler all-gathers the positions every iteration."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context('spawn')
+    out = ctx.Array('i', [0] * world)
+    port = 29800 + os.getpid() % 1000
+    procs = [ctx.Process(target=_mcmc_worker, args=(r, world, port, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world
