@@ -508,6 +508,55 @@ def test_composed_prior(pb):
             pb.ComposedLogPrior(pb.GaussianLogPrior(0.1, 0.02), OddPrior())))
 
 
+def test_host_buffer_entry_points(pb):
+    """pb200_eval_host / pb200_copy_async / pb200_host_is_pinned through ctypes:
+    the one-call host-buffer path gives what the device-pointer path gives."""
+    import ctypes
+    import torch
+    from pints_b200 import _lib
+    lib = _lib.load()
+    spec = po.headline_fhn_spec()
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    ev = pb.CudaEvaluator(ll, as_list=False)
+    dp = ev.device_problem()
+    n = 3000
+    xs = pb.pinned_empty((n, 3))
+    xs[:] = po.headline_fhn_points(n)
+    V = ctypes.c_void_p
+    assert lib.pb200_host_is_pinned(V(xs.ctypes.data)) == 1
+    assert lib.pb200_host_is_pinned(V(np.zeros(8).ctypes.data)) == 0
+    h_out = pb.pinned_empty((n,))
+    h_steps = torch.zeros(n, dtype=torch.int32).pin_memory()
+    d_in = torch.empty((n, 3), dtype=torch.float64, device='cuda')
+    d_out = torch.empty(n, dtype=torch.float64, device='cuda')
+    d_steps = torch.zeros(n, dtype=torch.int32, device='cuda')
+    ws = torch.empty(int(lib.pb200_sort_workspace_bytes(n)), dtype=torch.uint8,
+                     device='cuda')
+    stream = V(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.pb200_eval_host(
+        dp._handle, V(xs.ctypes.data), n, 3, V(h_out.ctypes.data),
+        V(h_steps.data_ptr()), V(d_in.data_ptr()), V(d_out.data_ptr()),
+        V(d_steps.data_ptr()), V(ws.data_ptr()), ws.numel(),
+        ctypes.byref(dp.opts), stream))
+    torch.cuda.synchronize()
+    want, steps = ev.evaluate_array(xs, True)
+    assert np.array_equal(h_out, want)
+    assert np.array_equal(h_steps.numpy(), steps)
+    # workspace too small / misaligned is refused with a message
+    rc = lib.pb200_eval_sorted(dp._handle, V(d_in.data_ptr()), n, 3,
+                               V(d_out.data_ptr()), None, ctypes.byref(dp.opts),
+                               V(ws.data_ptr()), 64, stream)
+    assert rc == -1 and b'workspace' in lib.pb200_last_error()
+    back = np.empty(n)
+    _lib.check(lib.pb200_copy_async(V(h_out.ctypes.data), V(d_out.data_ptr()),
+                                    n * 8, 0, stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(h_out, want)
+    assert lib.pb200_copy_async(None, None, -1, 0, stream) == -1
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)
