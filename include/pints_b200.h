@@ -85,7 +85,8 @@ typedef struct pb200_solver_opts {
     double  h0;          /* first step; <= 0 -> automatic                    */
     int32_t max_steps;   /* attempted steps per vector; <= 0 -> 1000000.     */
                          /* A vector that exceeds it scores NaN.             */
-    int32_t block;       /* threads per block; <= 0 -> automatic             */
+    int32_t block;       /* threads per block; <= 0 -> automatic (which also */
+                         /* allows the one-block-per-SM migrating layout)    */
     int32_t lanes;       /* GPU lanes per parameter vector: 1, or 2 (one per */
                          /* state, two-state models only); <= 0 -> automatic */
 } pb200_solver_opts;

@@ -1374,6 +1374,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     const bool use_smem = bytes <= 96 * 1024;   // keeps >= 2 blocks per SM
 #endif
     const bool traj = d_traj != nullptr;
+    const bool auto_layout = block <= 0;      // an explicit block size means the plain layout
     if (block <= 0) block = 64;
     if (block > PB200_MAXTHREADS) block = PB200_MAXTHREADS;
     block = (block + 31) & ~31;                 // whole warps: the kernel votes
@@ -1387,7 +1388,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     // single-wave populations with one or two warps per SM more than a
     // multiple of four: migrating layout, one block per SM (see MigDev)
     MigDev mig = {0, 0, 0, 0};
-    if (M::MIGRATES && use_smem && !traj && mig_enabled()) {
+    if (M::MIGRATES && auto_layout && use_smem && !traj && mig_enabled()) {
         const int64_t warps = (n + 31) / 32;
         const int sms = sm_count();
         const int64_t per_sm = (warps + sms - 1) / sms;

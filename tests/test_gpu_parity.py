@@ -557,6 +557,33 @@ def test_host_buffer_entry_points(pb):
     assert lib.pb200_copy_async(None, None, -1, 0, stream) == -1
 
 
+@pytest.mark.parametrize('n', [18945, 30000, 47000, 61569, 65536, 66304])
+def test_migrating_layout_is_bit_identical(pb, n):
+    """Populations of 5..14 warps per SM run one block per SM with warp
+    migration between the schedulers; an explicit block size
+    selects the plain layout.  Same scores and step counts, bit for bit,
+    including vectors decided early (prior box), vectors that fail (NaN) and
+    the ragged last block."""
+    spec = po.headline_fhn_spec()
+    rng = np.random.RandomState(n)
+    xs = po.headline_fhn_points(n, seed=n % 97)
+    wide = rng.uniform([0, 0, 1], [1, 1, 5], (n // 7, 3))
+    xs[rng.permutation(n)[:len(wide)]] = wide
+    xs[5] = [0.1, 0.5, 9.0]                       # outside the prior box
+    xs[n - 3] = [0.1, 0.5, np.nan]                # NaN parameter -> NaN score
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    post = pb.LogPosterior(pb.GaussianKnownSigmaLogLikelihood(problem, 0.5),
+                           pb.UniformLogPrior([0, 0, 0.5], [1, 1, 6]))
+    a, sa = pb.CudaEvaluator(post, chunk_rows=1 << 30).evaluate_array(xs, True)
+    b, sb = pb.CudaEvaluator(post, chunk_rows=1 << 30,
+                             block=64).evaluate_array(xs, True)
+    assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(sa, sb)
+    assert a[5] == -np.inf and sa[5] == 0 and np.isnan(a[n - 3])
+    assert np.isfinite(a).sum() >= n - 2
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)
