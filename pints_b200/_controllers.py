@@ -819,6 +819,8 @@ class CudaMCMCController(object):
             import torch.distributed as dist
             pool = torch.empty((self._n_chains, d), dtype=torch.float64,
                                device=device)
+        from ._samplers import HaarioBardenetACMC
+        store_in_tell = isinstance(sampler, HaarioBardenetACMC)
         start = time.perf_counter()
         with torch.cuda.device(device):
             for it in range(n_iter):
@@ -835,8 +837,11 @@ class CudaMCMCController(object):
                 else:
                     xs = sampler.ask()
                 problem.eval(xs, out=fx)
-                current, _, _ = sampler.tell(fx)
-                samples[:, it].copy_(current)
+                if store_in_tell:
+                    sampler.tell(fx, store=(samples, it))
+                else:
+                    current, _, _ = sampler.tell(fx)
+                    samples[:, it].copy_(current)
             if self._sharded:
                 import torch.distributed as dist
                 every = torch.empty((self._n_chains, n_iter, d),

@@ -63,6 +63,24 @@ class _DeviceOps(object):
                    _ptr(mu), _ptr(sigma), _ptr(log_lambda), n, d, float(gamma),
                    float(target))
 
+    def ac_ask(self, cur, sigma, log_lambda, prop, seed, offset):
+        n, d = cur.shape
+        self._call(self.lib.pb200_ac_ask, _ptr(cur), _ptr(sigma),
+                   _ptr(log_lambda), _ptr(prop), n, d, ctypes.c_uint64(seed),
+                   ctypes.c_uint64(offset))
+
+    def ac_tell(self, variant, cur, cur_f, prop, fx, accepted, acc_count, mu,
+                sigma, log_lambda, samples, stride, sample_offset, gamma,
+                target, seed, offset):
+        n, d = cur.shape
+        self._call(self.lib.pb200_ac_tell, int(variant), _ptr(cur), _ptr(cur_f),
+                   _ptr(prop), _ptr(fx), _ptr(accepted), _ptr(acc_count),
+                   _ptr(mu), _ptr(sigma), _ptr(log_lambda),
+                   _ptr(samples) if samples is not None else None,
+                   int(stride), int(sample_offset), n, d, float(gamma),
+                   float(target), ctypes.c_uint64(seed),
+                   ctypes.c_uint64(offset))
+
     def hbac_adapt(self, cur, accepted, mu, sigma, log_lambda, gamma, target):
         n, d = cur.shape
         self._call(self.lib.pb200_hbac_adapt, _ptr(cur), _ptr(accepted),
@@ -126,7 +144,11 @@ class HaarioBardenetACMC(object):
     _VARIANT = _lib.AC_HAARIO_BARDENET
 
     def __init__(self, x0, sigma0=None, device=None, rng='philox', seed=0,
-                 eta=0.6, target_acceptance=0.234):
+                 eta=0.6, target_acceptance=0.234, fused=True):
+        # fused: with device draws, one launch per ask() and one per tell()
+        # (pb200_ac_ask / pb200_ac_tell) instead of eight small ones; the
+        # chains are identical either way
+        self._fused = bool(fused)
         x0 = np.array(x0, dtype=np.float64, copy=True)
         if x0.ndim != 2:
             raise ValueError('x0 must have shape (n_chains, n_parameters).')
@@ -246,6 +268,10 @@ class HaarioBardenetACMC(object):
                     self._proposed.device))
             elif self._rng_mode == 'replay':
                 raise RuntimeError('replay mode: ask() needs the proposals')
+            elif self._fused:
+                off = self._rng.take(self._z.numel())
+                self._ops.ac_ask(self._current, self._sigma, self._log_lambda,
+                                 self._proposed, self._rng.seed, off)
             else:
                 off = self._rng.take(self._z.numel())
                 self._ops.normal(self._z, self._rng.seed, off)
@@ -255,10 +281,12 @@ class HaarioBardenetACMC(object):
         self._asked = True
         return self._proposed
 
-    def tell(self, fx, log_u=None):
+    def tell(self, fx, log_u=None, store=None):
         """Accept/reject and adapt.  ``fx`` holds the log-pdfs of the proposals
         (device tensor or array).  Returns ``(current, current_log_pdfs,
-        accepted)`` as device tensors."""
+        accepted)`` as device tensors.  ``store = (samples, it)`` also writes
+        the new current points to ``samples[:, it]`` (a contiguous device
+        tensor ``(n_chains, n_iterations, d)``)."""
         if not self._asked:
             raise RuntimeError('Tell called before proposal was set.')
         self._asked = False
@@ -274,6 +302,26 @@ class HaarioBardenetACMC(object):
             self._current_f.copy_(fx)
             self._accepted.fill_(1)
             self._have_current = True
+            if store is not None:
+                store[0][:, store[1]].copy_(self._current)
+            return self._current, self._current_f, self._accepted
+        if log_u is None and self._rng_mode != 'replay' and self._fused:
+            # one launch: log-uniform, accept, count, adapt, store
+            off = self._rng.take(self._n)
+            variant = -1
+            if self._adaptive and self._VARIANT is not None:
+                self._gamma = (self._adaptations + 1) ** -self._eta
+                self._adaptations += 1
+                variant = self._VARIANT
+            samples, stride, soff = None, 0, 0
+            if store is not None:
+                samples = store[0]
+                stride, soff = samples.stride(0), store[1] * samples.stride(1)
+            self._ops.ac_tell(variant, self._current, self._current_f,
+                              self._proposed, fx, self._accepted,
+                              self._acceptance_count, self._mu, self._sigma,
+                              self._log_lambda, samples, stride, soff,
+                              self._gamma, self._target, self._rng.seed, off)
             return self._current, self._current_f, self._accepted
         if log_u is not None:
             self._log_u.copy_(torch.as_tensor(log_u).to(self._log_u.device))
@@ -308,6 +356,8 @@ class HaarioBardenetACMC(object):
                     v, self._current, self._previous, self._proposed,
                     self._accepted, self._log_ratio, self._mu, self._sigma,
                     self._log_lambda, self._gamma, self._target)
+        if store is not None:
+            store[0][:, store[1]].copy_(self._current)
         return self._current, self._current_f, self._accepted
 
 

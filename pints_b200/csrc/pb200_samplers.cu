@@ -342,6 +342,146 @@ int pb200_de_propose(const double *d_current_all, int64_t first, const double *d
     return pb200_check_cuda(cudaGetLastError(), "de_propose_kernel launch");
 }
 
+// element `idx` of the stream pb200_philox_uniform / pb200_philox_normal would
+// write for (seed, offset): the fused kernels below draw in place and stay
+// bit-identical to the separate launches
+__device__ __forceinline__ double philox_uniform_at(int64_t idx, uint64_t seed, uint64_t offset) {
+    const U4 r = philox4x32_10(offset + (idx >> 1), 1, seed);
+    return (idx & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
+}
+__device__ __forceinline__ double philox_normal_at(int64_t idx, uint64_t seed, uint64_t offset) {
+    const U4 r = philox4x32_10(offset + (idx >> 1), 2, seed);
+    const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return (idx & 1) ? rad * sn : rad * cs;
+}
+
+// ask of the adaptive-covariance family on the device: normals + Cholesky
+// proposal in one launch (= pb200_philox_normal then pb200_hbac_propose)
+__global__ void ac_ask_kernel(const double *__restrict__ cur, const double *__restrict__ sigma,
+                              const double *__restrict__ log_lambda,
+                              double *__restrict__ prop, int64_t n, int d, uint64_t seed,
+                              uint64_t offset) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double scale = exp(log_lambda[j]);
+    const double *sg = sigma + j * static_cast<int64_t>(d) * d;
+    double L[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
+    for (int a = 0; a < d; ++a) {
+        for (int b = 0; b <= a; ++b) {
+            double s = scale * sg[a * d + b];
+            for (int k = 0; k < b; ++k) s -= L[a * d + k] * L[b * d + k];
+            if (a == b) {
+                L[a * d + a] = s > 0.0 ? sqrt(s) : 0.0;
+            } else {
+                const double piv = L[b * d + b];
+                L[a * d + b] = piv > 0.0 ? s / piv : 0.0;
+            }
+        }
+    }
+    double z[PB200_MAX_PARAMS];
+    for (int k = 0; k < d; ++k) z[k] = philox_normal_at(j * d + k, seed, offset);
+    for (int a = 0; a < d; ++a) {
+        double s = cur[j * d + a];
+        for (int k = 0; k <= a; ++k) s = fma(L[a * d + k], z[k], s);
+        prop[j * d + a] = s;
+    }
+}
+
+// tell of the family on the device, one launch: log-uniform, accept/reject,
+// acceptance count, adaptation (variant < 0: none) and the chain sample
+// (= pb200_philox_uniform, log, pb200_mh_accept[_ratio], pb200_ac_adapt, copy)
+__global__ void ac_tell_kernel(int variant, double *__restrict__ cur,
+                               double *__restrict__ cur_f, const double *__restrict__ prop,
+                               const double *__restrict__ fx, uint8_t *__restrict__ accepted,
+                               int64_t *__restrict__ acc_count, double *__restrict__ mu,
+                               double *__restrict__ sigma, double *__restrict__ log_lambda,
+                               double *__restrict__ samples, int64_t sample_stride,
+                               int64_t sample_offset, int64_t n, int d, double gamma,
+                               double target, uint64_t seed, uint64_t offset) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double log_u = log(philox_uniform_at(j, seed, offset));
+    const double f_new = fx[j];
+    const double lr = __dsub_rn(f_new, cur_f[j]);
+    const bool acc = (log_u < lr) && isfinite(f_new);
+    double x[PB200_MAX_PARAMS], prev[PB200_MAX_PARAMS], y[PB200_MAX_PARAMS];
+    for (int k = 0; k < d; ++k) {
+        prev[k] = cur[j * d + k];
+        y[k] = prop[j * d + k];
+        x[k] = acc ? y[k] : prev[k];
+    }
+    if (acc) {
+        for (int k = 0; k < d; ++k) cur[j * d + k] = x[k];
+        cur_f[j] = f_new;
+    }
+    accepted[j] = acc ? 1 : 0;
+    if (acc_count) acc_count[j] += acc ? 1 : 0;
+    if (samples)
+        for (int k = 0; k < d; ++k) samples[j * sample_stride + sample_offset + k] = x[k];
+    if (variant < 0) return;
+    // adaptation, as ac_adapt_kernel
+    const double keep = __dsub_rn(1.0, gamma);
+    double p = acc ? 1.0 : 0.0;
+    if (variant != PB200_AC_HAARIO_BARDENET) p = lr < 0.0 ? exp(lr) : 1.0;
+    double dev[PB200_MAX_PARAMS];
+    for (int k = 0; k < d; ++k) {
+        const double m = __dadd_rn(__dmul_rn(keep, mu[j * d + k]), __dmul_rn(gamma, x[k]));
+        mu[j * d + k] = m;
+        double v = x[k];
+        if (variant == PB200_AC_RAO_BLACKWELL)
+            v = __dadd_rn(__dmul_rn(p, y[k]), __dmul_rn(__dsub_rn(1.0, p), prev[k]));
+        dev[k] = __dsub_rn(v, m);
+    }
+    double *sg = sigma + j * static_cast<int64_t>(d) * d;
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+            const double outer = __dmul_rn(dev[a], dev[b]);
+            sg[a * d + b] = __dadd_rn(__dmul_rn(keep, sg[a * d + b]),
+                                      __dmul_rn(gamma, outer));
+        }
+    if (variant != PB200_AC_RAO_BLACKWELL)
+        log_lambda[j] = __dadd_rn(log_lambda[j], __dmul_rn(gamma, __dsub_rn(p, target)));
+}
+
+int pb200_ac_ask(const double *d_current, const double *d_sigma, const double *d_log_lambda,
+                 double *d_proposed, int64_t n, int32_t d, uint64_t seed, uint64_t offset,
+                 void *stream) {
+    if (n < 0 || d < 1 || d > PB200_MAX_PARAMS) {
+        pb200_set_error("pb200_ac_ask: bad n=%lld or d=%d", (long long)n, d);
+        return PB200_EINVAL;
+    }
+    if (n == 0) return PB200_OK;
+    ac_ask_kernel<<<blocks_for(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_current, d_sigma, d_log_lambda, d_proposed, n, d, seed, offset);
+    return pb200_check_cuda(cudaGetLastError(), "ac_ask_kernel launch");
+}
+
+int pb200_ac_tell(int32_t variant, double *d_current, double *d_current_f,
+                  const double *d_proposed, const double *d_fx, uint8_t *d_accepted,
+                  int64_t *d_acceptance_count, double *d_mu, double *d_sigma,
+                  double *d_log_lambda, double *d_samples, int64_t sample_stride,
+                  int64_t sample_offset, int64_t n, int32_t d, double gamma, double target,
+                  uint64_t seed, uint64_t offset, void *stream) {
+    if (n < 0 || d < 1 || d > PB200_MAX_PARAMS || variant > PB200_AC_RAO_BLACKWELL) {
+        pb200_set_error("pb200_ac_tell: bad n=%lld, d=%d or variant=%d", (long long)n, d, variant);
+        return PB200_EINVAL;
+    }
+    if (n == 0) return PB200_OK;
+    if (!d_current || !d_current_f || !d_proposed || !d_fx || !d_accepted ||
+        (variant >= 0 && (!d_mu || !d_sigma || !d_log_lambda))) {
+        pb200_set_error("pb200_ac_tell: a buffer this call needs is NULL");
+        return PB200_EINVAL;
+    }
+    ac_tell_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        variant, d_current, d_current_f, d_proposed, d_fx, d_accepted, d_acceptance_count,
+        d_mu, d_sigma, d_log_lambda, d_samples, sample_stride, sample_offset, n, d, gamma,
+        target, seed, offset);
+    return pb200_check_cuda(cudaGetLastError(), "ac_tell_kernel launch");
+}
+
 int pb200_philox_normal(double *d_out, int64_t n, uint64_t seed, uint64_t offset,
                         void *stream) {
     if (n < 0) { pb200_set_error("pb200_philox_normal: n < 0"); return PB200_EINVAL; }

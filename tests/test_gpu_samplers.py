@@ -310,3 +310,34 @@ def test_cuda_optimisation_controller_with_other_vectorised_optimisers(pb, name)
     x, f = opt.run()
     assert abs(x[0] - 0.1) < 1e-2 and abs(x[1] - 50) < 1.0, (x, f)
     assert f < 1.3
+
+
+@pytest.mark.parametrize('name', ['HaarioBardenetACMC', 'HaarioACMC',
+                                  'RaoBlackwellACMC',
+                                  'MetropolisRandomWalkMCMC'])
+def test_fused_ask_tell_gives_identical_chains(pb, name):
+    """pb200_ac_ask / pb200_ac_tell (one launch each) against the separate
+    launches (normals, proposal, uniforms, log, accept, adapt): same draws,
+    same arithmetic, so the chains, the adapted state and the acceptance
+    counts are identical bit for bit."""
+    post = logistic_posterior(pb)
+    dp = pb.CudaEvaluator(post, as_list=False).device_problem()
+    rng = np.random.RandomState(6)
+    n, n_iter = 96, 120
+    x0 = np.array([0.1, 50, 2]) * (1 + 0.05 * rng.randn(n, 3))
+    out = []
+    for fused in (True, False):
+        s = getattr(pb, name)(x0, seed=5, fused=fused)
+        samples = torch.zeros((n, n_iter, 3), dtype=torch.float64, device='cuda')
+        fx = torch.empty(n, dtype=torch.float64, device='cuda')
+        for it in range(n_iter):
+            if it == 30 and s.needs_initial_phase():
+                s.set_initial_phase(False)
+            dp.eval(s.ask(), out=fx)
+            s.tell(fx, store=(samples, it))
+        out.append((host(samples), s.state(), s.acceptance_rate()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out[0][2], out[1][2])
+    assert (np.diff(out[0][0][:, :, 0], axis=1) != 0).mean() > 0.02
