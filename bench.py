@@ -232,7 +232,17 @@ def run_ours(args):
         m = base.sample_size(args.cpu_seconds)
         dt, ref_scores = base.run(base.po.headline_fhn_points(m))
         base.close()
+        # the same on ONE core, in this process (= SequentialEvaluator)
+        spec1 = base.po.headline_fhn_spec()
+        xs1 = base.po.headline_fhn_points(256, seed=9)
+        t0 = time.perf_counter()
+        k1 = 0
+        while time.perf_counter() - t0 < 2.0 and k1 < len(xs1):
+            spec1.score(xs1[k1])
+            k1 += 1
+        one_core = k1 / (time.perf_counter() - t0)
         cpu = {'value': m / dt, 'unit': UNIT, 'cores': base.cores,
+               'value_1core': one_core,
                'kind': 'port',
                'sample': '%d evaluations of the same workload (%.1f s), oracle '
                          'port = scipy LSODA + reference RHS, %d worker '
