@@ -1,15 +1,29 @@
 // Fused adaptive Dormand-Prince 5(4) solve + objective for the ODE toy models
-// (FitzHugh-Nagumo, Lotka-Volterra, SIR).  One thread integrates one parameter
-// vector; the observed series sits in shared memory (bulk-copied once per
-// block); every accepted step is interpolated at the observation times that
-// fall inside it (4th-order dense output), the residuals are squared and
-// accumulated in registers, and only the score leaves the SM.
+// (FitzHugh-Nagumo, Lotka-Volterra, SIR, Goodwin, Hes1, Repressilator).  One
+// lane integrates one parameter vector; the observed series sits in shared
+// memory (bulk-copied once per block); every accepted step is interpolated at
+// the observation times that fall inside it (4th-order dense output), the
+// residuals are squared and accumulated in registers, and only the score
+// leaves the SM -- to the caller's array, or straight into the gathered arrays
+// of all GPUs of a job (ScatterDev).
+//
+// In this file, in order:
+//   tableau, models (load / rhs / scale(h) / hrhs = h f / cost_key)
+//   ode_kernel        one lane per vector; plain layout (64-thread blocks) or
+//                     the migrating layout (one block per SM, MigDev)
+//   ode_pair_kernel   two lanes per vector (option, two-state models)
+//   sort_kernel       cost-coherent scheduling (cooperative counting sort)
+//   launchers         layout selection, launch_ode
+// DESIGN.md section 3 has the measurements each choice rests on.
 //
 // Replaces, per parameter vector (citations relative to the reference root):
 //   ToyODEModel._simulate           pints/toy/_toy_classes.py:190-234
 //   FitzhughNagumoModel._rhs        pints/toy/_fitzhugh_nagumo_model.py:111-117
 //   LotkaVolterraModel._rhs         pints/toy/_lotka_volterra_model.py:91-97
 //   SIRModel.simulate/_rhs          pints/toy/_sir_model.py:96-111
+//   GoodwinOscillatorModel._rhs     pints/toy/_goodwin_oscillator_model.py:101-107
+//   Hes1Model._rhs                  pints/toy/_hes1_michaelis_menten.py:129-140
+//   RepressilatorModel._rhs/simulate  pints/toy/_repressilator_model.py:91-108
 //   Multi/SingleOutputProblem.evaluate   pints/_core.py:147-153, :257-265
 //   objective __call__              see objective_finish()
 // The reference integrates with LSODA (scipy odeint, rtol = atol = 1.49012e-8);
