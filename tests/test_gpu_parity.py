@@ -584,6 +584,41 @@ def test_migrating_layout_is_bit_identical(pb, n):
     assert np.isfinite(a).sum() >= n - 2
 
 
+def test_maximum_sizes(pb):
+    """The largest problem the ABI admits: 8 outputs (PB200_MAX_OUTPUTS), hence
+    16 parameters with the unknown-sigma likelihood (PB200_MAX_PARAMS); one
+    output more is refused, not truncated."""
+    from pints_b200 import _lib
+    no = _lib.MAX_OUTPUTS
+    times = np.linspace(0, 10, 257)
+    rng = np.random.RandomState(12)
+    model = pb.toy.ConstantModel(no)
+    truth = 1.0 + np.arange(no)
+    clean = po.constant_simulate(truth, times, False)
+    values = clean + rng.normal(0, 0.3, clean.shape)
+    problem = pb.MultiOutputProblem(model, times, values)
+    ll = pb.GaussianLogLikelihood(problem)
+    assert ll.n_parameters() == _lib.MAX_PARAMS
+    xs = np.hstack([truth * (1 + 0.1 * rng.randn(300, no)),
+                    0.3 * (1 + 0.1 * rng.rand(300, no))])
+    got = evaluate(pb, ll, xs)
+    spec = po.Spec('constant', times, values, 'gaussian')
+    want = po.scores(spec, xs)
+    assert np.max(rel_err(got, want)) < ANALYTIC_RTOL
+    sse = pb.SumOfSquaresError(problem, weights=np.arange(1, no + 1))
+    want = po.scores(po.Spec('constant', times, values, 'sse',
+                             np.arange(1, no + 1)), xs[:, :no])
+    assert np.max(rel_err(evaluate(pb, sse, xs[:, :no]), want)) < ANALYTIC_RTOL
+    # a box prior over all 16 parameters
+    post = pb.LogPosterior(ll, pb.UniformLogPrior([0] * 16, [20] * 16))
+    out = evaluate(pb, post, xs)
+    assert np.all(np.isfinite(out))
+    big = pb.toy.ConstantModel(no + 1)
+    with pytest.raises(TypeError):
+        pb.describe(pb.SumOfSquaresError(pb.MultiOutputProblem(
+            big, times, np.zeros((len(times), no + 1)))))
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)
