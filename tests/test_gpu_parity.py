@@ -619,6 +619,27 @@ def test_maximum_sizes(pb):
             big, times, np.zeros((len(times), no + 1)))))
 
 
+@pytest.mark.parametrize('nt', [1, 2, 3, 7])
+def test_migrating_layout_with_very_short_series(pb, nt):
+    """The hand-over point of the migrating layout is a fraction of the
+    observations: series of one to a few points must still work."""
+    spec = po.headline_fhn_spec()
+    times = spec.times[[0, 400, 650, 700, 900, 950, 999][:nt]] if nt > 1 \
+        else spec.times[[500]]
+    values = spec.values[[0, 400, 650, 700, 900, 950, 999][:nt]] if nt > 1 \
+        else spec.values[[500]]
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), times, values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    xs = po.headline_fhn_points(20000, seed=nt)
+    a = pb.CudaEvaluator(ll, chunk_rows=1 << 30, as_list=False).evaluate(xs)
+    b = pb.CudaEvaluator(ll, chunk_rows=1 << 30, as_list=False,
+                         block=64).evaluate(xs)
+    assert np.array_equal(a, b) and np.all(np.isfinite(a))
+    want = po.scores(po.Spec('fhn', times, values, 'gaussian_known_sigma', 0.5),
+                     xs[:4])
+    assert np.max(rel_err(a[:4], want)) < ODE_SCORE_RTOL
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)
