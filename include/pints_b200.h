@@ -353,7 +353,8 @@ int pb200_de_propose(const double *d_current_all, int64_t first,
  * the arithmetic is that of pb200_hbac_propose, pb200_mh_accept_ratio and
  * pb200_ac_adapt, so fused and unfused runs give identical chains.
  *   ask   x* = x + chol(sigma e^{log lambda}) z
- *   tell  accept iff isfinite(fx) and log(u) < fx - cur_f; count; adapt with
+ *   tell  accept iff [isfinite(fx) and] log(u) < fx - cur_f (require_finite as
+ *         in pb200_mh_accept); count; adapt with
  *         `variant` (PB200_AC_*, or < 0 for none: initial phase, Metropolis);
  *         optionally store the new current point of chain j at
  *         d_samples[j * sample_stride + sample_offset ..+d]
@@ -361,13 +362,24 @@ int pb200_de_propose(const double *d_current_all, int64_t first,
 int pb200_ac_ask(const double *d_current, const double *d_sigma,
                  const double *d_log_lambda, double *d_proposed, int64_t n,
                  int32_t d, uint64_t seed, uint64_t offset, void *stream);
-int pb200_ac_tell(int32_t variant, double *d_current, double *d_current_f,
-                  const double *d_proposed, const double *d_fx,
+int pb200_ac_tell(int32_t variant, int32_t require_finite, double *d_current,
+                  double *d_current_f, const double *d_proposed,
+                  const double *d_fx,
                   uint8_t *d_accepted, int64_t *d_acceptance_count,
                   double *d_mu, double *d_sigma, double *d_log_lambda,
                   double *d_samples, int64_t sample_stride,
                   int64_t sample_offset, int64_t n, int32_t d, double gamma,
                   double target, uint64_t seed, uint64_t offset, void *stream);
+
+/* The same for DifferentialEvolutionMCMC.ask
+ * (pints/_mcmc/_differential_evolution.py:103-115): eps_j = b* z_j with the
+ * normals of (seed, offset_eps), partners from (seed, offset_pairs) as
+ * pb200_philox_pairs draws them, then the proposal of pb200_de_propose; its
+ * tell() is pb200_ac_tell with variant < 0 and require_finite = 0. */
+int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
+                 const double *d_b_star, double *d_proposed, int64_t n,
+                 int32_t d, double gamma, uint64_t seed, uint64_t offset_eps,
+                 uint64_t offset_pairs, void *stream);
 
 /* Counter-based RNG (Philox4x32-10): n doubles, N(0,1) or U(0,1), for
  * (seed, stream_id, offset).  Used only in device-RNG sampler mode. */

@@ -819,8 +819,7 @@ class CudaMCMCController(object):
             import torch.distributed as dist
             pool = torch.empty((self._n_chains, d), dtype=torch.float64,
                                device=device)
-        from ._samplers import HaarioBardenetACMC
-        store_in_tell = isinstance(sampler, HaarioBardenetACMC)
+        store_in_tell = True        # the samplers write the chain sample in tell()
         start = time.perf_counter()
         with torch.cuda.device(device):
             for it in range(n_iter):

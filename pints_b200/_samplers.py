@@ -69,11 +69,20 @@ class _DeviceOps(object):
                    _ptr(log_lambda), _ptr(prop), n, d, ctypes.c_uint64(seed),
                    ctypes.c_uint64(offset))
 
+    def de_ask(self, cur_all, first, b_star, prop, gamma, seed, off_eps,
+               off_pairs):
+        n, d = prop.shape
+        self._call(self.lib.pb200_de_ask, _ptr(cur_all), int(first),
+                   int(cur_all.shape[0]), _ptr(b_star), _ptr(prop), n, d,
+                   float(gamma), ctypes.c_uint64(seed),
+                   ctypes.c_uint64(off_eps), ctypes.c_uint64(off_pairs))
+
     def ac_tell(self, variant, cur, cur_f, prop, fx, accepted, acc_count, mu,
                 sigma, log_lambda, samples, stride, sample_offset, gamma,
-                target, seed, offset):
+                target, seed, offset, require_finite=True):
         n, d = cur.shape
-        self._call(self.lib.pb200_ac_tell, int(variant), _ptr(cur), _ptr(cur_f),
+        self._call(self.lib.pb200_ac_tell, int(variant),
+                   1 if require_finite else 0, _ptr(cur), _ptr(cur_f),
                    _ptr(prop), _ptr(fx), _ptr(accepted), _ptr(acc_count),
                    _ptr(mu), _ptr(sigma), _ptr(log_lambda),
                    _ptr(samples) if samples is not None else None,
@@ -433,7 +442,8 @@ class DifferentialEvolutionMCMC(object):
     """
 
     def __init__(self, chains, x0, device=None, rng='philox', seed=0,
-                 first=0, n_total=None, x0_mean=None):
+                 first=0, n_total=None, x0_mean=None, fused=True):
+        self._fused = bool(fused)      # one launch per ask() / tell()
         x0 = np.array(x0, dtype=np.float64, copy=True)
         if x0.ndim != 2 or x0.shape[0] != int(chains):
             raise ValueError(
@@ -523,6 +533,18 @@ class DifferentialEvolutionMCMC(object):
                 self._r2.copy_(torch.as_tensor(np.asarray(r2, np.int32)).to(dev))
             elif self._rng_mode == 'replay':
                 raise RuntimeError('replay mode: ask() needs eps, r1 and r2')
+            elif self._fused:
+                off_eps = self._rng.take(self._eps.numel())
+                off_pairs = self._rng.take(2 * self._n)
+                pool = self._current if all_current is None else all_current
+                if pool.shape[0] != self._n_total:
+                    raise ValueError('all_current must hold all %d chains'
+                                     % self._n_total)
+                self._ops.de_ask(pool, self._first, self._d_b_star,
+                                 self._proposed, gamma, self._rng.seed,
+                                 off_eps, off_pairs)
+                self._asked = True
+                return self._proposed
             else:
                 off = self._rng.take(self._eps.numel())
                 self._ops.normal(self._eps, self._rng.seed, off)
@@ -539,7 +561,7 @@ class DifferentialEvolutionMCMC(object):
         self._asked = True
         return self._proposed
 
-    def tell(self, fx, log_u=None):
+    def tell(self, fx, log_u=None, store=None):
         if not self._asked:
             raise RuntimeError('Tell called before proposal was set.')
         self._asked = False
@@ -554,6 +576,19 @@ class DifferentialEvolutionMCMC(object):
             self._current_f.copy_(fx)
             self._accepted.fill_(1)
             self._have_current = True
+            if store is not None:
+                store[0][:, store[1]].copy_(self._current)
+            return self._current, self._current_f, self._accepted
+        if log_u is None and self._rng_mode != 'replay' and self._fused:
+            off = self._rng.take(self._n)
+            samples, stride, soff = None, 0, 0
+            if store is not None:
+                samples = store[0]
+                stride, soff = samples.stride(0), store[1] * samples.stride(1)
+            self._ops.ac_tell(-1, self._current, self._current_f,
+                              self._proposed, fx, self._accepted, None, None,
+                              None, None, samples, stride, soff, 0.0, 0.0,
+                              self._rng.seed, off, require_finite=False)
             return self._current, self._current_f, self._accepted
         if log_u is not None:
             self._log_u.copy_(torch.as_tensor(log_u).to(self._log_u.device))
@@ -565,4 +600,6 @@ class DifferentialEvolutionMCMC(object):
             torch.log_(self._log_u)
         self._ops.mh_accept(self._current, self._current_f, self._proposed, fx,
                             self._log_u, self._accepted, False)
+        if store is not None:
+            store[0][:, store[1]].copy_(self._current)
         return self._current, self._current_f, self._accepted

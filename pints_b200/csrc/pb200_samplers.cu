@@ -393,7 +393,7 @@ __global__ void ac_ask_kernel(const double *__restrict__ cur, const double *__re
 // tell of the family on the device, one launch: log-uniform, accept/reject,
 // acceptance count, adaptation (variant < 0: none) and the chain sample
 // (= pb200_philox_uniform, log, pb200_mh_accept[_ratio], pb200_ac_adapt, copy)
-__global__ void ac_tell_kernel(int variant, double *__restrict__ cur,
+__global__ void ac_tell_kernel(int variant, int require_finite, double *__restrict__ cur,
                                double *__restrict__ cur_f, const double *__restrict__ prop,
                                const double *__restrict__ fx, uint8_t *__restrict__ accepted,
                                int64_t *__restrict__ acc_count, double *__restrict__ mu,
@@ -406,7 +406,7 @@ __global__ void ac_tell_kernel(int variant, double *__restrict__ cur,
     const double log_u = log(philox_uniform_at(j, seed, offset));
     const double f_new = fx[j];
     const double lr = __dsub_rn(f_new, cur_f[j]);
-    const bool acc = (log_u < lr) && isfinite(f_new);
+    const bool acc = (log_u < lr) && (!require_finite || isfinite(f_new));
     double x[PB200_MAX_PARAMS], prev[PB200_MAX_PARAMS], y[PB200_MAX_PARAMS];
     for (int k = 0; k < d; ++k) {
         prev[k] = cur[j * d + k];
@@ -459,7 +459,52 @@ int pb200_ac_ask(const double *d_current, const double *d_sigma, const double *d
     return pb200_check_cuda(cudaGetLastError(), "ac_ask_kernel launch");
 }
 
-int pb200_ac_tell(int32_t variant, double *d_current, double *d_current_f,
+// ask of the differential-evolution sampler on the device, one launch:
+// error draws, partner indices and proposal (= pb200_philox_normal scaled by
+// b*, pb200_philox_pairs, pb200_de_propose)
+__global__ void de_ask_kernel(const double *__restrict__ cur_all, int64_t first,
+                              int64_t n_total, const double *__restrict__ b_star,
+                              double *__restrict__ prop, int64_t n, int d, double gamma,
+                              uint64_t seed, uint64_t offset_eps, uint64_t offset_pairs) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t self = first + j;
+    const U4 r = philox4x32_10(offset_pairs + j, 3, seed);
+    int64_t a = static_cast<int64_t>((static_cast<uint64_t>(r.x) * static_cast<uint64_t>(n_total - 1)) >> 32);
+    int64_t b = static_cast<int64_t>((static_cast<uint64_t>(r.y) * static_cast<uint64_t>(n_total - 2)) >> 32);
+    if (a >= self) ++a;
+    const int64_t lo = a < self ? a : self, hi = a < self ? self : a;
+    if (b >= lo) ++b;
+    if (b >= hi) ++b;
+    const double *xj = cur_all + self * d;
+    const double *xa = cur_all + a * d;
+    const double *xb = cur_all + b * d;
+    for (int k = 0; k < d; ++k) {
+        const double eps = philox_normal_at(j * d + k, seed, offset_eps) * b_star[k];
+        const double step = __dmul_rn(gamma, __dsub_rn(xa[k], xb[k]));
+        prop[j * d + k] = __dadd_rn(__dadd_rn(xj[k], step), eps);
+    }
+}
+
+int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
+                 const double *d_b_star, double *d_proposed, int64_t n, int32_t d,
+                 double gamma, uint64_t seed, uint64_t offset_eps, uint64_t offset_pairs,
+                 void *stream) {
+    if (n < 0 || first < 0 || n_total < 3 || first + n > n_total || d < 1 ||
+        d > PB200_MAX_PARAMS) {
+        pb200_set_error("pb200_de_ask: bad n=%lld, first=%lld, n_total=%lld or d=%d",
+                        (long long)n, (long long)first, (long long)n_total, d);
+        return PB200_EINVAL;
+    }
+    if (n == 0) return PB200_OK;
+    de_ask_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_current_all, first, n_total, d_b_star, d_proposed, n, d, gamma, seed, offset_eps,
+        offset_pairs);
+    return pb200_check_cuda(cudaGetLastError(), "de_ask_kernel launch");
+}
+
+int pb200_ac_tell(int32_t variant, int32_t require_finite, double *d_current,
+                  double *d_current_f,
                   const double *d_proposed, const double *d_fx, uint8_t *d_accepted,
                   int64_t *d_acceptance_count, double *d_mu, double *d_sigma,
                   double *d_log_lambda, double *d_samples, int64_t sample_stride,
@@ -476,7 +521,7 @@ int pb200_ac_tell(int32_t variant, double *d_current, double *d_current_f,
         return PB200_EINVAL;
     }
     ac_tell_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        variant, d_current, d_current_f, d_proposed, d_fx, d_accepted, d_acceptance_count,
+        variant, require_finite, d_current, d_current_f, d_proposed, d_fx, d_accepted, d_acceptance_count,
         d_mu, d_sigma, d_log_lambda, d_samples, sample_stride, sample_offset, n, d, gamma,
         target, seed, offset);
     return pb200_check_cuda(cudaGetLastError(), "ac_tell_kernel launch");

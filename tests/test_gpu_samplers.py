@@ -341,3 +341,24 @@ def test_fused_ask_tell_gives_identical_chains(pb, name):
         assert np.array_equal(a, b)
     assert np.array_equal(out[0][2], out[1][2])
     assert (np.diff(out[0][0][:, :, 0], axis=1) != 0).mean() > 0.02
+
+
+def test_fused_de_ask_tell_gives_identical_chains(pb):
+    """pb200_de_ask / pb200_ac_tell against the separate launches of the
+    differential-evolution sampler: identical chains."""
+    post = logistic_posterior(pb)
+    dp = pb.CudaEvaluator(post, as_list=False).device_problem()
+    rng = np.random.RandomState(7)
+    n, n_iter = 64, 150
+    x0 = np.array([0.1, 50, 2]) * (1 + 0.05 * rng.randn(n, 3))
+    out = []
+    for fused in (True, False):
+        s = pb.DifferentialEvolutionMCMC(n, x0, seed=5, fused=fused)
+        samples = torch.zeros((n, n_iter, 3), dtype=torch.float64, device='cuda')
+        fx = torch.empty(n, dtype=torch.float64, device='cuda')
+        for it in range(n_iter):
+            dp.eval(s.ask(), out=fx)
+            s.tell(fx, store=(samples, it))
+        out.append(host(samples))
+    assert np.array_equal(out[0], out[1])
+    assert (np.diff(out[0][:, :, 0], axis=1) != 0).mean() > 0.02
