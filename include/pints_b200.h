@@ -89,6 +89,10 @@ typedef struct pb200_solver_opts {
                          /* allows the one-block-per-SM migrating layout)    */
     int32_t lanes;       /* GPU lanes per parameter vector: 1, or 2 (one per */
                          /* state, two-state models only); <= 0 -> automatic */
+    int32_t wide_interpolation;  /* observations that pile up inside long     */
+                         /* steps are taken four at a time: > 0 on, < 0 off, */
+                         /* 0 -> automatic (on for the smooth models, off    */
+                         /* for FitzHugh-Nagumo's relaxation oscillations)   */
 } pb200_solver_opts;
 
 int         pb200_version(void);

@@ -42,11 +42,12 @@ def _stream_ptr(device):
 
 
 def solver_opts(rtol=None, atol=None, h0=None, max_steps=None, block=None,
-                lanes=None):
+                lanes=None, wide_interpolation=None):
     return _lib.SolverOpts(
         rtol if rtol else DEFAULT_RTOL, atol if atol else DEFAULT_ATOL,
         h0 if h0 else 0.0, int(max_steps) if max_steps else 0,
-        int(block) if block else 0, int(lanes) if lanes else 0)
+        int(block) if block else 0, int(lanes) if lanes else 0,
+        0 if wide_interpolation is None else (1 if wide_interpolation else -1))
 
 
 class DeviceProblem(object):

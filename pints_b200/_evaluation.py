@@ -202,6 +202,11 @@ class CudaEvaluator(Evaluator):
     lanes_per_vector
         GPU lanes that integrate one parameter vector: 1, or 2 (one lane per
         state component, two-state models only); default automatic.
+    wide_interpolation
+        ODE models: take the observations that pile up inside long steps four
+        at a time (pays when steps span many observations); ``None`` =
+        automatic per model, ``True`` / ``False`` force it.  Results do not
+        depend on it.
     sort
         Cost-coherent scheduling of the ODE models (vectors with similar
         dynamics share a warp; results do not depend on it): ``True``,
@@ -222,7 +227,8 @@ class CudaEvaluator(Evaluator):
 
     def __init__(self, function, args=None, devices=None, rtol=None, atol=None,
                  max_steps=None, h0=None, block=None, as_list=True,
-                 chunk_rows=65536, lanes_per_vector=None, sort=None):
+                 chunk_rows=65536, lanes_per_vector=None, sort=None,
+                 wide_interpolation=None):
         if isinstance(function, ProblemSpec):
             spec = function
             function = _SpecFunction(spec)
@@ -235,7 +241,8 @@ class CudaEvaluator(Evaluator):
         self._lib = _lib.load()                # fails now if the library is absent
         self._spec = spec if spec is not None else describe(function)
         self._opts = dict(rtol=rtol, atol=atol, max_steps=max_steps, h0=h0,
-                          block=block, lanes=lanes_per_vector)
+                          block=block, lanes=lanes_per_vector,
+                          wide_interpolation=wide_interpolation)
         self._sort = sort
         self._as_list = bool(as_list)
         self._chunk_rows = max(1, int(chunk_rows))

@@ -38,7 +38,7 @@ class SolverOpts(Structure):
     """``pb200_solver_opts``"""
     _fields_ = [('rtol', c_double), ('atol', c_double), ('h0', c_double),
                 ('max_steps', c_int32), ('block', c_int32),
-                ('lanes', c_int32)]
+                ('lanes', c_int32), ('wide_interpolation', c_int32)]
 
 
 class LibraryError(RuntimeError):

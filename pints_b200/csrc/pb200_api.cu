@@ -52,6 +52,7 @@ SolverDev resolve_opts(const pb200_solver_opts *o, int *block, int *lanes) {
     s.half_rtol = 0.5 * s.rtol;
     s.h0 = (o && o->h0 > 0) ? o->h0 : 0.0;
     s.max_steps = (o && o->max_steps > 0) ? o->max_steps : 1000000;
+    s.wide = (o && o->wide_interpolation != 0) ? (o->wide_interpolation > 0 ? 1 : 0) : -1;
     *block = (o && o->block > 0) ? o->block : 0;
     *lanes = (o && o->lanes > 0) ? o->lanes : 0;
     return s;

@@ -93,6 +93,7 @@ struct SolverDev {
     double rtol, atol, h0;
     double half_rtol;             // 0.5 * rtol, used every step
     int32_t max_steps;
+    int32_t wide;                 // take pending observations four at a time first
 };
 
 // ---------------------------------------------------------------------------

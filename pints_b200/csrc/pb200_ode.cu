@@ -452,6 +452,9 @@ struct Series {
 #ifndef PB200_MAXTHREADS
 #define PB200_MAXTHREADS 128
 #endif
+#ifndef PB200_CLOOP_WIDE
+#define PB200_CLOOP_WIDE 4      // observations per trip of the wide (C) loop (1 = off)
+#endif
 #ifndef PB200_CLOOP_WIDTH
 #define PB200_CLOOP_WIDTH 1     // observations per trip of the (C) loop
 #endif
@@ -465,6 +468,7 @@ struct Series {
 #define PB200_RCP_STEPS 1
 #endif
 static_assert(PB200_PIPE_U + 1 <= PB200_SENTINEL_ROWS, "not enough sentinel rows");
+static_assert(PB200_CLOOP_WIDE <= PB200_SENTINEL_ROWS, "not enough sentinel rows");
 
 // Control flow is warp-uniform: every lane of a warp runs the same number of
 // loop iterations (votes decide), finished lanes idle on harmless arithmetic.
@@ -503,7 +507,7 @@ struct MigDev {
     uint32_t buf_off;    // byte offset of the hand-over area in dynamic shared memory
 };
 
-template <class M, bool SMEM, bool TRAJ, bool MIG>
+template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE>
 __global__ void __launch_bounds__(MIG ? 512 : PB200_MAXTHREADS)
 ode_kernel(const __grid_constant__ ProblemDev P,
            const __grid_constant__ ModelConsts mc,
@@ -783,7 +787,27 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         const double facd = static_cast<double>(fac);
 #endif
         after_reject = !ok;
-        // ---- (C) pending observations beyond the U slots, W per trip ----
+        // ---- (C) pending observations beyond the U slots ----
+        // Smooth problems take few, long steps (Lotka-Volterra: 9 observations
+        // per step): while at least half of the lanes still have WIDE or more
+        // pending, take them WIDE at a time (independent chains, one vote per
+        // trip); the rest, and bursty problems, go one per trip below.
+        if constexpr (WIDE) {
+            constexpr int NW = PB200_CLOOP_WIDE;
+            double t_far = series.at(off + (NW - 1) * ROWB);
+            while (__popc(__ballot_sync(FULL, le_bits(t_far, t))) >= 16) {
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    const double tk = series.at(off + k * ROWB);
+                    const bool more = le_bits(tk, t);
+                    interpolate(tk, off + k * ROWB, more);
+                    cnt += more ? 1u : 0u;
+                }
+                off += cnt * ROWB;
+                t_far = series.at(off + (NW - 1) * ROWB);
+            }
+        }
         {
             constexpr int W = PB200_CLOOP_WIDTH;
             double tn[W];
@@ -1424,14 +1448,16 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
         const int64_t per_block = static_cast<int64_t>(mig.q4 + mig.r) * 32;
         const int64_t mgrid = (n + per_block - 1) / per_block;
         const size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
-        PB200_LAUNCH((ode_kernel<M, true, false, true>), mgrid, mblock, mdyn);
+        if (s.wide) PB200_LAUNCH((ode_kernel<M, true, false, true, true>), mgrid, mblock, mdyn);
+        else PB200_LAUNCH((ode_kernel<M, true, false, true, false>), mgrid, mblock, mdyn);
         }
     } else if (use_smem) {
-        if (traj) PB200_LAUNCH((ode_kernel<M, true, true, false>), grid, block, dyn);
-        else PB200_LAUNCH((ode_kernel<M, true, false, false>), grid, block, dyn);
+        if (traj) PB200_LAUNCH((ode_kernel<M, true, true, false, false>), grid, block, dyn);
+        else if (s.wide) PB200_LAUNCH((ode_kernel<M, true, false, false, true>), grid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, true, false, false, false>), grid, block, dyn);
     } else {
-        if (traj) PB200_LAUNCH((ode_kernel<M, false, true, false>), grid, block, dyn);
-        else PB200_LAUNCH((ode_kernel<M, false, false, false>), grid, block, dyn);
+        if (traj) PB200_LAUNCH((ode_kernel<M, false, true, false, false>), grid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, false, false, false, false>), grid, block, dyn);
     }
 #undef PB200_XARG
     return pb200_check_cuda(cudaGetLastError(), "ode_kernel launch");
@@ -1488,8 +1514,14 @@ int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
 
 int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
                int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
-               const SolverDev &s, int block, int lanes, void *sort_ws,
+               const SolverDev &s_in, int block, int lanes, void *sort_ws,
                const ScatterDev &sc, cudaStream_t st) {
+    SolverDev s = s_in;
+    // automatic: the wide pending-observation loop pays when steps span many
+    // observations (Lotka-Volterra, SIR, ...: 9+ per step, -35 % time); for
+    // FitzHugh-Nagumo's relaxation oscillations (2.6 per step) its extra
+    // ballot and load per attempt cost 3 %
+    if (s.wide < 0) s.wide = p->dev.model == PB200_MODEL_FHN ? 0 : 1;
     if (lanes <= 0) lanes = PB200_DEFAULT_LANES;
     if (lanes != 1 && lanes != 2) {
         pb200_set_error("lanes per vector must be 0 (automatic), 1 or 2, got %d", lanes);

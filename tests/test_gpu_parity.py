@@ -640,6 +640,31 @@ def test_migrating_layout_with_very_short_series(pb, nt):
     assert np.max(rel_err(a[:4], want)) < ODE_SCORE_RTOL
 
 
+def test_wide_interpolation_changes_nothing(pb):
+    """The four-at-a-time pending-observation loop (on by default for the
+    smooth models, off for FitzHugh-Nagumo) only regroups the same
+    interpolations: scores and step counts are bit-identical either way."""
+    g = load_golden('lotka_volterra')
+    problem = pb.MultiOutputProblem(pb.toy.LotkaVolterraModel(), g['times'],
+                                    g['values'])
+    f = pb.GaussianLogLikelihood(problem)
+    a, sa = pb.CudaEvaluator(f, wide_interpolation=True).evaluate_array(
+        g['xs'], True)
+    b, sb = pb.CudaEvaluator(f, wide_interpolation=False).evaluate_array(
+        g['xs'], True)
+    c = evaluate(pb, f, g['xs'])                     # automatic (= on)
+    assert np.array_equal(a, b) and np.array_equal(sa, sb)
+    assert np.array_equal(a, c)
+    spec = po.headline_fhn_spec()
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    xs = po.headline_fhn_points(20000)
+    a = evaluate(pb, ll, xs, wide_interpolation=True, chunk_rows=1 << 30)
+    b = evaluate(pb, ll, xs, wide_interpolation=False, chunk_rows=1 << 30)
+    assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize('seed', [101, 102])
 def test_live_oracle_random_problems(pb, seed):
     rng = np.random.RandomState(seed)

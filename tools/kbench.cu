@@ -71,7 +71,8 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&d_x, xs.size() * 8)); CK(cudaMalloc(&d_s, n * 8)); CK(cudaMalloc(&d_steps, n * 4));
     CK(cudaMemcpy(d_x, xs.data(), xs.size() * 8, cudaMemcpyHostToDevice));
     int lanes = argc > 6 ? atoi(argv[6]) : 0;
-    pb200_solver_opts opts = {0, 0, 0, 0, block, lanes};
+    int wide = argc > 9 ? atoi(argv[9]) : 0;
+    pb200_solver_opts opts = {0, 0, 0, 0, block, lanes, wide};
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int w = 0; w < 3; ++w) PB(pb200_eval_sorted(p, d_x, n, 3, d_s, d_steps, &opts, d_ws, ws_bytes, nullptr));
     CK(cudaDeviceSynchronize());
