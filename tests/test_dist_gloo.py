@@ -83,3 +83,48 @@ def test_sharded_evaluator_world_size_2(n):
         p.join(120)
         assert p.exitcode == 0
     assert list(out) == [1, 1]
+
+
+def _exchange_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from pints_b200._dist import ScoreExchange
+
+        class FakeProblem(object):
+            """Stands in for DeviceProblem: score of a row = its first entry."""
+            def eval(self, d_params, out=None, steps=None):
+                out.copy_(d_params[:, 0])
+
+        per = 5
+        ex = ScoreExchange(per, 'cpu')
+        ok = not ex.fused                      # no peer memory under gloo / CPU
+        for gen in range(3):                   # buffers are reused per generation
+            n_mine = per if rank == 0 else 3   # ragged last block
+            x = torch.arange(n_mine, dtype=torch.float64).reshape(-1, 1) \
+                + 100.0 * rank + 1000.0 * gen
+            every = ex.run(FakeProblem(), x.repeat(1, 2))
+            want0 = torch.arange(per, dtype=torch.float64) + 1000.0 * gen
+            want1 = torch.arange(3, dtype=torch.float64) + 100.0 + 1000.0 * gen
+            ok = ok and torch.equal(every[:per], want0)
+            ok = ok and torch.equal(every[per:per + 3], want1)
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_score_exchange_falls_back_to_all_gather_on_cpu():
+    world = 2
+    ctx = mp.get_context('spawn')
+    out = ctx.Array('i', [0] * world)
+    port = 29900 + os.getpid() % 1000
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world
