@@ -4,6 +4,7 @@
 that scores the whole batch of positions in one fused CUDA launch.
 """
 import ctypes
+import warnings
 
 import numpy as np
 import torch
@@ -105,7 +106,7 @@ class _Lane(object):
             self.a_d_steps = self.d_steps.data_ptr()
 
     #: rows staged into pinned memory (and sent) per slice
-    STAGE_ROWS = 16384
+    STAGE_ROWS = 32768
 
     def launch(self, lib, xs, want_steps, chunk_rows):
         """Stage `xs` into pinned memory and enqueue copy-in, kernel and
@@ -122,6 +123,11 @@ class _Lane(object):
         handle, opts = self.problem._handle, ctypes.byref(self.problem.opts)
         pinned = bool(xs.flags['C_CONTIGUOUS'] and m * d >= 4096 and
                       lib.pb200_host_is_pinned(V(xs.ctypes.data)))
+        src = None
+        if not pinned and m * d >= 32768 and torch.get_num_threads() > 1:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')     # read-only arrays from ask()
+                src = torch.from_numpy(xs)
         with torch.cuda.device(self.device):
             for c in range(n_chunks):
                 lo, hi = c * rows, min(m, (c + 1) * rows)
@@ -134,9 +140,16 @@ class _Lane(object):
                         V(self.a_d_in + lo * d * 8),
                         V(xs.ctypes.data + lo * d * 8), (hi - lo) * d * 8, 1, st))
                 else:
+                    # staging copy into pinned memory: torch's copy is
+                    # multi-threaded (11 us for 1.5 MB on 16 cores against
+                    # 85 us for numpy's), slice by slice so that a slice is on
+                    # its way while the next one is staged
                     for a in range(lo, hi, self.STAGE_ROWS):
                         b = min(hi, a + self.STAGE_ROWS)
-                        np.copyto(self.h_in_np[a:b], xs[a:b])
+                        if src is not None:
+                            self.h_in[a:b].copy_(src[a:b])
+                        else:
+                            np.copyto(self.h_in_np[a:b], xs[a:b])
                         _lib.check(lib.pb200_copy_async(
                             V(self.a_d_in + a * d * 8),
                             V(self.a_h_in + a * d * 8), (b - a) * d * 8, 1, st))
