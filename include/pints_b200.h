@@ -57,7 +57,8 @@ extern "C" {
 #define PB200_MODEL_GOODWIN         6   /* _goodwin_oscillator_model.py:101-107 */
 #define PB200_MODEL_HES1            7   /* _hes1_michaelis_menten.py:129-140   */
 #define PB200_MODEL_REPRESSILATOR   8   /* _repressilator_model.py:91-108      */
-#define PB200_N_MODELS              9
+#define PB200_MODEL_BEELER_REUTER   9   /* _beeler_reuter_model.py:105-183     */
+#define PB200_N_MODELS              10
 
 /* objectives */
 #define PB200_OBJ_SSE                   0  /* pints/_error_measures.py:373-376     */
@@ -124,6 +125,9 @@ int64_t pb200_series_len(int32_t n_times, int32_t n_outputs);
  *   GOODWIN         [y0_x, y0_y, y0_z]
  *   HES1            [m0, p1_0, p2_0, k_deg]          (output: m)
  *   REPRESSILATOR   [y0 (6 values)]                  (outputs: m1, m2, m3)
+ *   BEELER_REUTER   [V0, Ca0, m0, h0, j0, d0, f0, x10, C_m, E_Na, I_amp,
+ *                    I_period, I_length]             (outputs: V, Ca_i;
+ *                    parameters: log of gNa, gNaC, gCa, gK1, gx1)
  * obj_consts (host)
  *   SSE                   weights[n_outputs]
  *   GAUSSIAN_KNOWN_SIGMA  offset[n_outputs], multip[n_outputs]

@@ -300,6 +300,75 @@ def repressilator_simulate(parameters, times, y0=None, **tol):
     return y[:, :3]
 
 
+BEELER_REUTER_CONSTS = dict(
+    y0=(-84.622, 2e-7), m0=0.01, h0=0.99, j0=0.98, d0=0.003, f0=0.99,
+    x10=0.0004, C_m=1.0, E_Na=50.0, I_Stim_amp=25.0, I_Stim_period=1000.0,
+    I_Stim_length=2.0)
+
+
+def beeler_reuter_rhs(states, time, parameters, k=BEELER_REUTER_CONSTS):
+    """pints/toy/_beeler_reuter_model.py:105-183 (Beeler-Reuter 1977): states
+    (V, Ca_i, m, h, j, d, f, x1); the parameters are the logarithms of the
+    maximum conductances; the stimulus is on while time % period < length."""
+    V, Cai, m, h, j, d, f, x1 = states
+    gNaBar, gNaC, gCaBar, gK1Bar, gx1Bar = np.exp(parameters)
+    # INa
+    INa = (gNaBar * m**3 * h * j + gNaC) * (V - k['E_Na'])
+    alpha = (V + 47) / (1 - np.exp(-0.1 * (V + 47)))
+    beta = 40 * np.exp(-0.056 * (V + 72))
+    dmdt = alpha * (1 - m) - beta * m
+    alpha = 0.126 * np.exp(-0.25 * (V + 77))
+    beta = 1.7 / (1 + np.exp(-0.082 * (V + 22.5)))
+    dhdt = alpha * (1 - h) - beta * h
+    alpha = 0.055 * np.exp(-0.25 * (V + 78)) / (1 + np.exp(-0.2 * (V + 78)))
+    beta = 0.3 / (1 + np.exp(-0.1 * (V + 32)))
+    djdt = alpha * (1 - j) - beta * j
+    # ICa
+    E_Ca = -82.3 - 13.0287 * np.log(Cai)
+    ICa = gCaBar * d * f * (V - E_Ca)
+    alpha = 0.095 * np.exp(-0.01 * (V + -5)) / (np.exp(-0.072 * (V + -5)) + 1)
+    beta = 0.07 * np.exp(-0.017 * (V + 44)) / (np.exp(0.05 * (V + 44)) + 1)
+    dddt = alpha * (1 - d) - beta * d
+    alpha = 0.012 * np.exp(-0.008 * (V + 28)) / (np.exp(0.15 * (V + 28)) + 1)
+    beta = 0.0065 * np.exp(-0.02 * (V + 30)) / (np.exp(-0.2 * (V + 30)) + 1)
+    dfdt = alpha * (1 - f) - beta * f
+    # Cai
+    dCaidt = -1e-7 * ICa + 0.07 * (1e-7 - Cai)
+    # IK1
+    IK1 = gK1Bar * (
+        4 * (np.exp(0.04 * (V + 85)) - 1)
+        / (np.exp(0.08 * (V + 53)) + np.exp(0.04 * (V + 53)))
+        + 0.2 * (V + 23) / (1 - np.exp(-0.04 * (V + 23))))
+    # IX1
+    Ix1 = gx1Bar * x1 * (np.exp(0.04 * (V + 77)) - 1) \
+        / np.exp(0.04 * (V + 35))
+    alpha = 0.0005 * np.exp(0.083 * (V + 50)) / (np.exp(0.057 * (V + 50)) + 1)
+    beta = 0.0013 * np.exp(-0.06 * (V + 20)) / (np.exp(-0.04 * (V + 333)) + 1)
+    dx1dt = alpha * (1 - x1) - beta * x1
+    # stimulus and membrane potential
+    if (time % k['I_Stim_period']) < k['I_Stim_length']:
+        IStim = k['I_Stim_amp']
+    else:
+        IStim = 0
+    dVdt = -(1 / k['C_m']) * (IK1 + Ix1 + INa + ICa - IStim)
+    return np.array([dVdt, dCaidt, dmdt, dhdt, djdt, dddt, dfdt, dx1dt])
+
+
+def beeler_reuter_simulate(parameters, times, y0=None, all_states=False,
+                           **tol):
+    """pints/toy/_beeler_reuter_model.py:205-222: odeint from ``times[0]`` with
+    ``hmax`` = the stimulus length and the model's own default tolerances
+    rtol = 1e-4, atol = 1e-6 (:197-203); returns (V, Ca_i)."""
+    k = BEELER_REUTER_CONSTS
+    v0, cai0 = k['y0'] if y0 is None else y0
+    start = [v0, cai0, k['m0'], k['h0'], k['j0'], k['d0'], k['f0'], k['x10']]
+    opts = dict(rtol=1e-4, atol=1e-6)
+    opts.update(tol)
+    sol = odeint(beeler_reuter_rhs, start, times, args=(parameters,),
+                 hmax=k['I_Stim_length'], **opts)
+    return sol if all_states else sol[:, 0:2]
+
+
 TRUTH_TOL = dict(rtol=1e-13, atol=1e-13, mxstep=100000)
 
 
@@ -308,7 +377,7 @@ TRUTH_TOL = dict(rtol=1e-13, atol=1e-13, mxstep=100000)
 # --------------------------------------------------------------------------
 
 MODELS = ('logistic', 'hh_ik', 'constant', 'fhn', 'lotka_volterra', 'sir',
-          'goodwin', 'hes1', 'repressilator')
+          'goodwin', 'hes1', 'repressilator', 'beeler_reuter')
 
 
 def simulate(model, consts, parameters, times, **tol):
@@ -336,6 +405,9 @@ def simulate(model, consts, parameters, times, **tol):
                              consts.get('fixed', (5., 3., 0.03)), **tol)
     if model == 'repressilator':
         return repressilator_simulate(parameters, times, consts.get('y0'),
+                                      **tol)
+    if model == 'beeler_reuter':
+        return beeler_reuter_simulate(parameters, times, consts.get('y0'),
                                       **tol)
     raise ValueError('unknown model ' + str(model))
 
@@ -478,7 +550,8 @@ class Spec(object):
     def n_model_parameters(self):
         return {'logistic': 2, 'hh_ik': 5, 'fhn': 3, 'lotka_volterra': 4,
                 'sir': 3, 'goodwin': 5, 'hes1': 4,
-                'repressilator': 4}.get(self.model, self.n_outputs)
+                'repressilator': 4,
+                'beeler_reuter': 5}.get(self.model, self.n_outputs)
 
     def n_parameters(self):
         extra = self.n_outputs if self.objective == 'gaussian' else 0

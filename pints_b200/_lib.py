@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libpints_b200.so')
 MODEL_LOGISTIC, MODEL_HH_IK, MODEL_CONSTANT = 0, 1, 2
 MODEL_FHN, MODEL_LOTKA_VOLTERRA, MODEL_SIR = 3, 4, 5
 MODEL_GOODWIN, MODEL_HES1, MODEL_REPRESSILATOR = 6, 7, 8
+MODEL_BEELER_REUTER = 9
 OBJ_SSE, OBJ_GAUSSIAN_KNOWN_SIGMA, OBJ_GAUSSIAN, OBJ_MSE, OBJ_RMSE = 0, 1, 2, 3, 4
 MAX_OUTPUTS, MAX_PARAMS, MAX_EVENTS = 8, 16, 64
 SENTINEL_ROWS = 8
@@ -27,7 +28,8 @@ MODEL_NAMES = {MODEL_LOGISTIC: 'logistic', MODEL_HH_IK: 'hh_ik',
                MODEL_CONSTANT: 'constant', MODEL_FHN: 'fhn',
                MODEL_LOTKA_VOLTERRA: 'lotka_volterra', MODEL_SIR: 'sir',
                MODEL_GOODWIN: 'goodwin', MODEL_HES1: 'hes1',
-               MODEL_REPRESSILATOR: 'repressilator'}
+               MODEL_REPRESSILATOR: 'repressilator',
+               MODEL_BEELER_REUTER: 'beeler_reuter'}
 AC_HAARIO_BARDENET, AC_HAARIO, AC_RAO_BLACKWELL = 0, 1, 2
 OBJECTIVE_NAMES = {OBJ_SSE: 'sse',
                    OBJ_GAUSSIAN_KNOWN_SIGMA: 'gaussian_known_sigma',

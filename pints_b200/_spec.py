@@ -70,7 +70,8 @@ class ProblemSpec(object):
         fixed = {_lib.MODEL_LOGISTIC: 2, _lib.MODEL_HH_IK: 5,
                  _lib.MODEL_FHN: 3, _lib.MODEL_LOTKA_VOLTERRA: 4,
                  _lib.MODEL_SIR: 3, _lib.MODEL_GOODWIN: 5,
-                 _lib.MODEL_HES1: 4, _lib.MODEL_REPRESSILATOR: 4}
+                 _lib.MODEL_HES1: 4, _lib.MODEL_REPRESSILATOR: 4,
+                 _lib.MODEL_BEELER_REUTER: 5}
         return fixed.get(self.model, self.n_outputs)
 
     def n_parameters(self):
@@ -80,7 +81,8 @@ class ProblemSpec(object):
     def is_ode(self):
         return self.model in (_lib.MODEL_FHN, _lib.MODEL_LOTKA_VOLTERRA,
                               _lib.MODEL_SIR, _lib.MODEL_GOODWIN,
-                              _lib.MODEL_HES1, _lib.MODEL_REPRESSILATOR)
+                              _lib.MODEL_HES1, _lib.MODEL_REPRESSILATOR,
+                              _lib.MODEL_BEELER_REUTER)
 
     def packed_series(self):
         """Rows ``[t_j, v_j0 ..]``, then ``SENTINEL_ROWS`` rows with time
@@ -118,6 +120,10 @@ class ProblemSpec(object):
             return (3 * 64 + 6 * 14 + 10 + 54) * steps + 13.0 * nt
         if self.model == _lib.MODEL_REPRESSILATOR:
             return (6 * 64 + 6 * 27 + 10 + 108) * steps + 35.0 * nt
+        if self.model == _lib.MODEL_BEELER_REUTER:
+            # right-hand side: 27 exp + 1 log (counted 1 each, as the
+            # reference writes them) + 19 divisions + 106 add/mul = 153
+            return (8 * 64 + 6 * 153 + 10 + 144) * steps + 24.0 * nt
         if self.model == _lib.MODEL_HH_IK:
             return 0.0 * steps + 12.0 * nt + 750.0
         return 0.0 * steps + 8.0 * nt * self.n_outputs
@@ -169,11 +175,17 @@ def describe_model(model):
     if kind == 'RepressilatorModel':
         y0 = np.asarray(model._y0, dtype=float)
         return _lib.MODEL_REPRESSILATOR, list(y0)
+    if kind == 'ActionPotentialModel':
+        return _lib.MODEL_BEELER_REUTER, [float(v) for v in (
+            model._v0, model._cai0, model._m0, model._h0, model._j0,
+            model._d0, model._f0, model._x10, model._C_m, model._E_Na,
+            model._I_Stim_amp, model._I_Stim_period, model._I_Stim_length)]
     raise TypeError(
         'CudaEvaluator supports the toy models LogisticModel, '
         'HodgkinHuxleyIKModel, ConstantModel, FitzhughNagumoModel, '
-        'LotkaVolterraModel, SIRModel, GoodwinOscillatorModel, Hes1Model and '
-        'RepressilatorModel; got %s.%s (no CPU fallback).'
+        'LotkaVolterraModel, SIRModel, GoodwinOscillatorModel, Hes1Model, '
+        'RepressilatorModel and ActionPotentialModel (Beeler-Reuter); '
+        'got %s.%s (no CPU fallback).'
         % (type(model).__module__, type(model).__name__))
 
 

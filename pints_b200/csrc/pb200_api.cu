@@ -43,6 +43,7 @@ const ModelInfo kModels[PB200_N_MODELS] = {
     /* GOODWIN        */ {5, 3, 3, true},
     /* HES1           */ {4, 1, 4, true},
     /* REPRESSILATOR  */ {4, 3, 6, true},
+    /* BEELER_REUTER  */ {5, 2, 13, true},
 };
 
 SolverDev resolve_opts(const pb200_solver_opts *o, int *block, int *lanes) {

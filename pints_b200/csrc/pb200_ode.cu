@@ -120,6 +120,7 @@ __constant__ double TAB[N_TAB] = {
 // then work on h-scaled increments and need no further multiplication by h.
 struct FhnModel {
     static constexpr bool MIGRATES = true;
+    static constexpr bool TIMED = false;
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 3;
     // V' = c (V - V^3/3 + R) = (c - (c/3) V^2) V + c R
     // R' = -(V - a + b R) / c  = (-1/c) V + (a/c) + (-b/c) R
@@ -160,6 +161,7 @@ struct FhnModel {
 
 struct LvModel {
     static constexpr bool MIGRATES = true;
+    static constexpr bool TIMED = false;
     static constexpr int NS = 2, NO = 2, OUT0 = 0, NP = 4;
     double a, b, c, d;
     double ha, nhb, nhc, hd;
@@ -191,6 +193,7 @@ struct LvModel {
 
 struct SirModel {
     static constexpr bool MIGRATES = true;
+    static constexpr bool TIMED = false;
     static constexpr int NS = 3, NO = 2, OUT0 = 1, NP = 3;
     double gamma, v;
     double nhg, hv;
@@ -234,6 +237,7 @@ struct SirModel {
 struct GoodwinModel {
     static constexpr int NS = 3, NO = 3, OUT0 = 0, NP = 5;
     static constexpr bool MIGRATES = false;     // needs 146 registers
+    static constexpr bool TIMED = false;
     double k2, k3, m1, m2, m3;
     double h_, hk2, hk3, nhm1, nhm2, nhm3;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
@@ -273,6 +277,7 @@ struct GoodwinModel {
 struct Hes1Model {
     static constexpr int NS = 3, NO = 1, OUT0 = 0, NP = 4;
     static constexpr bool MIGRATES = false;     // pow() needs > 128 registers
+    static constexpr bool TIMED = false;
     double iP0, v, k1, hh, kdeg;
     double h_, hv, hk1, nhkd;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
@@ -309,6 +314,7 @@ struct Hes1Model {
 struct RepressilatorModel {
     static constexpr int NS = 6, NO = 3, OUT0 = 0, NP = 4;
     static constexpr bool MIGRATES = false;     // 6 states need > 128 registers
+    static constexpr bool TIMED = false;
     double a0, al, be, nn;
     double h_, ha0, hal, hbe;
     __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
@@ -344,6 +350,102 @@ struct RepressilatorModel {
         for (int k = 0; k < NS; ++k) s2 = fma(f[k], f[k], s2);
         return s2;
     }
+};
+
+// Beeler-Reuter 1977 ventricular action potential
+// (pints/toy/_beeler_reuter_model.py:105-183): eight states
+// (V, Ca_i, m, h, j, d, f, x1), the first two are the outputs; the parameters
+// are the natural logarithms of the five maximum conductances
+// (gNa, gNaC, gCa, gK1, gx1).  The stimulus makes the right-hand side depend
+// on time (TIMED): 25 uA/cm^2 while t mod 1000 < 2.  The m gate relaxes at
+// 20 - 90 per ms over the whole action potential, so the explicit pair is
+// stability-bound at h ~ 0.04 ms (7 - 8 thousand steps for 400 ms whatever
+// the tolerance); the reference's LSODA switches to BDF there.
+// Exponentials with the same rate share one exp() (14 instead of 27).
+// consts: [V0, Ca0, m0, h0, j0, d0, f0, x10, C_m, E_Na, I_amp, I_period, I_length]
+struct BeelerReuterModel {
+    static constexpr int NS = 8, NO = 2, OUT0 = 0, NP = 5;
+    static constexpr bool MIGRATES = false;
+    static constexpr bool TIMED = true;
+    double gNa, gNaC, gCa, gK1, gx1;
+    double inv_cm, e_na, amp, period, length, h_;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double t_first, double *t0) {
+        gNa = exp(x[0]); gNaC = exp(x[1]); gCa = exp(x[2]); gK1 = exp(x[3]); gx1 = exp(x[4]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = mc.c[k];
+        inv_cm = 1.0 / mc.c[8]; e_na = mc.c[9]; amp = mc.c[10]; period = mc.c[11];
+        length = mc.c[12];
+        h_ = 1.0;
+        *t0 = t_first;
+    }
+    __device__ __forceinline__ void rhs_t(const double *y, double *f, double time) const {
+        const double V = y[0], Cai = y[1], m = y[2], hh = y[3], j = y[4], d = y[5],
+                     ff = y[6], x1 = y[7];
+        // one exp() per distinct rate; the shifted ones are constant multiples
+        const double e_m01 = exp(-0.1 * (V + 47.0));            // also -0.1 (V + 32)
+        const double e_m056 = exp(-0.056 * (V + 72.0));
+        const double e_m25 = exp(-0.25 * (V + 77.0));           // also -0.25 (V + 78)
+        const double e_m082 = exp(-0.082 * (V + 22.5));
+        const double e_m2 = exp(-0.2 * (V + 78.0));             // also -0.2 (V + 30)
+        const double e_m01b = exp(-0.01 * (V - 5.0));
+        const double e_m072 = exp(-0.072 * (V - 5.0));
+        const double e_m017 = exp(-0.017 * (V + 44.0));
+        const double e_p05 = exp(0.05 * (V + 44.0));
+        const double e_m008 = exp(-0.008 * (V + 28.0));
+        const double e_p15 = exp(0.15 * (V + 28.0));
+        const double e_m02 = exp(-0.02 * (V + 30.0));
+        const double e_p04 = exp(0.04 * (V + 53.0));            // all the +-0.04 and 0.08 terms
+        const double e_p083 = exp(0.083 * (V + 50.0));
+        const double e_p057 = exp(0.057 * (V + 50.0));
+        const double e_m06 = exp(-0.06 * (V + 20.0));
+        const double inv_e04 = 1.0 / e_p04;
+        // INa and its gates
+        const double INa = (gNa * (m * m * m) * hh * j + gNaC) * (V - e_na);
+        double al = (V + 47.0) / (1.0 - e_m01);
+        double be = 40.0 * e_m056;
+        f[2] = al * (1.0 - m) - be * m;
+        al = 0.126 * e_m25;
+        be = 1.7 / (1.0 + e_m082);
+        f[3] = al * (1.0 - hh) - be * hh;
+        al = 0.055 * (e_m25 * 0.7788007830714049) / (1.0 + e_m2);           // exp(-0.25)
+        be = 0.3 / (1.0 + e_m01 * 4.4816890703380645);                       // exp(1.5)
+        f[4] = al * (1.0 - j) - be * j;
+        // ICa and its gates
+        const double E_Ca = -82.3 - 13.0287 * log(Cai);
+        const double ICa = gCa * d * ff * (V - E_Ca);
+        al = 0.095 * e_m01b / (e_m072 + 1.0);
+        be = 0.07 * e_m017 / (e_p05 + 1.0);
+        f[5] = al * (1.0 - d) - be * d;
+        al = 0.012 * e_m008 / (e_p15 + 1.0);
+        be = 0.0065 * e_m02 / (e_m2 * 14764.781565577267 + 1.0);             // exp(9.6)
+        f[6] = al * (1.0 - ff) - be * ff;
+        f[1] = -1e-7 * ICa + 0.07 * (1e-7 - Cai);
+        // IK1: exp(0.04 (V+85)) = e04 exp(1.28), exp(0.08 (V+53)) = e04^2,
+        // exp(-0.04 (V+23)) = exp(1.2) / e04
+        const double IK1 = gK1 * (
+            4.0 * (e_p04 * 3.5966397255692817 - 1.0) / (e_p04 * e_p04 + e_p04)
+            + 0.2 * (V + 23.0) / (1.0 - 3.3201169227365472 * inv_e04));
+        // Ix1: exp(0.04 (V+77)) = e04 exp(0.96), exp(0.04 (V+35)) = e04 exp(-0.72)
+        const double Ix1 = gx1 * x1 * (e_p04 * 2.611696473423118 - 1.0)
+                           * (inv_e04 * 2.0544332106438876);                 // exp(0.72)
+        al = 0.0005 * e_p083 / (e_p057 + 1.0);
+        be = 0.0013 * e_m06 / (1.3674196065680964e-05 * inv_e04 + 1.0);      // exp(-11.2)
+        f[7] = al * (1.0 - x1) - be * x1;
+        // stimulus: (time % period) < length, times are not negative
+        double ph = time - period * floor(time / period);
+        if (ph < 0.0) ph += period;
+        const double IStim = ph < length ? amp : 0.0;
+        f[0] = -inv_cm * (IK1 + Ix1 + INa + ICa - IStim);
+    }
+    __device__ __forceinline__ void scale(double h) { h_ = h; }
+    __device__ __forceinline__ void hrhs_t(const double *y, double *K, double time) const {
+        rhs_t(y, K, time);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) K[k] *= h_;
+    }
+    // every vector is stability-bound by the same gate: nothing to sort on
+    __device__ __forceinline__ double cost_key(const double *) const { return gx1; }
 };
 
 // MUFU.RCP64H: >= 20 good bits, on the XU pipe (off the FP64 pipe).
@@ -507,8 +609,26 @@ struct MigDev {
     uint32_t buf_off;    // byte offset of the hand-over area in dynamic shared memory
 };
 
+// Block shape the plain layout is compiled for.  The eight-state model would
+// take 232 registers (8 warps per SM: two waves for a population of 65 536,
+// 0.363 s); asking for 7 blocks of 64 threads per SM caps it at 144 registers,
+// part of the K arrays spills to local memory (touched once per stage, against
+// ~700 instructions of right-hand side) and the 13.8 warps per SM of that
+// population are resident at once: 0.205 s, bit-identical results.
+// (6 blocks / 168 registers: 0.360 s; 8 blocks / 128 registers: 0.208 s.)
+#ifndef PB200_BR_BLOCKS
+#define PB200_BR_BLOCKS 7
+#endif
+template <class M> struct LaunchShape {
+    static constexpr int THREADS = PB200_MAXTHREADS, BLOCKS = 1;
+};
+template <> struct LaunchShape<BeelerReuterModel> {
+    static constexpr int THREADS = 64, BLOCKS = PB200_BR_BLOCKS;
+};
+
 template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE>
-__global__ void __launch_bounds__(MIG ? 512 : PB200_MAXTHREADS)
+__global__ void __launch_bounds__(MIG ? 512 : LaunchShape<M>::THREADS,
+                                  MIG ? 1 : LaunchShape<M>::BLOCKS)
 ode_kernel(const __grid_constant__ ProblemDev P,
            const __grid_constant__ ModelConsts mc,
            const double *__restrict__ params, int64_t n, int64_t ld,
@@ -616,7 +736,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     const double half_rtol = S.half_rtol, atol = S.atol;
     double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], K6[NS], K7[NS];
     double yn[NS], w[NS];
-    model.rhs(y, K1);
+    if constexpr (M::TIMED) model.rhs_t(y, K1, t); else model.rhs(y, K1);
 
     // ---- first step (Hairer's hinit, as scipy's select_initial_step) ----
     double h = S.h0;
@@ -634,7 +754,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         double h_a = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
 #pragma unroll
         for (int j = 0; j < NS; ++j) w[j] = fma(h_a, K1[j], y[j]);
-        model.rhs(w, K2);
+        if constexpr (M::TIMED) model.rhs_t(w, K2, t + h_a); else model.rhs(w, K2);
         double d2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
@@ -711,6 +831,13 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         model.scale(h);
     }
 
+    // K = h f(w) of one stage; models with a time-dependent right-hand side
+    // (TIMED) also get the stage time t + c h
+    auto stage = [&](const double *w_, double *K_, double c) {
+        if constexpr (M::TIMED) model.hrhs_t(w_, K_, fma(c, h, t));
+        else model.hrhs(w_, K_);
+    };
+
     constexpr int kLoopUnroll = PB200_LOOP_UNROLL;
 #pragma unroll kLoopUnroll
     for (;;) {
@@ -741,27 +868,27 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         // ---- (B) six stages on K = h f (K1 is h f(y): first-same-as-last) ----
 #pragma unroll
         for (int j = 0; j < NS; ++j) w[j] = fma(A21, K1[j], y[j]);
-        model.hrhs(w, K2);
+        stage(w, K2, 0.2);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             w[j] = fma(A32, K2[j], fma(A31, K1[j], y[j]));
-        model.hrhs(w, K3);
+        stage(w, K3, 0.3);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             w[j] = fma(A43, K3[j], fma(A42, K2[j], fma(A41, K1[j], y[j])));
-        model.hrhs(w, K4);
+        stage(w, K4, 0.8);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             w[j] = fma(A54, K4[j], fma(A53, K3[j], fma(A52, K2[j], fma(A51, K1[j], y[j]))));
-        model.hrhs(w, K5);
+        stage(w, K5, 8.0 / 9.0);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             w[j] = fma(A65, K5[j], fma(A64, K4[j], fma(A63, K3[j], fma(A62, K2[j], fma(A61, K1[j], y[j])))));
-        model.hrhs(w, K6);
+        stage(w, K6, 1.0);
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             yn[j] = fma(B6, K6[j], fma(B5, K5[j], fma(B4, K4[j], fma(B3, K3[j], fma(B1, K1[j], y[j])))));
-        model.hrhs(yn, K7);
+        stage(yn, K7, 1.0);
         // ---- embedded error estimate, sum of squared scaled errors ----
         // scale atol + rtol (|y| + |ynew|) / 2: one DADD with |.| modifiers
         // instead of max (DSETP + 64-bit select); the 1e-6-accurate reciprocal
@@ -1414,7 +1541,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     const bool traj = d_traj != nullptr;
     const bool auto_layout = block <= 0;      // an explicit block size means the plain layout
     if (block <= 0) block = 64;
-    if (block > PB200_MAXTHREADS) block = PB200_MAXTHREADS;
+    if (block > LaunchShape<M>::THREADS) block = LaunchShape<M>::THREADS;
     block = (block + 31) & ~31;                 // whole warps: the kernel votes
     const int64_t grid = (n + block - 1) / block;
     if (grid <= 0) return PB200_OK;
@@ -1544,6 +1671,8 @@ int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
             return launch_model<Hes1Model>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_REPRESSILATOR:
             return launch_model<RepressilatorModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
+        case PB200_MODEL_BEELER_REUTER:
+            return launch_model<BeelerReuterModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
     }
     pb200_set_error("model %d is not an ODE model", p->dev.model);
     return PB200_EUNSUPPORTED;

@@ -340,6 +340,23 @@ def golden_repressilator():
                 truth_one, 33)
 
 
+def golden_beeler_reuter():
+    """Beeler-Reuter action potential (pints/toy/_beeler_reuter_model.py): the
+    reference at its default (1e-4, 1e-6) tolerances and a tight-tolerance
+    counterpart; per-output noise levels (mV and mM differ by 1e7)."""
+    model = pints.toy.ActionPotentialModel()
+    times = model.suggested_times()
+    y0 = [model._v0, model._cai0, model._m0, model._h0, model._j0, model._d0,
+          model._f0, model._x10]
+
+    def truth_one(x):
+        # Ca_i is 1e-7 .. 7e-6: the truth run uses relative control only
+        return odeint(model._rhs, y0, times, (x,), hmax=2.0, rtol=1e-12,
+                      atol=1e-20, mxstep=1000000)[:, :2]
+    _golden_ode('beeler_reuter', model, times, model.suggested_parameters(),
+                np.array([1.0, 2e-7]), 0.02, truth_one, 34)
+
+
 def golden_composed_prior():
     """LogPosterior with a ComposedLogPrior (uniform box on the first two FHN
     parameters, Gaussian on the third and on sigma_1, uniform on sigma_2)."""
@@ -569,6 +586,7 @@ if __name__ == '__main__':
     golden_goodwin()
     golden_hes1()
     golden_repressilator()
+    golden_beeler_reuter()
     golden_error_measures()
     golden_composed_prior()
     golden_hbac()

@@ -302,3 +302,16 @@ def test_cuda_evaluator_is_a_pints_evaluator(pints_ref):
         pints.toy.RepressilatorModel(), g['times'], np.zeros((1000, 3)))))
     assert spec.model == _lib.MODEL_REPRESSILATOR
     assert spec.model_consts == [0, 0, 0, 2, 1, 3]
+    br = pints.toy.ActionPotentialModel()
+    spec = pb.describe(pints.GaussianLogLikelihood(pints.MultiOutputProblem(
+        br, br.suggested_times(), np.zeros((800, 2)))))
+    assert spec.model == _lib.MODEL_BEELER_REUTER and spec.n_parameters() == 7
+    assert spec.model_consts == [-84.622, 2e-7, 0.01, 0.99, 0.98, 0.003, 0.99,
+                                 0.0004, 1.0, 50.0, 25.0, 1000.0, 2.0]
+    mirror = pb.toy.ActionPotentialModel()
+    assert pb.describe(pb.SumOfSquaresError(pb.MultiOutputProblem(
+        mirror, br.suggested_times(), np.zeros((800, 2))))).model_consts \
+        == spec.model_consts
+    assert np.array_equal(mirror.suggested_parameters(),
+                          br.suggested_parameters())
+    assert np.array_equal(mirror.suggested_times(), br.suggested_times())

@@ -427,7 +427,8 @@ def test_error_measures_golden():
         po.Spec('constant', times, values, 'rmse')
 
 
-@pytest.mark.parametrize('name', ['goodwin', 'hes1', 'repressilator'])
+@pytest.mark.parametrize('name', ['goodwin', 'hes1', 'repressilator',
+                                  'beeler_reuter'])
 def test_more_ode_models_golden(name):
     """(f) row 4: Goodwin, Hes1 and Repressilator restated in the oracle are
     bit-identical to the reference (same odeint call, same right-hand side)."""
@@ -452,6 +453,17 @@ def test_more_ode_models_reference_unit_tests():
     # pints/tests/test_toy_repressilator_model.py: starts at y0[:3]
     v = po.repressilator_simulate([1, 1000, 5, 2], np.linspace(0, 40, 400))
     assert v.shape == (400, 3) and np.all(v[0] == 0)
+    # pints/tests/test_toy_beeler_reuter_model.py:27-55: initial values, shapes
+    # and the all-states variant
+    p0 = np.log([4.0, 0.003, 0.09, 0.35, 0.8])
+    t = np.arange(0, 100, 0.5)
+    v = po.beeler_reuter_simulate(p0, t)
+    assert v.shape == (200, 2) and v[0, 0] == -84.622 and v[0, 1] == 2e-7
+    assert v[:, 0].max() > 20 and np.all(v[:, 1] > 0)     # an action potential
+    a = po.beeler_reuter_simulate(p0, t, all_states=True)
+    assert a.shape == (200, 8) and np.array_equal(a[:, :2], v)
+    v = po.beeler_reuter_simulate(p0, t, y0=[-80, 1e-5])
+    assert v[0, 0] == -80 and v[0, 1] == 1e-5
 
 
 def test_composed_prior_golden():
