@@ -415,7 +415,7 @@ def run_ours(args):
                     'value_pageable_input': total / e2e_pageable_s,
                     'api_pageable_input': 'same call with an ordinary ndarray: '
                                           'staged through pinned memory in '
-                                          'slices of 16384 rows',
+                                          'slices of 32768 rows (multi-threaded copy)',
                     'value_as_list': total / e2e_list_s,
                     'api_as_list': 'CudaEvaluator(f).evaluate(ndarray) -> list '
                                    '(the reference\'s return type)'},

@@ -352,102 +352,6 @@ struct RepressilatorModel {
     }
 };
 
-// Beeler-Reuter 1977 ventricular action potential
-// (pints/toy/_beeler_reuter_model.py:105-183): eight states
-// (V, Ca_i, m, h, j, d, f, x1), the first two are the outputs; the parameters
-// are the natural logarithms of the five maximum conductances
-// (gNa, gNaC, gCa, gK1, gx1).  The stimulus makes the right-hand side depend
-// on time (TIMED): 25 uA/cm^2 while t mod 1000 < 2.  The m gate relaxes at
-// 20 - 90 per ms over the whole action potential, so the explicit pair is
-// stability-bound at h ~ 0.04 ms (7 - 8 thousand steps for 400 ms whatever
-// the tolerance); the reference's LSODA switches to BDF there.
-// Exponentials with the same rate share one exp() (14 instead of 27).
-// consts: [V0, Ca0, m0, h0, j0, d0, f0, x10, C_m, E_Na, I_amp, I_period, I_length]
-struct BeelerReuterModel {
-    static constexpr int NS = 8, NO = 2, OUT0 = 0, NP = 5;
-    static constexpr bool MIGRATES = false;
-    static constexpr bool TIMED = true;
-    double gNa, gNaC, gCa, gK1, gx1;
-    double inv_cm, e_na, amp, period, length, h_;
-    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
-                                         double *y, double t_first, double *t0) {
-        gNa = exp(x[0]); gNaC = exp(x[1]); gCa = exp(x[2]); gK1 = exp(x[3]); gx1 = exp(x[4]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = mc.c[k];
-        inv_cm = 1.0 / mc.c[8]; e_na = mc.c[9]; amp = mc.c[10]; period = mc.c[11];
-        length = mc.c[12];
-        h_ = 1.0;
-        *t0 = t_first;
-    }
-    __device__ __forceinline__ void rhs_t(const double *y, double *f, double time) const {
-        const double V = y[0], Cai = y[1], m = y[2], hh = y[3], j = y[4], d = y[5],
-                     ff = y[6], x1 = y[7];
-        // one exp() per distinct rate; the shifted ones are constant multiples
-        const double e_m01 = exp(-0.1 * (V + 47.0));            // also -0.1 (V + 32)
-        const double e_m056 = exp(-0.056 * (V + 72.0));
-        const double e_m25 = exp(-0.25 * (V + 77.0));           // also -0.25 (V + 78)
-        const double e_m082 = exp(-0.082 * (V + 22.5));
-        const double e_m2 = exp(-0.2 * (V + 78.0));             // also -0.2 (V + 30)
-        const double e_m01b = exp(-0.01 * (V - 5.0));
-        const double e_m072 = exp(-0.072 * (V - 5.0));
-        const double e_m017 = exp(-0.017 * (V + 44.0));
-        const double e_p05 = exp(0.05 * (V + 44.0));
-        const double e_m008 = exp(-0.008 * (V + 28.0));
-        const double e_p15 = exp(0.15 * (V + 28.0));
-        const double e_m02 = exp(-0.02 * (V + 30.0));
-        const double e_p04 = exp(0.04 * (V + 53.0));            // all the +-0.04 and 0.08 terms
-        const double e_p083 = exp(0.083 * (V + 50.0));
-        const double e_p057 = exp(0.057 * (V + 50.0));
-        const double e_m06 = exp(-0.06 * (V + 20.0));
-        const double inv_e04 = 1.0 / e_p04;
-        // INa and its gates
-        const double INa = (gNa * (m * m * m) * hh * j + gNaC) * (V - e_na);
-        double al = (V + 47.0) / (1.0 - e_m01);
-        double be = 40.0 * e_m056;
-        f[2] = al * (1.0 - m) - be * m;
-        al = 0.126 * e_m25;
-        be = 1.7 / (1.0 + e_m082);
-        f[3] = al * (1.0 - hh) - be * hh;
-        al = 0.055 * (e_m25 * 0.7788007830714049) / (1.0 + e_m2);           // exp(-0.25)
-        be = 0.3 / (1.0 + e_m01 * 4.4816890703380645);                       // exp(1.5)
-        f[4] = al * (1.0 - j) - be * j;
-        // ICa and its gates
-        const double E_Ca = -82.3 - 13.0287 * log(Cai);
-        const double ICa = gCa * d * ff * (V - E_Ca);
-        al = 0.095 * e_m01b / (e_m072 + 1.0);
-        be = 0.07 * e_m017 / (e_p05 + 1.0);
-        f[5] = al * (1.0 - d) - be * d;
-        al = 0.012 * e_m008 / (e_p15 + 1.0);
-        be = 0.0065 * e_m02 / (e_m2 * 14764.781565577267 + 1.0);             // exp(9.6)
-        f[6] = al * (1.0 - ff) - be * ff;
-        f[1] = -1e-7 * ICa + 0.07 * (1e-7 - Cai);
-        // IK1: exp(0.04 (V+85)) = e04 exp(1.28), exp(0.08 (V+53)) = e04^2,
-        // exp(-0.04 (V+23)) = exp(1.2) / e04
-        const double IK1 = gK1 * (
-            4.0 * (e_p04 * 3.5966397255692817 - 1.0) / (e_p04 * e_p04 + e_p04)
-            + 0.2 * (V + 23.0) / (1.0 - 3.3201169227365472 * inv_e04));
-        // Ix1: exp(0.04 (V+77)) = e04 exp(0.96), exp(0.04 (V+35)) = e04 exp(-0.72)
-        const double Ix1 = gx1 * x1 * (e_p04 * 2.611696473423118 - 1.0)
-                           * (inv_e04 * 2.0544332106438876);                 // exp(0.72)
-        al = 0.0005 * e_p083 / (e_p057 + 1.0);
-        be = 0.0013 * e_m06 / (1.3674196065680964e-05 * inv_e04 + 1.0);      // exp(-11.2)
-        f[7] = al * (1.0 - x1) - be * x1;
-        // stimulus: (time % period) < length, times are not negative
-        double ph = time - period * floor(time / period);
-        if (ph < 0.0) ph += period;
-        const double IStim = ph < length ? amp : 0.0;
-        f[0] = -inv_cm * (IK1 + Ix1 + INa + ICa - IStim);
-    }
-    __device__ __forceinline__ void scale(double h) { h_ = h; }
-    __device__ __forceinline__ void hrhs_t(const double *y, double *K, double time) const {
-        rhs_t(y, K, time);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) K[k] *= h_;
-    }
-    // every vector is stability-bound by the same gate: nothing to sort on
-    __device__ __forceinline__ double cost_key(const double *) const { return gx1; }
-};
-
 // MUFU.RCP64H: >= 20 good bits, on the XU pipe (off the FP64 pipe).
 __device__ __forceinline__ double rcp_seed(double x) {
     double r;
@@ -464,6 +368,147 @@ __device__ __forceinline__ double rcp_newton(double x) {
     for (int k = 0; k < STEPS; ++k) r = fma(r, fma(-x, r, 1.0), r);
     return r;
 }
+
+// exp(x) for |x| <= 700 without the range branches of the library routine, so
+// that independent exponentials interleave (the eight-state model evaluates
+// sixteen per right-hand side): n = rint(x / ln 2) by the 1.5 * 2^52 shift,
+// two-step Cody-Waite reduction to |r| <= 0.347, Taylor polynomial of degree
+// 13 (remainder 4e-18), exponent added as an integer.  Within 1 ulp of exp().
+__device__ __forceinline__ double exp_bounded(double x) {
+    constexpr double SHIFT = 6755399441055744.0;
+    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const int n = __double2loint(t);
+    const double nf = t - SHIFT;
+    double r = fma(nf, -6.93147180559945286e-01, x);
+    r = fma(nf, -2.31904681384629956e-17, r);
+    double p = 1.6059043836821613e-10;                // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);              // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// a / b for a normal-range b, no slow path: reciprocal by two Newton steps,
+// quotient with one residual correction (last-place accurate).
+__device__ __forceinline__ double div_normal(double a, double b) {
+    const double r = rcp_newton<2>(b);
+    const double q = a * r;
+    return fma(r, fma(-b, q, a), q);
+}
+
+// Beeler-Reuter 1977 ventricular action potential
+// (pints/toy/_beeler_reuter_model.py:105-183): eight states
+// (V, Ca_i, m, h, j, d, f, x1), the first two are the outputs; the parameters
+// are the natural logarithms of the five maximum conductances
+// (gNa, gNaC, gCa, gK1, gx1).  The stimulus makes the right-hand side depend
+// on time (TIMED): 25 uA/cm^2 while t mod 1000 < 2.  The m gate relaxes at
+// 20 - 90 per ms over the whole action potential, so the explicit pair is
+// stability-bound at h ~ 0.04 ms (7 - 8 thousand steps for 400 ms whatever
+// the tolerance); the reference's LSODA switches to BDF there.
+// Exponentials with the same rate share one exp() (14 instead of 27).
+// consts: [V0, Ca0, m0, h0, j0, d0, f0, x10, C_m, E_Na, I_amp, I_period, I_length]
+struct BeelerReuterModel {
+    static constexpr int NS = 8, NO = 2, OUT0 = 0, NP = 5;
+    static constexpr bool MIGRATES = false;
+    static constexpr bool TIMED = true;
+    double gNa, gNaC, gCa, gK1, gx1;
+    double inv_cm, e_na, amp, period, inv_period, length, h_;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double t_first, double *t0) {
+        gNa = exp(x[0]); gNaC = exp(x[1]); gCa = exp(x[2]); gK1 = exp(x[3]); gx1 = exp(x[4]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = mc.c[k];
+        inv_cm = 1.0 / mc.c[8]; e_na = mc.c[9]; amp = mc.c[10]; period = mc.c[11];
+        length = mc.c[12];
+        inv_period = 1.0 / period;
+        h_ = 1.0;
+        *t0 = t_first;
+    }
+    __device__ __forceinline__ void rhs_t(const double *y, double *f, double time) const {
+        const double V = y[0], Cai = y[1], m = y[2], hh = y[3], j = y[4], d = y[5],
+                     ff = y[6], x1 = y[7];
+        // one exponential per distinct rate; the shifted ones are constant
+        // multiples.  Inside the exponentials V is clamped to +-800 mV (the
+        // physiological range is -90 .. +50), which keeps every argument
+        // within exp_bounded's range.
+        const double Vc = fmin(fmax(V, -800.0), 800.0);
+#define PB200_BR_EXP(rate, shift) exp_bounded((rate) * (Vc + (shift)))
+        const double e_m01 = PB200_BR_EXP(-0.1, 47.0);            // also -0.1 (V + 32)
+        const double e_m056 = PB200_BR_EXP(-0.056, 72.0);
+        const double e_m25 = PB200_BR_EXP(-0.25, 77.0);           // also -0.25 (V + 78)
+        const double e_m082 = PB200_BR_EXP(-0.082, 22.5);
+        const double e_m2 = PB200_BR_EXP(-0.2, 78.0);             // also -0.2 (V + 30)
+        const double e_m01b = PB200_BR_EXP(-0.01, -5.0);
+        const double e_m072 = PB200_BR_EXP(-0.072, -5.0);
+        const double e_m017 = PB200_BR_EXP(-0.017, 44.0);
+        const double e_p05 = PB200_BR_EXP(0.05, 44.0);
+        const double e_m008 = PB200_BR_EXP(-0.008, 28.0);
+        const double e_p15 = PB200_BR_EXP(0.15, 28.0);
+        const double e_m02 = PB200_BR_EXP(-0.02, 30.0);
+        const double e_p04 = PB200_BR_EXP(0.04, 53.0);            // all the +-0.04 and 0.08 terms
+        const double e_p083 = PB200_BR_EXP(0.083, 50.0);
+        const double e_p057 = PB200_BR_EXP(0.057, 50.0);
+        const double e_m06 = PB200_BR_EXP(-0.06, 20.0);
+        const double inv_e04 = rcp_newton<2>(e_p04);
+#undef PB200_BR_EXP
+        // INa and its gates
+        const double INa = (gNa * (m * m * m) * hh * j + gNaC) * (V - e_na);
+        double al = div_normal(V + 47.0, 1.0 - e_m01);
+        double be = 40.0 * e_m056;
+        f[2] = al * (1.0 - m) - be * m;
+        al = 0.126 * e_m25;
+        be = div_normal(1.7, 1.0 + e_m082);
+        f[3] = al * (1.0 - hh) - be * hh;
+        al = div_normal(0.055 * (e_m25 * 0.7788007830714049), 1.0 + e_m2);           // exp(-0.25)
+        be = div_normal(0.3, 1.0 + e_m01 * 4.4816890703380645);                       // exp(1.5)
+        f[4] = al * (1.0 - j) - be * j;
+        // ICa and its gates
+        const double E_Ca = -82.3 - 13.0287 * log(Cai);
+        const double ICa = gCa * d * ff * (V - E_Ca);
+        al = div_normal(0.095 * e_m01b, e_m072 + 1.0);
+        be = div_normal(0.07 * e_m017, e_p05 + 1.0);
+        f[5] = al * (1.0 - d) - be * d;
+        al = div_normal(0.012 * e_m008, e_p15 + 1.0);
+        be = div_normal(0.0065 * e_m02, e_m2 * 14764.781565577267 + 1.0);             // exp(9.6)
+        f[6] = al * (1.0 - ff) - be * ff;
+        f[1] = -1e-7 * ICa + 0.07 * (1e-7 - Cai);
+        // IK1: exp(0.04 (V+85)) = e04 exp(1.28), exp(0.08 (V+53)) = e04^2,
+        // exp(-0.04 (V+23)) = exp(1.2) / e04
+        const double IK1 = gK1 * (
+            div_normal(4.0 * (e_p04 * 3.5966397255692817 - 1.0), e_p04 * e_p04 + e_p04)
+            + div_normal(0.2 * (V + 23.0), 1.0 - 3.3201169227365472 * inv_e04));
+        // Ix1: exp(0.04 (V+77)) = e04 exp(0.96), exp(0.04 (V+35)) = e04 exp(-0.72)
+        const double Ix1 = gx1 * x1 * (e_p04 * 2.611696473423118 - 1.0)
+                           * (inv_e04 * 2.0544332106438876);                 // exp(0.72)
+        al = div_normal(0.0005 * e_p083, e_p057 + 1.0);
+        be = div_normal(0.0013 * e_m06, 1.3674196065680964e-05 * inv_e04 + 1.0);      // exp(-11.2)
+        f[7] = al * (1.0 - x1) - be * x1;
+        // stimulus: (time % period) < length, times are not negative
+        double ph = fma(-period, floor(time * inv_period), time);
+        if (ph < 0.0) ph += period;
+        if (ph >= period) ph -= period;
+        const double IStim = ph < length ? amp : 0.0;
+        f[0] = -inv_cm * (IK1 + Ix1 + INa + ICa - IStim);
+    }
+    __device__ __forceinline__ void scale(double h) { h_ = h; }
+    __device__ __forceinline__ void hrhs_t(const double *y, double *K, double time) const {
+        rhs_t(y, K, time);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) K[k] *= h_;
+    }
+    // every vector is stability-bound by the same gate: nothing to sort on
+    __device__ __forceinline__ double cost_key(const double *) const { return gx1; }
+};
 
 // ss += r * r only where `valid`: a predicated DFMA instead of a DFMA plus a
 // 64-bit select (two FSELs on the issue port).
@@ -611,19 +656,28 @@ struct MigDev {
 
 // Block shape the plain layout is compiled for.  The eight-state model would
 // take 232 registers (8 warps per SM: two waves for a population of 65 536,
-// 0.363 s); asking for 7 blocks of 64 threads per SM caps it at 144 registers,
-// part of the K arrays spills to local memory (touched once per stage, against
-// ~700 instructions of right-hand side) and the 13.8 warps per SM of that
-// population are resident at once: 0.205 s, bit-identical results.
-// (6 blocks / 168 registers: 0.360 s; 8 blocks / 128 registers: 0.208 s.)
+// 0.363 s).  Compiled for one block of up to 448 threads per SM it gets 128
+// registers, part of the K arrays spills to local memory (touched once per
+// stage, against ~700 instructions of right-hand side) and the 13.8 warps per
+// SM of that population are resident at once; a single copy of the series per
+// SM leaves the rest of the 256 KB for the spilled state in L1.  Measured at
+// populations 16 384 / 65 536 / 262 144 (branch-free exp and division):
+//   448 x 1, 128 registers   0.128 / 0.180 / 0.710 s      <- default
+//   64 x 7,  128 registers   0.129 / 0.216 / 0.798 s
+//   384 x 1, 168 registers   0.122 / 0.255 / 0.641 s      (two waves at 65 536)
+// and with the library exp() and division (branches keep the sixteen
+// exponentials of a right-hand side from interleaving): 0.192 / 0.205 / - s.
 #ifndef PB200_BR_BLOCKS
-#define PB200_BR_BLOCKS 7
+#define PB200_BR_BLOCKS 1
+#endif
+#ifndef PB200_BR_THREADS
+#define PB200_BR_THREADS 448
 #endif
 template <class M> struct LaunchShape {
     static constexpr int THREADS = PB200_MAXTHREADS, BLOCKS = 1;
 };
 template <> struct LaunchShape<BeelerReuterModel> {
-    static constexpr int THREADS = 64, BLOCKS = PB200_BR_BLOCKS;
+    static constexpr int THREADS = PB200_BR_THREADS, BLOCKS = PB200_BR_BLOCKS;
 };
 
 template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE>
@@ -1540,7 +1594,15 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
 #endif
     const bool traj = d_traj != nullptr;
     const bool auto_layout = block <= 0;      // an explicit block size means the plain layout
-    if (block <= 0) block = 64;
+    if (block <= 0) {
+        block = 64;
+        if (LaunchShape<M>::THREADS > 128) {
+            // one block per SM as long as the population fits a single wave
+            const int64_t per_sm = ((n + 31) / 32 + sm_count() - 1) / sm_count() * 32;
+            block = per_sm > LaunchShape<M>::THREADS ? LaunchShape<M>::THREADS
+                                                     : static_cast<int>(per_sm);
+        }
+    }
     if (block > LaunchShape<M>::THREADS) block = LaunchShape<M>::THREADS;
     block = (block + 31) & ~31;                 // whole warps: the kernel votes
     const int64_t grid = (n + block - 1) / block;
@@ -1648,7 +1710,8 @@ int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
     // observations (Lotka-Volterra, SIR, ...: 9+ per step, -35 % time); for
     // FitzHugh-Nagumo's relaxation oscillations (2.6 per step) its extra
     // ballot and load per attempt cost 3 %
-    if (s.wide < 0) s.wide = p->dev.model == PB200_MODEL_FHN ? 0 : 1;
+    if (s.wide < 0)
+        s.wide = (p->dev.model == PB200_MODEL_FHN || p->dev.model == PB200_MODEL_BEELER_REUTER) ? 0 : 1;
     if (lanes <= 0) lanes = PB200_DEFAULT_LANES;
     if (lanes != 1 && lanes != 2) {
         pb200_set_error("lanes per vector must be 0 (automatic), 1 or 2, got %d", lanes);
