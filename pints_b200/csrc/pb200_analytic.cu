@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int WARPS = 8;                 // warps per block
-constexpr int SEG_STRIDE = 4;            // doubles per HH-IK segment record
+constexpr int SEG_STRIDE = 5;            // doubles per HH-IK segment record
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -26,12 +26,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- per-vector model state (warp-uniform unless noted) -------------------
+struct NoBlockAux {};
+
 struct LogisticEval {
     static constexpr bool POINT_AUX = false;
+    using BlockAux = NoBlockAux;
     double r, k, c;
     bool zero;
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
-                                            double *, int, bool) {
+                                            double *, int, bool, const BlockAux &) {
         r = x[0]; k = x[1];
         const double p0 = mc.c[0];
         zero = (p0 == 0.0) || (k < 0.0);
@@ -47,9 +50,10 @@ struct LogisticEval {
 
 struct ConstantEval {
     static constexpr bool POINT_AUX = false;
+    using BlockAux = NoBlockAux;
     double p[PB200_MAX_OUTPUTS];
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &,
-                                            double *, int no, bool) {
+                                            double *, int no, bool, const BlockAux &) {
         for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
             p[o] = (o < no) ? __dmul_rn(x[o], static_cast<double>(o + 1)) : 0.0;
     }
@@ -70,15 +74,32 @@ struct ConstantEval {
 // replaced by t - t_start and the segment index goes to a byte array), so the
 // per-point work of every vector is one multiply, one exp and the polynomial
 // instead of a binary search over the events and an IEEE division as well.
+//
+// Inside a segment the decay is exp(-(t - t_start) / tau), and a lane visits
+// points 32 apart: where those are equally spaced (checked bit for bit, once
+// per block, per segment) the lane's next exponential is the previous one
+// times F = exp(-(32 dt) / tau), one multiplication instead of an exp().  The
+// point loop therefore runs segment by segment: one exp() for a lane's first
+// point in the segment, the recurrence after that (chains of ~6 factors on the
+// reference protocol, rounding <= 1e-15), plain exp() in segments whose
+// spacing is not uniform.
+struct HhBlockAux {
+    int lo[PB200_MAX_EVENTS + 2];          // first point of segment s (lo[n_seg] = n_times)
+    int uniform[PB200_MAX_EVENTS + 1];     // points 32 apart are equally spaced in s
+    double d32[PB200_MAX_EVENTS + 1];      // that spacing
+};
+
 struct HhEval {
     static constexpr bool POINT_AUX = true;
+    using BlockAux = HhBlockAux;
     double g_max, e_k;
     int n_ev;
     const double *events;     // in the kernel parameter (constant bank)
     // record of segment s: [inf, n_start, t_start, tau], or for the staged
-    // (fast) path [inf, inf - n_start, -1/tau, v - E_k]
+    // (fast) path [inf, inf - n_start, -1/tau, v - E_k, F]
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
-                                            double *table, int, bool fast) {
+                                            double *table, int, bool fast,
+                                            const BlockAux &aux) {
         const int lane = threadIdx.x & 31;
         const double n0 = mc.c[0];
         g_max = mc.c[1]; e_k = mc.c[2];
@@ -107,6 +128,8 @@ struct HhEval {
             table[s * SEG_STRIDE + 1] = decay;      // replaced by n_start below
             table[s * SEG_STRIDE + 2] = fast ? -1.0 / tau : t_start;
             table[s * SEG_STRIDE + 3] = fast ? __dsub_rn(v, e_k) : tau;
+            if (fast && aux.uniform[s] && aux.lo[s + 1] - aux.lo[s] > 32)
+                table[s * SEG_STRIDE + 4] = exp(__dmul_rn(aux.d32[s], -1.0 / tau));
         }
         __syncwarp();
         if (lane == 0) {
@@ -140,9 +163,11 @@ struct HhEval {
         const double n4 = __dmul_rn(n2, n2);
         return __dmul_rn(__dmul_rn(g_max, n4), __dsub_rn(volt, e_k));
     }
-    // once per block: segment index and time into the segment of every point
+    // once per block: segment index and time into the segment of every point,
+    // the point range of every segment and whether its spacing is uniform
     __device__ static void prepare_points(double *series, int nt, int row,
-                                          const ModelConsts &mc, uint8_t *seg) {
+                                          const ModelConsts &mc, uint8_t *seg,
+                                          BlockAux &aux) {
         const int n_ev = static_cast<int>(mc.c[4]);
         const double *events = &mc.c[5];
         for (int j = threadIdx.x; j < nt; j += blockDim.x) {
@@ -155,6 +180,28 @@ struct HhEval {
             seg[j] = static_cast<uint8_t>(lo);
             series[j * row] = __dsub_rn(t, lo == 0 ? 0.0 : events[lo - 1]);
         }
+        for (int s = threadIdx.x; s <= n_ev + 1; s += blockDim.x) {
+            aux.lo[s] = s > n_ev ? nt : -1;
+            if (s <= n_ev) { aux.uniform[s] = 1; aux.d32[s] = 0.0; }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < nt; j += blockDim.x)
+            if (j == 0 || seg[j] != seg[j - 1]) aux.lo[seg[j]] = j;
+        __syncthreads();
+        if (threadIdx.x == 0)                       // segments without points
+            for (int s = n_ev; s >= 0; --s)
+                if (aux.lo[s] < 0) aux.lo[s] = aux.lo[s + 1];
+        __syncthreads();
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+            const int s = seg[j], a = aux.lo[s];
+            if (j >= a + 32) {
+                const double d = __dsub_rn(series[j * row], series[(j - 32) * row]);
+                const double d0 = __dsub_rn(series[(a + 32) * row], series[a * row]);
+                if (j == a + 32) aux.d32[s] = d0;
+                if (d != d0) aux.uniform[s] = 0;
+            }
+        }
+        __syncthreads();
     }
     // n = inf - (inf - n_start) exp(-(t - t_start) / tau), with the division by
     // tau as a multiplication by -1/tau (argument error <= 2 ulp, i.e. a
@@ -174,8 +221,9 @@ struct HhEval {
 // dispatch on the per-point auxiliary data (HH-IK with a staged series)
 template <class E>
 __device__ __forceinline__ void point_aux(double *series, int nt, int row,
-                                          const ModelConsts &mc, uint8_t *seg) {
-    if constexpr (E::POINT_AUX) E::prepare_points(series, nt, row, mc, seg);
+                                          const ModelConsts &mc, uint8_t *seg,
+                                          typename E::BlockAux &aux) {
+    if constexpr (E::POINT_AUX) E::prepare_points(series, nt, row, mc, seg, aux);
 }
 template <class E, bool SMEM>
 __device__ __forceinline__ double point_value(const E &ev, double t, int o,
@@ -198,6 +246,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                 uint32_t table_off, uint32_t table_doubles, const ScatterDev sc) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ typename E::BlockAux aux;
     const int warps = blockDim.x >> 5;
 
     const int row = P.row, no = P.n_outputs, nt = P.n_times;
@@ -210,7 +259,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
         series = smem;
         if (E::POINT_AUX) {
             seg_of = reinterpret_cast<uint8_t *>(smem) + bytes;
-            point_aux<E>(smem, nt, row, mc, seg_of);
+            point_aux<E>(smem, nt, row, mc, seg_of, aux);
             __syncthreads();
         }
     } else {
@@ -239,13 +288,42 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
             }
         }
         E ev;
-        ev.prepare(x, mc, table, no, SMEM && E::POINT_AUX);
+        ev.prepare(x, mc, table, no, SMEM && E::POINT_AUX, aux);
 
         double ss[PB200_MAX_OUTPUTS];
 #pragma unroll
         for (int o = 0; o < PB200_MAX_OUTPUTS; ++o) ss[o] = 0.0;
         double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * no : nullptr;
 
+        if constexpr (SMEM && E::POINT_AUX) {
+            // segment by segment (see HhEval): a lane's points are 32 apart
+            const int n_seg = ev.n_ev + 1;
+            for (int s = 0; s < n_seg; ++s) {
+                const int a = aux.lo[s], b = aux.lo[s + 1];
+                if (a >= b) continue;
+                const double *rec = table + s * SEG_STRIDE;
+                const double inf = rec[0], dn = rec[1], mrt = rec[2], drive = rec[3];
+                const double F = rec[4];
+                const bool uni = aux.uniform[s] != 0;
+                double e = 0.0;
+                for (int base = a; base < b; base += 32) {
+                    const int j = base + lane;
+                    const bool valid = j < b;
+                    const double dt = series[(valid ? j : b - 1) * row];
+                    if (base == a || !uni) e = exp(__dmul_rn(dt, mrt));
+                    else e = __dmul_rn(e, F);
+                    const double nn = __dsub_rn(inf, __dmul_rn(dn, e));
+                    const double n2 = __dmul_rn(nn, nn);
+                    const double n4 = __dmul_rn(n2, n2);
+                    const double v = __dmul_rn(__dmul_rn(ev.g_max, n4), drive);
+                    if (valid) {
+                        if (TRAJ) my_traj[j] = v;
+                        const double r = __dsub_rn(series[j * row + 1], v);
+                        ss[0] = __dadd_rn(ss[0], __dmul_rn(r, r));
+                    }
+                }
+            }
+        } else
         for (int j = lane; j < nt; j += 32) {
             const double t = series[j * row];
 #pragma unroll

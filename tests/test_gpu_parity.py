@@ -126,6 +126,18 @@ def test_hh_ik(pb):
     problem = pb.SingleOutputProblem(model, g['times_1k'], g['values_1k'])
     got = evaluate(pb, pb.GaussianLogLikelihood(problem), g['xs'][:16])
     assert np.max(rel_err(got, g['scores_1k'])) < ANALYTIC_RTOL
+    # the decay recurrence of the kernel needs equally spaced points inside a
+    # segment: irregular and repeated times, a grid whose spacing is not exact
+    # in binary, and segments with fewer than 32 points take the other paths
+    rng = np.random.RandomState(3)
+    for t in (np.sort(np.concatenate([rng.uniform(0, 1300, 700),
+                                      [0, 0, 90, 90, 1200.0]])),
+              np.linspace(0, 1199.7, 3999), np.arange(0, 1200, 20.0),
+              np.arange(0.1, 1200, 0.3)):
+        want = np.array([po.hh_ik_simulate(x, t) for x in g['xs'][:4, :5]])
+        got = model.simulate(g['xs'][:4, :5], t)
+        assert got.shape == want.shape
+        assert np.max(rel_err(got, want)) < ANALYTIC_RTOL, len(t)
     # reference unit test (pints/tests/test_toy_hh_ik_model.py:44-74)
     v = model.simulate(model.suggested_parameters(), model.suggested_times())
     assert abs(v[0] - 3.790799999999997) < 1e-7
