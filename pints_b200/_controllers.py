@@ -28,7 +28,9 @@ import numpy as np
 import scipy.linalg
 
 from ._compat import pints_or_none
-from ._util import vector
+import functools
+
+from ._util import single_thread_blas, vector
 
 
 @contextlib.contextmanager
@@ -80,6 +82,14 @@ class _MultiCudaEvaluator(object):
 # ----------------------------------------------------------------------
 # vectorised xNES
 # ----------------------------------------------------------------------
+
+def _with_single_thread_blas(method):
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        with single_thread_blas():
+            return method(self, *args, **kwargs)
+    return wrapped
+
 
 class _PopulationOptimiser(object):
     """What the vectorised optimisers share with
@@ -174,6 +184,33 @@ class _PopulationOptimiser(object):
     def stop(self):
         return False
 
+    def __init_subclass__(cls, **kwargs):
+        # ask() and tell() run their small matrix products on one BLAS thread
+        super().__init_subclass__(**kwargs)
+        for name in ('ask', 'tell'):
+            method = cls.__dict__.get(name)
+            if method is not None:
+                setattr(cls, name, _with_single_thread_blas(method))
+
+    def _select(self, xs):
+        """``(ids, user_xs)``: the points of the population that lie inside
+        the boundaries, as the reference filters them before evaluation
+        (pints/_optimisers/_xnes.py:79-87); ``ids`` is None when all do (no
+        copy is made then)."""
+        if self._boundaries is None:
+            return None, xs
+        if _vector_check(self._boundaries):
+            # whole population inside (the common case): two reductions
+            # instead of a row-wise test and a gather
+            # (column by column: numpy's axis-0 reduction of an (n, 3) array
+            # is ten times slower than three strided 1-d ones)
+            lo, hi = self._boundaries.lower(), self._boundaries.upper()
+            if all(xs[:, k].min() >= lo[k] and xs[:, k].max() < hi[k]
+                   for k in range(xs.shape[1])):
+                return None, xs
+        ids = np.nonzero(self._inside(xs))
+        return ids, xs[ids]
+
     def _inside(self, xs):
         """Row-wise ``boundaries.check`` of an (n, d) array."""
         if _vector_check(self._boundaries):
@@ -184,7 +221,7 @@ class _PopulationOptimiser(object):
         """Scores of the whole population: out-of-bounds points count as inf
         (pints/_optimisers/_xnes.py:154-157 and the same lines elsewhere)."""
         fx = np.asarray(fx, dtype=float)
-        if self._boundaries is not None and len(fx) < self._population_size:
+        if ids is not None and len(fx) < self._population_size:
             full = np.ones((self._population_size,)) * np.inf
             full[ids] = fx
             fx = full
@@ -224,15 +261,9 @@ class XNES(_PopulationOptimiser):
         self._ready_for_tell = True
         n, d = self._population_size, self._n_parameters
         self._zs = np.random.normal(0, 1, (n, d))
-        self._xs = self._mu + self._zs @ self._A.T
-        if self._boundaries is not None:
-            inside = self._boundaries.check(self._xs) \
-                if self._xs.ndim == 2 and _vector_check(self._boundaries) \
-                else np.array([self._boundaries.check(x) for x in self._xs])
-            self._bounded_ids = np.nonzero(inside)
-            self._bounded_xs = self._xs[self._bounded_ids]
-        else:
-            self._bounded_xs = self._xs
+        self._xs = self._zs @ self._A.T
+        self._xs += self._mu                # in place: the sum commutes
+        self._bounded_ids, self._bounded_xs = self._select(self._xs)
         self._bounded_xs.setflags(write=False)
         return self._bounded_xs
 
@@ -241,11 +272,7 @@ class XNES(_PopulationOptimiser):
             raise Exception('ask() not called before tell()')
         self._ready_for_tell = False
         n = self._population_size
-        fx = np.asarray(fx, dtype=float)
-        if self._boundaries is not None and len(fx) < n:
-            full = np.ones((n,)) * np.inf
-            full[self._bounded_ids] = fx
-            fx = full
+        fx = self._full_scores(fx, self._bounded_ids)
         order = np.argsort(fx)
         zs = self._zs[order]
         self._zs = zs
@@ -296,12 +323,7 @@ class SNES(_PopulationOptimiser):
         n, d = self._population_size, self._n_parameters
         self._ss = np.random.normal(0, 1, (n, d))
         self._xs = self._mu + self._sigmas * self._ss
-        self._user_ids = None
-        if self._boundaries is not None:
-            self._user_ids = np.nonzero(self._inside(self._xs))
-            self._user_xs = self._xs[self._user_ids]
-        else:
-            self._user_xs = self._xs
+        self._user_ids, self._user_xs = self._select(self._xs)
         self._user_xs.setflags(write=False)
         return self._user_xs
 
@@ -362,11 +384,7 @@ class PSO(_PopulationOptimiser):
         return self.x_best()
 
     def _filter(self):
-        self._user_ids = None
-        self._user_xs = self._xs
-        if self._boundaries is not None:
-            self._user_ids = np.nonzero(self._inside(self._xs))
-            self._user_xs = self._xs[self._user_ids]
+        self._user_ids, self._user_xs = self._select(self._xs)
 
     def _initialise(self):
         n, d = self._population_size, self._n_parameters
@@ -521,12 +539,7 @@ class BareCMAES(_PopulationOptimiser):
         self._zs = np.random.normal(0, 1, (n, d))
         self._ys = self._zs @ self._R.dot(self._S).T
         self._xs = self._mu + self._eta * self._ys
-        self._user_ids = None
-        if self._boundaries is not None:
-            self._user_ids = np.nonzero(self._inside(self._xs))
-            self._user_xs = self._xs[self._user_ids]
-        else:
-            self._user_xs = self._xs
+        self._user_ids, self._user_xs = self._select(self._xs)
         self._user_xs.setflags(write=False)
         return self._user_xs
 
