@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc(), '-O3', '-std=c++17', '-lineinfo', '-shared',
+    cmd = [nvcc(), '-O3', '-std=c++17', '-lineinfo', '-shared', '--threads', '4',
            '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '-cudart', 'static',
            *ARCH]
     if verbose:
