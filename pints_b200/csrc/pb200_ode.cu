@@ -667,6 +667,10 @@ struct MigDev {
 //   384 x 1, 168 registers   0.122 / 0.255 / 0.641 s      (two waves at 65 536)
 // and with the library exp() and division (branches keep the sixteen
 // exponentials of a right-hand side from interleaving): 0.192 / 0.205 / - s.
+// Not unrolling the step loop for this model (halves 300 KB of code) brings
+// the default to 0.087 / 0.159 / 0.630 s; a non-inlined right-hand side
+// (25 KB of code, arguments through local memory) is slower: 0.112 / 0.193 /
+// 0.80 s.
 #ifndef PB200_BR_BLOCKS
 #define PB200_BR_BLOCKS 1
 #endif
@@ -892,7 +896,9 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         else model.hrhs(w_, K_);
     };
 
-    constexpr int kLoopUnroll = PB200_LOOP_UNROLL;
+    // the eight-state model's step is 150 KB of code: unrolling it would only
+    // thrash the instruction cache (0.180 -> 0.159 s at population 65 536)
+    constexpr int kLoopUnroll = M::NS >= 8 ? 1 : PB200_LOOP_UNROLL;
 #pragma unroll kLoopUnroll
     for (;;) {
         const bool fin = (off >= end) || failed;
