@@ -232,126 +232,6 @@ struct SirModel {
     }
 };
 
-// Goodwin oscillator (pints/toy/_goodwin_oscillator_model.py:101-107):
-//   x' = 1 / (1 + z^10) - m1 x,  y' = k2 x - m2 y,  z' = k3 y - m3 z
-struct GoodwinModel {
-    static constexpr int NS = 3, NO = 3, OUT0 = 0, NP = 5;
-    static constexpr bool MIGRATES = false;     // needs 146 registers
-    static constexpr bool TIMED = false;
-    double k2, k3, m1, m2, m3;
-    double h_, hk2, hk3, nhm1, nhm2, nhm3;
-    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
-                                         double *y, double, double *t0) {
-        k2 = x[0]; k3 = x[1]; m1 = x[2]; m2 = x[3]; m3 = x[4];
-        y[0] = mc.c[0]; y[1] = mc.c[1]; y[2] = mc.c[2];
-        *t0 = 0.0;
-    }
-    __device__ __forceinline__ static double pow10(double z) {
-        const double z2 = z * z, z4 = z2 * z2;
-        return (z4 * z4) * z2;
-    }
-    __device__ __forceinline__ void rhs(const double *y, double *f) const {
-        f[0] = 1.0 / (1.0 + pow10(y[2])) - m1 * y[0];
-        f[1] = k2 * y[0] - m2 * y[1];
-        f[2] = k3 * y[1] - m3 * y[2];
-    }
-    __device__ __forceinline__ void scale(double h) {
-        h_ = h; hk2 = h * k2; hk3 = h * k3; nhm1 = -h * m1; nhm2 = -h * m2; nhm3 = -h * m3;
-    }
-    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
-        K[0] = fma(nhm1, y[0], h_ / (1.0 + pow10(y[2])));
-        K[1] = fma(hk2, y[0], nhm2 * y[1]);
-        K[2] = fma(hk3, y[1], nhm3 * y[2]);
-    }
-    __device__ __forceinline__ double cost_key(const double *y) const {
-        double f[NS];
-        rhs(y, f);
-        return fma(f[0], f[0], fma(f[1], f[1], f[2] * f[2]));
-    }
-};
-
-// Hes1 Michaelis-Menten model (pints/toy/_hes1_michaelis_menten.py:129-140),
-// output = m; constants [m0, p1_0, p2_0, k_deg]:
-//   m'  = -k_deg m + 1 / (1 + (p2 / P0)^h)
-//   p1' = -k_deg p1 + v m - k1 p1,   p2' = -k_deg p2 + k1 p1
-struct Hes1Model {
-    static constexpr int NS = 3, NO = 1, OUT0 = 0, NP = 4;
-    static constexpr bool MIGRATES = false;     // pow() needs > 128 registers
-    static constexpr bool TIMED = false;
-    double iP0, v, k1, hh, kdeg;
-    double h_, hv, hk1, nhkd;
-    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
-                                         double *y, double, double *t0) {
-        iP0 = 1.0 / x[0]; v = x[1]; k1 = x[2]; hh = x[3];
-        y[0] = mc.c[0]; y[1] = mc.c[1]; y[2] = mc.c[2];
-        kdeg = mc.c[3];
-        *t0 = 0.0;
-    }
-    __device__ __forceinline__ void rhs(const double *y, double *f) const {
-        f[0] = -kdeg * y[0] + 1.0 / (1.0 + pow(y[2] * iP0, hh));
-        f[1] = -kdeg * y[1] + v * y[0] - k1 * y[1];
-        f[2] = -kdeg * y[2] + k1 * y[1];
-    }
-    __device__ __forceinline__ void scale(double h) {
-        h_ = h; hv = h * v; hk1 = h * k1; nhkd = -h * kdeg;
-    }
-    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
-        K[0] = fma(nhkd, y[0], h_ / (1.0 + pow(y[2] * iP0, hh)));
-        K[1] = fma(hv, y[0], (nhkd - hk1) * y[1]);
-        K[2] = fma(hk1, y[1], nhkd * y[2]);
-    }
-    __device__ __forceinline__ double cost_key(const double *y) const {
-        double f[NS];
-        rhs(y, f);
-        return fma(f[0], f[0], fma(f[1], f[1], f[2] * f[2]));
-    }
-};
-
-// Repressilator (pints/toy/_repressilator_model.py:91-108), six states, the
-// three mRNA levels are the outputs; like SIR it is integrated from times[0]:
-//   m_i' = -m_i + alpha / (1 + p_j^n) + alpha_0,   p_i' = -beta (p_i - m_i)
-// with (i, j) = (0, 2), (1, 0), (2, 1) (protein j represses gene i).
-struct RepressilatorModel {
-    static constexpr int NS = 6, NO = 3, OUT0 = 0, NP = 4;
-    static constexpr bool MIGRATES = false;     // 6 states need > 128 registers
-    static constexpr bool TIMED = false;
-    double a0, al, be, nn;
-    double h_, ha0, hal, hbe;
-    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
-                                         double *y, double t_first, double *t0) {
-        a0 = x[0]; al = x[1]; be = x[2]; nn = x[3];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) y[k] = mc.c[k];
-        *t0 = t_first;
-    }
-    __device__ __forceinline__ void rhs(const double *y, double *f) const {
-        f[0] = -y[0] + al / (1.0 + pow(y[5], nn)) + a0;
-        f[1] = -y[1] + al / (1.0 + pow(y[3], nn)) + a0;
-        f[2] = -y[2] + al / (1.0 + pow(y[4], nn)) + a0;
-        f[3] = -be * (y[3] - y[0]);
-        f[4] = -be * (y[4] - y[1]);
-        f[5] = -be * (y[5] - y[2]);
-    }
-    __device__ __forceinline__ void scale(double h) {
-        h_ = h; ha0 = h * a0; hal = h * al; hbe = h * be;
-    }
-    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
-        K[0] = fma(-h_, y[0], hal / (1.0 + pow(y[5], nn))) + ha0;
-        K[1] = fma(-h_, y[1], hal / (1.0 + pow(y[3], nn))) + ha0;
-        K[2] = fma(-h_, y[2], hal / (1.0 + pow(y[4], nn))) + ha0;
-        K[3] = hbe * (y[0] - y[3]);
-        K[4] = hbe * (y[1] - y[4]);
-        K[5] = hbe * (y[2] - y[5]);
-    }
-    __device__ __forceinline__ double cost_key(const double *y) const {
-        double f[NS], s2 = 0.0;
-        rhs(y, f);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) s2 = fma(f[k], f[k], s2);
-        return s2;
-    }
-};
-
 // MUFU.RCP64H: >= 20 good bits, on the XU pipe (off the FP64 pipe).
 __device__ __forceinline__ double rcp_seed(double x) {
     double r;
@@ -405,6 +285,177 @@ __device__ __forceinline__ double div_normal(double a, double b) {
     const double q = a * r;
     return fma(r, fma(-b, q, a), q);
 }
+
+// log(x) for a positive normal x without branches: x = m 2^e with m in
+// [sqrt(1/2), sqrt(2)), log m = 2 atanh((m - 1) / (m + 1)) as an odd series up
+// to s^19 (|s| <= 0.1716, remainder 8e-18).  Within a few ulp.
+__device__ __forceinline__ double log_positive(double x) {
+    const int hi = __double2hiint(x);
+    const int e = (hi - 0x3fe6a09e) >> 20;
+    const double m = __hiloint2double(hi - (e << 20), __double2loint(x));
+    const double s = div_normal(m - 1.0, m + 1.0);
+    const double s2 = s * s;
+    double p = 1.0 / 19.0;
+    p = fma(p, s2, 1.0 / 17.0);
+    p = fma(p, s2, 1.0 / 15.0);
+    p = fma(p, s2, 1.0 / 13.0);
+    p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, 1.0 / 3.0);
+    const double r = fma(p * s2, s, s);              // atanh(s)
+    const double ef = static_cast<double>(e);
+    return fma(ef, 6.93147180559945286e-01, fma(ef, 2.31904681384629956e-17, r + r));
+}
+
+// An exponent n and what numpy's power needs to know about it for a negative
+// base (an integer-valued n keeps the sign rule, anything else gives NaN).
+struct RealExponent {
+    double n;
+    bool integer, odd;
+    __device__ __forceinline__ void set(double v) {
+        n = v;
+        integer = v == rint(v);
+        odd = integer && (fmod(fabs(v), 2.0) == 1.0);
+    }
+};
+
+// x^n = exp(n log |x|) with the branch-free pieces above (the library pow()
+// is ~250 instructions with slow paths, and the Hill terms call it in every
+// stage); the product n log|x| is clamped to exp_bounded's range (1e+-304).
+// Relative error ~ |n log x| * 2e-16.  x = 0 gives 0 (n > 0), 1 (n = 0), inf.
+__device__ __forceinline__ double pow_real(double x, const RealExponent &ex) {
+    const double ax = fabs(x);
+    const double a = fmin(fmax(ex.n * log_positive(ax), -700.0), 700.0);
+    double r = exp_bounded(a);
+    if (ax == 0.0) r = ex.n > 0.0 ? 0.0 : (ex.n == 0.0 ? 1.0 : INFINITY);
+    if (x < 0.0) r = ex.integer ? (ex.odd ? -r : r) : NAN;
+    if (!(ax == ax)) r = NAN;
+    return r;
+}
+
+// Goodwin oscillator (pints/toy/_goodwin_oscillator_model.py:101-107):
+//   x' = 1 / (1 + z^10) - m1 x,  y' = k2 x - m2 y,  z' = k3 y - m3 z
+struct GoodwinModel {
+    static constexpr int NS = 3, NO = 3, OUT0 = 0, NP = 5;
+    static constexpr bool MIGRATES = false;     // needs 146 registers
+    static constexpr bool TIMED = false;
+    double k2, k3, m1, m2, m3;
+    double h_, hk2, hk3, nhm1, nhm2, nhm3;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double, double *t0) {
+        k2 = x[0]; k3 = x[1]; m1 = x[2]; m2 = x[3]; m3 = x[4];
+        y[0] = mc.c[0]; y[1] = mc.c[1]; y[2] = mc.c[2];
+        *t0 = 0.0;
+    }
+    __device__ __forceinline__ static double pow10(double z) {
+        const double z2 = z * z, z4 = z2 * z2;
+        return (z4 * z4) * z2;
+    }
+    __device__ __forceinline__ void rhs(const double *y, double *f) const {
+        f[0] = 1.0 / (1.0 + pow10(y[2])) - m1 * y[0];
+        f[1] = k2 * y[0] - m2 * y[1];
+        f[2] = k3 * y[1] - m3 * y[2];
+    }
+    __device__ __forceinline__ void scale(double h) {
+        h_ = h; hk2 = h * k2; hk3 = h * k3; nhm1 = -h * m1; nhm2 = -h * m2; nhm3 = -h * m3;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        K[0] = fma(nhm1, y[0], h_ / (1.0 + pow10(y[2])));
+        K[1] = fma(hk2, y[0], nhm2 * y[1]);
+        K[2] = fma(hk3, y[1], nhm3 * y[2]);
+    }
+    __device__ __forceinline__ double cost_key(const double *y) const {
+        double f[NS];
+        rhs(y, f);
+        return fma(f[0], f[0], fma(f[1], f[1], f[2] * f[2]));
+    }
+};
+
+// Hes1 Michaelis-Menten model (pints/toy/_hes1_michaelis_menten.py:129-140),
+// output = m; constants [m0, p1_0, p2_0, k_deg]:
+//   m'  = -k_deg m + 1 / (1 + (p2 / P0)^h)
+//   p1' = -k_deg p1 + v m - k1 p1,   p2' = -k_deg p2 + k1 p1
+struct Hes1Model {
+    static constexpr int NS = 3, NO = 1, OUT0 = 0, NP = 4;
+    static constexpr bool MIGRATES = false;     // pow() needs > 128 registers
+    static constexpr bool TIMED = false;
+    double iP0, v, k1, kdeg;
+    RealExponent hh;
+    double h_, hv, hk1, nhkd;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double, double *t0) {
+        iP0 = 1.0 / x[0]; v = x[1]; k1 = x[2]; hh.set(x[3]);
+        y[0] = mc.c[0]; y[1] = mc.c[1]; y[2] = mc.c[2];
+        kdeg = mc.c[3];
+        *t0 = 0.0;
+    }
+    __device__ __forceinline__ void rhs(const double *y, double *f) const {
+        f[0] = -kdeg * y[0] + 1.0 / (1.0 + pow_real(y[2] * iP0, hh));
+        f[1] = -kdeg * y[1] + v * y[0] - k1 * y[1];
+        f[2] = -kdeg * y[2] + k1 * y[1];
+    }
+    __device__ __forceinline__ void scale(double h) {
+        h_ = h; hv = h * v; hk1 = h * k1; nhkd = -h * kdeg;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        K[0] = fma(nhkd, y[0], div_normal(h_, 1.0 + pow_real(y[2] * iP0, hh)));
+        K[1] = fma(hv, y[0], (nhkd - hk1) * y[1]);
+        K[2] = fma(hk1, y[1], nhkd * y[2]);
+    }
+    __device__ __forceinline__ double cost_key(const double *y) const {
+        double f[NS];
+        rhs(y, f);
+        return fma(f[0], f[0], fma(f[1], f[1], f[2] * f[2]));
+    }
+};
+
+// Repressilator (pints/toy/_repressilator_model.py:91-108), six states, the
+// three mRNA levels are the outputs; like SIR it is integrated from times[0]:
+//   m_i' = -m_i + alpha / (1 + p_j^n) + alpha_0,   p_i' = -beta (p_i - m_i)
+// with (i, j) = (0, 2), (1, 0), (2, 1) (protein j represses gene i).
+struct RepressilatorModel {
+    static constexpr int NS = 6, NO = 3, OUT0 = 0, NP = 4;
+    static constexpr bool MIGRATES = false;     // 6 states need > 128 registers
+    static constexpr bool TIMED = false;
+    double a0, al, be;
+    RealExponent nn;
+    double h_, ha0, hal, hbe;
+    __device__ __forceinline__ void load(const double *x, const ModelConsts &mc,
+                                         double *y, double t_first, double *t0) {
+        a0 = x[0]; al = x[1]; be = x[2]; nn.set(x[3]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) y[k] = mc.c[k];
+        *t0 = t_first;
+    }
+    __device__ __forceinline__ void rhs(const double *y, double *f) const {
+        f[0] = -y[0] + al / (1.0 + pow_real(y[5], nn)) + a0;
+        f[1] = -y[1] + al / (1.0 + pow_real(y[3], nn)) + a0;
+        f[2] = -y[2] + al / (1.0 + pow_real(y[4], nn)) + a0;
+        f[3] = -be * (y[3] - y[0]);
+        f[4] = -be * (y[4] - y[1]);
+        f[5] = -be * (y[5] - y[2]);
+    }
+    __device__ __forceinline__ void scale(double h) {
+        h_ = h; ha0 = h * a0; hal = h * al; hbe = h * be;
+    }
+    __device__ __forceinline__ void hrhs(const double *y, double *K) const {
+        K[0] = fma(-h_, y[0], div_normal(hal, 1.0 + pow_real(y[5], nn))) + ha0;
+        K[1] = fma(-h_, y[1], div_normal(hal, 1.0 + pow_real(y[3], nn))) + ha0;
+        K[2] = fma(-h_, y[2], div_normal(hal, 1.0 + pow_real(y[4], nn))) + ha0;
+        K[3] = hbe * (y[0] - y[3]);
+        K[4] = hbe * (y[1] - y[4]);
+        K[5] = hbe * (y[2] - y[5]);
+    }
+    __device__ __forceinline__ double cost_key(const double *y) const {
+        double f[NS], s2 = 0.0;
+        rhs(y, f);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) s2 = fma(f[k], f[k], s2);
+        return s2;
+    }
+};
 
 // Beeler-Reuter 1977 ventricular action potential
 // (pints/toy/_beeler_reuter_model.py:105-183): eight states
@@ -683,6 +734,14 @@ template <class M> struct LaunchShape {
 template <> struct LaunchShape<BeelerReuterModel> {
     static constexpr int THREADS = PB200_BR_THREADS, BLOCKS = PB200_BR_BLOCKS;
 };
+#ifdef PB200_REP_THREADS
+template <> struct LaunchShape<RepressilatorModel> {
+    static constexpr int THREADS = PB200_REP_THREADS, BLOCKS = 1;
+};
+#endif
+#ifndef PB200_BIG_UNROLL
+#define PB200_BIG_UNROLL 2
+#endif
 
 template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE>
 __global__ void __launch_bounds__(MIG ? 512 : LaunchShape<M>::THREADS,
@@ -898,7 +957,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 
     // the eight-state model's step is 150 KB of code: unrolling it would only
     // thrash the instruction cache (0.180 -> 0.159 s at population 65 536)
-    constexpr int kLoopUnroll = M::NS >= 8 ? 1 : PB200_LOOP_UNROLL;
+    constexpr int kLoopUnroll = M::NS >= 8 ? 1 : (M::NS >= 6 ? PB200_BIG_UNROLL : PB200_LOOP_UNROLL);
 #pragma unroll kLoopUnroll
     for (;;) {
         const bool fin = (off >= end) || failed;
