@@ -43,6 +43,21 @@ WORKLOAD = ('FitzhughNagumoModel (3 params, 1000 times on [0,20]) + '
 TRAFFIC_BYTES_PER_LAUNCH = 1918208
 
 
+def hbm_side(kernel_ms):
+    """The same launch against the HBM roofline (why the bound is not 'hbm'):
+    measured DRAM bytes of the launch / its duration, against the driver's
+    measured copy bandwidth (MEASURED_PEAKS.json) or the recipe's fallback."""
+    peak, source = 6650.0, 'fallback of B200_PROFILING.md'
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peak, source = float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json'
+    except Exception:
+        pass
+    achieved = TRAFFIC_BYTES_PER_LAUNCH / (kernel_ms * 1e-3) / 1e9
+    return {'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'peak_source': source}
+
+
 # ------------------------------------------------------------ CPU baseline
 
 _worker_spec = None
@@ -405,7 +420,8 @@ def run_ours(args):
                                ' MEASURED_PEAKS.json has no FP64 entry; '
                                'nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2',
                 'flop_per_launch': flops_per_launch,
-                'kernel_ms': kern_ms / args.steps},
+                'kernel_ms': kern_ms / args.steps,
+                'hbm': hbm_side(kern_ms / args.steps)},
             'e2e': {'value': total / e2e_s, 'unit': UNIT,
                     'h2d_bytes_per_step': int(xs.nbytes) * world,
                     'd2h_bytes_per_step': int(pop * 8) * world,
