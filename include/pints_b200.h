@@ -389,6 +389,23 @@ int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
                  int32_t d, double gamma, uint64_t seed, uint64_t offset_eps,
                  uint64_t offset_pairs, void *stream);
 
+/* Device-resident xNES (pints/_optimisers/_xnes.py:63-91 ask, :147-182 tell).
+ * ask: z (n, d) standard normals = pb200_philox_normal(n d, seed, offset),
+ * x = mu + A z (A row-major (d, d)), inside[i] = boundary test of row i
+ * (d_lower / d_upper both NULL: no boundaries); x_eval = x where inside, mu
+ * elsewhere -- the reference never evaluates a point outside the boundaries,
+ * the caller overrides those scores with +inf.
+ * sums: out[0..d) = sum_r us[r] z[order[r]], out[d + a d + b] = sum_r us[r]
+ * z[order[r]][a] z[order[r]][b]; d_partial holds n_blocks (d + d d) doubles;
+ * deterministic (fixed summation order). */
+int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
+                   const double *d_upper, double *d_z, double *d_x,
+                   double *d_x_eval, uint8_t *d_inside, int64_t n, int32_t d,
+                   uint64_t seed, uint64_t offset, void *stream);
+int pb200_xnes_sums(const double *d_z, const int64_t *d_order,
+                    const double *d_us, double *d_partial, int32_t n_blocks,
+                    double *d_out, int64_t n, int32_t d, void *stream);
+
 /* Counter-based RNG (Philox4x32-10): n doubles, N(0,1) or U(0,1), for
  * (seed, stream_id, offset).  Used only in device-RNG sampler mode. */
 int pb200_philox_normal(double *d_out, int64_t n, uint64_t seed,

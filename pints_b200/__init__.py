@@ -13,7 +13,8 @@ reference's own interfaces for that path:
   SumOfSquaresError, GaussianKnownSigmaLogLikelihood, GaussianLogLikelihood,
   ProbabilityBasedError, LogPosterior, UniformLogPrior, RectangularBoundaries
   HaarioBardenetACMC, DifferentialEvolutionMCMC   device-resident samplers
-  XNES (vectorised), CudaOptimisationController, CudaMCMCController,
+  XNES (vectorised), DeviceXNES, CudaOptimisationController,
+  CudaMCMCController,
   cuda_evaluators()                   run the reference's own controllers on GPU
 
 Host code is Python; compute is hand-written CUDA behind the C ABI of
@@ -50,6 +51,7 @@ _LAZY = {
     'DifferentialEvolutionMCMC': '_samplers',
     'XNES': '_controllers', 'SNES': '_controllers', 'PSO': '_controllers',
     'BareCMAES': '_controllers', 'cuda_evaluators': '_controllers',
+    'DeviceXNES': '_device_optimisers',
     'CudaOptimisationController': '_controllers',
     'CudaMCMCController': '_controllers',
 }

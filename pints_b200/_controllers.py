@@ -672,10 +672,19 @@ class CudaOptimisationController(object):
         start = time.perf_counter()
         unchanged, f_sig = 0, np.inf
         opt = self._optimiser
+        on_device = getattr(opt, 'device_resident', False)
+        if on_device:
+            # population, scores and ranking stay in HBM (DeviceXNES)
+            problem = self._evaluator.device_problem()
+            opt._device_arg = problem.device
         while True:
             xs = opt.ask()
-            fs = self._evaluator.evaluate(xs)
-            opt.tell(self._sign * fs if self._sign < 0 else fs)
+            if on_device:
+                fs = problem.eval(xs)
+                opt.tell(-fs if self._sign < 0 else fs)
+            else:
+                fs = self._evaluator.evaluate(xs)
+                opt.tell(self._sign * fs if self._sign < 0 else fs)
             self._evaluations += len(fs)
             self._iterations += 1
             f_new = opt.f_best()

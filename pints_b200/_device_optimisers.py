@@ -1,0 +1,247 @@
+"""
+Device-resident optimiser: the caller of the evaluation path at population
+sizes where the host update itself becomes the bottleneck.
+
+``DeviceXNES`` is the exponential natural evolution strategy of
+``pints.XNES`` (pints/_optimisers/_xnes.py:63-91 ask, :147-182 tell) with the
+population kept in HBM: ``ask()`` returns the ``(population, d)`` candidate
+points as a device tensor, ``tell(fx)`` takes their scores as a device tensor.
+At population 65 536 the vectorised host ``XNES`` of this package needs 12 ms
+per generation (6 ms of them NumPy's Mersenne-Twister normals, which identity
+with the reference's random stream requires) against 0.4 ms for scoring the
+population; here a generation's update costs a sort and three small kernels.
+
+Same hyper-parameters, utilities and update equations as the reference.  The
+samples come from the counter-based Philox generator of the C ABI instead of
+``numpy.random`` -- a different stream, so trajectories agree with the reference
+statistically, while *given the same normals and scores* the update is the
+reference's (``tests/test_gpu_samplers.py::test_device_xnes_replays_host_xnes``
+feeds the device's normals to the host ``XNES`` through ``numpy.random``).
+"""
+import ctypes
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from . import _lib
+from ._engine import _ptr, _stream_ptr, require_cuda
+from ._util import vector
+
+_SUM_BLOCKS = 148          # one block of ranks per SM
+
+
+class DeviceXNES(object):
+    """xNES with the population on the GPU.
+
+    Parameters as ``pints.XNES`` plus ``seed`` (Philox key) and ``device``.
+    ``boundaries`` must be ``RectangularBoundaries`` (of this package or of the
+    reference); a sampled point outside them is never scored -- its row of the
+    tensor ``ask()`` returns holds the current mean instead and its score is
+    replaced by ``+inf`` in ``tell()``, which ranks it exactly as the reference
+    ranks the points it withholds from the evaluator
+    (pints/_optimisers/_xnes.py:79-87, :154-157)."""
+
+    device_resident = True
+
+    def __init__(self, x0, sigma0=None, boundaries=None, seed=1, device=None):
+        self._x0 = vector(x0)
+        self._d = len(self._x0)
+        if self._d < 1:
+            raise ValueError('Problem dimension must be greater than zero.')
+        if self._d > 7:
+            # pb200_xnes_sums: (d + d^2) * 16 threads in one block
+            raise ValueError('DeviceXNES supports at most 7 parameters.')
+        self._boundaries = boundaries
+        if boundaries is not None:
+            if boundaries.n_parameters() != self._d:
+                raise ValueError(
+                    'Boundaries must have same dimension as starting point.')
+            if not boundaries.check(self._x0):
+                raise ValueError(
+                    'Initial position must lie within given boundaries.')
+            if not (hasattr(boundaries, 'lower') and hasattr(boundaries, 'upper')):
+                raise TypeError('DeviceXNES needs RectangularBoundaries.')
+        if sigma0 is None:
+            # pints/_optimisers/__init__.py:113-126
+            try:
+                self._sigma0 = (1 / 6) * boundaries.range()
+            except AttributeError:
+                self._sigma0 = (1 / 3) * np.abs(self._x0)
+                self._sigma0 = self._sigma0 + (self._sigma0 == 0)
+        elif np.isscalar(sigma0):
+            if float(sigma0) <= 0:
+                raise ValueError(
+                    'Initial standard deviation must be greater than zero.')
+            self._sigma0 = np.ones(self._d) * float(sigma0)
+        else:
+            self._sigma0 = vector(sigma0)
+            if len(self._sigma0) != self._d:
+                raise ValueError(
+                    'Initial standard deviation must be None, scalar, or have'
+                    ' dimension ' + str(self._d) + '.')
+            if np.any(self._sigma0 <= 0):
+                raise ValueError(
+                    'Initial standard deviations must be greater than zero.')
+        self._population_size = 4 + int(3 * np.log(self._d))
+        self._seed = int(seed) & (2 ** 64 - 1)
+        self._offset = 0
+        self._device_arg = device
+        self._running = False
+        self._ready_for_tell = False
+        self._x_best = np.array(self._x0, copy=True)
+        self._f_best = np.inf
+        self._f_guessed = np.inf
+
+    # -- pints.PopulationBasedOptimiser interface -----------------------
+    @classmethod
+    def name(cls):
+        return 'Exponential Natural Evolution Strategy (xNES), device resident'
+
+    def population_size(self):
+        return self._population_size
+
+    def set_population_size(self, population_size=None):
+        if self._running:
+            raise Exception('Cannot change population size during run.')
+        if population_size is None:
+            population_size = 4 + int(3 * np.log(self._d))
+        population_size = int(population_size)
+        if population_size < 1:
+            raise ValueError('Population size must be at least 1.')
+        self._population_size = population_size
+
+    def suggested_population_size(self, round_up_to_multiple_of=None):
+        p = 4 + int(3 * np.log(self._d))
+        if round_up_to_multiple_of is not None:
+            n = int(round_up_to_multiple_of)
+            if n > 1:
+                p = n * (((p - 1) // n) + 1)
+        return p
+
+    def running(self):
+        return self._running
+
+    def needs_sensitivities(self):
+        return False
+
+    def stop(self):
+        return False
+
+    def f_best(self):
+        return self._f_best
+
+    def f_guessed(self):
+        return self._f_guessed
+
+    def x_best(self):
+        return self._x_best
+
+    def x_guessed(self):
+        return self._mu if self._running else self._x0
+
+    # -- state -----------------------------------------------------------
+    def _initialise(self):
+        n, d = self._population_size, self._d
+        self._device = require_cuda(self._device_arg)
+        self._lib = _lib.load()
+        dev = self._device
+        # Table 1 of Glasmachers et al. 2010 (pints/_optimisers/_xnes.py:93-121)
+        self._eta_mu = 1
+        self._eta_A = 0.6 * (3 + np.log(d)) * d ** -1.5
+        us = np.maximum(0, np.log(n / 2 + 1) - np.log(1 + np.arange(n)))
+        us /= np.sum(us)
+        us -= 1 / n
+        self._sum_us = float(np.sum(us))
+        self._mu = np.array(self._x0, copy=True)
+        self._A = np.eye(d) * self._sigma0
+        self._I = np.eye(d)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self._d_us = torch.from_numpy(us).to(dev)
+        self._d_state = torch.empty(d + d * d, **f64)        # mu, then A
+        self._d_z = torch.empty((n, d), **f64)
+        self._d_x = torch.empty((n, d), **f64)
+        self._d_x_eval = torch.empty((n, d), **f64)
+        self._d_inside = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._d_partial = torch.empty(_SUM_BLOCKS * (d + d * d), **f64)
+        # sums, then the best point and its score (one read-back per tell)
+        self._d_out = torch.empty(d + d * d + d + 1, **f64)
+        self._h_out = torch.empty(d + d * d + d + 1, dtype=torch.float64,
+                                  pin_memory=True)
+        self._h_state = torch.empty(d + d * d, dtype=torch.float64,
+                                    pin_memory=True)
+        self._d_lower = self._d_upper = None
+        if self._boundaries is not None:
+            self._d_lower = torch.from_numpy(np.array(
+                self._boundaries.lower(), dtype=np.float64)).to(dev)
+            self._d_upper = torch.from_numpy(np.array(
+                self._boundaries.upper(), dtype=np.float64)).to(dev)
+        self._running = True
+
+    def normals(self):
+        """The standard normals of the last ``ask()``, ``(population, d)``."""
+        return self._d_z
+
+    def points(self):
+        """The sampled points of the last ``ask()`` (rows outside the
+        boundaries included), ``(population, d)``."""
+        return self._d_x
+
+    def inside(self):
+        """Which of them lie inside the boundaries (uint8)."""
+        return self._d_inside
+
+    # -- ask / tell ------------------------------------------------------
+    def ask(self):
+        if not self._running:
+            self._initialise()
+        self._ready_for_tell = True
+        n, d = self._population_size, self._d
+        h = self._h_state.numpy()
+        h[:d] = self._mu
+        h[d:] = self._A.reshape(-1)
+        with torch.cuda.device(self._device):
+            self._d_state.copy_(self._h_state, non_blocking=True)
+            offset = self._offset
+            self._offset += (n * d + 1) // 2 + 1
+            state = self._d_state.data_ptr()
+            _lib.check(self._lib.pb200_xnes_ask(
+                ctypes.c_void_p(state), ctypes.c_void_p(state + 8 * d),
+                _ptr(self._d_lower), _ptr(self._d_upper), _ptr(self._d_z),
+                _ptr(self._d_x), _ptr(self._d_x_eval), _ptr(self._d_inside),
+                n, d, ctypes.c_uint64(self._seed), ctypes.c_uint64(offset),
+                _stream_ptr(self._device)))
+        return self._d_x_eval
+
+    def tell(self, fx):
+        """``fx``: device tensor ``(population,)`` of the scores of the rows
+        ``ask()`` returned (to be minimised)."""
+        if not self._ready_for_tell:
+            raise Exception('ask() not called before tell()')
+        self._ready_for_tell = False
+        n, d = self._population_size, self._d
+        m = d + d * d
+        with torch.cuda.device(self._device):
+            if self._d_lower is not None:
+                fx = fx.masked_fill(self._d_inside == 0, float('inf'))
+            # ranks: a library sort of 8 n bytes (NaN scores rank last)
+            order = torch.sort(fx)[1]
+            _lib.check(self._lib.pb200_xnes_sums(
+                _ptr(self._d_z), _ptr(order), _ptr(self._d_us),
+                _ptr(self._d_partial), _SUM_BLOCKS, _ptr(self._d_out), n, d,
+                _stream_ptr(self._device)))
+            best = order[0]
+            self._d_out[m:m + d].copy_(self._d_x[best])
+            self._d_out[m + d].copy_(fx[best])
+            self._h_out.copy_(self._d_out, non_blocking=True)
+            torch.cuda.current_stream(self._device).synchronize()
+        out = self._h_out.numpy()
+        Gd = out[:d]
+        Gm = out[d:m].reshape((d, d)) - self._sum_us * self._I
+        # pints/_optimisers/_xnes.py:170-176
+        self._mu = self._mu + self._eta_mu * np.dot(self._A, Gd)
+        self._A = np.dot(self._A, scipy.linalg.expm(0.5 * self._eta_A * Gm))
+        self._f_guessed = float(out[m + d])
+        if self._f_guessed < self._f_best:
+            self._f_best = self._f_guessed
+            self._x_best = np.array(out[m:m + d], copy=True)

@@ -527,6 +527,118 @@ int pb200_ac_tell(int32_t variant, int32_t require_finite, double *d_current,
     return pb200_check_cuda(cudaGetLastError(), "ac_tell_kernel launch");
 }
 
+// ---- device-resident xNES (pints/_optimisers/_xnes.py:63-91, :147-182) ----
+// ask: z_i ~ N(0, I) from Philox (the numbers pb200_philox_normal(n d, seed,
+// offset) gives), x_i = mu + A z_i, and the boundary test of :79-87.  A point
+// outside the boundaries is never evaluated by the reference; here its row of
+// x_eval holds mu instead (a harmless point, no stream compaction, no host
+// round trip) and the caller overrides its score with +inf from `inside`.
+__global__ void xnes_ask_kernel(const double *__restrict__ mu, const double *__restrict__ A,
+                                const double *__restrict__ lower,
+                                const double *__restrict__ upper, double *__restrict__ z,
+                                double *__restrict__ x, double *__restrict__ x_eval,
+                                uint8_t *__restrict__ inside, int64_t n, int d,
+                                uint64_t seed, uint64_t offset) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double zi[PB200_MAX_PARAMS];
+    for (int k = 0; k < d; ++k) {
+        zi[k] = philox_normal_at(i * d + k, seed, offset);
+        z[i * d + k] = zi[k];
+    }
+    bool in = true;
+    double xi[PB200_MAX_PARAMS];
+    for (int a = 0; a < d; ++a) {
+        // mu + dot(A[a, :], z) with the products added left to right
+        double acc = __dmul_rn(A[a * d], zi[0]);
+        for (int k = 1; k < d; ++k) acc = __dadd_rn(acc, __dmul_rn(A[a * d + k], zi[k]));
+        xi[a] = __dadd_rn(mu[a], acc);
+        x[i * d + a] = xi[a];
+        if (lower) in = in && !(xi[a] < lower[a]) && !(xi[a] >= upper[a]);
+    }
+    inside[i] = in ? 1 : 0;
+    for (int a = 0; a < d; ++a) x_eval[i * d + a] = in ? xi[a] : mu[a];
+}
+
+// tell: the utility-weighted sums  Gd = sum_r u_r z_(r),  Gm = sum_r u_r z_(r) z_(r)^T
+// over the population in rank order (order[r] = index of the r-th best).
+// Deterministic: block b sums a contiguous range of ranks serially, one thread
+// per output quantity; a second single-block pass adds the partial sums in
+// block order.
+constexpr int XNES_SPLIT = 16;     // threads per output quantity
+__global__ void xnes_sums_kernel(const double *__restrict__ z, const int64_t *__restrict__ order,
+                                 const double *__restrict__ us, double *__restrict__ partial,
+                                 int64_t n, int d) {
+    // thread (q, s): quantity q over the ranks r0 + s, r0 + s + SPLIT, ... of
+    // this block's range (independent gathers in flight), then the SPLIT
+    // partial sums of a quantity are added in a fixed order
+    extern __shared__ double part[];
+    const int m = d + d * d;
+    const int q = threadIdx.x / XNES_SPLIT, sub = threadIdx.x % XNES_SPLIT;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = per * blockIdx.x, r1 = r0 + per < n ? r0 + per : n;
+    if (q < m) {
+        const int a = q < d ? q : (q - d) / d, b = q < d ? -1 : (q - d) % d;
+        double acc = 0.0;
+        for (int64_t r = r0 + sub; r < r1; r += XNES_SPLIT) {
+            const double *zr = z + order[r] * d;
+            const double term = b < 0 ? zr[a] : zr[a] * zr[b];
+            acc = fma(us[r], term, acc);
+        }
+        part[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (q < m && sub == 0) {
+        double acc = 0.0;
+        for (int k = 0; k < XNES_SPLIT; ++k) acc += part[q * XNES_SPLIT + k];
+        partial[static_cast<int64_t>(blockIdx.x) * m + q] = acc;
+    }
+}
+
+__global__ void xnes_sums_final_kernel(const double *__restrict__ partial, double *__restrict__ out,
+                                       int blocks, int m) {
+    const int q = threadIdx.x;
+    if (q >= m) return;
+    double acc = 0.0;
+    for (int b = 0; b < blocks; ++b) acc += partial[static_cast<int64_t>(b) * m + q];
+    out[q] = acc;
+}
+
+int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
+                   const double *d_upper, double *d_z, double *d_x, double *d_x_eval,
+                   uint8_t *d_inside, int64_t n, int32_t d, uint64_t seed, uint64_t offset,
+                   void *stream) {
+    if (n < 0 || d < 1 || d > PB200_MAX_PARAMS || (d_lower == nullptr) != (d_upper == nullptr)) {
+        pb200_set_error("pb200_xnes_ask: bad n=%lld, d=%d or half a boundary", (long long)n, d);
+        return PB200_EINVAL;
+    }
+    if (n == 0) return PB200_OK;
+    xnes_ask_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_mu, d_A, d_lower, d_upper, d_z, d_x, d_x_eval, d_inside, n, d, seed, offset);
+    return pb200_check_cuda(cudaGetLastError(), "xnes_ask_kernel launch");
+}
+
+int pb200_xnes_sums(const double *d_z, const int64_t *d_order, const double *d_us,
+                    double *d_partial, int32_t n_blocks, double *d_out, int64_t n, int32_t d,
+                    void *stream) {
+    const int m = d + d * d;
+    if (n < 1 || d < 1 || d > PB200_MAX_PARAMS || n_blocks < 1) {
+        pb200_set_error("pb200_xnes_sums: bad n=%lld, d=%d or n_blocks=%d", (long long)n, d, n_blocks);
+        return PB200_EINVAL;
+    }
+    const int threads = (m + 31) & ~31;
+    const int wide = (m * XNES_SPLIT + 31) & ~31;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (wide > 1024) {
+        pb200_set_error("pb200_xnes_sums: d=%d needs %d threads per block", d, wide);
+        return PB200_EINVAL;
+    }
+    xnes_sums_kernel<<<n_blocks, wide, wide * sizeof(double), st>>>(d_z, d_order, d_us, d_partial,
+                                                                    n, d);
+    xnes_sums_final_kernel<<<1, threads, 0, st>>>(d_partial, d_out, n_blocks, m);
+    return pb200_check_cuda(cudaGetLastError(), "xnes_sums_kernel launch");
+}
+
 int pb200_philox_normal(double *d_out, int64_t n, uint64_t seed, uint64_t offset,
                         void *stream) {
     if (n < 0) { pb200_set_error("pb200_philox_normal: n < 0"); return PB200_EINVAL; }

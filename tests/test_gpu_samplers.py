@@ -362,3 +362,87 @@ def test_fused_de_ask_tell_gives_identical_chains(pb):
         out.append(host(samples))
     assert np.array_equal(out[0], out[1])
     assert (np.diff(out[0][:, :, 0], axis=1) != 0).mean() > 0.02
+
+
+def test_device_xnes_replays_host_xnes(pb, monkeypatch):
+    """The device-resident xNES draws from Philox instead of numpy.random, so
+    its trajectory differs from the reference's; but fed the SAME normals and
+    scores its update is the reference's: the host XNES of this package (itself
+    checked against pints.XNES, tests/test_controllers_cpu.py) reproduces it
+    generation by generation when numpy.random.normal hands out the device's
+    normals."""
+    x0 = np.array([0.3, 20.0, 1.5])
+    lower, upper = [0.0, 1.0, 0.5], [1.0, 200.0, 1.8]
+    target = np.array([0.1, 50.0, 1.0])
+    n = 2000
+
+    def score(x):                       # a smooth bowl, minimised at `target`
+        return np.sum(((x - target) / [0.1, 10.0, 1.0]) ** 2, axis=1)
+
+    dev = pb.DeviceXNES(x0, [0.05, 5.0, 0.3],
+                        pb.RectangularBoundaries(lower, upper), seed=11)
+    ref = pb.XNES(x0, [0.05, 5.0, 0.3], pb.RectangularBoundaries(lower, upper))
+    dev.set_population_size(n)
+    ref.set_population_size(n)
+    outside = 0
+    for generation in range(25):
+        d_x = dev.ask()
+        z = host(dev.normals())
+        # the draws are the documented Philox stream of the C ABI
+        if generation == 0:
+            from pints_b200._samplers import _DeviceOps
+            buf = torch.empty(n * 3, dtype=torch.float64, device=d_x.device)
+            _DeviceOps(None).normal(buf, 11, 0)
+            assert np.array_equal(host(buf).reshape(n, 3), z)
+        monkeypatch.setattr(np.random, 'normal', lambda *a, **k: z.copy())
+        xs = ref.ask()
+        monkeypatch.undo()
+        inside = host(dev.inside()).astype(bool)
+        outside += int((~inside).sum())
+        assert len(xs) == inside.sum()
+        # same points where inside; the mean where the reference withholds them
+        assert np.allclose(host(dev.points())[inside], xs, rtol=1e-12, atol=1e-12)
+        assert np.array_equal(host(d_x)[~inside],
+                              np.tile(dev.x_guessed(), ((~inside).sum(), 1)))
+        fx = score(host(d_x))           # the same scores to both: same ranks
+        ref.tell(fx[inside])
+        dev.tell(torch.from_numpy(fx).to(d_x.device))
+        assert np.allclose(dev.x_guessed(), ref.x_guessed(), rtol=1e-8)
+        assert dev.f_best() == ref.f_best()
+        assert np.allclose(dev.x_best(), ref.x_best(), rtol=1e-12)
+    assert outside > 0                  # the boundary path was exercised
+    assert np.allclose(dev.x_guessed(), target, rtol=0.05)
+    with pytest.raises(Exception):
+        dev.tell(torch.zeros(n, dtype=torch.float64, device=d_x.device))
+    with pytest.raises(ValueError):
+        pb.DeviceXNES([0.5, 0.5], boundaries=pb.RectangularBoundaries([0], [1]))
+
+
+def test_cuda_optimisation_controller_with_device_xnes(pb):
+    """BASELINE configs[1] end to end: FitzHugh-Nagumo, known-sigma Gaussian
+    log-likelihood, xNES with the population resident on the GPU."""
+    h = po.headline_fhn_spec()
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), h.times,
+                                    h.values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    b = pb.RectangularBoundaries([0.01, 0.1, 1.0], [1.0, 1.0, 5.0])
+    opt = pb.CudaOptimisationController(ll, [0.3, 0.7, 2.5], boundaries=b,
+                                        method=pb.DeviceXNES)
+    opt.optimiser().set_population_size(4096)
+    opt.set_max_iterations(40)
+    x, f = opt.run()
+    # the maximum-likelihood point of the noisy series, near the true values
+    assert np.allclose(x, [0.1, 0.5, 3.0], rtol=0.15)
+    # the maximum is at least as good as the likelihood at the true parameters
+    at_truth = pb.CudaEvaluator(ll, as_list=False).evaluate(
+        np.array([[0.1, 0.5, 3.0]]))[0]
+    assert f >= at_truth - 1e-6 * abs(at_truth)
+    assert opt.evaluations() == 40 * 4096
+    # minimising the error measure of the same problem finds the same point
+    opt = pb.CudaOptimisationController(
+        pb.SumOfSquaresError(problem), [0.3, 0.7, 2.5], boundaries=b,
+        method=pb.DeviceXNES)
+    opt.optimiser().set_population_size(4096)
+    opt.set_max_iterations(40)
+    x2, f2 = opt.run()
+    assert np.allclose(x2, x, rtol=1e-3) and f2 > 0
