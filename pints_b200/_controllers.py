@@ -602,7 +602,7 @@ class CudaOptimisationController(object):
     in the reference (:414-417)."""
 
     def __init__(self, function, x0, sigma0=None, boundaries=None,
-                 method=None, **evaluator_options):
+                 method=None, sharded=False, group=None, **evaluator_options):
         from ._evaluation import CudaEvaluator
         from ._objectives import LogPDF
         from ._compat import base
@@ -617,6 +617,17 @@ class CudaOptimisationController(object):
         self._optimiser = method(x0, sigma0, boundaries)
         self._evaluator = CudaEvaluator(function, as_list=False,
                                         **evaluator_options)
+        # sharded (one process per GPU, torch.distributed initialised, device-
+        # resident optimiser only): every rank draws the same population (same
+        # Philox key), scores its own block, the scores are exchanged by the
+        # kernel itself (ScoreExchange) and every rank applies the same update
+        self._sharded = bool(sharded)
+        self._group = group
+        if self._sharded and not getattr(self._optimiser, 'device_resident',
+                                         False):
+            raise ValueError('sharded=True needs a device-resident optimiser '
+                             '(DeviceXNES); ShardedEvaluator covers the host '
+                             'optimisers.')
         self._sign = 1.0 if self._minimising else -1.0
         self._max_iterations = 10000
         self._unchanged_max = 200
@@ -677,9 +688,22 @@ class CudaOptimisationController(object):
             # population, scores and ranking stay in HBM (DeviceXNES)
             problem = self._evaluator.device_problem()
             opt._device_arg = problem.device
+        exchange = None
+        if self._sharded:
+            import torch.distributed as dist
+            from ._dist import ScoreExchange
+            world = dist.get_world_size(self._group)
+            rank = dist.get_rank(self._group)
+            n = opt.population_size()
+            per = (n + world - 1) // world
+            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            exchange = ScoreExchange(per, problem.device, self._group)
         while True:
             xs = opt.ask()
-            if on_device:
+            if exchange is not None:
+                fs = exchange.run(problem, xs[lo:hi])[:n]
+                opt.tell(-fs if self._sign < 0 else fs)
+            elif on_device:
                 fs = problem.eval(xs)
                 opt.tell(-fs if self._sign < 0 else fs)
             else:

@@ -145,3 +145,54 @@ def test_sharded_device_mcmc():
         p.join(600)
         assert p.exitcode == 0
     assert list(out) == [1] * world
+
+
+def _xnes_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        import pints_b200 as pb
+        f = build_function(pb)
+        b = pb.RectangularBoundaries([0.01, 0.1, 1.0], [1.0, 1.0, 5.0])
+        results = []
+        for sharded in (False, True):
+            ctl = pb.CudaOptimisationController(
+                f, [0.3, 0.7, 2.5], boundaries=b, method=pb.DeviceXNES,
+                sharded=sharded, devices='cuda:%d' % rank)
+            ctl.optimiser().set_population_size(4099)       # ragged blocks
+            ctl.set_max_iterations(25)
+            ctl.set_max_unchanged_iterations(None)
+            results.append(ctl.run())
+        (x1, f1), (x2, f2) = results
+        # the sharded run scores the same population block by block: identical
+        ok = np.array_equal(x1, x2) and f1 == f2
+        ok = ok and np.allclose(x1, [0.1, 0.5, 3.0], rtol=0.15)
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason='needs 2 GPUs')
+def test_sharded_device_xnes():
+    """DeviceXNES over two GPUs: every rank draws the same population, scores
+    its block, the kernel exchanges the scores; same result as one GPU."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context('spawn')
+    out = ctx.Array('i', [0] * world)
+    port = 29800 + os.getpid() % 1000
+    procs = [ctx.Process(target=_xnes_worker, args=(r, world, port, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+    assert list(out) == [1] * world
