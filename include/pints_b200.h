@@ -397,14 +397,17 @@ int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
  * the caller overrides those scores with +inf.
  * sums: out[0..d) = sum_r us[r] z[order[r]], out[d + a d + b] = sum_r us[r]
  * z[order[r]][a] z[order[r]][b]; d_partial holds n_blocks (d + d d) doubles;
- * deterministic (fixed summation order). */
+ * deterministic (fixed summation order).  With d_x and d_fx (both optional)
+ * out[d + d d ..] also receives the best point x[order[0]] (d values) and its
+ * score fx[order[0]]. */
 int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
                    const double *d_upper, double *d_z, double *d_x,
                    double *d_x_eval, uint8_t *d_inside, int64_t n, int32_t d,
                    uint64_t seed, uint64_t offset, void *stream);
 int pb200_xnes_sums(const double *d_z, const int64_t *d_order,
                     const double *d_us, double *d_partial, int32_t n_blocks,
-                    double *d_out, int64_t n, int32_t d, void *stream);
+                    double *d_out, const double *d_x, const double *d_fx,
+                    int64_t n, int32_t d, void *stream);
 
 /* Counter-based RNG (Philox4x32-10): n doubles, N(0,1) or U(0,1), for
  * (seed, stream_id, offset).  Used only in device-RNG sampler mode. */

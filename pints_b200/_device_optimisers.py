@@ -163,6 +163,8 @@ class DeviceXNES(object):
         self._d_x = torch.empty((n, d), **f64)
         self._d_x_eval = torch.empty((n, d), **f64)
         self._d_inside = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._d_inside_bool = self._d_inside.view(torch.bool)
+        self._d_inf = torch.full((), float('inf'), **f64)
         self._d_partial = torch.empty(_SUM_BLOCKS * (d + d * d), **f64)
         # sums, then the best point and its score (one read-back per tell)
         self._d_out = torch.empty(d + d * d + d + 1, **f64)
@@ -223,16 +225,13 @@ class DeviceXNES(object):
         m = d + d * d
         with torch.cuda.device(self._device):
             if self._d_lower is not None:
-                fx = fx.masked_fill(self._d_inside == 0, float('inf'))
+                fx = torch.where(self._d_inside_bool, fx, self._d_inf)
             # ranks: a library sort of 8 n bytes (NaN scores rank last)
             order = torch.sort(fx)[1]
             _lib.check(self._lib.pb200_xnes_sums(
                 _ptr(self._d_z), _ptr(order), _ptr(self._d_us),
-                _ptr(self._d_partial), _SUM_BLOCKS, _ptr(self._d_out), n, d,
-                _stream_ptr(self._device)))
-            best = order[0]
-            self._d_out[m:m + d].copy_(self._d_x[best])
-            self._d_out[m + d].copy_(fx[best])
+                _ptr(self._d_partial), _SUM_BLOCKS, _ptr(self._d_out),
+                _ptr(self._d_x), _ptr(fx), n, d, _stream_ptr(self._device)))
             self._h_out.copy_(self._d_out, non_blocking=True)
             torch.cuda.current_stream(self._device).synchronize()
         out = self._h_out.numpy()

@@ -94,8 +94,8 @@ SIGNATURES = {
                                 c_double, c_double, c_uint64, c_uint64, _P]),
     'pb200_xnes_ask': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64,
                                  c_int32, c_uint64, c_uint64, _P]),
-    'pb200_xnes_sums': (c_int32, [_P, _P, _P, _P, c_int32, _P, c_int64,
-                                  c_int32, _P]),
+    'pb200_xnes_sums': (c_int32, [_P, _P, _P, _P, c_int32, _P, _P, _P,
+                                  c_int64, c_int32, _P]),
     'pb200_hbac_adapt': (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32,
                                    c_double, c_double, _P]),
     'pb200_hbac_propose': (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32,

@@ -596,8 +596,15 @@ __global__ void xnes_sums_kernel(const double *__restrict__ z, const int64_t *__
 }
 
 __global__ void xnes_sums_final_kernel(const double *__restrict__ partial, double *__restrict__ out,
-                                       int blocks, int m) {
+                                       int blocks, int m, const int64_t *__restrict__ order,
+                                       const double *__restrict__ x,
+                                       const double *__restrict__ fx, int d) {
     const int q = threadIdx.x;
+    if (x && q < d + 1) {
+        // the best point of the generation and its score, for the same read-back
+        const int64_t best = order[0];
+        out[m + q] = q < d ? x[best * d + q] : fx[best];
+    }
     if (q >= m) return;
     double acc = 0.0;
     for (int b = 0; b < blocks; ++b) acc += partial[static_cast<int64_t>(b) * m + q];
@@ -619,8 +626,8 @@ int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
 }
 
 int pb200_xnes_sums(const double *d_z, const int64_t *d_order, const double *d_us,
-                    double *d_partial, int32_t n_blocks, double *d_out, int64_t n, int32_t d,
-                    void *stream) {
+                    double *d_partial, int32_t n_blocks, double *d_out, const double *d_x,
+                    const double *d_fx, int64_t n, int32_t d, void *stream) {
     const int m = d + d * d;
     if (n < 1 || d < 1 || d > PB200_MAX_PARAMS || n_blocks < 1) {
         pb200_set_error("pb200_xnes_sums: bad n=%lld, d=%d or n_blocks=%d", (long long)n, d, n_blocks);
@@ -635,7 +642,8 @@ int pb200_xnes_sums(const double *d_z, const int64_t *d_order, const double *d_u
     }
     xnes_sums_kernel<<<n_blocks, wide, wide * sizeof(double), st>>>(d_z, d_order, d_us, d_partial,
                                                                     n, d);
-    xnes_sums_final_kernel<<<1, threads, 0, st>>>(d_partial, d_out, n_blocks, m);
+    xnes_sums_final_kernel<<<1, threads, 0, st>>>(d_partial, d_out, n_blocks, m, d_order,
+                                                  (d_x && d_fx) ? d_x : nullptr, d_fx, d);
     return pb200_check_cuda(cudaGetLastError(), "xnes_sums_kernel launch");
 }
 
