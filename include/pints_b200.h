@@ -390,7 +390,9 @@ int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
                  uint64_t offset_pairs, void *stream);
 
 /* Device-resident xNES (pints/_optimisers/_xnes.py:63-91 ask, :147-182 tell).
- * ask: z (n, d) standard normals = pb200_philox_normal(n d, seed, offset),
+ * ask: z (n, d) standard normals = pb200_philox_normal(n d, seed, *d_offset)
+ * (mean, A and the offset are read from device memory, so that a generation
+ * captured in a CUDA graph can be replayed with new values),
  * x = mu + A z (A row-major (d, d)), inside[i] = boundary test of row i
  * (d_lower / d_upper both NULL: no boundaries); x_eval = x where inside, mu
  * elsewhere -- the reference never evaluates a point outside the boundaries,
@@ -403,7 +405,7 @@ int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
 int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
                    const double *d_upper, double *d_z, double *d_x,
                    double *d_x_eval, uint8_t *d_inside, int64_t n, int32_t d,
-                   uint64_t seed, uint64_t offset, void *stream);
+                   uint64_t seed, const uint64_t *d_offset, void *stream);
 int pb200_xnes_sums(const double *d_z, const int64_t *d_order,
                     const double *d_us, double *d_partial, int32_t n_blocks,
                     double *d_out, const double *d_x, const double *d_fx,

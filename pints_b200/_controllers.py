@@ -699,17 +699,20 @@ class CudaOptimisationController(object):
             lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
             exchange = ScoreExchange(per, problem.device, self._group)
         while True:
-            xs = opt.ask()
             if exchange is not None:
+                xs = opt.ask()
                 fs = exchange.run(problem, xs[lo:hi])[:n]
                 opt.tell(-fs if self._sign < 0 else fs)
+                self._evaluations += len(fs)
             elif on_device:
-                fs = problem.eval(xs)
-                opt.tell(-fs if self._sign < 0 else fs)
+                # ask + score + tell with one synchronisation (CUDA graph)
+                opt.generation(problem, negate=self._sign < 0)
+                self._evaluations += opt.population_size()
             else:
+                xs = opt.ask()
                 fs = self._evaluator.evaluate(xs)
                 opt.tell(self._sign * fs if self._sign < 0 else fs)
-            self._evaluations += len(fs)
+                self._evaluations += len(fs)
             self._iterations += 1
             f_new = opt.f_best()
             if np.abs(f_new - f_sig) >= self._unchanged_threshold:

@@ -43,6 +43,7 @@ class DeviceXNES(object):
     (pints/_optimisers/_xnes.py:79-87, :154-157)."""
 
     device_resident = True
+    use_graph = True
 
     def __init__(self, x0, sigma0=None, boundaries=None, seed=1, device=None):
         self._x0 = vector(x0)
@@ -158,7 +159,7 @@ class DeviceXNES(object):
         self._I = np.eye(d)
         f64 = dict(dtype=torch.float64, device=dev)
         self._d_us = torch.from_numpy(us).to(dev)
-        self._d_state = torch.empty(d + d * d, **f64)        # mu, then A
+        self._d_state = torch.empty(d + d * d + 1, **f64)    # mu, A, Philox offset
         self._d_z = torch.empty((n, d), **f64)
         self._d_x = torch.empty((n, d), **f64)
         self._d_x_eval = torch.empty((n, d), **f64)
@@ -170,8 +171,10 @@ class DeviceXNES(object):
         self._d_out = torch.empty(d + d * d + d + 1, **f64)
         self._h_out = torch.empty(d + d * d + d + 1, dtype=torch.float64,
                                   pin_memory=True)
-        self._h_state = torch.empty(d + d * d, dtype=torch.float64,
+        self._h_state = torch.empty(d + d * d + 1, dtype=torch.float64,
                                     pin_memory=True)
+        self._graph = self._graph_key = self._graph_failed = None
+        self._eager_generations = 0
         self._d_lower = self._d_upper = None
         if self._boundaries is not None:
             self._d_lower = torch.from_numpy(np.array(
@@ -194,25 +197,63 @@ class DeviceXNES(object):
         return self._d_inside
 
     # -- ask / tell ------------------------------------------------------
+    def _stage_state(self):
+        """mean, A and the Philox offset of the coming generation go to the
+        pinned staging buffer (the kernels read them from device memory, so
+        that a captured generation can be replayed with new values)."""
+        n, d = self._population_size, self._d
+        h = self._h_state.numpy()
+        h[:d] = self._mu
+        h[d:d + d * d] = self._A.reshape(-1)
+        h[d + d * d:].view(np.uint64)[0] = self._offset
+        self._offset += (n * d + 1) // 2 + 1
+
+    def _enqueue_ask(self):
+        n, d = self._population_size, self._d
+        self._d_state.copy_(self._h_state, non_blocking=True)
+        state = self._d_state.data_ptr()
+        _lib.check(self._lib.pb200_xnes_ask(
+            ctypes.c_void_p(state), ctypes.c_void_p(state + 8 * d),
+            _ptr(self._d_lower), _ptr(self._d_upper), _ptr(self._d_z),
+            _ptr(self._d_x), _ptr(self._d_x_eval), _ptr(self._d_inside),
+            n, d, ctypes.c_uint64(self._seed),
+            ctypes.c_void_p(state + 8 * (d + d * d)),
+            _stream_ptr(self._device)))
+
+    def _enqueue_tell(self, fx):
+        n, d = self._population_size, self._d
+        if self._d_lower is not None:
+            fx = torch.where(self._d_inside_bool, fx, self._d_inf)
+        # ranks: a library sort of 8 n bytes (NaN scores rank last)
+        order = torch.sort(fx)[1]
+        _lib.check(self._lib.pb200_xnes_sums(
+            _ptr(self._d_z), _ptr(order), _ptr(self._d_us),
+            _ptr(self._d_partial), _SUM_BLOCKS, _ptr(self._d_out),
+            _ptr(self._d_x), _ptr(fx), n, d, _stream_ptr(self._device)))
+        self._h_out.copy_(self._d_out, non_blocking=True)
+
+    def _update(self):
+        """The d x d part of tell() on the host
+        (pints/_optimisers/_xnes.py:170-182)."""
+        d = self._d
+        m = d + d * d
+        out = self._h_out.numpy()
+        Gd = out[:d]
+        Gm = out[d:m].reshape((d, d)) - self._sum_us * self._I
+        self._mu = self._mu + self._eta_mu * np.dot(self._A, Gd)
+        self._A = np.dot(self._A, scipy.linalg.expm(0.5 * self._eta_A * Gm))
+        self._f_guessed = float(out[m + d])
+        if self._f_guessed < self._f_best:
+            self._f_best = self._f_guessed
+            self._x_best = np.array(out[m:m + d], copy=True)
+
     def ask(self):
         if not self._running:
             self._initialise()
         self._ready_for_tell = True
-        n, d = self._population_size, self._d
-        h = self._h_state.numpy()
-        h[:d] = self._mu
-        h[d:] = self._A.reshape(-1)
+        self._stage_state()
         with torch.cuda.device(self._device):
-            self._d_state.copy_(self._h_state, non_blocking=True)
-            offset = self._offset
-            self._offset += (n * d + 1) // 2 + 1
-            state = self._d_state.data_ptr()
-            _lib.check(self._lib.pb200_xnes_ask(
-                ctypes.c_void_p(state), ctypes.c_void_p(state + 8 * d),
-                _ptr(self._d_lower), _ptr(self._d_upper), _ptr(self._d_z),
-                _ptr(self._d_x), _ptr(self._d_x_eval), _ptr(self._d_inside),
-                n, d, ctypes.c_uint64(self._seed), ctypes.c_uint64(offset),
-                _stream_ptr(self._device)))
+            self._enqueue_ask()
         return self._d_x_eval
 
     def tell(self, fx):
@@ -221,26 +262,46 @@ class DeviceXNES(object):
         if not self._ready_for_tell:
             raise Exception('ask() not called before tell()')
         self._ready_for_tell = False
-        n, d = self._population_size, self._d
-        m = d + d * d
         with torch.cuda.device(self._device):
-            if self._d_lower is not None:
-                fx = torch.where(self._d_inside_bool, fx, self._d_inf)
-            # ranks: a library sort of 8 n bytes (NaN scores rank last)
-            order = torch.sort(fx)[1]
-            _lib.check(self._lib.pb200_xnes_sums(
-                _ptr(self._d_z), _ptr(order), _ptr(self._d_us),
-                _ptr(self._d_partial), _SUM_BLOCKS, _ptr(self._d_out),
-                _ptr(self._d_x), _ptr(fx), n, d, _stream_ptr(self._device)))
-            self._h_out.copy_(self._d_out, non_blocking=True)
+            self._enqueue_tell(fx)
             torch.cuda.current_stream(self._device).synchronize()
-        out = self._h_out.numpy()
-        Gd = out[:d]
-        Gm = out[d:m].reshape((d, d)) - self._sum_us * self._I
-        # pints/_optimisers/_xnes.py:170-176
-        self._mu = self._mu + self._eta_mu * np.dot(self._A, Gd)
-        self._A = np.dot(self._A, scipy.linalg.expm(0.5 * self._eta_A * Gm))
-        self._f_guessed = float(out[m + d])
-        if self._f_guessed < self._f_best:
-            self._f_best = self._f_guessed
-            self._x_best = np.array(out[m:m + d], copy=True)
+        self._update()
+
+    def generation(self, problem, negate=False):
+        """One whole generation -- ask, score on ``problem`` (a
+        ``DeviceProblem``), tell -- with a single host synchronisation.
+        ``negate``: maximise the scores.  After two eager generations the
+        device work (state upload, sampling kernel, sort + solve kernels,
+        ranking, sums, read-back: about ten launches) is captured in a CUDA
+        graph and replayed; set ``use_graph = False`` to keep it eager."""
+        if not self._running:
+            self._initialise()
+        self._stage_state()
+        key = (id(problem), bool(negate))
+        with torch.cuda.device(self._device):
+            if self._graph is not None and self._graph_key == key:
+                self._graph.replay()
+            elif self.use_graph and self._eager_generations >= 2 \
+                    and self._graph_failed is None:
+                try:
+                    torch.cuda.synchronize(self._device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._enqueue_generation(problem, negate)
+                    self._graph, self._graph_key = graph, key
+                    graph.replay()
+                except Exception as e:          # keep going without a graph
+                    self._graph_failed = e
+                    self._graph = None
+                    torch.cuda.synchronize(self._device)
+                    self._enqueue_generation(problem, negate)
+            else:
+                self._enqueue_generation(problem, negate)
+                self._eager_generations += 1
+            torch.cuda.current_stream(self._device).synchronize()
+        self._update()
+
+    def _enqueue_generation(self, problem, negate):
+        self._enqueue_ask()
+        fx = problem.eval(self._d_x_eval)
+        self._enqueue_tell(-fx if negate else fx)

@@ -93,7 +93,7 @@ SIGNATURES = {
                                 _P, c_int64, c_int64, c_int64, c_int32,
                                 c_double, c_double, c_uint64, c_uint64, _P]),
     'pb200_xnes_ask': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64,
-                                 c_int32, c_uint64, c_uint64, _P]),
+                                 c_int32, c_uint64, _P, _P]),
     'pb200_xnes_sums': (c_int32, [_P, _P, _P, _P, c_int32, _P, _P, _P,
                                   c_int64, c_int32, _P]),
     'pb200_hbac_adapt': (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32,

@@ -538,9 +538,10 @@ __global__ void xnes_ask_kernel(const double *__restrict__ mu, const double *__r
                                 const double *__restrict__ upper, double *__restrict__ z,
                                 double *__restrict__ x, double *__restrict__ x_eval,
                                 uint8_t *__restrict__ inside, int64_t n, int d,
-                                uint64_t seed, uint64_t offset) {
+                                uint64_t seed, const uint64_t *__restrict__ d_offset) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint64_t offset = *d_offset;
     double zi[PB200_MAX_PARAMS];
     for (int k = 0; k < d; ++k) {
         zi[k] = philox_normal_at(i * d + k, seed, offset);
@@ -613,15 +614,16 @@ __global__ void xnes_sums_final_kernel(const double *__restrict__ partial, doubl
 
 int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
                    const double *d_upper, double *d_z, double *d_x, double *d_x_eval,
-                   uint8_t *d_inside, int64_t n, int32_t d, uint64_t seed, uint64_t offset,
-                   void *stream) {
-    if (n < 0 || d < 1 || d > PB200_MAX_PARAMS || (d_lower == nullptr) != (d_upper == nullptr)) {
+                   uint8_t *d_inside, int64_t n, int32_t d, uint64_t seed,
+                   const uint64_t *d_offset, void *stream) {
+    if (n < 0 || d < 1 || d > PB200_MAX_PARAMS || !d_offset ||
+        (d_lower == nullptr) != (d_upper == nullptr)) {
         pb200_set_error("pb200_xnes_ask: bad n=%lld, d=%d or half a boundary", (long long)n, d);
         return PB200_EINVAL;
     }
     if (n == 0) return PB200_OK;
     xnes_ask_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_mu, d_A, d_lower, d_upper, d_z, d_x, d_x_eval, d_inside, n, d, seed, offset);
+        d_mu, d_A, d_lower, d_upper, d_z, d_x, d_x_eval, d_inside, n, d, seed, d_offset);
     return pb200_check_cuda(cudaGetLastError(), "xnes_ask_kernel launch");
 }
 

@@ -392,7 +392,7 @@ def test_device_xnes_replays_host_xnes(pb, monkeypatch):
         if generation == 0:
             from pints_b200._samplers import _DeviceOps
             buf = torch.empty(n * 3, dtype=torch.float64, device=d_x.device)
-            _DeviceOps(None).normal(buf, 11, 0)
+            _DeviceOps(None).normal(buf, 11, 0)      # seed 11, offset 0
             assert np.array_equal(host(buf).reshape(n, 3), z)
         monkeypatch.setattr(np.random, 'normal', lambda *a, **k: z.copy())
         xs = ref.ask()
@@ -438,6 +438,17 @@ def test_cuda_optimisation_controller_with_device_xnes(pb):
         np.array([[0.1, 0.5, 3.0]]))[0]
     assert f >= at_truth - 1e-6 * abs(at_truth)
     assert opt.evaluations() == 40 * 4096
+    # the generations after the second were replayed from a CUDA graph, and
+    # an eager run (no graph) follows exactly the same trajectory
+    assert opt.optimiser()._graph is not None, opt.optimiser()._graph_failed
+    eager = pb.CudaOptimisationController(ll, [0.3, 0.7, 2.5], boundaries=b,
+                                          method=pb.DeviceXNES)
+    eager.optimiser().use_graph = False
+    eager.optimiser().set_population_size(4096)
+    eager.set_max_iterations(40)
+    xe, fe = eager.run()
+    assert eager.optimiser()._graph is None
+    assert np.array_equal(xe, x) and fe == f
     # minimising the error measure of the same problem finds the same point
     opt = pb.CudaOptimisationController(
         pb.SumOfSquaresError(problem), [0.3, 0.7, 2.5], boundaries=b,

@@ -17,6 +17,7 @@ problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), h.times, h.values)
 ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
 b = pb.RectangularBoundaries([0.01, 0.1, 1.0], [1.0, 1.0, 5.0])
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+GENERATIONS = 300
 for method in (pb.XNES, pb.DeviceXNES):
     np.random.seed(1)
     ctl = pb.CudaOptimisationController(ll, [0.1, 0.5, 3.0], [0.005, 0.025, 0.15],
@@ -29,7 +30,7 @@ for method in (pb.XNES, pb.DeviceXNES):
     ctl = pb.CudaOptimisationController(ll, [0.1, 0.5, 3.0], [0.005, 0.025, 0.15],
                                         boundaries=b, method=method)
     ctl.optimiser().set_population_size(n)
-    ctl.set_max_iterations(50)
+    ctl.set_max_iterations(GENERATIONS)
     ctl.set_max_unchanged_iterations(None)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -37,4 +38,4 @@ for method in (pb.XNES, pb.DeviceXNES):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print('%-11s population %d: %.3f ms per generation, %.3e evaluations/s, x = %s f = %.6f'
-          % (method.__name__, n, dt / 50 * 1e3, 50 * n / dt, np.round(x, 5), f))
+          % (method.__name__, n, dt / GENERATIONS * 1e3, GENERATIONS * n / dt, np.round(x, 5), f))

@@ -31,4 +31,5 @@ for _ in range(200): scipy.linalg.expm(G)
 print('expm host %.1f us' % ((time.perf_counter() - t0) / 200 * 1e6))
 def gen():
     x = opt.ask(); f = dp.eval(x); opt.tell(-f)
-print('generation %.1f us' % T(gen))
+print("generation eager %.1f us" % T(gen))
+print("generation() %.1f us (graph: %s)" % (T(lambda: opt.generation(dp, True)), opt._graph is not None))
