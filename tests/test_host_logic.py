@@ -315,3 +315,40 @@ def test_cuda_evaluator_is_a_pints_evaluator(pints_ref):
     assert np.array_equal(mirror.suggested_parameters(),
                           br.suggested_parameters())
     assert np.array_equal(mirror.suggested_times(), br.suggested_times())
+
+
+def test_device_xnes_host_side_contract():
+    """Constructor checks and the population-size interface of DeviceXNES are
+    those of pints.PopulationBasedOptimiser (pints/_optimisers/__init__.py:
+    24-312); nothing touches the GPU before the first ask()."""
+    b = pb.RectangularBoundaries([0, 0], [1, 2])
+    opt = pb.DeviceXNES([0.5, 1.0], boundaries=b)
+    assert opt.population_size() == 4 + int(3 * np.log(2))
+    assert np.allclose(opt._sigma0, [1 / 6, 2 / 6])
+    assert not opt.running() and not opt.needs_sensitivities()
+    assert np.array_equal(opt.x_guessed(), [0.5, 1.0])
+    assert opt.f_best() == np.inf
+    opt.set_population_size(100)
+    assert opt.population_size() == 100
+    assert opt.suggested_population_size(8) == 8
+    with pytest.raises(ValueError):
+        opt.set_population_size(0)
+    with pytest.raises(ValueError):
+        pb.DeviceXNES([0.5, 3.0], boundaries=b)          # outside
+    with pytest.raises(ValueError):
+        pb.DeviceXNES([0.5], boundaries=b)                # dimension
+    with pytest.raises(ValueError):
+        pb.DeviceXNES([0.5, 1.0], sigma0=-1.0)
+    with pytest.raises(ValueError):
+        pb.DeviceXNES([0.5, 1.0], sigma0=[1.0, 2.0, 3.0])
+    with pytest.raises(ValueError):
+        pb.DeviceXNES(np.ones(8))                         # more than 7 parameters
+    assert np.allclose(pb.DeviceXNES([0.0, -3.0])._sigma0, [1.0, 1.0])
+    with pytest.raises(Exception):
+        opt.tell(None)                                    # before ask()
+    # sharding needs a device-resident optimiser
+    problem = pb.SingleOutputProblem(pb.toy.LogisticModel(),
+                                     np.linspace(0, 10, 20), np.zeros(20))
+    with pytest.raises(ValueError):
+        pb.CudaOptimisationController(pb.SumOfSquaresError(problem),
+                                      [0.1, 10.0], method=pb.XNES, sharded=True)
