@@ -296,8 +296,14 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
         double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * no : nullptr;
 
         if constexpr (SMEM && E::POINT_AUX) {
-            // segment by segment (see HhEval): a lane's points are 32 apart
+            // segment by segment (see HhEval): a lane's points are 32 apart.
+            // The first point of a lane in a segment takes an exp(); the loop
+            // over the rest is branch-free: one multiplication by F for the
+            // decay, the polynomial, a residual that is zeroed for lanes past
+            // the end of the segment, pointers instead of index arithmetic.
             const int n_seg = ev.n_ev + 1;
+            const double g_max = ev.g_max;
+            double acc = 0.0;
             for (int s = 0; s < n_seg; ++s) {
                 const int a = aux.lo[s], b = aux.lo[s + 1];
                 if (a >= b) continue;
@@ -305,24 +311,35 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                 const double inf = rec[0], dn = rec[1], mrt = rec[2], drive = rec[3];
                 const double F = rec[4];
                 const bool uni = aux.uniform[s] != 0;
-                double e = 0.0;
-                for (int base = a; base < b; base += 32) {
-                    const int j = base + lane;
-                    const bool valid = j < b;
-                    const double dt = series[(valid ? j : b - 1) * row];
-                    if (base == a || !uni) e = exp(__dmul_rn(dt, mrt));
-                    else e = __dmul_rn(e, F);
+                const int last = b - 1;
+                auto point = [&](int j, double e) {
+                    const bool valid = j <= last;
                     const double nn = __dsub_rn(inf, __dmul_rn(dn, e));
                     const double n2 = __dmul_rn(nn, nn);
                     const double n4 = __dmul_rn(n2, n2);
-                    const double v = __dmul_rn(__dmul_rn(ev.g_max, n4), drive);
-                    if (valid) {
-                        if (TRAJ) my_traj[j] = v;
-                        const double r = __dsub_rn(series[j * row + 1], v);
-                        ss[0] = __dadd_rn(ss[0], __dmul_rn(r, r));
+                    const double v = __dmul_rn(__dmul_rn(g_max, n4), drive);
+                    const int jj = valid ? j : last;
+                    if (TRAJ) { if (valid) my_traj[j] = v; }
+                    double r = __dsub_rn(series[jj * row + 1], v);
+                    r = valid ? r : 0.0;
+                    acc = __dadd_rn(acc, __dmul_rn(r, r));
+                };
+                int j = a + lane;
+                double e = exp(__dmul_rn(series[(j <= last ? j : last) * row], mrt));
+                point(j, e);
+                if (uni) {
+                    for (j += 32; j - lane <= last; j += 32) {
+                        e = __dmul_rn(e, F);
+                        point(j, e);
+                    }
+                } else {
+                    for (j += 32; j - lane <= last; j += 32) {
+                        e = exp(__dmul_rn(series[(j <= last ? j : last) * row], mrt));
+                        point(j, e);
                     }
                 }
             }
+            ss[0] = acc;
         } else
         for (int j = lane; j < nt; j += 32) {
             const double t = series[j * row];
