@@ -50,9 +50,9 @@ class DeviceXNES(object):
         self._d = len(self._x0)
         if self._d < 1:
             raise ValueError('Problem dimension must be greater than zero.')
-        if self._d > 7:
-            # pb200_xnes_sums: (d + d^2) * 16 threads in one block
-            raise ValueError('DeviceXNES supports at most 7 parameters.')
+        if self._d > _lib.MAX_PARAMS:
+            raise ValueError('DeviceXNES supports at most %d parameters.'
+                             % _lib.MAX_PARAMS)
         self._boundaries = boundaries
         if boundaries is not None:
             if boundaries.n_parameters() != self._d:

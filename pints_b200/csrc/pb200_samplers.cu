@@ -566,22 +566,22 @@ __global__ void xnes_ask_kernel(const double *__restrict__ mu, const double *__r
 // Deterministic: block b sums a contiguous range of ranks serially, one thread
 // per output quantity; a second single-block pass adds the partial sums in
 // block order.
-constexpr int XNES_SPLIT = 16;     // threads per output quantity
+constexpr int XNES_SPLIT = 16;     // threads per output quantity (fewer for large d)
 __global__ void xnes_sums_kernel(const double *__restrict__ z, const int64_t *__restrict__ order,
                                  const double *__restrict__ us, double *__restrict__ partial,
-                                 int64_t n, int d) {
+                                 int64_t n, int d, int split) {
     // thread (q, s): quantity q over the ranks r0 + s, r0 + s + SPLIT, ... of
     // this block's range (independent gathers in flight), then the SPLIT
     // partial sums of a quantity are added in a fixed order
     extern __shared__ double part[];
     const int m = d + d * d;
-    const int q = threadIdx.x / XNES_SPLIT, sub = threadIdx.x % XNES_SPLIT;
+    const int q = threadIdx.x / split, sub = threadIdx.x % split;
     const int64_t per = (n + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = per * blockIdx.x, r1 = r0 + per < n ? r0 + per : n;
     if (q < m) {
         const int a = q < d ? q : (q - d) / d, b = q < d ? -1 : (q - d) % d;
         double acc = 0.0;
-        for (int64_t r = r0 + sub; r < r1; r += XNES_SPLIT) {
+        for (int64_t r = r0 + sub; r < r1; r += split) {
             const double *zr = z + order[r] * d;
             const double term = b < 0 ? zr[a] : zr[a] * zr[b];
             acc = fma(us[r], term, acc);
@@ -591,7 +591,7 @@ __global__ void xnes_sums_kernel(const double *__restrict__ z, const int64_t *__
     __syncthreads();
     if (q < m && sub == 0) {
         double acc = 0.0;
-        for (int k = 0; k < XNES_SPLIT; ++k) acc += part[q * XNES_SPLIT + k];
+        for (int k = 0; k < split; ++k) acc += part[q * split + k];
         partial[static_cast<int64_t>(blockIdx.x) * m + q] = acc;
     }
 }
@@ -636,14 +636,11 @@ int pb200_xnes_sums(const double *d_z, const int64_t *d_order, const double *d_u
         return PB200_EINVAL;
     }
     const int threads = (m + 31) & ~31;
-    const int wide = (m * XNES_SPLIT + 31) & ~31;
+    const int split = 1024 / m < XNES_SPLIT ? 1024 / m : XNES_SPLIT;   // m <= 272
+    const int wide = (m * split + 31) & ~31;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (wide > 1024) {
-        pb200_set_error("pb200_xnes_sums: d=%d needs %d threads per block", d, wide);
-        return PB200_EINVAL;
-    }
     xnes_sums_kernel<<<n_blocks, wide, wide * sizeof(double), st>>>(d_z, d_order, d_us, d_partial,
-                                                                    n, d);
+                                                                    n, d, split);
     xnes_sums_final_kernel<<<1, threads, 0, st>>>(d_partial, d_out, n_blocks, m, d_order,
                                                   (d_x && d_fx) ? d_x : nullptr, d_fx, d);
     return pb200_check_cuda(cudaGetLastError(), "xnes_sums_kernel launch");

@@ -457,3 +457,30 @@ def test_cuda_optimisation_controller_with_device_xnes(pb):
     opt.set_max_iterations(40)
     x2, f2 = opt.run()
     assert np.allclose(x2, x, rtol=1e-3) and f2 > 0
+
+
+def test_device_xnes_twelve_parameters(pb, monkeypatch):
+    """The sums kernel splits its block differently for large d (d + d^2
+    output quantities): twelve parameters, no boundaries, against the host
+    XNES fed the same normals and scores."""
+    d, n = 12, 600
+    rng = np.random.RandomState(4)
+    target = rng.uniform(-1, 1, d)
+    x0 = target + 0.3
+    dev = pb.DeviceXNES(x0, 0.2, seed=5)
+    ref = pb.XNES(x0, 0.2)
+    dev.set_population_size(n)
+    ref.set_population_size(n)
+    for generation in range(12):
+        d_x = dev.ask()
+        z = host(dev.normals())
+        monkeypatch.setattr(np.random, 'normal', lambda *a, **k: z.copy())
+        xs = ref.ask()
+        monkeypatch.undo()
+        assert np.allclose(host(d_x), xs, rtol=1e-12, atol=1e-12)
+        fx = np.sum((host(d_x) - target) ** 2, axis=1)
+        ref.tell(fx)
+        dev.tell(torch.from_numpy(fx).to(d_x.device))
+        assert np.allclose(dev.x_guessed(), ref.x_guessed(), rtol=1e-8, atol=1e-10)
+        assert dev.f_best() == ref.f_best()
+    assert dev.f_best() < np.sum(0.3 ** 2 * np.ones(d))

@@ -342,7 +342,7 @@ def test_device_xnes_host_side_contract():
     with pytest.raises(ValueError):
         pb.DeviceXNES([0.5, 1.0], sigma0=[1.0, 2.0, 3.0])
     with pytest.raises(ValueError):
-        pb.DeviceXNES(np.ones(8))                         # more than 7 parameters
+        pb.DeviceXNES(np.ones(17))                        # more than 16 parameters
     assert np.allclose(pb.DeviceXNES([0.0, -3.0])._sigma0, [1.0, 1.0])
     with pytest.raises(Exception):
         opt.tell(None)                                    # before ask()
