@@ -13,7 +13,7 @@ reference's own interfaces for that path:
   SumOfSquaresError, GaussianKnownSigmaLogLikelihood, GaussianLogLikelihood,
   ProbabilityBasedError, LogPosterior, UniformLogPrior, RectangularBoundaries
   HaarioBardenetACMC, DifferentialEvolutionMCMC   device-resident samplers
-  XNES (vectorised), DeviceXNES, CudaOptimisationController,
+  XNES (vectorised), DeviceXNES, DeviceSNES, CudaOptimisationController,
   CudaMCMCController,
   cuda_evaluators()                   run the reference's own controllers on GPU
 
@@ -51,7 +51,7 @@ _LAZY = {
     'DifferentialEvolutionMCMC': '_samplers',
     'XNES': '_controllers', 'SNES': '_controllers', 'PSO': '_controllers',
     'BareCMAES': '_controllers', 'cuda_evaluators': '_controllers',
-    'DeviceXNES': '_device_optimisers',
+    'DeviceXNES': '_device_optimisers', 'DeviceSNES': '_device_optimisers',
     'CudaOptimisationController': '_controllers',
     'CudaMCMCController': '_controllers',
 }

@@ -305,3 +305,36 @@ class DeviceXNES(object):
         self._enqueue_ask()
         fx = problem.eval(self._d_x_eval)
         self._enqueue_tell(-fx if negate else fx)
+
+
+class DeviceSNES(DeviceXNES):
+    """Separable natural evolution strategy (``pints.SNES``,
+    pints/_optimisers/_snes.py:56-166) with the population on the GPU: the
+    same kernels as :class:`DeviceXNES` with a diagonal ``A``; the update uses
+    ``sum_r u_r s_r`` and the diagonal of ``sum_r u_r s_r s_r^T``."""
+
+    @classmethod
+    def name(cls):
+        return 'Seperable Natural Evolution Strategy (SNES), device resident'
+
+    def _initialise(self):
+        super()._initialise()
+        d = self._d
+        self._eta_sigmas = 0.2 * (3 + np.log(d)) * d ** -0.5
+        self._sigmas = np.array(self._sigma0, copy=True)
+        self._A = np.diag(self._sigmas)
+
+    def _update(self):
+        # pints/_optimisers/_snes.py:150-166
+        d = self._d
+        m = d + d * d
+        out = self._h_out.numpy()
+        Gd = out[:d]
+        Gs = np.diagonal(out[d:m].reshape((d, d))) - self._sum_us
+        self._mu = self._mu + self._eta_mu * self._sigmas * Gd
+        self._sigmas = self._sigmas * np.exp(0.5 * self._eta_sigmas * Gs)
+        self._A = np.diag(self._sigmas)
+        self._f_guessed = float(out[m + d])
+        if self._f_guessed < self._f_best:
+            self._f_best = self._f_guessed
+            self._x_best = np.array(out[m:m + d], copy=True)

@@ -459,16 +459,17 @@ def test_cuda_optimisation_controller_with_device_xnes(pb):
     assert np.allclose(x2, x, rtol=1e-3) and f2 > 0
 
 
-def test_device_xnes_twelve_parameters(pb, monkeypatch):
+@pytest.mark.parametrize('pair', [('DeviceXNES', 'XNES'), ('DeviceSNES', 'SNES')])
+def test_device_xnes_twelve_parameters(pb, monkeypatch, pair):
     """The sums kernel splits its block differently for large d (d + d^2
     output quantities): twelve parameters, no boundaries, against the host
-    XNES fed the same normals and scores."""
+    XNES / SNES fed the same normals and scores."""
     d, n = 12, 600
     rng = np.random.RandomState(4)
     target = rng.uniform(-1, 1, d)
     x0 = target + 0.3
-    dev = pb.DeviceXNES(x0, 0.2, seed=5)
-    ref = pb.XNES(x0, 0.2)
+    dev = getattr(pb, pair[0])(x0, 0.2, seed=5)
+    ref = getattr(pb, pair[1])(x0, 0.2)
     dev.set_population_size(n)
     ref.set_population_size(n)
     for generation in range(12):
