@@ -411,6 +411,17 @@ int pb200_xnes_sums(const double *d_z, const int64_t *d_order,
                     double *d_out, const double *d_x, const double *d_fx,
                     int64_t n, int32_t d, void *stream);
 
+/* Ranking of the scores for the device-resident optimisers: ascending argsort
+ * of n <= PB200_ARGSORT_MAX doubles (`order = np.argsort(fx)`,
+ * pints/_optimisers/_xnes.py:159), NaN last, ties by index, deterministic.
+ * d_ws: pb200_argsort_workspace_bytes(n) bytes; *d_status becomes 1 if the
+ * sample sort met a bucket it cannot hold (sort another way then), else 0. */
+#define PB200_ARGSORT_MAX 262144
+int64_t pb200_argsort_workspace_bytes(int64_t n);
+int pb200_argsort_f64(const double *d_values, int64_t *d_order, int64_t n,
+                      void *d_ws, int64_t ws_bytes, int32_t *d_status,
+                      void *stream);
+
 /* Counter-based RNG (Philox4x32-10): n doubles, N(0,1) or U(0,1), for
  * (seed, stream_id, offset).  Used only in device-RNG sampler mode. */
 int pb200_philox_normal(double *d_out, int64_t n, uint64_t seed,

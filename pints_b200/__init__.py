@@ -52,6 +52,7 @@ _LAZY = {
     'XNES': '_controllers', 'SNES': '_controllers', 'PSO': '_controllers',
     'BareCMAES': '_controllers', 'cuda_evaluators': '_controllers',
     'DeviceXNES': '_device_optimisers', 'DeviceSNES': '_device_optimisers',
+    'DeviceArgsort': '_device_optimisers',
     'CudaOptimisationController': '_controllers',
     'CudaMCMCController': '_controllers',
 }

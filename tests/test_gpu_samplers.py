@@ -449,6 +449,20 @@ def test_cuda_optimisation_controller_with_device_xnes(pb):
     xe, fe = eager.run()
     assert eager.optimiser()._graph is None
     assert np.array_equal(xe, x) and fe == f
+    # ranking with pb200_argsort_f64 instead of the library sort: the same
+    # optimum (tied +inf scores of out-of-bounds points may be ordered
+    # differently, which only changes the order of a sum)
+    for n in (4096, 6000):
+        runs = []
+        for native in (False, True):
+            ctl = pb.CudaOptimisationController(
+                ll, [0.3, 0.7, 2.5], boundaries=b, method=pb.DeviceXNES)
+            ctl.optimiser().native_sort = native
+            ctl.optimiser().set_population_size(n)
+            ctl.set_max_iterations(30)
+            runs.append(ctl.run())
+        assert np.allclose(runs[0][0], runs[1][0], rtol=1e-9)
+        assert np.isclose(runs[0][1], runs[1][1], rtol=1e-12)
     # minimising the error measure of the same problem finds the same point
     opt = pb.CudaOptimisationController(
         pb.SumOfSquaresError(problem), [0.3, 0.7, 2.5], boundaries=b,
@@ -485,3 +499,28 @@ def test_device_xnes_twelve_parameters(pb, monkeypatch, pair):
         assert np.allclose(dev.x_guessed(), ref.x_guessed(), rtol=1e-8, atol=1e-10)
         assert dev.f_best() == ref.f_best()
     assert dev.f_best() < np.sum(0.3 ** 2 * np.ones(d))
+
+
+@pytest.mark.parametrize('n', [1, 5, 1000, 4096, 4097, 65536, 200001])
+def test_device_argsort(pb, n):
+    """pb200_argsort_f64 (sample sort) against numpy's stable argsort: NaN
+    last, ties by index, infinities, signed zeros, heavy tails and constant
+    arrays (every bucket boundary is a tie then)."""
+    rng = np.random.RandomState(n)
+    cases = [rng.randn(n), np.exp(8 * rng.randn(n)), np.zeros(n),
+             np.round(rng.randn(n), 1), -np.arange(n, dtype=float)]
+    special = rng.randn(n)
+    special[rng.rand(n) < 0.05] = np.inf
+    special[rng.rand(n) < 0.05] = -np.inf
+    special[rng.rand(n) < 0.05] = np.nan
+    special[rng.rand(n) < 0.05] = 0.0
+    special[rng.rand(n) < 0.05] = -0.0
+    cases.append(special)
+    sorter = pb.DeviceArgsort(n, None, force_native=True)
+    assert sorter.native
+    for values in cases:
+        d = torch.from_numpy(values).to(sorter.device)
+        got = host(sorter(d))
+        assert int(sorter.status.item()) == 0
+        want = np.argsort(values, kind='stable')
+        assert np.array_equal(got, want)

@@ -21,7 +21,8 @@ xs = opt.ask()
 print('eval %.1f us' % T(lambda: dp.eval(xs)))
 fx = -dp.eval(xs)
 print('masked_fill %.1f us' % T(lambda: fx.masked_fill(opt._d_inside == 0, float('inf'))))
-print('sort %.1f us' % T(lambda: torch.sort(fx)))
+print("sort (torch) %.1f us" % T(lambda: torch.sort(fx)))
+print("sort (pb200_argsort_f64) %.1f us" % T(lambda: opt._sorter(fx)))
 def tell():
     opt._ready_for_tell = True; opt.tell(fx)
 print('tell total %.1f us' % T(tell))
