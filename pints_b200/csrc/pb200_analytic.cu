@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int WARPS = 8;                 // warps per block
-constexpr int SEG_STRIDE = 5;            // doubles per HH-IK segment record
+constexpr int SEG_STRIDE = 11;           // doubles per HH-IK segment record
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -87,6 +87,9 @@ struct HhBlockAux {
     int lo[PB200_MAX_EVENTS + 2];          // first point of segment s (lo[n_seg] = n_times)
     int uniform[PB200_MAX_EVENTS + 1];     // points 32 apart are equally spaced in s
     double d32[PB200_MAX_EVENTS + 1];      // that spacing
+    int uniform1[PB200_MAX_EVENTS + 1];    // the first 32 points of s are equally spaced
+    double d1[PB200_MAX_EVENTS + 1];       // that spacing
+    double dt0[PB200_MAX_EVENTS + 1];      // time of the first point into the segment
 };
 
 struct HhEval {
@@ -96,7 +99,10 @@ struct HhEval {
     int n_ev;
     const double *events;     // in the kernel parameter (constant bank)
     // record of segment s: [inf, n_start, t_start, tau], or for the staged
-    // (fast) path [inf, inf - n_start, -1/tau, v - E_k, F]
+    // (fast) path [inf, inf - n_start, -1/tau, v - E_k, F, E_a, G, G^2, G^4,
+    // G^8, G^16]: a lane's first decay factor in the segment is
+    // E_a G^lane = exp(-(dt_a + lane d1) / tau), five selected factors
+    // instead of an exp()
     __device__ __forceinline__ void prepare(const double *x, const ModelConsts &mc,
                                             double *table, int, bool fast,
                                             const BlockAux &aux) {
@@ -130,6 +136,15 @@ struct HhEval {
             table[s * SEG_STRIDE + 3] = fast ? __dsub_rn(v, e_k) : tau;
             if (fast && aux.uniform[s] && aux.lo[s + 1] - aux.lo[s] > 32)
                 table[s * SEG_STRIDE + 4] = exp(__dmul_rn(aux.d32[s], -1.0 / tau));
+            if (fast && aux.uniform1[s]) {
+                double *rec = table + s * SEG_STRIDE;
+                rec[5] = exp(__dmul_rn(aux.dt0[s], -1.0 / tau));
+                const double g = exp(__dmul_rn(aux.d1[s], -1.0 / tau));
+                const double g2 = __dmul_rn(g, g), g4 = __dmul_rn(g2, g2);
+                const double g8 = __dmul_rn(g4, g4);
+                rec[6] = g; rec[7] = g2; rec[8] = g4; rec[9] = g8;
+                rec[10] = __dmul_rn(g8, g8);
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -182,7 +197,10 @@ struct HhEval {
         }
         for (int s = threadIdx.x; s <= n_ev + 1; s += blockDim.x) {
             aux.lo[s] = s > n_ev ? nt : -1;
-            if (s <= n_ev) { aux.uniform[s] = 1; aux.d32[s] = 0.0; }
+            if (s <= n_ev) {
+                aux.uniform[s] = 1; aux.d32[s] = 0.0;
+                aux.uniform1[s] = 1; aux.d1[s] = 0.0; aux.dt0[s] = 0.0;
+            }
         }
         __syncthreads();
         for (int j = threadIdx.x; j < nt; j += blockDim.x)
@@ -199,6 +217,16 @@ struct HhEval {
                 const double d0 = __dsub_rn(series[(a + 32) * row], series[a * row]);
                 if (j == a + 32) aux.d32[s] = d0;
                 if (d != d0) aux.uniform[s] = 0;
+            }
+            if (j == a) aux.dt0[s] = series[j * row];
+            if (j > a && j < a + 32) {
+                const double d = __dsub_rn(series[j * row], series[(j - 1) * row]);
+                const double d0 = __dsub_rn(series[(a + 1) * row], series[a * row]);
+                // lane k's time must be dt_a + k d1 exactly
+                const double want = __dadd_rn(series[a * row],
+                                              __dmul_rn(static_cast<double>(j - a), d0));
+                if (j == a + 1) aux.d1[s] = d0;
+                if (d != d0 || want != series[j * row]) aux.uniform1[s] = 0;
             }
         }
         __syncthreads();
@@ -325,7 +353,17 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                     acc = __dadd_rn(acc, __dmul_rn(r, r));
                 };
                 int j = a + lane;
-                double e = exp(__dmul_rn(series[(j <= last ? j : last) * row], mrt));
+                double e;
+                if (aux.uniform1[s] != 0) {             // block-uniform
+                    e = rec[5];
+                    e = (lane & 1) ? __dmul_rn(e, rec[6]) : e;
+                    e = (lane & 2) ? __dmul_rn(e, rec[7]) : e;
+                    e = (lane & 4) ? __dmul_rn(e, rec[8]) : e;
+                    e = (lane & 8) ? __dmul_rn(e, rec[9]) : e;
+                    e = (lane & 16) ? __dmul_rn(e, rec[10]) : e;
+                } else {
+                    e = exp(__dmul_rn(series[(j <= last ? j : last) * row], mrt));
+                }
                 point(j, e);
                 if (uni) {
                     for (j += 32; j - lane <= last; j += 32) {
