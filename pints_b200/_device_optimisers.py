@@ -267,6 +267,7 @@ class DeviceXNES(object):
 
     def _enqueue_tell(self, fx):
         n, d = self._population_size, self._d
+        self._last_fx = fx
         if self._d_lower is not None:
             fx = torch.where(self._d_inside_bool, fx, self._d_inf)
         # ranks (NaN scores rank last): the sample sort of the C ABI, or the
@@ -299,13 +300,14 @@ class DeviceXNES(object):
 
     def _check_sort(self):
         if int(self._h_status[0]) != 0:
-            # never seen: the sample sort met a bucket it cannot hold
+            # never seen: the sample sort met a bucket it cannot hold.  Rank
+            # this generation again with the library sort, and keep to it.
             self._sort_gave_up = True
             self._graph = None
-            raise RuntimeError(
-                'pb200_argsort_f64 gave up on this generation\'s scores; '
-                'call tell() / generation() again (the library sort is used '
-                'from now on)')
+            with torch.cuda.device(self._device):
+                self._sorter.status.zero_()
+                self._enqueue_tell(self._last_fx)
+                torch.cuda.current_stream(self._device).synchronize()
 
     def ask(self):
         if not self._running:
