@@ -34,10 +34,9 @@ _SUM_BLOCKS = 148          # one block of ranks per SM
 class DeviceArgsort(object):
     """Ascending argsort of ``n`` scores on the device (``pb200_argsort_f64``:
     sample sort, NaN last, ties by index) with its workspace.  Measured on
-    B200 against the library sort (``tools/argsort_time.py``): 66 / 90 us
-    against 116 / 119 us at n = 16 384 / 65 536, but 66 against 51 us at 4096
-    (one block) and 182 against 136 us at 262 144, so ``native`` is chosen
-    for 4096 < n <= 131 072 unless ``force_native``."""
+    B200 against the library sort (``tools/argsort_time.py``): 53 / 62 / 82 /
+    137 us against 53 / 116 / 120 / 137 us at n = 4096 / 16 384 / 65 536 /
+    262 144; beyond ``PB200_ARGSORT_MAX`` the library sort is used."""
 
     MAX = 262144
 
@@ -45,8 +44,7 @@ class DeviceArgsort(object):
         self.n = int(n)
         self.device = require_cuda(device)
         self._lib = _lib.load()
-        self.native = (4096 < self.n <= 131072) or \
-            (force_native and self.n <= self.MAX)
+        self.native = self.n <= self.MAX
         self.order = torch.empty(self.n, dtype=torch.int64, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         nbytes = int(self._lib.pb200_argsort_workspace_bytes(self.n))
@@ -81,11 +79,8 @@ class DeviceXNES(object):
 
     device_resident = True
     use_graph = True
-    #: rank with pb200_argsort_f64 instead of the library sort.  Alone it is
-    #: faster at populations of 16 384 .. 65 536 (90 against 119 us), but inside
-    #: a generation the library sort's kernels end up cheaper (0.50 against
-    #: 0.52 ms per generation at 65 536), so it is off by default.
-    native_sort = False
+    #: rank with pb200_argsort_f64 (False: the library sort)
+    native_sort = True
 
     def __init__(self, x0, sigma0=None, boundaries=None, seed=1, device=None):
         self._x0 = vector(x0)

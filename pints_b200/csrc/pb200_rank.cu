@@ -43,7 +43,11 @@ __device__ __forceinline__ bool pair_less(uint64_t ka, uint32_t ia, uint64_t kb,
     return ka < kb || (ka == kb && ia < ib);
 }
 
-// bitonic sort of p (power of two) (key, index) pairs in shared memory
+// bitonic sort of p (power of two) (key, index) pairs in shared memory.
+// Thread t owns the t-th pair of every stage; for partner distances j <= 32
+// the 32 pairs of a warp lie in one aligned block of 64 elements that no other
+// warp touches, so those stages (51 of the 66 for 2048 pairs) only need a warp
+// barrier; a block barrier separates them from the stages with j >= 64.
 __device__ void bitonic_sort(uint64_t *key, uint32_t *idx, int p) {
     for (int k = 2; k <= p; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -57,7 +61,8 @@ __device__ void bitonic_sort(uint64_t *key, uint32_t *idx, int p) {
                 const bool swap = up ? pair_less(kb, ib, ka, ia) : pair_less(ka, ia, kb, ib);
                 if (swap) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
             }
-            __syncthreads();
+            const int next_j = j > 1 ? (j >> 1) : k;
+            if (j >= 64 || next_j >= 64) __syncthreads(); else __syncwarp();
         }
     }
 }
