@@ -543,3 +543,26 @@ def test_device_argsort(pb, n):
         assert int(sorter.status.item()) == 0
         want = np.argsort(values, kind='stable')
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('d,n', [(1, 7), (2, 1), (5, 33), (16, 100)])
+def test_device_xnes_small_and_odd_shapes(pb, monkeypatch, d, n):
+    """One parameter, one sample, sixteen parameters: every block split of the
+    sums kernel and the single-block ranking path against the host XNES."""
+    target = np.linspace(-1, 1, d)
+    x0 = target + 0.5
+    dev = pb.DeviceXNES(x0, 0.3, seed=3)
+    ref = pb.XNES(x0, 0.3)
+    dev.set_population_size(n)
+    ref.set_population_size(n)
+    for generation in range(15):
+        d_x = dev.ask()
+        z = host(dev.normals())
+        monkeypatch.setattr(np.random, 'normal', lambda *a, **k: z.copy())
+        ref.ask()
+        monkeypatch.undo()
+        fx = np.sum((host(d_x) - target) ** 2, axis=1)
+        ref.tell(fx)
+        dev.tell(torch.from_numpy(fx).to(d_x.device))
+        assert np.allclose(dev.x_guessed(), ref.x_guessed(), rtol=1e-8, atol=1e-10)
+    assert dev.f_best() == ref.f_best()
