@@ -389,6 +389,34 @@ int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
                  int32_t d, double gamma, uint64_t seed, uint64_t offset_eps,
                  uint64_t offset_pairs, void *stream);
 
+/* The same three launches with their per-iteration scalars read from DEVICE
+ * memory, so that one captured MCMC iteration (ask, solve, tell, advance) can
+ * be replayed from a CUDA graph with no host work in the loop.  d_rows: a
+ * table planned in advance, eight 64-bit slots per iteration
+ *   0 ask offset   1 second ask offset (DE partner pairs)   2 tell offset
+ *   3 sample_offset   4 gamma of ask (DE, double bits)   5 gamma of tell
+ *   (double bits)   6 variant of tell   7 unused;
+ * row *d_counter is used, pb200_iter_advance adds one to the counter.  The
+ * `variant` argument of pb200_ac_tell_it only says which buffers must be
+ * present (the row's variant is the one applied). */
+int pb200_ac_ask_it(const double *d_current, const double *d_sigma,
+                    const double *d_log_lambda, double *d_proposed, int64_t n,
+                    int32_t d, uint64_t seed, const int64_t *d_rows,
+                    const int64_t *d_counter, void *stream);
+int pb200_de_ask_it(const double *d_current_all, int64_t first, int64_t n_total,
+                    const double *d_b_star, double *d_proposed, int64_t n,
+                    int32_t d, uint64_t seed, const int64_t *d_rows,
+                    const int64_t *d_counter, void *stream);
+int pb200_ac_tell_it(int32_t variant, int32_t require_finite, double *d_current,
+                     double *d_current_f, const double *d_proposed,
+                     const double *d_fx, uint8_t *d_accepted,
+                     int64_t *d_acceptance_count, double *d_mu, double *d_sigma,
+                     double *d_log_lambda, double *d_samples,
+                     int64_t sample_stride, int64_t n, int32_t d, double target,
+                     uint64_t seed, const int64_t *d_rows,
+                     const int64_t *d_counter, void *stream);
+int pb200_iter_advance(int64_t *d_counter, void *stream);
+
 /* Device-resident xNES (pints/_optimisers/_xnes.py:63-91 ask, :147-182 tell).
  * ask: z (n, d) standard normals = pb200_philox_normal(n d, seed, *d_offset)
  * (mean, A and the offset are read from device memory, so that a generation

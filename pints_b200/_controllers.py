@@ -742,6 +742,9 @@ class CudaMCMCController(object):
     ``DifferentialEvolutionMCMC`` from this package).
     """
 
+    #: replay the iterations from a CUDA graph (see ``run``)
+    use_graph = True
+
     def __init__(self, log_pdf, chains, x0, sigma0=None, method=None,
                  device=None, seed=0, sharded=False, group=None,
                  **evaluator_options):
@@ -869,9 +872,51 @@ class CudaMCMCController(object):
             pool = torch.empty((self._n_chains, d), dtype=torch.float64,
                                device=device)
         store_in_tell = True        # the samplers write the chain sample in tell()
+        switch_at = self._initial_phase_iterations \
+            if sampler.needs_initial_phase() else None
+        graph_ok = self.use_graph and pool is None and \
+            hasattr(sampler, 'plan_iterations')
+        self.graph_replayed = 0
         start = time.perf_counter()
         with torch.cuda.device(device):
-            for it in range(n_iter):
+            it = 0
+            while it < n_iter:
+                if graph_ok and it >= 2 and n_iter - it >= 4 and \
+                        sampler.graph_ready():
+                    # The rest of the run from a CUDA graph: the scalars that
+                    # change from one iteration to the next (Philox offsets,
+                    # store offset, gamma, phase) are planned into a device
+                    # table, a device counter picks the row, and one captured
+                    # iteration -- ask, solve, tell, advance -- is replayed
+                    # with no other host work in the loop.
+                    k = n_iter - it
+                    rows = torch.from_numpy(sampler.plan_iterations(
+                        k, samples, it, switch_at)).to(device)
+                    counter = torch.zeros(1, dtype=torch.int64, device=device)
+
+                    def one_iteration():
+                        xs = sampler.enqueue_ask_it(rows, counter)
+                        problem.eval(xs, out=fx)
+                        sampler.enqueue_tell_it(fx, samples, rows, counter)
+                        sampler._ops.iter_advance(counter)
+                    try:
+                        torch.cuda.synchronize(device)
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            one_iteration()
+                        for _ in range(k):
+                            graph.replay()
+                        self.graph_replayed = k
+                    except Exception:
+                        # the planned launches work without a graph as well;
+                        # start again from the first planned row
+                        torch.cuda.synchronize(device)
+                        counter.zero_()
+                        for _ in range(k):
+                            one_iteration()
+                    self._graph_rows = rows         # alive until the sync below
+                    it = n_iter
+                    break
                 if self._initial_phase_iterations is not None and \
                         it == self._initial_phase_iterations:
                     sampler.set_initial_phase(False)
@@ -890,6 +935,7 @@ class CudaMCMCController(object):
                 else:
                     current, _, _ = sampler.tell(fx)
                     samples[:, it].copy_(current)
+                it += 1
             if self._sharded:
                 import torch.distributed as dist
                 every = torch.empty((self._n_chains, n_iter, d),

@@ -90,6 +90,33 @@ class _DeviceOps(object):
                    float(target), ctypes.c_uint64(seed),
                    ctypes.c_uint64(offset))
 
+    # the same launches with per-iteration scalars from a device table
+    def ac_ask_it(self, cur, sigma, log_lambda, prop, seed, rows, counter):
+        n, d = cur.shape
+        self._call(self.lib.pb200_ac_ask_it, _ptr(cur), _ptr(sigma),
+                   _ptr(log_lambda), _ptr(prop), n, d, ctypes.c_uint64(seed),
+                   _ptr(rows), _ptr(counter))
+
+    def de_ask_it(self, cur_all, first, b_star, prop, seed, rows, counter):
+        n, d = prop.shape
+        self._call(self.lib.pb200_de_ask_it, _ptr(cur_all), int(first),
+                   cur_all.shape[0], _ptr(b_star), _ptr(prop), n, d,
+                   ctypes.c_uint64(seed), _ptr(rows), _ptr(counter))
+
+    def ac_tell_it(self, variant, cur, cur_f, prop, fx, accepted, acc_count,
+                   mu, sigma, log_lambda, samples, stride, target, seed, rows,
+                   counter, require_finite=True):
+        n, d = cur.shape
+        self._call(self.lib.pb200_ac_tell_it, int(variant),
+                   1 if require_finite else 0, _ptr(cur), _ptr(cur_f),
+                   _ptr(prop), _ptr(fx), _ptr(accepted), _ptr(acc_count),
+                   _ptr(mu), _ptr(sigma), _ptr(log_lambda), _ptr(samples),
+                   int(stride), n, d, float(target), ctypes.c_uint64(seed),
+                   _ptr(rows), _ptr(counter))
+
+    def iter_advance(self, counter):
+        self._call(self.lib.pb200_iter_advance, _ptr(counter))
+
     def hbac_adapt(self, cur, accepted, mu, sigma, log_lambda, gamma, target):
         n, d = cur.shape
         self._call(self.lib.pb200_hbac_adapt, _ptr(cur), _ptr(accepted),
@@ -121,6 +148,15 @@ class _DeviceOps(object):
                    ctypes.c_uint64(seed), ctypes.c_uint64(offset))
 
 
+class _GraphIterationsBase(object):
+    """See ``_GraphIterations`` below (kept first so that both sampler
+    families can inherit from it)."""
+
+    def graph_ready(self):
+        return (getattr(self, '_fused', False) and self._rng_mode == 'philox'
+                and self._have_current and not self._asked)
+
+
 class _Philox(object):
     """Bookkeeping of the counter space: every draw gets a fresh offset."""
 
@@ -134,7 +170,7 @@ class _Philox(object):
         return off
 
 
-class HaarioBardenetACMC(object):
+class HaarioBardenetACMC(_GraphIterationsBase):
     """All chains of the Haario-Bardenet adaptive covariance sampler
     (pints/_mcmc/_haario_bardenet_ac.py).
 
@@ -260,6 +296,44 @@ class HaarioBardenetACMC(object):
         return (self._mu.cpu().numpy(), self._sigma.cpu().numpy(),
                 self._log_lambda.cpu().numpy())
 
+    # -- graph replay (see CudaMCMCController) --------------------------
+    def plan_iterations(self, k, samples, first_it, switch_at=None):
+        """Rows of the device table for iterations ``first_it ..
+        first_it + k - 1`` (``(k, 8)`` int64), advancing the host bookkeeping
+        as ``k`` eager ask/tell rounds would; the initial phase ends at
+        iteration ``switch_at``."""
+        rows = np.zeros((k, 8), dtype=np.int64)
+        step = samples.stride(1)
+        for i in range(k):
+            it = first_it + i
+            if switch_at is not None and it == switch_at:
+                self.set_initial_phase(False)
+            rows[i, 0] = self._rng.take(self._z.numel())
+            rows[i, 2] = self._rng.take(self._n)
+            variant = -1
+            if self._adaptive and self._VARIANT is not None:
+                self._gamma = (self._adaptations + 1) ** -self._eta
+                self._adaptations += 1
+                variant = self._VARIANT
+            rows[i, 3] = it * step
+            rows[i, 5] = _f64_bits(self._gamma)
+            rows[i, 6] = variant
+            self._iterations += 1
+        return rows
+
+    def enqueue_ask_it(self, rows, counter, all_current=None):
+        self._ops.ac_ask_it(self._current, self._sigma, self._log_lambda,
+                            self._proposed, self._rng.seed, rows, counter)
+        return self._proposed
+
+    def enqueue_tell_it(self, fx, samples, rows, counter):
+        variant = self._VARIANT if self._VARIANT is not None else -1
+        self._ops.ac_tell_it(variant, self._current, self._current_f,
+                             self._proposed, fx, self._accepted,
+                             self._acceptance_count, self._mu, self._sigma,
+                             self._log_lambda, samples, samples.stride(0),
+                             self._target, self._rng.seed, rows, counter)
+
     @classmethod
     def name(cls):
         return 'Haario-Bardenet adaptive covariance MCMC'
@@ -370,6 +444,10 @@ class HaarioBardenetACMC(object):
         return self._current, self._current_f, self._accepted
 
 
+def _f64_bits(v):
+    return int(np.float64(v).view(np.int64))
+
+
 class HaarioACMC(HaarioBardenetACMC):
     """All chains of the Haario adaptive covariance sampler
     (pints/_mcmc/_haario_ac.py): as Haario-Bardenet, but log lambda moves with
@@ -431,7 +509,7 @@ class MetropolisRandomWalkMCMC(HaarioBardenetACMC):
         return 'Metropolis random walk MCMC'
 
 
-class DifferentialEvolutionMCMC(object):
+class DifferentialEvolutionMCMC(_GraphIterationsBase):
     """Differential-evolution MCMC with the reference's default settings
     (Gaussian error, relative scaling, ``gamma = 2.38 / sqrt(2 d)`` and
     ``gamma = 1`` on every tenth proposal round).
@@ -506,6 +584,36 @@ class DifferentialEvolutionMCMC(object):
     @classmethod
     def name(cls):
         return 'Differential Evolution MCMC'
+
+    # -- graph replay (see CudaMCMCController) --------------------------
+    def plan_iterations(self, k, samples, first_it, switch_at=None):
+        """As ``HaarioBardenetACMC.plan_iterations``: error-draw, partner and
+        uniform offsets, the gamma schedule (1 on every tenth round)."""
+        rows = np.zeros((k, 8), dtype=np.int64)
+        step = samples.stride(1)
+        for i in range(k):
+            gamma = self.next_gamma()
+            self._iter_count += 1
+            rows[i, 0] = self._rng.take(self._eps.numel())
+            rows[i, 1] = self._rng.take(2 * self._n)
+            rows[i, 2] = self._rng.take(self._n)
+            rows[i, 3] = (first_it + i) * step
+            rows[i, 4] = _f64_bits(gamma)
+            rows[i, 6] = -1
+        return rows
+
+    def enqueue_ask_it(self, rows, counter, all_current=None):
+        pool = self._current if all_current is None else all_current
+        self._ops.de_ask_it(pool, self._first, self._d_b_star, self._proposed,
+                            self._rng.seed, rows, counter)
+        return self._proposed
+
+    def enqueue_tell_it(self, fx, samples, rows, counter):
+        self._ops.ac_tell_it(-1, self._current, self._current_f,
+                             self._proposed, fx, self._accepted, None, None,
+                             None, None, samples, samples.stride(0), 0.0,
+                             self._rng.seed, rows, counter,
+                             require_finite=False)
 
     def next_gamma(self):
         """The gamma the coming proposal round uses

@@ -358,14 +358,33 @@ __device__ __forceinline__ double philox_normal_at(int64_t idx, uint64_t seed, u
     return (idx & 1) ? rad * sn : rad * cs;
 }
 
+// Per-iteration scalars of a sampler loop read from DEVICE memory, so that one
+// captured iteration (ask, solve, tell) can be replayed from a CUDA graph
+// without the host in the loop: row `*counter` of a table planned in advance,
+// eight 64-bit slots per iteration
+//   0 ask offset (normals)   1 second ask offset (DE partner pairs)
+//   2 tell offset (uniforms) 3 sample offset   4 gamma of ask (DE)
+//   5 gamma of tell          6 variant of tell 7 unused
+// and a counter that pb200_iter_advance increments at the end of the
+// iteration.  rows == nullptr: the by-value arguments are used.
+struct IterTable {
+    const int64_t *rows;
+    const int64_t *counter;
+    __device__ __forceinline__ const int64_t *row() const { return rows + 8 * (*counter); }
+};
+__device__ __forceinline__ double slot_f64(int64_t v) { return __longlong_as_double(v); }
+
+__global__ void iter_advance_kernel(int64_t *counter) { *counter += 1; }
+
 // ask of the adaptive-covariance family on the device: normals + Cholesky
 // proposal in one launch (= pb200_philox_normal then pb200_hbac_propose)
 __global__ void ac_ask_kernel(const double *__restrict__ cur, const double *__restrict__ sigma,
                               const double *__restrict__ log_lambda,
                               double *__restrict__ prop, int64_t n, int d, uint64_t seed,
-                              uint64_t offset) {
+                              uint64_t offset, const IterTable it) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    if (it.rows) offset = static_cast<uint64_t>(it.row()[0]);
     const double scale = exp(log_lambda[j]);
     const double *sg = sigma + j * static_cast<int64_t>(d) * d;
     double L[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
@@ -400,9 +419,17 @@ __global__ void ac_tell_kernel(int variant, int require_finite, double *__restri
                                double *__restrict__ sigma, double *__restrict__ log_lambda,
                                double *__restrict__ samples, int64_t sample_stride,
                                int64_t sample_offset, int64_t n, int d, double gamma,
-                               double target, uint64_t seed, uint64_t offset) {
+                               double target, uint64_t seed, uint64_t offset,
+                               const IterTable it) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    if (it.rows) {
+        const int64_t *r = it.row();
+        offset = static_cast<uint64_t>(r[2]);
+        sample_offset = r[3];
+        gamma = slot_f64(r[5]);
+        variant = static_cast<int>(r[6]);
+    }
     const double log_u = log(philox_uniform_at(j, seed, offset));
     const double f_new = fx[j];
     const double lr = __dsub_rn(f_new, cur_f[j]);
@@ -446,17 +473,44 @@ __global__ void ac_tell_kernel(int variant, int require_finite, double *__restri
         log_lambda[j] = __dadd_rn(log_lambda[j], __dmul_rn(gamma, __dsub_rn(p, target)));
 }
 
-int pb200_ac_ask(const double *d_current, const double *d_sigma, const double *d_log_lambda,
-                 double *d_proposed, int64_t n, int32_t d, uint64_t seed, uint64_t offset,
-                 void *stream) {
+static int ac_ask_impl(const double *d_current, const double *d_sigma,
+                       const double *d_log_lambda, double *d_proposed, int64_t n, int32_t d,
+                       uint64_t seed, uint64_t offset, IterTable it, void *stream) {
     if (n < 0 || d < 1 || d > PB200_MAX_PARAMS) {
         pb200_set_error("pb200_ac_ask: bad n=%lld or d=%d", (long long)n, d);
         return PB200_EINVAL;
     }
     if (n == 0) return PB200_OK;
     ac_ask_kernel<<<blocks_for(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_current, d_sigma, d_log_lambda, d_proposed, n, d, seed, offset);
+        d_current, d_sigma, d_log_lambda, d_proposed, n, d, seed, offset, it);
     return pb200_check_cuda(cudaGetLastError(), "ac_ask_kernel launch");
+}
+
+int pb200_ac_ask(const double *d_current, const double *d_sigma, const double *d_log_lambda,
+                 double *d_proposed, int64_t n, int32_t d, uint64_t seed, uint64_t offset,
+                 void *stream) {
+    return ac_ask_impl(d_current, d_sigma, d_log_lambda, d_proposed, n, d, seed, offset,
+                       IterTable{nullptr, nullptr}, stream);
+}
+
+static int iter_table_ok(const int64_t *d_rows, const int64_t *d_counter, const char *who) {
+    if (d_rows && d_counter) return PB200_OK;
+    pb200_set_error("%s: the iteration table and its counter are required", who);
+    return PB200_EINVAL;
+}
+
+int pb200_ac_ask_it(const double *d_current, const double *d_sigma, const double *d_log_lambda,
+                    double *d_proposed, int64_t n, int32_t d, uint64_t seed,
+                    const int64_t *d_rows, const int64_t *d_counter, void *stream) {
+    if (int rc = iter_table_ok(d_rows, d_counter, "pb200_ac_ask_it")) return rc;
+    return ac_ask_impl(d_current, d_sigma, d_log_lambda, d_proposed, n, d, seed, 0,
+                       IterTable{d_rows, d_counter}, stream);
+}
+
+int pb200_iter_advance(int64_t *d_counter, void *stream) {
+    if (!d_counter) { pb200_set_error("pb200_iter_advance: NULL counter"); return PB200_EINVAL; }
+    iter_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_counter);
+    return pb200_check_cuda(cudaGetLastError(), "iter_advance_kernel launch");
 }
 
 // ask of the differential-evolution sampler on the device, one launch:
@@ -465,9 +519,16 @@ int pb200_ac_ask(const double *d_current, const double *d_sigma, const double *d
 __global__ void de_ask_kernel(const double *__restrict__ cur_all, int64_t first,
                               int64_t n_total, const double *__restrict__ b_star,
                               double *__restrict__ prop, int64_t n, int d, double gamma,
-                              uint64_t seed, uint64_t offset_eps, uint64_t offset_pairs) {
+                              uint64_t seed, uint64_t offset_eps, uint64_t offset_pairs,
+                              const IterTable it) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    if (it.rows) {
+        const int64_t *r = it.row();
+        offset_eps = static_cast<uint64_t>(r[0]);
+        offset_pairs = static_cast<uint64_t>(r[1]);
+        gamma = slot_f64(r[4]);
+    }
     const int64_t self = first + j;
     const U4 r = philox4x32_10(offset_pairs + j, 3, seed);
     int64_t a = static_cast<int64_t>((static_cast<uint64_t>(r.x) * static_cast<uint64_t>(n_total - 1)) >> 32);
@@ -486,10 +547,10 @@ __global__ void de_ask_kernel(const double *__restrict__ cur_all, int64_t first,
     }
 }
 
-int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
-                 const double *d_b_star, double *d_proposed, int64_t n, int32_t d,
-                 double gamma, uint64_t seed, uint64_t offset_eps, uint64_t offset_pairs,
-                 void *stream) {
+static int de_ask_impl(const double *d_current_all, int64_t first, int64_t n_total,
+                       const double *d_b_star, double *d_proposed, int64_t n, int32_t d,
+                       double gamma, uint64_t seed, uint64_t offset_eps,
+                       uint64_t offset_pairs, IterTable it, void *stream) {
     if (n < 0 || first < 0 || n_total < 3 || first + n > n_total || d < 1 ||
         d > PB200_MAX_PARAMS) {
         pb200_set_error("pb200_de_ask: bad n=%lld, first=%lld, n_total=%lld or d=%d",
@@ -499,17 +560,34 @@ int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
     if (n == 0) return PB200_OK;
     de_ask_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         d_current_all, first, n_total, d_b_star, d_proposed, n, d, gamma, seed, offset_eps,
-        offset_pairs);
+        offset_pairs, it);
     return pb200_check_cuda(cudaGetLastError(), "de_ask_kernel launch");
 }
 
-int pb200_ac_tell(int32_t variant, int32_t require_finite, double *d_current,
-                  double *d_current_f,
-                  const double *d_proposed, const double *d_fx, uint8_t *d_accepted,
-                  int64_t *d_acceptance_count, double *d_mu, double *d_sigma,
-                  double *d_log_lambda, double *d_samples, int64_t sample_stride,
-                  int64_t sample_offset, int64_t n, int32_t d, double gamma, double target,
-                  uint64_t seed, uint64_t offset, void *stream) {
+int pb200_de_ask(const double *d_current_all, int64_t first, int64_t n_total,
+                 const double *d_b_star, double *d_proposed, int64_t n, int32_t d,
+                 double gamma, uint64_t seed, uint64_t offset_eps, uint64_t offset_pairs,
+                 void *stream) {
+    return de_ask_impl(d_current_all, first, n_total, d_b_star, d_proposed, n, d, gamma, seed,
+                       offset_eps, offset_pairs, IterTable{nullptr, nullptr}, stream);
+}
+
+int pb200_de_ask_it(const double *d_current_all, int64_t first, int64_t n_total,
+                    const double *d_b_star, double *d_proposed, int64_t n, int32_t d,
+                    uint64_t seed, const int64_t *d_rows, const int64_t *d_counter,
+                    void *stream) {
+    if (int rc = iter_table_ok(d_rows, d_counter, "pb200_de_ask_it")) return rc;
+    return de_ask_impl(d_current_all, first, n_total, d_b_star, d_proposed, n, d, 0.0, seed, 0, 0,
+                       IterTable{d_rows, d_counter}, stream);
+}
+
+static int ac_tell_impl(int32_t variant, int32_t require_finite, double *d_current,
+                        double *d_current_f,
+                        const double *d_proposed, const double *d_fx, uint8_t *d_accepted,
+                        int64_t *d_acceptance_count, double *d_mu, double *d_sigma,
+                        double *d_log_lambda, double *d_samples, int64_t sample_stride,
+                        int64_t sample_offset, int64_t n, int32_t d, double gamma, double target,
+                        uint64_t seed, uint64_t offset, IterTable it, void *stream) {
     if (n < 0 || d < 1 || d > PB200_MAX_PARAMS || variant > PB200_AC_RAO_BLACKWELL) {
         pb200_set_error("pb200_ac_tell: bad n=%lld, d=%d or variant=%d", (long long)n, d, variant);
         return PB200_EINVAL;
@@ -523,8 +601,34 @@ int pb200_ac_tell(int32_t variant, int32_t require_finite, double *d_current,
     ac_tell_kernel<<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         variant, require_finite, d_current, d_current_f, d_proposed, d_fx, d_accepted, d_acceptance_count,
         d_mu, d_sigma, d_log_lambda, d_samples, sample_stride, sample_offset, n, d, gamma,
-        target, seed, offset);
+        target, seed, offset, it);
     return pb200_check_cuda(cudaGetLastError(), "ac_tell_kernel launch");
+}
+
+int pb200_ac_tell(int32_t variant, int32_t require_finite, double *d_current,
+                  double *d_current_f,
+                  const double *d_proposed, const double *d_fx, uint8_t *d_accepted,
+                  int64_t *d_acceptance_count, double *d_mu, double *d_sigma,
+                  double *d_log_lambda, double *d_samples, int64_t sample_stride,
+                  int64_t sample_offset, int64_t n, int32_t d, double gamma, double target,
+                  uint64_t seed, uint64_t offset, void *stream) {
+    return ac_tell_impl(variant, require_finite, d_current, d_current_f, d_proposed, d_fx,
+                        d_accepted, d_acceptance_count, d_mu, d_sigma, d_log_lambda, d_samples,
+                        sample_stride, sample_offset, n, d, gamma, target, seed, offset,
+                        IterTable{nullptr, nullptr}, stream);
+}
+
+int pb200_ac_tell_it(int32_t variant, int32_t require_finite, double *d_current,
+                     double *d_current_f, const double *d_proposed, const double *d_fx,
+                     uint8_t *d_accepted, int64_t *d_acceptance_count, double *d_mu,
+                     double *d_sigma, double *d_log_lambda, double *d_samples,
+                     int64_t sample_stride, int64_t n, int32_t d, double target, uint64_t seed,
+                     const int64_t *d_rows, const int64_t *d_counter, void *stream) {
+    if (int rc = iter_table_ok(d_rows, d_counter, "pb200_ac_tell_it")) return rc;
+    return ac_tell_impl(variant, require_finite, d_current, d_current_f, d_proposed, d_fx,
+                        d_accepted, d_acceptance_count, d_mu, d_sigma, d_log_lambda, d_samples,
+                        sample_stride, 0, n, d, 0.0, target, seed, 0,
+                        IterTable{d_rows, d_counter}, stream);
 }
 
 // ---- device-resident xNES (pints/_optimisers/_xnes.py:63-91, :147-182) ----

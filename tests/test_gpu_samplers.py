@@ -566,3 +566,40 @@ def test_device_xnes_small_and_odd_shapes(pb, monkeypatch, d, n):
         dev.tell(torch.from_numpy(fx).to(d_x.device))
         assert np.allclose(dev.x_guessed(), ref.x_guessed(), rtol=1e-8, atol=1e-10)
     assert dev.f_best() == ref.f_best()
+
+
+@pytest.mark.parametrize('name', ['HaarioBardenetACMC', 'HaarioACMC',
+                                  'RaoBlackwellACMC',
+                                  'MetropolisRandomWalkMCMC',
+                                  'DifferentialEvolutionMCMC'])
+def test_mcmc_graph_replay_gives_identical_chains(pb, name):
+    """CudaMCMCController replays the iterations after the second from a CUDA
+    graph (per-iteration scalars from a device table): every sample of every
+    chain equals the eager run's, across the end of the initial phase."""
+    rng = np.random.RandomState(12)
+    times = np.linspace(0, 100, 120)
+    values = po.logistic_simulate([0.1, 50], times) + rng.normal(0, 2, 120)
+    problem = pb.SingleOutputProblem(pb.toy.LogisticModel(), times, values)
+    post = pb.LogPosterior(pb.GaussianLogLikelihood(problem),
+                           pb.UniformLogPrior([0, 10, 0.1], [1, 100, 10]))
+    n_chains = 24
+    x0 = np.array([0.1, 50, 2.0]) * (1 + 0.02 * rng.randn(n_chains, 3))
+    chains, rates = [], []
+    for use_graph in (True, False):
+        mc = pb.CudaMCMCController(post, n_chains, x0,
+                                   method=getattr(pb, name), seed=3)
+        mc.use_graph = use_graph
+        mc.set_max_iterations(90)
+        if mc.sampler().needs_initial_phase():
+            mc.set_initial_phase_iterations(30)
+        chains.append(mc.run())
+        assert mc.graph_replayed == (88 if use_graph else 0)
+        if hasattr(mc.sampler(), 'acceptance_rate'):
+            rates.append(mc.sampler().acceptance_rate())
+            assert np.all(rates[-1] >= 0) and np.all(rates[-1] <= 1)
+    if rates:                       # same host bookkeeping after the run
+        assert np.array_equal(rates[0], rates[1])
+    assert chains[0].shape == (n_chains, 90, 3)
+    assert np.array_equal(chains[0], chains[1])
+    assert np.isfinite(chains[0]).all()
+    assert len(np.unique(chains[0][:, :, 0])) > n_chains        # they moved
