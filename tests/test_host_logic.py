@@ -33,6 +33,11 @@ def test_library_builds_loads_and_exports_the_header():
     for name in declared:
         assert hasattr(lib, name), name + ' is declared but not exported'
     assert sorted(_lib.SIGNATURES) == declared
+    # every entry point is tied to the reference code it replaces
+    with open(os.path.join(ROOT, 'INTEGRATION.md')) as f:
+        doc = f.read()
+    for name in declared:
+        assert name in doc, name + ' is not documented in INTEGRATION.md'
     assert lib.pb200_version() == 100
     assert lib.pb200_series_len(1000, 2) == 3 * (1000 + _lib.SENTINEL_ROWS)
     # (3 + 8) rows * 3 doubles = 33, padded to whole 16-byte units
