@@ -22,6 +22,7 @@ Callers of the hot path.
    iteration -- propose, evaluate, accept, adapt, store -- enqueued on the GPU.
 """
 import contextlib
+import os
 import time
 
 import numpy as np
@@ -742,8 +743,14 @@ class CudaMCMCController(object):
     ``DifferentialEvolutionMCMC`` from this package).
     """
 
-    #: replay the iterations from a CUDA graph (see ``run``)
-    use_graph = True
+    #: replay the iterations from a CUDA graph (see ``run``);
+    #: PB200_MCMC_GRAPH=0 in the environment turns it off
+    use_graph = os.environ.get('PB200_MCMC_GRAPH', '1') != '0'
+    #: ... for runs with at least this many iterations left: capturing costs
+    #: about 2 ms, and only loops whose iteration is shorter on the GPU than
+    #: the host's 40-60 us of launch work gain from the replay (7 us per
+    #: iteration for a few chains on a closed-form model)
+    graph_min_iterations = 1000
 
     def __init__(self, log_pdf, chains, x0, sigma0=None, method=None,
                  device=None, seed=0, sharded=False, group=None,
@@ -881,7 +888,8 @@ class CudaMCMCController(object):
         with torch.cuda.device(device):
             it = 0
             while it < n_iter:
-                if graph_ok and it >= 2 and n_iter - it >= 4 and \
+                if graph_ok and it >= 2 and \
+                        n_iter - it >= max(4, self.graph_min_iterations) and \
                         sampler.graph_ready():
                     # The rest of the run from a CUDA graph: the scalars that
                     # change from one iteration to the next (Philox offsets,
@@ -900,10 +908,8 @@ class CudaMCMCController(object):
                         sampler.enqueue_tell_it(fx, samples, rows, counter)
                         sampler._ops.iter_advance(counter)
                     try:
-                        torch.cuda.synchronize(device)
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph):
-                            one_iteration()
+                        from ._engine import capture_graph
+                        graph = capture_graph(device, one_iteration)
                         for _ in range(k):
                             graph.replay()
                         self.graph_replayed = k

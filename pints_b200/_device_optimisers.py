@@ -25,7 +25,7 @@ import scipy.linalg
 import torch
 
 from . import _lib
-from ._engine import _ptr, _stream_ptr, require_cuda
+from ._engine import _ptr, _stream_ptr, capture_graph, require_cuda
 from ._util import vector
 
 _SUM_BLOCKS = 148          # one block of ranks per SM
@@ -341,10 +341,9 @@ class DeviceXNES(object):
             elif self.use_graph and self._eager_generations >= 2 \
                     and self._graph_failed is None:
                 try:
-                    torch.cuda.synchronize(self._device)
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        self._enqueue_generation(problem, negate)
+                    graph = capture_graph(
+                        self._device,
+                        lambda: self._enqueue_generation(problem, negate))
                     self._graph, self._graph_key = graph, key
                     graph.replay()
                 except Exception as e:          # keep going without a graph

@@ -41,6 +41,35 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def capture_graph(device, enqueue):
+    """Captures the launches ``enqueue()`` makes (on the stream that is
+    current while it runs) in a CUDA graph and returns it; replay with
+    ``graph.replay()`` on the caller's current stream.
+
+    ``torch.cuda.graph`` is not used on purpose: on entry it runs the garbage
+    collector and ``torch.cuda.empty_cache()``, which in a process holding
+    gigabytes of cached blocks costs 60 ms and more -- longer than the loops
+    captured here run.  ``capture_begin`` alone puts the allocator in
+    graph-private-pool mode, which is all the capture needs."""
+    current = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device)
+    side.wait_stream(current)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        graph.capture_begin()
+        try:
+            enqueue()
+        except BaseException:
+            try:
+                graph.capture_end()
+            except Exception:
+                pass
+            raise
+        graph.capture_end()
+    current.wait_stream(side)
+    return graph
+
+
 def solver_opts(rtol=None, atol=None, h0=None, max_steps=None, block=None,
                 lanes=None, wide_interpolation=None):
     return _lib.SolverOpts(

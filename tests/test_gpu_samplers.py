@@ -589,6 +589,7 @@ def test_mcmc_graph_replay_gives_identical_chains(pb, name):
         mc = pb.CudaMCMCController(post, n_chains, x0,
                                    method=getattr(pb, name), seed=3)
         mc.use_graph = use_graph
+        mc.graph_min_iterations = 4
         mc.set_max_iterations(90)
         if mc.sampler().needs_initial_phase():
             mc.set_initial_phase_iterations(30)

@@ -216,6 +216,29 @@ def main():
         rows.append(('DifferentialEvolutionMCMC 4096 chains on %s (device loop)' % name, per_it * 1e3,
                      n_ch / per_it, 'reference host ask() alone 1630 ms/iteration'))
 
+    # ---- config 2 as a whole optimisation loop: xNES generations ----
+    b = pb.RectangularBoundaries([0.01, 0.1, 1.0], [1.0, 1.0, 5.0])
+    out['xnes_generation_ms'] = {}
+    for method, gens in ((pb.XNES, 40), (pb.DeviceXNES, 200)):
+        per_gen = None
+        for attempt in range(2):                  # the first run warms up
+            np.random.seed(1)
+            ctl = pb.CudaOptimisationController(
+                ll, [0.1, 0.5, 3.0], [0.005, 0.025, 0.15], boundaries=b,
+                method=method)
+            ctl.optimiser().set_population_size(65536)
+            ctl.set_max_iterations(gens)
+            ctl.set_max_unchanged_iterations(None)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctl.run()
+            torch.cuda.synchronize()
+            per_gen = (time.perf_counter() - t0) / gens
+        out['xnes_generation_ms'][method.__name__] = per_gen * 1e3
+        rows.append(('xNES generation (ask + score + tell), population 65536, %s'
+                     % method.__name__, per_gen * 1e3, 65536 / per_gen,
+                     'reference: 0.7 s of host loops per generation + scoring'))
+
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'configs.json'), 'w') as f:
         json.dump(out, f, indent=1)

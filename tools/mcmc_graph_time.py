@@ -35,6 +35,7 @@ for label, f, x, n, iters, method in cases:
     for use_graph in (False, True):
         mc = pb.CudaMCMCController(f, n, x0, method=getattr(pb, method), seed=1)
         mc.use_graph = use_graph
+        mc.graph_min_iterations = 4
         mc.set_max_iterations(iters)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
