@@ -78,11 +78,35 @@ def _worker_score(chunk):
     return [_worker_spec.score(x) for x in chunk]
 
 
-class CpuBaseline(object):
-    """The reference's CPU path for this workload: the oracle port (scipy LSODA
-    with the reference's right-hand side, bit-identical to
+def _worker_truth(chunk):
+    # the same solver driven to convergence: the "truth" both arms are set against
+    return [_worker_spec.score(x, rtol=1e-13, atol=1e-13) for x in chunk]
+
+
+def load_reference():
+    """The unmodified reference package, installed from /root/reference into
+    the git-ignored baseline/_ref (see __graft_entry__.build), or None."""
+    path = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(path, 'pints')):
+        return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    try:
+        import pints
+        import pints.toy  # noqa: F401
+    except Exception:
+        return None
+    return pints
+
+
+class PortBaseline(object):
+    """The oracle port of the reference's CPU path (scipy LSODA with the
+    reference's right-hand side, bit-identical to
     SequentialEvaluator(f).evaluate) fanned out over all host cores with worker
-    processes, as ParallelEvaluator does (pints/_evaluation.py:126-413)."""
+    processes.  Used for the truth sample, as the second CPU figure, and as the
+    reference arm where baseline/_ref is absent."""
+    kind = 'port'
+    what = 'oracle port = scipy LSODA + reference RHS, multiprocessing.Pool'
 
     def __init__(self, cores=None):
         self.cores = cores or len(os.sched_getaffinity(0))
@@ -94,13 +118,19 @@ class CpuBaseline(object):
         # workers alive between calls
         self.run(po.headline_fhn_points(self.cores * 4, seed=7))
 
-    def run(self, xs):
+    def _map(self, fn, xs):
         per = max(1, min(32, len(xs) // (self.cores * 4) or 1))
         chunks = [xs[i:i + per] for i in range(0, len(xs), per)]
         t0 = time.perf_counter()
-        out = self.pool.map(_worker_score, chunks)
+        out = self.pool.map(fn, chunks)
         dt = time.perf_counter() - t0
         return dt, np.array([v for part in out for v in part])
+
+    def run(self, xs):
+        return self._map(_worker_score, xs)
+
+    def truth(self, xs):
+        return self._map(_worker_truth, xs)[1]
 
     def sample_size(self, seconds):
         dt, _ = self.run(self.po.headline_fhn_points(self.cores * 16, seed=8))
@@ -112,12 +142,68 @@ class CpuBaseline(object):
         self.pool.join()
 
 
+class ReferenceBaseline(object):
+    """The reference's own CPU implementation of the path, unmodified:
+    pints.ParallelEvaluator over the reference's FitzhughNagumoModel /
+    MultiOutputProblem / GaussianKnownSigmaLogLikelihood objects
+    (pints/_evaluation.py:126-413), one worker per host core."""
+    kind = 'reference'
+    what = 'pints.ParallelEvaluator (unmodified reference from baseline/_ref)'
+
+    def __init__(self, pints, cores=None):
+        from oracle import pints_oracle as po
+        self.po = po
+        self.cores = cores or len(os.sched_getaffinity(0))
+        spec = po.headline_fhn_spec()          # the synthetic series only
+        model = pints.toy.FitzhughNagumoModel()
+        problem = pints.MultiOutputProblem(model, spec.times, spec.values)
+        self.f = pints.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+        self.pints = pints
+        self.ev = pints.ParallelEvaluator(self.f, n_workers=self.cores)
+        # warm-up: worker start-up is excluded, the reference keeps its
+        # workers alive between calls (pints/_evaluation.py:153-154)
+        self.run(po.headline_fhn_points(self.cores * 8, seed=7))
+
+    def run(self, xs):
+        t0 = time.perf_counter()
+        out = self.ev.evaluate(xs)
+        dt = time.perf_counter() - t0
+        return dt, np.array(out)
+
+    def one_core(self, seconds=2.0):
+        """SequentialEvaluator on one core, in this process."""
+        ev = self.pints.SequentialEvaluator(self.f)
+        xs = self.po.headline_fhn_points(64, seed=9)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            ev.evaluate(xs[:16])
+            n += 16
+        return n / (time.perf_counter() - t0)
+
+    def sample_size(self, seconds):
+        dt, _ = self.run(self.po.headline_fhn_points(self.cores * 16, seed=8))
+        rate = self.cores * 16 / dt
+        return max(self.cores * 8, int(rate * seconds))
+
+    def close(self):
+        try:
+            self.ev._stop()
+        except Exception:
+            pass
+
+
+def cpu_arm():
+    pints = load_reference()
+    return ReferenceBaseline(pints) if pints is not None else PortBaseline()
+
+
 def run_reference_arm(args):
     """`--impl reference`: the CPU path alone, same metric / unit / config."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    base = CpuBaseline()
+    base = cpu_arm()
     m = base.sample_size(6.0)
     xs = base.po.headline_fhn_points(m)
     for _ in range(args.warmup):
@@ -128,7 +214,8 @@ def run_reference_arm(args):
         total += dt
     base.close()
     value = m * args.steps / total
-    sample = '%d evaluations per step (~6 s of %d-core CPU work)' % (m, base.cores)
+    sample = '%d evaluations per step (~6 s of %d-core CPU work); %s' % (
+        m, base.cores, base.what)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -138,7 +225,7 @@ def run_reference_arm(args):
         'config': {'workload': WORKLOAD, 'population_per_step': m,
                    'solver': 'scipy odeint (LSODA) rtol=atol=1.49012e-8'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': base.cores,
-                         'kind': 'port', 'sample': sample},
+                         'kind': base.kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -229,6 +316,57 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------- our arm
 
+TRUTH_SAMPLE = 4096        # vectors solved to convergence on the CPU (N = 1)
+TRUTH_SAMPLE_MULTI = 1024  # the same at N > 1 (rank 0 only, the others wait)
+
+
+def cpu_side(args, world):
+    """Everything the host cores do, before CUDA is touched (rank 0 only):
+    the reference arm's throughput on a bounded sample, the oracle port beside
+    it, and a truth sample (the same LSODA driven to rtol = atol = 1e-13) that
+    the GPU scores are checked against afterwards."""
+    from oracle import pints_oracle as po
+    port = PortBaseline()
+    n_truth = TRUTH_SAMPLE if world == 1 else TRUTH_SAMPLE_MULTI
+    pick = np.linspace(0, args.pop - 1, n_truth).astype(np.int64)
+    xs_all = po.headline_fhn_points(args.pop * world)
+    truth = port.truth(xs_all[pick])
+    out = {'truth_rows': pick, 'truth': truth, 'cpu': None}
+    if world == 1 and not args.no_cpu:
+        m = port.sample_size(min(4.0, args.cpu_seconds))
+        dt_port, port_scores = port.run(xs_all[:m])
+        port_value = m / dt_port
+        port.close()
+        pints = load_reference()
+        if pints is not None:
+            base = ReferenceBaseline(pints)
+            m = base.sample_size(args.cpu_seconds)
+            dt, ref_scores = base.run(xs_all[:m])
+            one_core = base.one_core()
+            base.close()
+            kind, what, value = base.kind, base.what, m / dt
+            assert np.array_equal(ref_scores[:len(port_scores)],
+                                  port_scores[:len(ref_scores)]), \
+                'oracle port and reference disagree'
+        else:
+            ref_scores, dt = port_scores, dt_port
+            kind, what, value, one_core = port.kind, port.what, port_value, None
+        out['cpu'] = {
+            'value': value, 'unit': UNIT, 'cores': port.cores, 'kind': kind,
+            'value_1core': one_core, 'value_port': port_value,
+            'sample': '%d evaluations of the same workload (%.1f s); %s; %d '
+                      'workers' % (m, dt, what, port.cores)}
+        out['ref_rows'] = np.arange(len(ref_scores))
+        out['ref'] = ref_scores
+    else:
+        port.close()
+    return out
+
+
+def rel_err(a, b):
+    return np.abs(a - b) / np.abs(b)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -240,29 +378,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit('launch with torchrun for --gpus %d' % args.gpus)
 
-    # the CPU baseline runs first (rank 0, N=1 only), before CUDA is touched
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        base = CpuBaseline()
-        m = base.sample_size(args.cpu_seconds)
-        dt, ref_scores = base.run(base.po.headline_fhn_points(m))
-        base.close()
-        # the same on ONE core, in this process (= SequentialEvaluator)
-        spec1 = base.po.headline_fhn_spec()
-        xs1 = base.po.headline_fhn_points(256, seed=9)
-        t0 = time.perf_counter()
-        k1 = 0
-        while time.perf_counter() - t0 < 2.0 and k1 < len(xs1):
-            spec1.score(xs1[k1])
-            k1 += 1
-        one_core = k1 / (time.perf_counter() - t0)
-        cpu = {'value': m / dt, 'unit': UNIT, 'cores': base.cores,
-               'value_1core': one_core,
-               'kind': 'port',
-               'sample': '%d evaluations of the same workload (%.1f s), oracle '
-                         'port = scipy LSODA + reference RHS, %d worker '
-                         'processes' % (m, dt, base.cores)}
-        cpu_check = (m, ref_scores)
+    host = cpu_side(args, world) if rank == 0 else None
 
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
@@ -272,6 +388,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
 
+    load_reference()           # mirror classes then derive from the reference's
     import pints_b200 as pb
     from pints_b200._engine import fp64_probe
     from oracle import pints_oracle as po      # inputs only (synthetic series)
@@ -284,122 +401,241 @@ def run_ours(args):
     dp = ev.device_problem()
     spec = ev.spec()
 
-    pop = args.pop
+    pop, K = args.pop, args.steps
     # every rank scores its own shard of the global population (weak scaling)
     xs_all = po.headline_fhn_points(pop * world)
     xs = np.ascontiguousarray(xs_all[rank * pop:(rank + 1) * pop])
     d_x = torch.from_numpy(xs).to(device)
     d_scores = torch.empty(pop, dtype=torch.float64, device=device)
-    exchange = None
-    if world > 1:
-        from pints_b200._dist import ScoreExchange
-        exchange = ScoreExchange(pop, device, fused=not args.nccl_allgather)
     d_steps = dp.new_steps(pop)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    exchanges = {}
+    mode = 'none'
+    if world > 1:
+        from pints_b200._dist import ScoreExchange
+        mode = args.exchange
+        exchanges['nccl'] = ScoreExchange(pop, device, fused=False)
+        exchanges['fused'] = ScoreExchange(pop, device, multicast=False)
+        mc = ScoreExchange(pop, device, multicast=True)
+        if mc.fused and mc.multicast:
+            exchanges['multicast'] = mc
+        if not exchanges['fused'].fused:
+            del exchanges['fused']
+        if mode not in exchanges:
+            mode = 'fused' if 'fused' in exchanges else 'nccl'
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def step(steps_buf=None):
+    def step(which, mid=None):
         # N = 1: sort + fused solve.  N > 1: the same, and the exchange step
-        # (every rank ends up with all scores): fused into the kernel over
-        # NVLink peer memory + a device barrier, or solve + NCCL all-gather
-        if world > 1:
-            exchange.run(dp, d_x, steps=steps_buf)
-        else:
-            dp.eval(d_x, out=d_scores, steps=steps_buf)
+        # (every rank ends up with all scores): stored by the kernel into every
+        # rank's staging array over NVLink + reading-side kernel, or solve +
+        # NCCL all-gather
+        if which == 'local':
+            dp.eval(d_x, out=d_scores)
+            return d_scores
+        return exchanges[which].run(dp, d_x, mid_event=mid)
 
-    # parity spot-check against the CPU oracle numbers produced above
+    def timed(which):
+        """K steps, L2 flushed between steps, events per step; returns per-step
+        ms of the whole step, of its first part (sort + evaluation kernel) and
+        of the rest (reading side / all-gather)."""
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        k0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        for _ in range(max(args.warmup, 3)):
+            step(which)
+        barrier()
+        for i in range(K):
+            flush.fill_(i & 0xff)
+            e0[i].record()
+            if which == 'local':
+                step(which)
+                k0[i].record()
+            else:
+                step(which, mid=k0[i])
+            e1[i].record()
+        barrier()
+        whole = np.array([a.elapsed_time(b) for a, b in zip(e0, e1)])
+        first = np.array([a.elapsed_time(b) for a, b in zip(e0, k0)])
+        return whole, first, whole - first
+
+    # ---- parity: whole population against the CPU numbers produced above ---
     dp.eval(d_x, out=d_scores, steps=d_steps)
     torch.cuda.synchronize(device)
     flops_per_launch = float(spec.flops_per_eval(d_steps.cpu().numpy()).sum())
     mean_steps = float(d_steps.double().mean().item())
-    if cpu is not None:
-        m, ref_scores = cpu_check
-        k = min(m, pop, 512)
-        got = d_scores[:k].cpu().numpy()
-        rel = np.max(np.abs(got - ref_scores[:k]) / np.abs(ref_scores[:k]))
-        cpu['parity_max_rel'] = float(rel)
-        # LSODA's own error on this distribution reaches 9.6e-7;
-        # the strict 1e-6 bound lives in tests/, this is a sanity stop
-        assert rel < 5e-6, 'GPU/CPU parity %g' % rel
+    parity = {}
+    if rank == 0:
+        got = d_scores.cpu().numpy()
+        assert np.all(np.isfinite(got)), 'non-finite score in the population'
+        e_truth = rel_err(got[host['truth_rows']], host['truth'])
+        parity['truth_sample'] = int(len(e_truth))
+        parity['max_rel_vs_truth'] = float(e_truth.max())
+        parity['truth'] = 'the same LSODA at rtol = atol = 1e-13'
+        if host.get('ref') is not None:
+            k = min(len(host['ref']), pop)
+            e_ref = rel_err(got[:k], host['ref'][:k])
+            ref_truth = None
+            parity['reference_sample'] = int(k)
+            parity['max_rel_vs_reference'] = float(e_ref.max())
+            parity['frac_within_1e-6_of_reference'] = float(np.mean(e_ref <= 1e-6))
+            both = np.intersect1d(host['truth_rows'], np.arange(k))
+            if len(both):
+                at = np.searchsorted(host['truth_rows'], both)
+                ref_truth = rel_err(host['ref'][both], host['truth'][at])
+                parity['reference_max_rel_vs_truth'] = float(ref_truth.max())
+        # north_star: ODE log-likelihoods within 1e-6 relative
+        assert parity['max_rel_vs_truth'] < 1e-6, \
+            'GPU vs truth parity %g' % parity['max_rel_vs_truth']
+    if world > 1:
+        # the gathered array of every exchange equals the single-rank scores
+        want = torch.empty(pop * world, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(want, d_scores)
+        for name, ex in exchanges.items():
+            got_all = ex.run(dp, d_x)
+            torch.cuda.synchronize(device)
+            same = bool(torch.equal(got_all.view(torch.int64),
+                                    want.view(torch.int64)))
+            flag = torch.tensor([1 if same else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity['gathered_equals_local_bitwise_' + name] = bool(flag.item())
+            assert flag.item() == 1, 'exchange %s changed the scores' % name
 
     peak_tflops = fp64_probe(device)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-
-    # ---- device-timed: K steps, L2 flushed between steps, events per step --
-    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        e0[i].record()
-        step()
-        k0[i].record()
-        e1[i].record()
-    barrier()
+    main_which = 'local' if world == 1 else mode
+    whole, first, rest = timed(main_which)
     wall = time.perf_counter() - wall0
-    step_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
-    kern_ms = sum(a.elapsed_time(b) for a, b in zip(e0, k0))
+    compare = {}
+    if world > 1:
+        for name in ['local'] + [m for m in exchanges if m != mode]:
+            compare[name] = timed(name)
 
     # ---- end to end through the evaluator: host arrays in, host scores out -
-    # (a) positions in page-locked host memory (what the contract times):
-    #     H2D from where they lie + sort + fused solve + D2H + copy-out
-    xs_pinned = pb.pinned_empty(xs.shape)
-    np.copyto(xs_pinned, xs)
-    for _ in range(3):
-        ev.evaluate(xs_pinned)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = ev.evaluate(xs_pinned)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    # (b) an ordinary (pageable) ndarray, as numpy's ask() returns it: staged
-    #     through pinned memory in slices
-    for _ in range(2):
-        ev.evaluate(xs)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = ev.evaluate(xs)
-    barrier()
-    e2e_pageable_s = time.perf_counter() - t0
-    clocks = sampler.finish()
-    # (c) the same with the reference's return type (a Python list of floats):
-    # the boxing of 65 536 floats alone costs about as much as the solve
-    ev_list = pb.CudaEvaluator(ll, devices=device)
-    ev_list.evaluate(xs)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = ev_list.evaluate(xs)
-    barrier()
-    e2e_list_s = time.perf_counter() - t0
+    def e2e_loop(evaluator, arg, warm=3):
+        for _ in range(warm):
+            evaluator.evaluate(arg)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            evaluator.evaluate(arg)
+        barrier()
+        return time.perf_counter() - t0
 
+    e2e = {}
+    if world == 1:
+        # (a) positions in page-locked host memory: H2D from where they lie +
+        #     sort + fused solve + D2H into the (page-locked) result array
+        xs_pinned = pb.pinned_empty(xs.shape)
+        np.copyto(xs_pinned, xs)
+        e2e_s = e2e_loop(ev, xs_pinned)
+        # (b) an ordinary (pageable) ndarray, as numpy's ask() returns it:
+        #     staged through pinned memory in slices by the library's threads
+        e2e_pageable_s = e2e_loop(ev, xs)
+        # (c) the drop-in's default call: pageable ndarray in, ScoreList out
+        ev_default = pb.CudaEvaluator(ll, devices=device)
+        e2e_default_s = e2e_loop(ev_default, xs)
+        # (d) the reference's exact return type, a list of Python floats
+        ev_boxed = pb.CudaEvaluator(ll, devices=device, as_list='boxed')
+        e2e_boxed_s = e2e_loop(ev_boxed, xs)
+        total = pop * K
+        e2e = {'value': total / e2e_s, 'unit': UNIT,
+               'h2d_bytes_per_step': int(xs.nbytes),
+               'd2h_bytes_per_step': int(pop * 8),
+               'api': 'CudaEvaluator(f, as_list=False).evaluate(ndarray) -> '
+                      'ndarray; positions in page-locked host memory '
+                      '(pints_b200.pinned_empty), scores back in host memory',
+               'value_pageable_input': total / e2e_pageable_s,
+               'api_pageable_input': 'same call with an ordinary ndarray: '
+                                     'staged through pinned memory in slices '
+                                     'of 32768 rows (pb200_host_copy threads)',
+               'value_as_list': total / e2e_default_s,
+               'api_as_list': 'CudaEvaluator(f).evaluate(ndarray) -> ScoreList'
+                              ' (the default: list-compatible view, boxed '
+                              'lazily); pageable input',
+               'value_boxed_list': total / e2e_boxed_s,
+               'api_boxed_list': "CudaEvaluator(f, as_list='boxed') -> list of "
+                                 'Python floats (the reference\'s exact type)'}
+    else:
+        # the multi-GPU API: every rank passes the WHOLE population (as an SPMD
+        # controller loop does), scores its block, and gets all scores back in
+        # host memory -- H2D of the block, kernel + exchange, D2H of all scores
+        sharded = pb.ShardedEvaluator(ll, device=device, as_list=False)
+        xs_all_pinned = pb.pinned_empty(xs_all.shape)
+        np.copyto(xs_all_pinned, xs_all)
+        e2e_s = e2e_loop(sharded, xs_all_pinned)
+        got_all = sharded.evaluate(xs_all_pinned)
+        if rank == 0:
+            e_truth = rel_err(got_all[host['truth_rows']], host['truth'])
+            parity['e2e_max_rel_vs_truth'] = float(e_truth.max())
+        xs_pinned = pb.pinned_empty(xs.shape)
+        np.copyto(xs_pinned, xs)
+        e2e_private_s = e2e_loop(ev, xs_pinned)
+        total = pop * world * K
+        e2e = {'h2d_bytes_per_step': int(xs.nbytes) * world,
+               'd2h_bytes_per_step': int(pop * world * 8) * world,
+               'api': 'ShardedEvaluator(f, as_list=False).evaluate(all '
+                      'positions, page-locked) on every rank -> all scores in '
+                      'every rank\'s host memory (exchange included)',
+               'api_no_exchange': 'each rank its own CudaEvaluator on its own '
+                                  'block, nothing exchanged (N independent '
+                                  'single-GPU calls)'}
+    clocks = sampler.finish()
+
+    # ---- gather the per-rank numbers on rank 0 ------------------------------
+    def stats(x):
+        return {'median': float(np.median(x)), 'p95': float(np.percentile(x, 95)),
+                'mean': float(np.mean(x)), 'max': float(np.max(x))}
+
+    mine = {'rank': rank, 'step_ms': stats(whole), 'kernel_ms': stats(first),
+            'exchange_wait_ms': stats(rest), 'sum_step_ms': float(whole.sum()),
+            'sum_kernel_ms': float(first.sum())}
+    for name, (w, f, r) in compare.items():
+        mine['compare_' + name] = {'sum_step_ms': float(w.sum()),
+                                   'step_ms_median': float(np.median(w)),
+                                   'kernel_ms_median': float(np.median(f))}
+    mine['e2e_s'] = e2e_s
     if world > 1:
-        t = torch.tensor([step_ms, kern_ms, e2e_s, e2e_list_s, e2e_pageable_s],
-                         dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, kern_ms, e2e_s, e2e_list_s, e2e_pageable_s = t.tolist()
+        mine['e2e_private_s'] = e2e_private_s
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+    else:
+        everyone = [mine]
 
     if rank == 0:
-        total = pop * world * args.steps
+        step_ms = max(r['sum_step_ms'] for r in everyone)       # max over ranks
+        kern_ms = max(r['sum_kernel_ms'] for r in everyone)
+        total = pop * world * K
         value = total / (step_ms * 1e-3)
-        achieved = flops_per_launch / (kern_ms / args.steps * 1e-3) / 1e12
+        achieved = flops_per_launch / (kern_ms / K * 1e-3) / 1e12
+        if world > 1:
+            e2e['value'] = total / max(r['e2e_s'] for r in everyone)
+            e2e['unit'] = UNIT
+            e2e['value_no_exchange'] = total / max(r['e2e_private_s'] for r in everyone)
+        exchange_text = {
+            'none': 'none (one GPU)',
+            'fused': 'fused: the kernel stores {score, row} pairs into every '
+                     'rank\'s staging array over NVLink (512-byte runs per '
+                     'warp), its last block raises flags, a reading-side '
+                     'kernel waits for them and files the scores; no barrier '
+                     'launch, no NCCL call',
+            'multicast': 'fused, one multimem.st per vector through the '
+                         'NVSwitch multicast mapping instead of one store per '
+                         'rank',
+            'nccl': 'solve + NCCL all-gather'}[mode]
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': step_ms / args.steps, 'higher_is_better': True,
+            'steps': K, 'warmup': max(args.warmup, 3),
+            'ms_per_step': step_ms / K, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'population_per_gpu': pop,
@@ -408,10 +644,7 @@ def run_ours(args):
                        'mean_rk_steps': mean_steps,
                        'l2': 'flushed between steps (256 MiB fill)',
                        'parallelism': 'dp%d' % world,
-                       'exchange': 'none (one GPU)' if world == 1 else (
-                           'fused: kernel stores scores into every rank\'s '
-                           'array over NVLink (symmetric memory) + barrier'
-                           if exchange.fused else 'NCCL all-gather')},
+                       'exchange': exchange_text},
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops,
                 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
@@ -420,28 +653,36 @@ def run_ours(args):
                                ' MEASURED_PEAKS.json has no FP64 entry; '
                                'nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2',
                 'flop_per_launch': flops_per_launch,
-                'kernel_ms': kern_ms / args.steps,
-                'hbm': hbm_side(kern_ms / args.steps)},
-            'e2e': {'value': total / e2e_s, 'unit': UNIT,
-                    'h2d_bytes_per_step': int(xs.nbytes) * world,
-                    'd2h_bytes_per_step': int(pop * 8) * world,
-                    'api': 'CudaEvaluator(f, as_list=False).evaluate(ndarray) '
-                           '-> ndarray; positions in page-locked host memory '
-                           '(pints_b200.pinned_empty), scores back in host memory',
-                    'value_pageable_input': total / e2e_pageable_s,
-                    'api_pageable_input': 'same call with an ordinary ndarray: '
-                                          'staged through pinned memory in '
-                                          'slices of 32768 rows (multi-threaded copy)',
-                    'value_as_list': total / e2e_list_s,
-                    'api_as_list': 'CudaEvaluator(f).evaluate(ndarray) -> list '
-                                   '(the reference\'s return type)'},
-            # per step and rank: the counting-sort kernel + the fused ODE kernel
-            'gpu_launches': args.steps * world * 2,
+                'kernel_ms': kern_ms / K,
+                'hbm': hbm_side(kern_ms / K)},
+            'e2e': e2e,
+            'parity': parity,
+            # per step and rank: the counting-sort kernel + the fused ODE
+            # kernel (+ the reading side of the exchange)
+            'gpu_launches': K * world * (2 if world == 1 else 3),
             'clocks': clocks,
             'wall_s_timed_region': wall,
+            # where the time of a step goes, per rank: kernel_ms = sort +
+            # evaluation kernel (with its peer stores and flags when N > 1),
+            # exchange_wait_ms = reading side (waits for the slowest rank)
+            'per_rank': [{k: v for k, v in r.items()
+                          if not k.startswith('compare_') and not k.startswith('e2e')}
+                         for r in everyone],
         }
-        if cpu is not None:
-            line['cpu_baseline'] = cpu
+        if world > 1:
+            cmp_out = {}
+            for name in compare:
+                sums = [r['compare_' + name]['sum_step_ms'] for r in everyone]
+                cmp_out[name] = {
+                    'ms_per_step': max(sums) / K,
+                    'step_ms_median_per_rank': [r['compare_' + name]['step_ms_median'] for r in everyone],
+                    'kernel_ms_median_per_rank': [r['compare_' + name]['kernel_ms_median'] for r in everyone]}
+            cmp_out['_what'] = ('same invocation, same inputs: "local" = sort + '
+                                'evaluation kernel alone (no exchange); the '
+                                'others = the whole step with that exchange')
+            line['exchange_compare'] = cmp_out
+        if host['cpu'] is not None:
+            line['cpu_baseline'] = host['cpu']
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -457,9 +698,10 @@ def main():
                     help='parameter vectors per GPU per step')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--nccl-allgather', action='store_true',
-                    help='N > 1: exchange the scores with an NCCL all-gather '
-                         'after the kernel instead of the fused peer stores')
+    ap.add_argument('--exchange', default=os.environ.get('PB200_BENCH_EXCHANGE', 'fused'),
+                    choices=['fused', 'multicast', 'nccl'],
+                    help='N > 1: how the scores are exchanged in the headline '
+                         'number (the other ways are timed beside it)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -209,20 +209,57 @@ int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
 /*
  * Multi-GPU variant with the exchange step fused in (the
  * one collective of the path is the all-gather of the scores, which replaces
- * the result queue of ParallelEvaluator, pints/_evaluation.py:330-372).
- * Rank r scores its block of n rows and the kernel stores every score
- * directly into the gathered array of EVERY rank at row `offset + i`:
- * peer_scores[q] is the device address, valid in this process, of rank q's
- * gathered array (its own allocation for q = r, a peer mapping over NVLink
- * otherwise -- e.g. torch symmetric memory).  No separate all-gather is
- * needed afterwards, only a barrier before the arrays are read.
- * d_sort_ws as in pb200_eval_sorted (NULL = no sorting).
+ * the result queue of ParallelEvaluator, pints/_evaluation.py:316-337).
+ *
+ * Every rank owns, in memory that all ranks of the job have mapped (e.g. torch
+ * symmetric memory over NVLink / NVSwitch):
+ *   a staging array of n_ranks * per_rank pairs of 16 bytes {double score,
+ *   int64 row}: rank r's block starts at pair r * per_rank;
+ *   a flag array of n_ranks uint64, zero before the first generation.
+ * pb200_eval_exchange scores this rank's n (<= per_rank) rows and the kernel
+ * stores each score, with its row number, into the staging array of EVERY rank
+ * in launch order -- after the cost sort a warp's 32 vectors are 32 consecutive
+ * pairs, i.e. one contiguous 512-byte run per destination, not 32 scattered
+ * 8-byte stores -- or, when stage_multicast is given (a multicast mapping of
+ * the staging arrays: NVSwitch replicates the store), with one multimem.st per
+ * vector.  The last block of the launch then writes `epoch` into this rank's
+ * slot of every rank's flag array (release, system scope); with n = 0 a
+ * one-thread kernel only raises the flags.  There is no barrier launch.
+ *
+ * pb200_exchange_finish (the reading side, same stream, after the call above)
+ * waits until all n_ranks local flags have reached `epoch` (acquire; it traps
+ * after 30 s without progress rather than hang the GPU) and writes the
+ * n_total scores of the whole population in row order to d_scores_all, where
+ * rank r scored the rows [r * rows_per_rank, min(n_total, (r + 1) *
+ * rows_per_rank)) (rows_per_rank <= per_rank: the blocks of this generation
+ * may be shorter than the staging blocks).
+ *
+ * Use epoch = 1, 2, 3, ... and alternate between TWO staging arrays (one flag
+ * array serves both): a rank can then run at most one generation ahead of the
+ * slowest reader, which is still on the other array.  d_done is a device word
+ * owned by the caller, zero before the first call (the kernel returns it to
+ * zero).  d_sort_ws as in pb200_eval_sorted (NULL = no sorting).
  */
-int pb200_eval_scatter(const pb200_problem *p, const double *d_params, int64_t n,
-                       int64_t ld, int32_t *d_steps,
-                       const pb200_solver_opts *opts, void *d_sort_ws,
-                       int64_t sort_ws_bytes, void *const *peer_scores,
-                       int32_t n_peers, int64_t offset, void *stream);
+typedef struct pb200_exchange_desc {
+    int32_t  n_ranks;                    /* 1 .. PB200_MAX_PEERS                */
+    int32_t  rank;                       /* this rank                           */
+    int64_t  per_rank;                   /* rows per rank block                 */
+    void    *stage[PB200_MAX_PEERS];     /* rank q's staging array, as mapped in
+                                            this process (q = rank: its own)    */
+    void    *flags[PB200_MAX_PEERS];     /* rank q's flag array, as mapped here */
+    void    *stage_multicast;            /* multicast address of the staging
+                                            arrays, or NULL                     */
+    void    *d_done;                     /* uint32 on this device               */
+    uint64_t epoch;                      /* generation number, >= 1, increasing */
+} pb200_exchange_desc;
+
+int pb200_eval_exchange(const pb200_problem *p, const double *d_params, int64_t n,
+                        int64_t ld, int32_t *d_steps,
+                        const pb200_solver_opts *opts, void *d_sort_ws,
+                        int64_t sort_ws_bytes, const pb200_exchange_desc *ex,
+                        void *stream);
+int pb200_exchange_finish(const pb200_exchange_desc *ex, int64_t rows_per_rank,
+                          int64_t n_total, double *d_scores_all, void *stream);
 
 /*
  * The same through HOST buffers, for callers that hold their positions in host
@@ -250,6 +287,12 @@ int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n,
  */
 int pb200_copy_async(void *dst, const void *src, int64_t bytes,
                      int32_t to_device, void *stream);
+/* Host-side staging copy (an ordinary, pageable array of positions into a
+ * page-locked buffer that pb200_copy_async can send): cut into slices and done
+ * by `threads` persistent threads of this library (<= 0: automatic, from the
+ * CPUs this process may run on divided by LOCAL_WORLD_SIZE; PB200_COPY_THREADS
+ * overrides), independent of the host program's OpenMP settings.  Synchronous. */
+int pb200_host_copy(void *dst, const void *src, int64_t bytes, int32_t threads);
 /* 1 if `ptr` points into page-locked host memory (then a batch can be sent
  * from where it lies, without staging), else 0. */
 int pb200_host_is_pinned(const void *ptr);

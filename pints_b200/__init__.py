@@ -42,9 +42,10 @@ __version__ = '0.1.0'
 
 _LAZY = {
     'Evaluator': '_evaluation', 'CudaEvaluator': '_evaluation',
-    'pinned_empty': '_evaluation',
+    'pinned_empty': '_evaluation', 'ScoreList': '_evaluation',
     'DeviceProblem': '_engine', 'fp64_probe': '_engine',
     'require_cuda': '_engine',
+    'ShardedEvaluator': '_dist', 'ScoreExchange': '_dist',
     'HaarioBardenetACMC': '_samplers', 'HaarioACMC': '_samplers',
     'RaoBlackwellACMC': '_samplers',
     'MetropolisRandomWalkMCMC': '_samplers',

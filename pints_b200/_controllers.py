@@ -46,19 +46,23 @@ def cuda_evaluators(**options):
         raise RuntimeError('the reference package `pints` is not importable')
     from ._evaluation import CudaEvaluator
 
-    def make(function, *args, **kwargs):
-        # n_workers / max_tasks_per_worker / n_fn_evals_per_worker have no
-        # meaning on the GPU; `args` keeps its meaning
-        return CudaEvaluator(function, args=kwargs.get('args'), **options)
+    # the reference's signatures (pints/_evaluation.py:178-187, :470-471):
+    # n_workers / max_tasks_per_worker / n_fn_evals_per_worker have no meaning
+    # on the GPU; `args` keeps its meaning, positional or by keyword
+    def make(function, args=None):
+        return CudaEvaluator(function, args=args, **options)
+
+    def make_parallel(function, n_workers=None, max_tasks_per_worker=500,
+                      n_numpy_threads=1, args=None):
+        return CudaEvaluator(function, args=args, **options)
 
     def make_multi(functions, args=None):
-        evs = [CudaEvaluator(f, **options) for f in functions]
-        return _MultiCudaEvaluator(evs)
+        return _MultiCudaEvaluator(functions, args, options)
 
     saved = (pints.SequentialEvaluator, pints.ParallelEvaluator,
              pints.MultiSequentialEvaluator)
     pints.SequentialEvaluator = make
-    pints.ParallelEvaluator = make
+    pints.ParallelEvaluator = make_parallel
     pints.MultiSequentialEvaluator = make_multi
     try:
         yield
@@ -68,16 +72,44 @@ def cuda_evaluators(**options):
 
 
 class _MultiCudaEvaluator(object):
-    """Position i goes to function i (pints/_evaluation.py:416-454)."""
+    """Position i goes to function i (pints/_evaluation.py:416-454).  Positions
+    that share a function (the same object) are scored in one launch; the
+    launches of distinct functions are all enqueued, each on its evaluator's
+    own streams, before the first result is awaited."""
 
-    def __init__(self, evaluators):
-        self._evs = evaluators
+    def __init__(self, functions, args=None, options=None):
+        from ._evaluation import CudaEvaluator
+        for function in functions:
+            if not callable(function):
+                raise ValueError('The given functions must be callable.')
+        self._n = len(functions)
+        self._groups = []                 # (evaluator, rows it scores)
+        seen = {}
+        for i, f in enumerate(functions):
+            if id(f) not in seen:
+                seen[id(f)] = len(self._groups)
+                self._groups.append((CudaEvaluator(f, args=args, as_list=False,
+                                                   **(options or {})), []))
+            self._groups[seen[id(f)]][1].append(i)
 
     def evaluate(self, positions):
-        if len(positions) != len(self._evs):
+        try:
+            len(positions)
+        except TypeError:
+            raise ValueError(
+                'The argument `positions` must be a sequence of input values'
+                ' to the evaluator\'s function.')
+        if len(positions) != self._n:
             raise ValueError('Number of positions does not equal number of '
                              'functions.')
-        return [ev.evaluate([x])[0] for ev, x in zip(self._evs, positions)]
+        pending = [(ev, rows, ev.begin([positions[i] for i in rows]))
+                   for ev, rows in self._groups]
+        out = [None] * self._n
+        for ev, rows, work in pending:
+            scores, _ = ev.finish(work)
+            for i, v in zip(rows, scores.tolist()):
+                out[i] = v
+        return out
 
 
 # ----------------------------------------------------------------------
@@ -702,7 +734,7 @@ class CudaOptimisationController(object):
         while True:
             if exchange is not None:
                 xs = opt.ask()
-                fs = exchange.run(problem, xs[lo:hi])[:n]
+                fs = exchange.run(problem, xs[lo:hi], n_total=n)
                 opt.tell(-fs if self._sign < 0 else fs)
                 self._evaluations += len(fs)
             elif on_device:

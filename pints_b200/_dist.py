@@ -9,12 +9,16 @@ update, which is O(population) and stays on the CPU -- sees all of them.  This
 replaces the task/result queues of ``ParallelEvaluator``
 (pints/_evaluation.py:284-372, :489-565).
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from ._evaluation import Evaluator
-from ._engine import positions_to_array
+from ._engine import exchange_finish, positions_to_array
 
 
 def shard_bounds(n, world, rank):
@@ -27,66 +31,140 @@ def shard_bounds(n, world, rank):
 
 class ScoreExchange(object):
     """The exchange step of the sharded path: after it, every rank holds the
-    scores of all ranks.
+    scores of all ranks, in row order.
 
-    With NCCL on NVLink-connected GPUs the gathered array lives in torch
-    symmetric memory, every rank's copy is mapped into every process, and the
-    evaluation kernel itself stores each score into all copies
-    (``DeviceProblem.eval_scatter`` -> ``pb200_eval_scatter``): the all-gather
-    is fused into the solve and only a device-side barrier remains.  Two
-    arrays alternate, so a rank may start the next generation while a slower
-    peer still reads the previous one.  Anywhere else (gloo on CPU, no peer
-    access) it is a plain ``all_gather_into_tensor``.
+    With NCCL on NVLink-connected GPUs the exchange is fused into the
+    evaluation kernel (``pb200_eval_exchange`` / ``pb200_exchange_finish``,
+    see ``include/pints_b200.h``): every rank owns a staging array of
+    ``{score, row}`` pairs and a flag array in torch symmetric memory, mapped
+    into every process; the kernel stores each score into all staging arrays
+    as the vector finishes (contiguous 512-byte runs per warp and destination,
+    or one multicast store through NVSwitch), its last block raises the
+    rank's flags, and a small kernel on the reading side waits for the flags
+    and files the scores under their rows.  No barrier launch, no NCCL call.
+    Two staging arrays alternate, so a rank may start the next generation
+    while a slower peer still reads the previous one.  Anywhere else (gloo on
+    CPU, no peer access) it is a plain ``all_gather_into_tensor``; the choice
+    is made collectively, so all ranks take the same path.
     """
 
-    def __init__(self, per_rank, device, group=None, fused=None):
+    def __init__(self, per_rank, device, group=None, fused=None,
+                 multicast=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.per = int(per_rank)
         self.device = torch.device(device)
         self.fused = False
-        self._turn = 0
+        self.fused_error = None          # why the fused path was not taken
+        self.multicast = False
+        self._epoch = 0
         if fused is None:
             fused = self.device.type == 'cuda' and self.world > 1 and \
-                self.world <= 16 and dist.get_backend(group) == 'nccl'
+                self.world <= _lib.MAX_PEERS and \
+                dist.get_backend(group) == 'nccl'
         if fused:
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                g = group if group is not None else dist.group.WORLD
-                self._arrays, self._handles = [], []
-                for _ in range(2):
-                    t = symm_mem.empty(self.per * self.world,
-                                       dtype=torch.float64, device=self.device)
-                    self._handles.append(symm_mem.rendezvous(t, g))
-                    self._arrays.append(t)
-                self.fused = True
-            except Exception:                              # no peer mapping
-                self.fused = False
+            self._setup_fused(multicast)
         if not self.fused:
             self._mine = torch.zeros(self.per, dtype=torch.float64,
                                      device=self.device)
             self._every = torch.empty(self.per * self.world,
                                       dtype=torch.float64, device=self.device)
 
-    def run(self, problem, d_params, steps=None):
+    def _setup_fused(self, multicast):
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            g = self.group if self.group is not None else dist.group.WORLD
+            pairs = self.per * self.world
+            flag_words = -(-self.world // 16) * 16          # whole 128-byte lines
+            # one allocation, in doubles: [stage 0][stage 1][flags]
+            self._symm = symm_mem.empty(2 * 2 * pairs + flag_words,
+                                        dtype=torch.float64,
+                                        device=self.device)
+            self._symm.zero_()
+            self._hdl = symm_mem.rendezvous(self._symm, g)
+        except Exception as e:             # no peer mapping on this rank
+            ok = 0
+            self.fused_error = e
+        # every rank must take the same path: one that fell back to the
+        # all-gather would wait for peers that spin on its flags
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if self.fused_error is None:
+                self.fused_error = RuntimeError(
+                    'symmetric memory is not available on a peer rank')
+            self._symm = self._hdl = None
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)     # flags are zero everywhere
+        pairs = self.per * self.world
+        ptrs = [int(q) for q in self._hdl.buffer_ptrs]
+        self._stage_ptrs = [[q + k * pairs * 16 for q in ptrs] for k in (0, 1)]
+        self._flag_ptrs = [q + 2 * pairs * 16 for q in ptrs]
+        mc = 0
+        if multicast is None:
+            multicast = os.environ.get('PB200_EXCHANGE_MULTICAST', '0') == '1'
+        if multicast:
+            try:
+                mc = int(self._hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+        self._mc_ptrs = [mc + k * pairs * 16 if mc else 0 for k in (0, 1)]
+        self.multicast = bool(mc)
+        self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._every = torch.empty(pairs, dtype=torch.float64,
+                                  device=self.device)
+        self.fused = True
+
+    def _desc(self, k):
+        d = _lib.ExchangeDesc()
+        d.n_ranks, d.rank, d.per_rank = self.world, self.rank, self.per
+        for q in range(self.world):
+            d.stage[q] = self._stage_ptrs[k][q]
+            d.flags[q] = self._flag_ptrs[q]
+        d.stage_multicast = self._mc_ptrs[k] or None
+        d.d_done = self._done.data_ptr()
+        d.epoch = self._epoch
+        return d
+
+    def run(self, problem, d_params, steps=None, rows_per_rank=None,
+            n_total=None, mid_event=None):
         """Scores ``d_params`` (this rank's block, at most ``per_rank`` rows) on
-        ``problem`` and returns the gathered array (device tensor,
-        ``per_rank * world`` entries, rank r's block at ``r * per_rank``)."""
+        ``problem`` and returns the scores of all ranks in row order (device
+        tensor).  ``rows_per_rank`` (default ``per_rank``) is the block length
+        of this generation and ``n_total`` (default ``rows_per_rank * world``)
+        the number of rows of the whole population: rank r holds the rows
+        ``[r * rows_per_rank, min(n_total, (r + 1) * rows_per_rank))`` --
+        ``n_total`` must be given whenever a block is shorter than the others.
+        ``mid_event`` (a CUDA event, for timing) is recorded between the
+        evaluation kernel and the reading side."""
         n = d_params.shape[0]
+        rows = self.per if rows_per_rank is None else int(rows_per_rank)
+        total = rows * self.world if n_total is None else int(n_total)
+        if rows > self.per or n > rows:
+            raise ValueError('block of %d rows does not fit the exchange (%d)'
+                             % (max(n, rows), self.per))
         if self.fused:
-            k = self._turn
-            self._turn ^= 1
-            hdl = self._handles[k]
-            if n:
-                problem.eval_scatter(d_params, list(hdl.buffer_ptrs),
-                                     self.rank * self.per, steps=steps)
-            hdl.barrier(channel=0)
-            return self._arrays[k]
+            self._epoch += 1
+            desc = self._desc(self._epoch & 1)
+            problem.eval_exchange(d_params, desc, steps=steps)
+            if mid_event is not None:
+                mid_event.record()
+            exchange_finish(desc, rows, total, self._every)
+            return self._every[:total]
         if n:
             problem.eval(d_params, out=self._mine[:n], steps=steps)
-        dist.all_gather_into_tensor(self._every, self._mine, group=self.group)
-        return self._every
+        if mid_event is not None:
+            mid_event.record()
+        if rows == self.per:
+            dist.all_gather_into_tensor(self._every, self._mine,
+                                        group=self.group)
+            return self._every[:total]
+        every = self._every[:rows * self.world]
+        dist.all_gather_into_tensor(every, self._mine[:rows], group=self.group)
+        return every[:total]
 
 
 class ShardedEvaluator(Evaluator):
@@ -111,7 +189,7 @@ class ShardedEvaluator(Evaluator):
             raise ValueError(
                 'ShardedEvaluator does not support extra function arguments.')
         self._group = group
-        self._as_list = bool(as_list)
+        self._as_list = as_list if as_list == 'boxed' else bool(as_list)
         self._device = device
         self._options = options
         self._local = None
@@ -170,20 +248,14 @@ class ShardedEvaluator(Evaluator):
         device = self._collective_device()
         if self._fused_possible(device):
             # fused exchange: the kernel stores the scores into every rank's
-            # gathered array (symmetric memory over NVLink)
+            # staging array (symmetric memory over NVLink)
             ex = self._exchange
             if ex is None or ex.per < per:
+                self._exchange = None                 # frees the old buffers
                 ex = self._exchange = ScoreExchange(
                     max(per, 1024), device, self._group)
             if ex.fused:
-                problem = self._local.device_problem()
-                d_x = torch.from_numpy(
-                    np.ascontiguousarray(xs[lo:hi])).to(device,
-                                                        non_blocking=True)
-                every = ex.run(problem, d_x)
-                parts = [every[r * ex.per: r * ex.per + min(per, max(0, n - r * per))]
-                         for r in range(world)]
-                return torch.cat(parts).cpu().numpy()
+                return self._evaluate_fused(ex, xs, lo, hi, per, n)
         mine = self._buffer('mine', per, device)[:per]
         every = self._buffer('all', per * world, device)[:per * world]
         if hi - lo < per:
@@ -193,6 +265,31 @@ class ShardedEvaluator(Evaluator):
         dist.all_gather_into_tensor(every, mine, group=self._group)
         return every[:n].cpu().numpy() if per * world >= n else None
 
+    def _evaluate_fused(self, ex, xs, lo, hi, per, n):
+        """H2D of this rank's rows, evaluation kernel with the exchange fused
+        in, reading side, D2H of all ``n`` scores into a page-locked array that
+        is handed to the caller -- all on one stream of the local evaluator."""
+        from ._evaluation import _Lane, pinned_result
+        lane = self._local._setup()[0]
+        lib = self._local._lib
+        stream = lane.streams[0]
+        m, d = hi - lo, xs.shape[1]
+        lane.reserve(max(m, 1), d, False)
+        scores = pinned_result(n)
+        with torch.cuda.device(lane.device), torch.cuda.stream(stream):
+            if m:
+                mine = xs[lo:hi]
+                lane.send(lib, mine, 0, m, lane.stream_ptrs[0],
+                          _Lane.is_pinned(lib, mine))
+            every = ex.run(lane.problem, lane.d_in[:m], rows_per_rank=per,
+                           n_total=n)
+            _lib.check(lib.pb200_copy_async(
+                ctypes.c_void_p(scores.ctypes.data),
+                ctypes.c_void_p(every.data_ptr()), n * 8, 0,
+                lane.stream_ptrs[0]))
+        stream.synchronize()
+        return scores
+
     def _evaluate(self, positions):
-        scores = self.evaluate_array(positions)
-        return scores.tolist() if self._as_list else scores
+        from ._evaluation import wrap_scores
+        return wrap_scores(self.evaluate_array(positions), self._as_list)

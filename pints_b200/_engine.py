@@ -184,26 +184,26 @@ class DeviceProblem(object):
                 ws, ws_bytes, ctypes.c_void_p(stream)))
         return out
 
-    def eval_scatter(self, d_params, peer_ptrs, offset, steps=None):
-        """Scores of the rows of ``d_params`` stored straight into the
-        gathered score arrays of all ranks (``peer_ptrs``: device addresses of
-        every rank's array as seen from this process, e.g. the ``buffer_ptrs``
-        of a torch symmetric-memory handle) at rows ``offset + i``:
-        ``pb200_eval_scatter``.  Asynchronous on the current stream; the
-        caller puts a barrier between this and any read of the arrays."""
-        d_params = self._check_params(d_params, self.n_parameters)
+    def eval_exchange(self, d_params, desc, steps=None):
+        """Scores of the rows of ``d_params`` (this rank's block of a multi-GPU
+        job; may be empty) stored straight into the staging arrays of all
+        ranks, followed by this rank's flags: ``pb200_eval_exchange`` with the
+        ``_lib.ExchangeDesc`` ``desc``.  Asynchronous on the current stream;
+        :func:`exchange_finish` is the reading side."""
         n = d_params.shape[0]
-        ptrs = (ctypes.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+        if n:
+            d_params = self._check_params(d_params, self.n_parameters)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             ws, ws_bytes = None, 0
-            if self.wants_sort(n):
+            if n and self.wants_sort(n):
                 t = self.sort_workspace(n, stream)
                 ws, ws_bytes = ctypes.c_void_p(t.data_ptr()), t.numel()
-            _lib.check(self._lib.pb200_eval_scatter(
-                self._handle, _ptr(d_params), n, d_params.stride(0),
-                _ptr(steps), ctypes.byref(self.opts), ws, ws_bytes, ptrs,
-                len(peer_ptrs), int(offset), ctypes.c_void_p(stream)))
+            _lib.check(self._lib.pb200_eval_exchange(
+                self._handle, _ptr(d_params) if n else None, n,
+                d_params.stride(0) if n else self.n_parameters,
+                _ptr(steps), ctypes.byref(self.opts), ws, ws_bytes,
+                ctypes.byref(desc), ctypes.c_void_p(stream)))
 
     def simulate(self, d_params, out=None, steps=None):
         """Trajectories ``(n, n_times, n_outputs)`` of the rows of
@@ -235,6 +235,19 @@ class DeviceProblem(object):
 
     def new_steps(self, n):
         return torch.zeros(n, dtype=torch.int32, device=self.device)
+
+
+def exchange_finish(desc, rows_per_rank, n_total, out):
+    """Reading side of the fused exchange: waits for every rank's flag of
+    generation ``desc.epoch`` and writes the ``n_total`` scores in row order
+    into ``out`` (device tensor): ``pb200_exchange_finish``.  Asynchronous on
+    the current stream of ``out``'s device."""
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.pb200_exchange_finish(
+            ctypes.byref(desc), int(rows_per_rank), int(n_total), _ptr(out),
+            _stream_ptr(out.device)))
+    return out
 
 
 def positions_to_array(positions, width=None):

@@ -3,8 +3,8 @@
 ``pints.ParallelEvaluator`` (pints/_evaluation.py:63-123, :126-413, :457-482)
 that scores the whole batch of positions in one fused CUDA launch.
 """
+import collections.abc
 import ctypes
-import warnings
 
 import numpy as np
 import torch
@@ -49,6 +49,86 @@ class Evaluator(base('Evaluator')):
         raise NotImplementedError
 
 
+class ScoreList(collections.abc.Sequence):
+    """What ``evaluate`` returns by default: a read-only, list-compatible view
+    of the scores as they came back from the GPU (a float64 ndarray), without
+    boxing every score into a Python float up front -- ``tolist()`` of 65 536
+    scores costs more than solving them.  It supports what the reference's
+    consumers do with the list: ``len(fs)``, ``fs[i]``
+    (a Python ``float``), slices, ``iter(fs)`` / ``next`` (boxed lazily, on
+    first iteration: pints/_mcmc/__init__.py:733-735), ``np.argsort(fs)``,
+    ``np.array(fs)``, ``full[ids] = fs`` (pints/_optimisers/_xnes.py:154-160),
+    ``fs == [..]``, ``fs + [..]``, ``min`` / ``max`` / ``sorted``;
+    ``fs.tolist()`` is the plain list."""
+
+    __slots__ = ('_a', '_boxed')
+
+    def __init__(self, array):
+        self._a = array
+        self._boxed = None
+
+    def tolist(self):
+        if self._boxed is None:
+            self._boxed = self._a.tolist()
+        return self._boxed
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._a
+        if dtype is not None and np.dtype(dtype) != a.dtype:
+            return a.astype(dtype)
+        return a.copy() if copy else a
+
+    def __len__(self):
+        return self._a.shape[0]
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return ScoreList(self._a[k])
+        try:
+            return self._a.item(k)
+        except (TypeError, ValueError):
+            return self._a[k]                 # index arrays: an ndarray
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def __reversed__(self):
+        return reversed(self.tolist())
+
+    def __contains__(self, v):
+        return v in self.tolist()
+
+    def index(self, *args):
+        return self.tolist().index(*args)
+
+    def count(self, v):
+        return self.tolist().count(v)
+
+    def __eq__(self, other):
+        if isinstance(other, ScoreList):
+            other = other._a
+        if isinstance(other, (list, tuple, np.ndarray)):
+            other = np.asarray(other)
+            return other.shape == self._a.shape and bool(
+                np.all((other == self._a) | ((other != other) & (self._a != self._a))))
+        return NotImplemented
+
+    def __ne__(self, other):
+        r = self.__eq__(other)
+        return r if r is NotImplemented else not r
+
+    __hash__ = None
+
+    def __add__(self, other):
+        return self.tolist() + list(other)
+
+    def __radd__(self, other):
+        return list(other) + self.tolist()
+
+    def __repr__(self):
+        return repr(self.tolist())
+
+
 class _SpecFunction(object):
     """Stands in for ``function`` when a CudaEvaluator is built directly from
     a ``ProblemSpec``: there is no Python callable to fall back to."""
@@ -62,8 +142,8 @@ class _SpecFunction(object):
 
 
 class _Lane(object):
-    """Per-device state of a CudaEvaluator: problem handle, a stream, pinned
-    host staging buffers and device workspaces (grown geometrically)."""
+    """Per-device state of a CudaEvaluator: problem handle, streams, a pinned
+    host staging buffer and device workspaces (grown geometrically)."""
 
     N_STREAMS = 4
 
@@ -77,82 +157,79 @@ class _Lane(object):
         self.used = 0
         self.capacity = 0
         self.width = 0
-        self.h_steps = None
+        self.d_steps = None
 
     def reserve(self, n, d, want_steps):
         if n > self.capacity or d != self.width:
             cap = max(n, int(self.capacity * 1.5), 1024)
             self.h_in = torch.empty((cap, d), dtype=torch.float64,
                                     pin_memory=True)
-            self.h_out = torch.empty(cap, dtype=torch.float64, pin_memory=True)
             self.d_in = torch.empty((cap, d), dtype=torch.float64,
                                     device=self.device)
             self.d_out = torch.empty(cap, dtype=torch.float64,
                                      device=self.device)
-            # numpy views and raw pointers, so a call does no tensor slicing
-            self.h_in_np = self.h_in.numpy()
-            self.h_out_np = self.h_out.numpy()
-            self.a_h_in, self.a_h_out = self.h_in.data_ptr(), self.h_out.data_ptr()
+            # raw pointers, so a call does no tensor slicing
+            self.a_h_in = self.h_in.data_ptr()
             self.a_d_in, self.a_d_out = self.d_in.data_ptr(), self.d_out.data_ptr()
-            self.h_steps = None
+            self.d_steps = None
             self.capacity, self.width = cap, d
-        if want_steps and self.h_steps is None:
+        if want_steps and self.d_steps is None:
             self.d_steps = torch.zeros(self.capacity, dtype=torch.int32,
                                        device=self.device)
-            self.h_steps = torch.zeros(self.capacity, dtype=torch.int32,
-                                       pin_memory=True)
-            self.h_steps_np = self.h_steps.numpy()
-            self.a_h_steps = self.h_steps.data_ptr()
             self.a_d_steps = self.d_steps.data_ptr()
 
     #: rows staged into pinned memory (and sent) per slice
     STAGE_ROWS = 32768
 
-    def launch(self, lib, xs, want_steps, chunk_rows):
-        """Stage `xs` into pinned memory and enqueue copy-in, kernel and
-        copy-out.  The batch is cut into at most N_STREAMS compute chunks of
-        `chunk_rows` rows or more, one fused launch each on its own stream; a
-        chunk is staged in slices of STAGE_ROWS rows, and each slice is on its
-        way to the device while the host stages the next one."""
+    def send(self, lib, xs, lo, hi, st, pinned):
+        """Rows ``[lo, hi)`` of the host array ``xs`` to the same rows of
+        ``d_in`` on stream ``st``.  Page-locked input is sent from where it
+        lies; anything else is staged through the pinned buffer in slices of
+        STAGE_ROWS rows by the library's copy threads (``pb200_host_copy``),
+        each slice on its way while the next one is staged."""
+        V = ctypes.c_void_p
+        d = xs.shape[1]
+        if pinned:
+            _lib.check(lib.pb200_copy_async(
+                V(self.a_d_in + lo * d * 8), V(xs.ctypes.data + lo * d * 8),
+                (hi - lo) * d * 8, 1, st))
+            return
+        for a in range(lo, hi, self.STAGE_ROWS):
+            b = min(hi, a + self.STAGE_ROWS)
+            _lib.check(lib.pb200_host_copy(
+                V(self.a_h_in + a * d * 8), V(xs.ctypes.data + a * d * 8),
+                (b - a) * d * 8, 0))
+            _lib.check(lib.pb200_copy_async(
+                V(self.a_d_in + a * d * 8), V(self.a_h_in + a * d * 8),
+                (b - a) * d * 8, 1, st))
+
+    @staticmethod
+    def is_pinned(lib, xs):
+        return bool(xs.flags['C_CONTIGUOUS'] and xs.size >= 4096 and
+                    lib.pb200_host_is_pinned(ctypes.c_void_p(xs.ctypes.data)))
+
+    def launch(self, lib, xs, a_scores, a_steps, chunk_rows):
+        """Enqueue copy-in, kernel and copy-out for the rows of ``xs``; the
+        scores (and step counts, if ``a_steps``) go to the page-locked host
+        addresses given.  The batch is cut into at most N_STREAMS compute
+        chunks of ``chunk_rows`` rows or more, one fused launch each on its
+        own stream."""
         m, d = xs.shape
+        want_steps = a_steps is not None
         self.reserve(m, d, want_steps)
         V = ctypes.c_void_p
         n_chunks = max(1, min(len(self.streams), m // max(1, chunk_rows)))
         rows = -(-m // n_chunks)
         self.used = 0
         handle, opts = self.problem._handle, ctypes.byref(self.problem.opts)
-        pinned = bool(xs.flags['C_CONTIGUOUS'] and m * d >= 4096 and
-                      lib.pb200_host_is_pinned(V(xs.ctypes.data)))
-        src = None
-        if not pinned and m * d >= 32768 and torch.get_num_threads() > 1:
-            with warnings.catch_warnings():
-                warnings.simplefilter('ignore')     # read-only arrays from ask()
-                src = torch.from_numpy(xs)
+        pinned = self.is_pinned(lib, xs)
         with torch.cuda.device(self.device):
             for c in range(n_chunks):
                 lo, hi = c * rows, min(m, (c + 1) * rows)
                 if hi <= lo:
                     break
                 st = self.stream_ptrs[c]
-                if pinned:
-                    # page-locked input: sent from where it lies
-                    _lib.check(lib.pb200_copy_async(
-                        V(self.a_d_in + lo * d * 8),
-                        V(xs.ctypes.data + lo * d * 8), (hi - lo) * d * 8, 1, st))
-                else:
-                    # staging copy into pinned memory: torch's copy is
-                    # multi-threaded (11 us for 1.5 MB on 16 cores against
-                    # 85 us for numpy's), slice by slice so that a slice is on
-                    # its way while the next one is staged
-                    for a in range(lo, hi, self.STAGE_ROWS):
-                        b = min(hi, a + self.STAGE_ROWS)
-                        if src is not None:
-                            self.h_in[a:b].copy_(src[a:b])
-                        else:
-                            np.copyto(self.h_in_np[a:b], xs[a:b])
-                        _lib.check(lib.pb200_copy_async(
-                            V(self.a_d_in + a * d * 8),
-                            V(self.a_h_in + a * d * 8), (b - a) * d * 8, 1, st))
+                self.send(lib, xs, lo, hi, st, pinned)
                 ws, ws_bytes = None, 0
                 if self.problem.wants_sort(hi - lo):
                     t = self.problem.sort_workspace(rows, ('chunk', c))
@@ -163,17 +240,25 @@ class _Lane(object):
                     V(self.a_d_steps + lo * 4) if want_steps else None,
                     opts, ws, ws_bytes, st))
                 _lib.check(lib.pb200_copy_async(
-                    V(self.a_h_out + lo * 8), V(self.a_d_out + lo * 8),
+                    V(a_scores + lo * 8), V(self.a_d_out + lo * 8),
                     (hi - lo) * 8, 0, st))
                 if want_steps:
                     _lib.check(lib.pb200_copy_async(
-                        V(self.a_h_steps + lo * 4), V(self.a_d_steps + lo * 4),
+                        V(a_steps + lo * 4), V(self.a_d_steps + lo * 4),
                         (hi - lo) * 4, 0, st))
                 self.used = c + 1
 
     def wait(self):
         for s in self.streams[:self.used]:
             s.synchronize()
+
+
+def pinned_result(n, dtype=torch.float64):
+    """A fresh 1-d array in page-locked host memory from torch's caching host
+    allocator: the device-to-host copy of a result lands in the array that is
+    handed to the caller, with no copy-out; the block goes back to the cache
+    when the caller drops the array."""
+    return torch.empty(n, dtype=dtype, pin_memory=True).numpy()
 
 
 def pinned_empty(shape):
@@ -225,8 +310,11 @@ class CudaEvaluator(Evaluator):
         dynamics share a warp; results do not depend on it): ``True``,
         ``False`` or ``None`` = automatic (on for batches of 1024 rows or more).
     as_list
-        Return a Python list like the reference (default) or, if ``False``, a
-        float64 ndarray (every consumer in the reference accepts either).
+        ``True`` (default): return a :class:`ScoreList`, a list-compatible
+        read-only sequence over the scores as they came back from the GPU
+        (boxed into Python floats lazily; ``.tolist()`` is the plain list);
+        ``'boxed'``: a plain Python ``list`` of floats, exactly the
+        reference's return type; ``False``: a float64 ndarray.
     chunk_rows
         Host batches of several times this many rows are cut into up to four
         compute chunks (one fused launch each, on separate streams), so that
@@ -257,7 +345,7 @@ class CudaEvaluator(Evaluator):
                           block=block, lanes=lanes_per_vector,
                           wide_interpolation=wide_interpolation)
         self._sort = sort
-        self._as_list = bool(as_list)
+        self._as_list = as_list if as_list == 'boxed' else bool(as_list)
         self._chunk_rows = max(1, int(chunk_rows))
         if devices is None or isinstance(devices, (int, str, torch.device)):
             devices = [devices]
@@ -293,14 +381,28 @@ class CudaEvaluator(Evaluator):
             raise ValueError(
                 'The argument `positions` must be a sequence of input values'
                 ' to the evaluator\'s function.')
+        scores, steps = self.finish(self.begin(positions, return_steps))
+        if return_steps:
+            self.last_steps = steps
+            return scores, steps
+        return scores
+
+    def begin(self, positions, return_steps=False):
+        """Enqueues the evaluation of ``positions`` (copy-in, kernels,
+        copy-out) without waiting for it; :meth:`finish` waits and returns the
+        result.  One evaluation may be in flight per evaluator; evaluators of
+        different functions run on streams of their own, so several can be in
+        flight at once."""
         d = self._spec.n_parameters()
         xs = positions_to_array(positions, d)
         n = xs.shape[0]
-        scores = np.empty(n, dtype=np.float64)
-        steps = np.zeros(n, dtype=np.int32) if return_steps else None
         if n == 0:
-            return (scores, steps) if return_steps else scores
-        lanes = self._setup()
+            return (np.empty(0, dtype=np.float64),
+                    np.zeros(0, dtype=np.int32) if return_steps else None, [])
+        lanes = self._setup()          # raises when there is no GPU
+        # results land in page-locked arrays that are handed to the caller
+        scores = pinned_result(n)
+        steps = pinned_result(n, torch.int32) if return_steps else None
         g = len(lanes)
         per = (n + g - 1) // g
         work = []
@@ -308,19 +410,25 @@ class CudaEvaluator(Evaluator):
             lo, hi = k * per, min(n, (k + 1) * per)
             if hi <= lo:
                 continue
-            lane.launch(self._lib, xs[lo:hi], return_steps, self._chunk_rows)
-            work.append((lane, lo, hi))
-        for lane, lo, hi in work:
+            lane.launch(self._lib, xs[lo:hi], scores.ctypes.data + lo * 8,
+                        steps.ctypes.data + lo * 4 if return_steps else None,
+                        self._chunk_rows)
+            work.append(lane)
+        return scores, steps, work
+
+    @staticmethod
+    def finish(pending):
+        scores, steps, work = pending
+        for lane in work:
             lane.wait()
-            m = hi - lo
-            scores[lo:hi] = lane.h_out_np[:m]
-            if return_steps:
-                steps[lo:hi] = lane.h_steps_np[:m]
-        if return_steps:
-            self.last_steps = steps
-            return scores, steps
-        return scores
+        return scores, steps
 
     def _evaluate(self, positions):
-        scores = self.evaluate_array(positions)
-        return scores.tolist() if self._as_list else scores
+        return wrap_scores(self.evaluate_array(positions), self._as_list)
+
+
+def wrap_scores(scores, as_list):
+    """The return type of ``evaluate`` for the ``as_list`` option."""
+    if as_list == 'boxed':
+        return scores.tolist()
+    return ScoreList(scores) if as_list else scores

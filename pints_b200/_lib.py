@@ -21,7 +21,7 @@ MODEL_FHN, MODEL_LOTKA_VOLTERRA, MODEL_SIR = 3, 4, 5
 MODEL_GOODWIN, MODEL_HES1, MODEL_REPRESSILATOR = 6, 7, 8
 MODEL_BEELER_REUTER = 9
 OBJ_SSE, OBJ_GAUSSIAN_KNOWN_SIGMA, OBJ_GAUSSIAN, OBJ_MSE, OBJ_RMSE = 0, 1, 2, 3, 4
-MAX_OUTPUTS, MAX_PARAMS, MAX_EVENTS = 8, 16, 64
+MAX_OUTPUTS, MAX_PARAMS, MAX_EVENTS, MAX_PEERS = 8, 16, 64, 16
 SENTINEL_ROWS = 8
 
 MODEL_NAMES = {MODEL_LOGISTIC: 'logistic', MODEL_HH_IK: 'hh_ik',
@@ -41,6 +41,16 @@ class SolverOpts(Structure):
     _fields_ = [('rtol', c_double), ('atol', c_double), ('h0', c_double),
                 ('max_steps', c_int32), ('block', c_int32),
                 ('lanes', c_int32), ('wide_interpolation', c_int32)]
+
+
+class ExchangeDesc(Structure):
+    """``pb200_exchange_desc``"""
+    _fields_ = [('n_ranks', c_int32), ('rank', c_int32),
+                ('per_rank', c_int64),
+                ('stage', c_void_p * MAX_PEERS),
+                ('flags', c_void_p * MAX_PEERS),
+                ('stage_multicast', c_void_p), ('d_done', c_void_p),
+                ('epoch', c_uint64)]
 
 
 class LibraryError(RuntimeError):
@@ -68,12 +78,15 @@ SIGNATURES = {
     'pb200_sort_workspace_bytes': (c_int64, [c_int64]),
     'pb200_eval_sorted': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                                     POINTER(SolverOpts), _P, c_int64, _P]),
-    'pb200_eval_scatter': (c_int32, [_P, _P, c_int64, c_int64, _P,
-                                     POINTER(SolverOpts), _P, c_int64,
-                                     POINTER(c_void_p), c_int32, c_int64, _P]),
+    'pb200_eval_exchange': (c_int32, [_P, _P, c_int64, c_int64, _P,
+                                      POINTER(SolverOpts), _P, c_int64,
+                                      POINTER(ExchangeDesc), _P]),
+    'pb200_exchange_finish': (c_int32, [POINTER(ExchangeDesc), c_int64,
+                                        c_int64, _P, _P]),
     'pb200_eval_host': (c_int32, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P,
                                   _P, c_int64, POINTER(SolverOpts), _P]),
     'pb200_copy_async': (c_int32, [_P, _P, c_int64, c_int32, _P]),
+    'pb200_host_copy': (c_int32, [_P, _P, c_int64, c_int32]),
     'pb200_host_is_pinned': (c_int32, [_P]),
     'pb200_simulate': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                                  POINTER(SolverOpts), _P]),
@@ -159,5 +172,5 @@ def doubles(values):
     return (c_double * n)(*values), n
 
 
-__all__ = ['load', 'check', 'doubles', 'SolverOpts', 'LibraryError', 'byref',
+__all__ = ['load', 'check', 'doubles', 'SolverOpts', 'ExchangeDesc', 'LibraryError', 'byref',
            'SIGNATURES', 'LIB_PATH']

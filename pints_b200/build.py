@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libpints_b200.so')
 SOURCES = ['pb200_api.cu', 'pb200_ode.cu', 'pb200_analytic.cu',
-           'pb200_samplers.cu', 'pb200_rank.cu']
+           'pb200_samplers.cu', 'pb200_rank.cu', 'pb200_exchange.cu']
 HEADERS = [os.path.join(CSRC, 'pb200_common.cuh'),
            os.path.join(os.path.dirname(HERE), 'include', 'pints_b200.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']

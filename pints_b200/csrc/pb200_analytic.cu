@@ -311,7 +311,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
         if (!TRAJ) {
             double early;
             if (objective_precheck(P, x, &early)) {     // warp-uniform
-                if (lane == 0) put_score(sc, scores, i, early);
+                if (lane == 0) put_score(sc, scores, i, i, early);
                 continue;
             }
         }
@@ -395,10 +395,11 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
 #pragma unroll
             for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
                 if (o < no) ss[o] = warp_sum(ss[o]);
-            if (lane == 0) put_score(sc, scores, i, objective_finish(P, ss, x));
+            if (lane == 0) put_score(sc, scores, i, i, objective_finish(P, ss, x));
         }
         __syncwarp();
     }
+    if (!TRAJ) exchange_signal(sc);
 }
 
 template <class E>

@@ -6,7 +6,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
+#include <pthread.h>
+#include <sched.h>
 #include "pb200_common.cuh"
 
 static thread_local char g_error[512] = "";
@@ -77,6 +85,109 @@ int check_batch(const pb200_problem *p, const void *d_params, int64_t n, int64_t
     }
     return PB200_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Staging copies (pageable host array -> page-locked buffer) cut into slices
+// and done by a few persistent threads of this library, so that their speed
+// does not depend on the host program's OpenMP settings (torchrun starts every
+// rank with OMP_NUM_THREADS=1).  Workers sleep on a condition variable after a
+// short spin; the caller takes the first slice itself.
+class CopyPool {
+public:
+    // never destroyed: the (detached) workers may outlive static destruction
+    static CopyPool &instance() {
+        static CopyPool *pool = [] {
+            CopyPool *p = new CopyPool();
+            pthread_atfork(nullptr, nullptr, [] { instance().forget_workers(); });
+            return p;
+        }();
+        return *pool;
+    }
+    // in a forked child the worker threads do not exist: start over
+    void forget_workers() {
+        workers_ = 0;
+        jobs_.clear();
+        pending_.store(0);
+    }
+    void copy(char *dst, const char *src, size_t bytes, int threads) {
+        int t = threads > 0 ? threads : default_threads_;
+        if (t > kMaxThreads) t = kMaxThreads;
+        const size_t min_slice = 128 * 1024;
+        if (static_cast<size_t>(t) > bytes / min_slice) t = static_cast<int>(bytes / min_slice);
+        if (t <= 1) { memcpy(dst, src, bytes); return; }
+        std::lock_guard<std::mutex> serial(call_mutex_);       // one copy at a time
+        grow(t - 1);
+        const size_t slice = ((bytes + t - 1) / t + 63) & ~size_t(63);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (int w = 0; w < t - 1; ++w) {
+                const size_t lo = static_cast<size_t>(w + 1) * slice;
+                const size_t hi = lo + slice < bytes ? lo + slice : bytes;
+                jobs_[w] = Job{dst + lo, src + lo, lo < bytes ? hi - lo : 0};
+            }
+            for (size_t w = t - 1; w < jobs_.size(); ++w) jobs_[w] = Job{nullptr, nullptr, 0};
+            pending_.store(t - 1, std::memory_order_relaxed);
+            generation_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        memcpy(dst, src, slice < bytes ? slice : bytes);
+        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+
+private:
+    static constexpr int kMaxThreads = 16;
+    struct Job { char *dst; const char *src; size_t bytes; };
+    CopyPool() {
+        int cores = static_cast<int>(std::thread::hardware_concurrency());
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+        int share = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;
+        int t = cores / share / 2;
+        if (const char *e = getenv("PB200_COPY_THREADS")) t = atoi(e);
+        default_threads_ = t < 1 ? 1 : (t > 8 ? 8 : t);
+        jobs_.reserve(kMaxThreads);
+    }
+    void grow(int n) {
+        std::lock_guard<std::mutex> lk(m_);
+        while (workers_ < n) {
+            const int id = workers_++;
+            jobs_.push_back(Job{nullptr, nullptr, 0});
+            const uint64_t seen = generation_.load(std::memory_order_relaxed);
+            std::thread([this, id, seen] { run(id, seen); }).detach();
+        }
+    }
+    void run(int id, uint64_t seen) {
+        for (;;) {
+            // spin for about a millisecond (an evaluate loop calls again within
+            // that time), then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            while (generation_.load(std::memory_order_acquire) == seen) {
+                for (int k = 0; k < 64; ++k) __builtin_ia32_pause();
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(1000)) break;
+            }
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_.load(std::memory_order_acquire) != seen; });
+                seen = generation_.load(std::memory_order_relaxed);
+                job = jobs_[id];
+                jobs_[id].dst = nullptr;
+            }
+            if (job.dst) {
+                if (job.bytes) memcpy(job.dst, job.src, job.bytes);
+                pending_.fetch_sub(1, std::memory_order_release);
+            }
+        }
+    }
+    std::mutex m_, call_mutex_;
+    std::condition_variable cv_;
+    int workers_ = 0;
+    std::vector<Job> jobs_;
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<int> pending_{0};
+    int default_threads_ = 1;
+};
 
 }  // namespace
 
@@ -228,7 +339,7 @@ int eval_impl(const pb200_problem *p, const double *d_params, int64_t n, int64_t
               double *d_scores, int32_t *d_steps, const pb200_solver_opts *opts,
               void *d_sort_ws, int64_t sort_ws_bytes, const ScatterDev &sc, void *stream,
               const char *who) {
-    int rc = check_batch(p, d_params, n, ld, sc.n ? static_cast<const void *>(sc.dst[0]) : d_scores,
+    int rc = check_batch(p, d_params, n, ld, sc.n ? static_cast<const void *>(sc.stage[0]) : d_scores,
                          who);
     if (rc || n == 0) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -256,6 +367,38 @@ int eval_impl(const pb200_problem *p, const double *d_params, int64_t n, int64_t
     return launch_analytic(p, d_params, n, ld, d_scores, nullptr, sc, st);
 }
 const ScatterDev kNoScatter = {};
+
+// checks an exchange descriptor and turns it into the kernels' view of it
+int exchange_scatter(const pb200_exchange_desc *ex, ScatterDev *sc, const char *who) {
+    if (!ex) { pb200_set_error("%s: exchange descriptor is NULL", who); return PB200_EINVAL; }
+    if (ex->n_ranks < 1 || ex->n_ranks > PB200_MAX_PEERS || ex->rank < 0 ||
+        ex->rank >= ex->n_ranks || ex->per_rank < 1 || ex->epoch < 1 || !ex->d_done) {
+        pb200_set_error("%s: needs 1..%d ranks, a rank among them, per_rank >= 1, epoch >= 1 "
+                        "and a d_done word", who, PB200_MAX_PEERS);
+        return PB200_EINVAL;
+    }
+    *sc = ScatterDev{};
+    for (int q = 0; q < ex->n_ranks; ++q) {
+        if (!ex->stage[q] || !ex->flags[q] ||
+            (reinterpret_cast<uintptr_t>(ex->stage[q]) & 15) != 0 ||
+            (reinterpret_cast<uintptr_t>(ex->flags[q]) & 7) != 0) {
+            pb200_set_error("%s: staging / flag array of rank %d is NULL or misaligned", who, q);
+            return PB200_EINVAL;
+        }
+        sc->stage[q] = ex->stage[q];
+        sc->flag[q] = static_cast<unsigned long long *>(ex->flags[q]) + ex->rank;
+    }
+    if ((reinterpret_cast<uintptr_t>(ex->stage_multicast) & 15) != 0) {
+        pb200_set_error("%s: multicast address is misaligned", who);
+        return PB200_EINVAL;
+    }
+    sc->stage_mc = ex->stage_multicast;
+    sc->done = static_cast<unsigned int *>(ex->d_done);
+    sc->n = ex->n_ranks;
+    sc->offset = static_cast<int64_t>(ex->rank) * ex->per_rank;
+    sc->epoch = ex->epoch;
+    return PB200_OK;
+}
 }  // namespace
 
 int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
@@ -265,27 +408,37 @@ int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
                      kNoScatter, stream, "pb200_eval");
 }
 
-int pb200_eval_scatter(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
-                       int32_t *d_steps, const pb200_solver_opts *opts, void *d_sort_ws,
-                       int64_t sort_ws_bytes, void *const *peer_scores, int32_t n_peers,
-                       int64_t offset, void *stream) {
-    if (!peer_scores || n_peers < 1 || n_peers > PB200_MAX_PEERS || offset < 0) {
-        pb200_set_error("pb200_eval_scatter: 1..%d peer arrays and a non-negative offset needed",
-                        PB200_MAX_PEERS);
+int pb200_eval_exchange(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
+                        int32_t *d_steps, const pb200_solver_opts *opts, void *d_sort_ws,
+                        int64_t sort_ws_bytes, const pb200_exchange_desc *ex, void *stream) {
+    ScatterDev sc;
+    int rc = exchange_scatter(ex, &sc, "pb200_eval_exchange");
+    if (rc) return rc;
+    if (n < 0 || n > ex->per_rank) {
+        pb200_set_error("pb200_eval_exchange: n = %lld rows do not fit a block of %lld",
+                        (long long)n, (long long)ex->per_rank);
         return PB200_EINVAL;
     }
-    ScatterDev sc = {};
-    sc.n = n_peers;
-    sc.offset = offset;
-    for (int r = 0; r < n_peers; ++r) {
-        if (!peer_scores[r]) {
-            pb200_set_error("pb200_eval_scatter: peer array %d is NULL", r);
-            return PB200_EINVAL;
-        }
-        sc.dst[r] = static_cast<double *>(peer_scores[r]);
-    }
+    if (n == 0) return launch_exchange_signal(sc, static_cast<cudaStream_t>(stream));
     return eval_impl(p, d_params, n, ld, nullptr, d_steps, opts, d_sort_ws, sort_ws_bytes, sc,
-                     stream, "pb200_eval_scatter");
+                     stream, "pb200_eval_exchange");
+}
+
+int pb200_exchange_finish(const pb200_exchange_desc *ex, int64_t rows_per_rank, int64_t n_total,
+                          double *d_scores_all, void *stream) {
+    ScatterDev sc;
+    int rc = exchange_scatter(ex, &sc, "pb200_exchange_finish");
+    if (rc) return rc;
+    if (rows_per_rank < 1 || rows_per_rank > ex->per_rank || n_total < 0 ||
+        n_total > rows_per_rank * ex->n_ranks || (n_total > 0 && !d_scores_all)) {
+        pb200_set_error("pb200_exchange_finish: %lld scores do not fit %d blocks of %lld rows "
+                        "(staged in blocks of %lld)", (long long)n_total, ex->n_ranks,
+                        (long long)rows_per_rank, (long long)ex->per_rank);
+        return PB200_EINVAL;
+    }
+    return launch_exchange_finish(ex->stage[ex->rank], ex->flags[ex->rank], ex->n_ranks,
+                                  ex->per_rank, rows_per_rank, ex->epoch, n_total, d_scores_all,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,
@@ -342,6 +495,17 @@ int pb200_copy_async(void *dst, const void *src, int64_t bytes, int32_t to_devic
                         to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
                         static_cast<cudaStream_t>(stream)),
         "pb200_copy_async");
+}
+
+int pb200_host_copy(void *dst, const void *src, int64_t bytes, int32_t threads) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) {
+        pb200_set_error("pb200_host_copy: bad arguments");
+        return PB200_EINVAL;
+    }
+    if (bytes == 0) return PB200_OK;
+    CopyPool::instance().copy(static_cast<char *>(dst), static_cast<const char *>(src),
+                              static_cast<size_t>(bytes), threads);
+    return PB200_OK;
 }
 
 int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, int64_t ld,

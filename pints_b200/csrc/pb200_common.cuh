@@ -68,24 +68,77 @@ struct pb200_problem {
     int64_t series_bytes;         // bytes staged into shared memory
 };
 
-// Where a score goes.  n = 0: the caller's d_scores[i].  n > 0: straight into
-// the gathered score arrays of all ranks of a multi-GPU job (this GPU's own
-// and its peers', mapped over NVLink), at row offset + i of each -- the
-// all-gather of the scores happens inside the kernel, store by store, while
-// other vectors are still being integrated.
+// Where a score goes.  n = 0: the caller's d_scores[i].  n > 0: the exchange
+// step of a multi-GPU job is fused into the kernel.  Every rank owns a staging
+// array of 16-byte pairs {score, row} (symmetric memory: each rank's copy is
+// mapped into every process over NVLink) and a vector's score is stored into
+// ALL copies at pair `offset + slot`, where `slot` is the vector's position in
+// the launch order (after the cost sort) and `row` its original row: the lanes
+// of a warp hold 32 consecutive slots, so a warp's stores to one rank are one
+// contiguous 512-byte run (4 NVLink write packets) however the sort has
+// permuted the rows; exchange_finish_kernel on the reading side puts the
+// scores back in row order.  With a multicast mapping of the staging array
+// (NVSwitch replicates the store) one multimem.st per lane replaces the n
+// unicast stores.  When the last block of the launch has stored, it raises
+// this rank's flag on every rank (release at system scope); the reader spins
+// on its local flags (acquire), so there is no separate barrier launch.
 struct ScatterDev {
-    double *dst[PB200_MAX_PEERS];
-    int32_t n;
+    void *stage[PB200_MAX_PEERS];        // rank q's staging array, as mapped in this process
+    unsigned long long *flag[PB200_MAX_PEERS];   // this rank's flag word in rank q's flag array
+    void *stage_mc;                      // multicast address of the staging arrays (or NULL)
+    unsigned int *done;                  // local count of finished blocks (returns to zero)
+    int32_t n;                           // ranks (0 = no exchange)
     int32_t pad;
-    int64_t offset;
+    int64_t offset;                      // first pair of this rank's block
+    unsigned long long epoch;            // generation number written to the flags
 };
 
 __device__ __forceinline__ void put_score(const ScatterDev &sc, double *scores,
-                                          int64_t i, double v) {
+                                          int64_t slot, int64_t i, double v) {
     if (sc.n == 0) {
         scores[i] = v;
+        return;
+    }
+    const int64_t at = (sc.offset + slot) * 16;
+    if (sc.stage_mc) {
+        const long long ib = static_cast<long long>(i);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(static_cast<char *>(sc.stage_mc) + at),
+                     "f"(__int_as_float(__double2loint(v))), "f"(__int_as_float(__double2hiint(v))),
+                     "f"(__int_as_float(static_cast<int>(ib & 0xffffffffll))),
+                     "f"(__int_as_float(static_cast<int>(ib >> 32)))
+                     : "memory");
     } else {
-        for (int r = 0; r < sc.n; ++r) sc.dst[r][sc.offset + i] = v;
+        const double2 pair = make_double2(v, __longlong_as_double(i));
+        for (int r = 0; r < sc.n; ++r)
+            *reinterpret_cast<double2 *>(static_cast<char *>(sc.stage[r]) + at) = pair;
+    }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// End of a kernel that stored scores through put_score with sc.n > 0; every
+// thread of the block must reach it (none may have exited).  The block
+// barrier orders all stores of the block before thread 0's system-scope
+// fence; the block that finds itself last raises the flags.
+__device__ __forceinline__ void exchange_signal(const ScatterDev &sc) {
+    if (sc.n == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(sc.done, 1u) == total - 1u) {
+            *sc.done = 0u;                               // ready for the next launch
+            __threadfence_system();
+            for (int r = 0; r < sc.n; ++r) st_release_sys(sc.flag[r], sc.epoch);
+        }
     }
 }
 
@@ -238,5 +291,9 @@ int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
 int launch_score_traj(const pb200_problem *p, const double *d_traj,
                       const double *d_params, int64_t n, int64_t ld,
                       double *d_scores, cudaStream_t st);
+int launch_exchange_signal(const ScatterDev &sc, cudaStream_t st);
+int launch_exchange_finish(const void *stage, const void *flags, int n_ranks, int64_t per_rank,
+                           int64_t rows_per_rank, unsigned long long epoch, int64_t n_total,
+                           double *d_scores_all, cudaStream_t st);
 void pb200_set_error(const char *fmt, ...);
 int pb200_check_cuda(cudaError_t e, const char *what);

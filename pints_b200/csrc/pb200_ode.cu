@@ -811,7 +811,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         double early;
         if (objective_precheck(P, x, &early)) {
             if (live && !is_receiver) {
-                put_score(sc, scores, i, early);
+                put_score(sc, scores, slot, i, early);
                 if (steps_out) steps_out[i] = 0;
             }
             idle = true;
@@ -963,9 +963,12 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         const bool fin = (off >= end) || failed;
         if (__all_sync(FULL, fin)) break;
         if (is_source && __any_sync(FULL, off >= mig.off_mid)) break;
-        // an attempt is counted while the solution has not reached the last
-        // observation; the iteration after that only empties the pending interval
-        if (!fin && t < t_last) {
+        // an attempt counts (and may fail the vector) only while the solution
+        // has not reached the last observation; a lane that has consumed all its
+        // observations is frozen (its attempts are forced to "rejected", so t, y
+        // and h stay put while the slowest lane of the warp finishes)
+        const bool working = !fin && t < t_last;
+        if (working) {
             if (attempts >= max_steps) failed = true;
             else ++attempts;
         }
@@ -1022,8 +1025,8 @@ ode_kernel(const __grid_constant__ ProblemDev P,
             sum2 = j == 0 ? q * q : fma(q, q, sum2);
         }
         // accepted iff mean square <= 1; NaN compares as "rejected"
-        const bool ok = static_cast<uint64_t>(__double_as_longlong(sum2)) <=
-                        static_cast<uint64_t>(__double_as_longlong(static_cast<double>(NS)));
+        const bool ok = !fin && static_cast<uint64_t>(__double_as_longlong(sum2)) <=
+                                    static_cast<uint64_t>(__double_as_longlong(static_cast<double>(NS)));
         // no growth on the step right after a rejection, none on a rejection
 #if PB200_CTRL_BITS
         const double facd = step_factor_bits<NS>(sum2, !ok || after_reject);
@@ -1100,7 +1103,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         }
         model.scale(h);
         // step size underflow: give up on this vector
-        if (!ok && __double2hiint(h) < __double2hiint(h_min)) failed = true;
+        if (working && !ok && __double2hiint(h) < __double2hiint(h_min)) failed = true;
     }
 
     if (is_source) {
@@ -1124,20 +1127,20 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         mig_w[64] = (failed ? 1u : 0u) | (after_reject ? 2u : 0u);
         __threadfence_block();
         asm volatile("bar.arrive %0, 64;" ::"r"(1 + mig_j) : "memory");
-        return;
-    }
-
-    if (idle) return;
-    if (steps_out) steps_out[i] = attempts;
-    if (TRAJ) {
-        if (failed) {
-            const int64_t first = static_cast<int64_t>(off / ROWB) * NO;
-            const int64_t total = static_cast<int64_t>(nt) * NO;
-            for (int64_t q = first; q < total; ++q) my_traj[q] = NAN;
+    } else if (!idle) {
+        if (steps_out) steps_out[i] = attempts;
+        if (TRAJ) {
+            if (failed) {
+                const int64_t first = static_cast<int64_t>(off / ROWB) * NO;
+                const int64_t total = static_cast<int64_t>(nt) * NO;
+                for (int64_t q = first; q < total; ++q) my_traj[q] = NAN;
+            }
+        } else {
+            put_score(sc, scores, slot, i, failed ? NAN : objective_finish(P, ss, x));
         }
-    } else {
-        put_score(sc, scores, i, failed ? NAN : objective_finish(P, ss, x));
     }
+    // multi-GPU launches: the last block to get here raises this rank's flags
+    if (!TRAJ) exchange_signal(sc);
 }
 
 // ======================================================================
@@ -1243,7 +1246,7 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
         double early;
         if (objective_precheck(P, x, &early)) {
             if (live && s == 0) {
-                put_score(sc, scores, i, early);
+                put_score(sc, scores, slot, i, early);
                 if (steps_out) steps_out[i] = 0;
             }
             idle = true;
@@ -1324,7 +1327,12 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
     for (;;) {
         const bool fin = (off >= end) || failed;
         if (__all_sync(FULL, fin)) break;
-        if (!fin && t < t_last) {
+        // an attempt counts (and may fail the vector) only while the solution
+        // has not reached the last observation; a lane that has consumed all its
+        // observations is frozen (its attempts are forced to "rejected", so t, y
+        // and h stay put while the slowest lane of the warp finishes)
+        const bool working = !fin && t < t_last;
+        if (working) {
             if (attempts >= max_steps) failed = true;
             else ++attempts;
         }
@@ -1371,8 +1379,8 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
         const double q = e * rcp_seed(sc);
         const double q2 = q * q;
         const double sum2 = q2 + pair_other(q2);          // commutative: same bits in both lanes
-        const bool ok = static_cast<uint64_t>(__double_as_longlong(sum2)) <=
-                        static_cast<uint64_t>(__double_as_longlong(2.0));
+        const bool ok = !fin && static_cast<uint64_t>(__double_as_longlong(sum2)) <=
+                                    static_cast<uint64_t>(__double_as_longlong(2.0));
 #if PB200_CTRL_BITS
         const double facd = step_factor_bits<2>(sum2, !ok || after_reject);
 #else
@@ -1402,12 +1410,13 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
         K1 = (ok ? K7 : K1) * facd;
 #pragma unroll
         for (int k = 0; k < NC; ++k) C[k] *= facd;
-        if (!ok && __double2hiint(h) < __double2hiint(h_min)) failed = true;
+        if (working && !ok && __double2hiint(h) < __double2hiint(h_min)) failed = true;
     }
 
     const double ss_other = pair_other(ss);
-    if (idle) return;
-    if (TRAJ) {
+    if (idle) {
+        // decided before the solve, or past the end of the population
+    } else if (TRAJ) {
         if (failed) {
             for (uint32_t row = off; row < end; row += ROWB) my_traj[row / ROWB * NO] = NAN;
         }
@@ -1415,8 +1424,9 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
     } else if (s == 0) {
         if (steps_out) steps_out[i] = attempts;
         const double both[2] = {ss, ss_other};
-        put_score(sc, scores, i, failed ? NAN : objective_finish(P, both, x));
+        put_score(sc, scores, slot, i, failed ? NAN : objective_finish(P, both, x));
     }
+    if (!TRAJ) exchange_signal(sc);
 }
 
 // ======================================================================

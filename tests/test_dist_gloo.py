@@ -61,8 +61,8 @@ def _worker(rank, world, port, n, out):
         xs = np.array([0.1, 50]) * (1 + 0.1 * rng.randn(n, 2))
         got = ev.evaluate(xs)
         want = po.scores(spec, xs)
-        ok = isinstance(got, list) and len(got) == n and \
-            np.array_equal(np.array(got), want)
+        ok = isinstance(got, pb.ScoreList) and len(got) == n and \
+            np.array_equal(np.array(got), want) and got.tolist() == list(want)
         # list-of-arrays input and an empty batch
         ok = ok and ev.evaluate([x for x in xs]) == got
         ok = ok and ev.evaluate([]) == []
@@ -105,7 +105,8 @@ def _exchange_worker(rank, world, port, out):
             n_mine = per if rank == 0 else 3   # ragged last block
             x = torch.arange(n_mine, dtype=torch.float64).reshape(-1, 1) \
                 + 100.0 * rank + 1000.0 * gen
-            every = ex.run(FakeProblem(), x.repeat(1, 2))
+            every = ex.run(FakeProblem(), x.repeat(1, 2), n_total=per + 3)
+            ok = ok and every.shape[0] == per + 3
             want0 = torch.arange(per, dtype=torch.float64) + 1000.0 * gen
             want1 = torch.arange(3, dtype=torch.float64) + 100.0 + 1000.0 * gen
             ok = ok and torch.equal(every[:per], want0)
