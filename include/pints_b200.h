@@ -79,10 +79,12 @@ typedef struct pb200_problem pb200_problem;
 
 /* Adaptive Dormand-Prince 5(4) controls for the ODE models.  The reference
  * integrates with scipy's LSODA at rtol = atol = 1.49012e-8
- * (pints/toy/_toy_classes.py:225-233); the defaults here match that. */
+ * (pints/toy/_toy_classes.py:225-233); the defaults here match that, except
+ * for Lotka-Volterra (5e-9), whose benchmark log-likelihood needs it to stay
+ * within 1e-6 of a converged solve (pb200_api.cu: default_tolerance). */
 typedef struct pb200_solver_opts {
-    double  rtol;        /* <= 0 -> 1.49012e-8                               */
-    double  atol;        /* <= 0 -> 1.49012e-8                               */
+    double  rtol;        /* <= 0 -> the model's default (1.49012e-8; LV 5e-9) */
+    double  atol;        /* <= 0 -> the same                                  */
     double  h0;          /* first step; <= 0 -> automatic                    */
     int32_t max_steps;   /* attempted steps per vector; <= 0 -> 1000000.     */
                          /* A vector that exceeds it scores NaN.             */
@@ -222,23 +224,25 @@ int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
  * pairs, i.e. one contiguous 512-byte run per destination, not 32 scattered
  * 8-byte stores -- or, when stage_multicast is given (a multicast mapping of
  * the staging arrays: NVSwitch replicates the store), with one multimem.st per
- * vector.  The last block of the launch then writes `epoch` into this rank's
- * slot of every rank's flag array (release, system scope); with n = 0 a
- * one-thread kernel only raises the flags.  There is no barrier launch.
+ * vector.  Every block of the launch, once its scores are stored, adds its
+ * share of 2^20 to this rank's counter in every rank's flag array (one
+ * system-scope fence, then relaxed remote atomics; the shares of one launch
+ * sum to exactly 2^20 whatever the grid); with n = 0 a one-thread kernel adds
+ * the whole 2^20.  There is no barrier launch.
  *
  * pb200_exchange_finish (the reading side, same stream, after the call above)
- * waits until all n_ranks local flags have reached `epoch` (acquire; it traps
- * after 30 s without progress rather than hang the GPU) and writes the
- * n_total scores of the whole population in row order to d_scores_all, where
- * rank r scored the rows [r * rows_per_rank, min(n_total, (r + 1) *
+ * waits until all n_ranks local counters have reached epoch * 2^20 (acquire;
+ * it traps after 30 s without progress rather than hang the GPU) and writes
+ * the n_total scores of the whole population in row order to d_scores_all,
+ * where rank r scored the rows [r * rows_per_rank, min(n_total, (r + 1) *
  * rows_per_rank)) (rows_per_rank <= per_rank: the blocks of this generation
  * may be shorter than the staging blocks).
  *
- * Use epoch = 1, 2, 3, ... and alternate between TWO staging arrays (one flag
- * array serves both): a rank can then run at most one generation ahead of the
- * slowest reader, which is still on the other array.  d_done is a device word
- * owned by the caller, zero before the first call (the kernel returns it to
- * zero).  d_sort_ws as in pb200_eval_sorted (NULL = no sorting).
+ * Use epoch = 1, 2, 3, ... -- every rank takes part in every generation -- and
+ * alternate between TWO staging arrays (one flag array serves both): a rank
+ * can then run at most one generation ahead of the slowest reader, which is
+ * still on the other array.  d_sort_ws as in pb200_eval_sorted (NULL = no
+ * sorting).
  */
 typedef struct pb200_exchange_desc {
     int32_t  n_ranks;                    /* 1 .. PB200_MAX_PEERS                */
@@ -249,7 +253,6 @@ typedef struct pb200_exchange_desc {
     void    *flags[PB200_MAX_PEERS];     /* rank q's flag array, as mapped here */
     void    *stage_multicast;            /* multicast address of the staging
                                             arrays, or NULL                     */
-    void    *d_done;                     /* uint32 on this device               */
     uint64_t epoch;                      /* generation number, >= 1, increasing */
 } pb200_exchange_desc;
 

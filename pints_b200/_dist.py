@@ -113,7 +113,6 @@ class ScoreExchange(object):
                 mc = 0
         self._mc_ptrs = [mc + k * pairs * 16 if mc else 0 for k in (0, 1)]
         self.multicast = bool(mc)
-        self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._every = torch.empty(pairs, dtype=torch.float64,
                                   device=self.device)
         self.fused = True
@@ -125,7 +124,6 @@ class ScoreExchange(object):
             d.stage[q] = self._stage_ptrs[k][q]
             d.flags[q] = self._flag_ptrs[q]
         d.stage_multicast = self._mc_ptrs[k] or None
-        d.d_done = self._done.data_ptr()
         d.epoch = self._epoch
         return d
 

@@ -72,8 +72,10 @@ def capture_graph(device, enqueue):
 
 def solver_opts(rtol=None, atol=None, h0=None, max_steps=None, block=None,
                 lanes=None, wide_interpolation=None):
+    # 0 = the model's default (1.49012e-8; Lotka-Volterra 5e-9), chosen by the
+    # library (pb200_api.cu: default_tolerance)
     return _lib.SolverOpts(
-        rtol if rtol else DEFAULT_RTOL, atol if atol else DEFAULT_ATOL,
+        rtol if rtol else 0.0, atol if atol else 0.0,
         h0 if h0 else 0.0, int(max_steps) if max_steps else 0,
         int(block) if block else 0, int(lanes) if lanes else 0,
         0 if wide_interpolation is None else (1 if wide_interpolation else -1))

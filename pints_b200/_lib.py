@@ -49,8 +49,7 @@ class ExchangeDesc(Structure):
                 ('per_rank', c_int64),
                 ('stage', c_void_p * MAX_PEERS),
                 ('flags', c_void_p * MAX_PEERS),
-                ('stage_multicast', c_void_p), ('d_done', c_void_p),
-                ('epoch', c_uint64)]
+                ('stage_multicast', c_void_p), ('epoch', c_uint64)]
 
 
 class LibraryError(RuntimeError):

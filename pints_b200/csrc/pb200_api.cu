@@ -54,10 +54,22 @@ const ModelInfo kModels[PB200_N_MODELS] = {
     /* BEELER_REUTER  */ {5, 2, 13, true},
 };
 
-SolverDev resolve_opts(const pb200_solver_opts *o, int *block, int *lanes) {
+// Default tolerance of a model.  The reference integrates everything with
+// scipy odeint's rtol = atol = 1.49012e-8 (pints/toy/_toy_classes.py:225-233)
+// and DP5(4) is run at the same value -- except Lotka-Volterra: its benchmark
+// likelihood (sigma = 0.1, 1000 points) turns a trajectory error of 1e-7 into a
+// log-likelihood error of 1.2e-6 at that tolerance (LSODA itself: 1.9e-5), and
+// the error is proportional to the tolerance (sweep in
+// profiles/r02_lv_tolerance.md), so its default is 5e-9: 3.8e-7, inside the
+// 1e-6 bar with margin, for 23 % more steps.
+double default_tolerance(int model) {
+    return model == PB200_MODEL_LOTKA_VOLTERRA ? 5e-9 : 1.49012e-8;
+}
+
+SolverDev resolve_opts(const pb200_solver_opts *o, int model, int *block, int *lanes) {
     SolverDev s;
-    s.rtol = (o && o->rtol > 0) ? o->rtol : 1.49012e-8;
-    s.atol = (o && o->atol > 0) ? o->atol : 1.49012e-8;
+    s.rtol = (o && o->rtol > 0) ? o->rtol : default_tolerance(model);
+    s.atol = (o && o->atol > 0) ? o->atol : default_tolerance(model);
     s.half_rtol = 0.5 * s.rtol;
     s.h0 = (o && o->h0 > 0) ? o->h0 : 0.0;
     s.max_steps = (o && o->max_steps > 0) ? o->max_steps : 1000000;
@@ -345,7 +357,7 @@ int eval_impl(const pb200_problem *p, const double *d_params, int64_t n, int64_t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kModels[p->dev.model].ode) {
         int block, lanes;
-        SolverDev s = resolve_opts(opts, &block, &lanes);
+        SolverDev s = resolve_opts(opts, p->dev.model, &block, &lanes);
         if (d_sort_ws) {
             if (sort_ws_bytes < ode_sort_workspace_bytes(n) ||
                 (reinterpret_cast<uintptr_t>(d_sort_ws) & 15) != 0) {
@@ -372,9 +384,9 @@ const ScatterDev kNoScatter = {};
 int exchange_scatter(const pb200_exchange_desc *ex, ScatterDev *sc, const char *who) {
     if (!ex) { pb200_set_error("%s: exchange descriptor is NULL", who); return PB200_EINVAL; }
     if (ex->n_ranks < 1 || ex->n_ranks > PB200_MAX_PEERS || ex->rank < 0 ||
-        ex->rank >= ex->n_ranks || ex->per_rank < 1 || ex->epoch < 1 || !ex->d_done) {
-        pb200_set_error("%s: needs 1..%d ranks, a rank among them, per_rank >= 1, epoch >= 1 "
-                        "and a d_done word", who, PB200_MAX_PEERS);
+        ex->rank >= ex->n_ranks || ex->per_rank < 1 || ex->epoch < 1) {
+        pb200_set_error("%s: needs 1..%d ranks, a rank among them, per_rank >= 1 and "
+                        "epoch >= 1", who, PB200_MAX_PEERS);
         return PB200_EINVAL;
     }
     *sc = ScatterDev{};
@@ -393,10 +405,8 @@ int exchange_scatter(const pb200_exchange_desc *ex, ScatterDev *sc, const char *
         return PB200_EINVAL;
     }
     sc->stage_mc = ex->stage_multicast;
-    sc->done = static_cast<unsigned int *>(ex->d_done);
     sc->n = ex->n_ranks;
     sc->offset = static_cast<int64_t>(ex->rank) * ex->per_rank;
-    sc->epoch = ex->epoch;
     return PB200_OK;
 }
 }  // namespace
@@ -516,7 +526,7 @@ int pb200_simulate(const pb200_problem *p, const double *d_params, int64_t n, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kModels[p->dev.model].ode) {
         int block, lanes;
-        SolverDev s = resolve_opts(opts, &block, &lanes);
+        SolverDev s = resolve_opts(opts, p->dev.model, &block, &lanes);
         return launch_ode(p, d_params, n, ld, nullptr, d_traj, d_steps, s, block, lanes, nullptr,
                           ScatterDev{}, st);
     }

@@ -79,18 +79,20 @@ struct pb200_problem {
 // permuted the rows; exchange_finish_kernel on the reading side puts the
 // scores back in row order.  With a multicast mapping of the staging array
 // (NVSwitch replicates the store) one multimem.st per lane replaces the n
-// unicast stores.  When the last block of the launch has stored, it raises
-// this rank's flag on every rank (release at system scope); the reader spins
-// on its local flags (acquire), so there is no separate barrier launch.
+// unicast stores.  A block that has stored all its scores adds its share of
+// EXCHANGE_UNIT to this rank's counter on every rank (one system-scope fence,
+// then relaxed remote atomics: the shares of a launch add up to exactly
+// EXCHANGE_UNIT whatever the grid size); the reader spins (acquire) until the
+// counters of all ranks have reached epoch * EXCHANGE_UNIT, so there is no
+// barrier launch and no block waits for another one.
+#define PB200_EXCHANGE_UNIT_LOG2 20
 struct ScatterDev {
     void *stage[PB200_MAX_PEERS];        // rank q's staging array, as mapped in this process
-    unsigned long long *flag[PB200_MAX_PEERS];   // this rank's flag word in rank q's flag array
+    unsigned long long *flag[PB200_MAX_PEERS];   // this rank's counter in rank q's flag array
     void *stage_mc;                      // multicast address of the staging arrays (or NULL)
-    unsigned int *done;                  // local count of finished blocks (returns to zero)
     int32_t n;                           // ranks (0 = no exchange)
     int32_t pad;
     int64_t offset;                      // first pair of this rank's block
-    unsigned long long epoch;            // generation number written to the flags
 };
 
 __device__ __forceinline__ void put_score(const ScatterDev &sc, double *scores,
@@ -115,8 +117,8 @@ __device__ __forceinline__ void put_score(const ScatterDev &sc, double *scores,
     }
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void red_add_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
@@ -127,18 +129,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // End of a kernel that stored scores through put_score with sc.n > 0; every
 // thread of the block must reach it (none may have exited).  The block
 // barrier orders all stores of the block before thread 0's system-scope
-// fence; the block that finds itself last raises the flags.
+// fence (one fence for all destinations; a st.release per destination would
+// serialise one fence each), then the block's share goes to every rank.
 __device__ __forceinline__ void exchange_signal(const ScatterDev &sc) {
     if (sc.n == 0) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-        if (atomicAdd(sc.done, 1u) == total - 1u) {
-            *sc.done = 0u;                               // ready for the next launch
-            __threadfence_system();
-            for (int r = 0; r < sc.n; ++r) st_release_sys(sc.flag[r], sc.epoch);
-        }
+        const unsigned long long blocks = gridDim.x, b = blockIdx.x;
+        const unsigned long long share = (((b + 1) << PB200_EXCHANGE_UNIT_LOG2) / blocks) -
+                                         ((b << PB200_EXCHANGE_UNIT_LOG2) / blocks);
+        for (int r = 0; r < sc.n; ++r) red_add_relaxed_sys(sc.flag[r], share);
     }
 }
 

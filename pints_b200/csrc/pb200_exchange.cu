@@ -18,8 +18,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// flags[q] >= epoch: rank q has stored the whole of its block for this
-// generation (and everything before its release is visible after the acquire).
+// flags[q] >= epoch * EXCHANGE_UNIT: every block of rank q's launch of this
+// generation has added its share, i.e. rank q has stored the whole of its block
+// (and everything before the blocks' fences is visible after the acquire).
 // One thread per rank spins; the block barrier hands the visibility on to the
 // other threads, which read the pairs through L2 (ld.global.cg: the lines were
 // written by peers, never cached in this SM's L1).
@@ -30,7 +31,8 @@ exchange_finish_kernel(const double2 *__restrict__ stage,
                        int64_t n_total, double *__restrict__ out) {
     if (threadIdx.x < n_ranks) {
         const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+        const unsigned long long target = epoch << PB200_EXCHANGE_UNIT_LOG2;
+        while (ld_acquire_sys(flags + threadIdx.x) < target) {
             if (global_timer_ns() - t0 > 30000000000ull) __trap();   // a peer died
             __nanosleep(64);
         }
@@ -52,7 +54,8 @@ exchange_finish_kernel(const double2 *__restrict__ stage,
 // a rank without rows still tells everybody that it has reached this generation
 __global__ void exchange_signal_kernel(const ScatterDev sc) {
     __threadfence_system();
-    for (int r = 0; r < sc.n; ++r) st_release_sys(sc.flag[r], sc.epoch);
+    for (int r = 0; r < sc.n; ++r)
+        red_add_relaxed_sys(sc.flag[r], 1ull << PB200_EXCHANGE_UNIT_LOG2);
 }
 
 }  // namespace

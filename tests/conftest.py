@@ -13,7 +13,14 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 # Make the real reference importable (when it is mounted) BEFORE pints_b200 is
 # imported, so the mirror classes pick up the reference's base classes.  Set
 # PINTS_B200_NO_PINTS=1 to run the suite as on the GPU box (no reference).
-_REF = os.environ.get('PINTS_REFERENCE', '/root/reference')
+# The unmodified reference is installed into the git-ignored baseline/_ref by
+# __graft_entry__.build() and travels to the GPU box with the snapshot;
+# /root/reference (build container only) is the second choice.
+_REF = os.environ.get('PINTS_REFERENCE')
+if _REF is None:
+    _REF = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(_REF, 'pints')):
+        _REF = '/root/reference'
 if os.environ.get('PINTS_B200_NO_PINTS') != '1' and \
         os.path.isdir(os.path.join(_REF, 'pints')) and _REF not in sys.path:
     sys.path.append(_REF)
@@ -24,7 +31,7 @@ def pytest_configure(config):
     config.addinivalue_line(
         'markers', 'gpu: needs a CUDA device (run with -m gpu on a B200)')
     config.addinivalue_line(
-        'markers', 'reference: needs the real reference at /root/reference')
+        'markers', 'reference: needs the real reference (baseline/_ref)')
 
 
 def load_golden(name):

@@ -260,14 +260,17 @@ def test_lotka_volterra(pb):
     problem = pb.MultiOutputProblem(model, g['times'], g['values'])
     f = pb.GaussianLogLikelihood(problem)
     got = evaluate(pb, f, g['xs'])
-    # sigma = 0.1 amplifies trajectory error: at the matched tolerance the
-    # device is within 2e-6 of the truth (reference: 1.9e-5) ...
-    check_ode_scores(got, g['scores'], g['truth_scores'], truth_rtol=2e-6)
+    # sigma = 0.1 amplifies trajectory error (the reference's LSODA is 1.9e-5
+    # from the truth here); the default call -- Lotka-Volterra's default
+    # tolerance is 5e-9, see default_tolerance() in pb200_api.cu -- is within
+    # 1e-6 of the truth, with margin
+    check_ode_scores(got, g['scores'], g['truth_scores'])
+    assert np.max(rel_err(got, g['truth_scores'])) < 5e-7
     assert np.max(rel_err(got, g['truth_scores'])) < \
         0.1 * np.max(rel_err(g['scores'], g['truth_scores']))
-    # ... and within 1e-6 once the tolerance is tightened to 5e-9
+    # the default is what an explicit 5e-9 gives
     tight = evaluate(pb, f, g['xs'], rtol=5e-9, atol=5e-9)
-    check_ode_scores(tight, g['scores'], g['truth_scores'])
+    assert np.array_equal(tight, got)
     # the 21-point hare/lynx series on log scale
     problem = pb.MultiOutputProblem(model, model.suggested_times(),
                                     np.log(model.suggested_values()))
@@ -414,7 +417,7 @@ def test_mean_squared_and_root_mean_squared_errors(pb):
         pb.MeanSquaredError(fproblem, [1.0])
     # inside ProbabilityBasedError-free minimisation they are plain errors:
     # the sign stays +1 and the evaluator returns them as they are
-    ev = pb.CudaEvaluator(pb.RootMeanSquaredError(problem), as_list=True)
+    ev = pb.CudaEvaluator(pb.RootMeanSquaredError(problem), as_list='boxed')
     out = ev.evaluate(g['xs'][:4])
     assert isinstance(out, list) and np.allclose(out, g['rmse'][:4], rtol=1e-12)
 
@@ -786,7 +789,10 @@ def test_edge_cases(pb):
     ev = pb.CudaEvaluator(ll)
     assert ev.evaluate([]) == []
     one = ev.evaluate([g['xs'][0]])
-    assert isinstance(one, list) and len(one) == 1
+    assert isinstance(one, pb.ScoreList) and len(one) == 1
+    assert isinstance(one[0], float) and one.tolist() == [one[0]]
+    boxed = pb.CudaEvaluator(ll, as_list='boxed').evaluate([g['xs'][0]])
+    assert type(boxed) is list and boxed == one
     assert abs(one[0] - g['scores'][0]) < 1e-6 * abs(g['scores'][0])
     assert ll(g['xs'][0]) == one[0]                 # scalar __call__
     # list of 1-d arrays, as MCMCController passes (pints/_mcmc/__init__.py:718)

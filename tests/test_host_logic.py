@@ -357,3 +357,80 @@ def test_device_xnes_host_side_contract():
     with pytest.raises(ValueError):
         pb.CudaOptimisationController(pb.SumOfSquaresError(problem),
                                       [0.1, 10.0], method=pb.XNES, sharded=True)
+
+
+def test_score_list_serves_every_consumer_of_the_reference():
+    """What the reference does with the list an evaluator returns (SURVEY.md
+    section 8b): len, indexing, iteration, np.argsort, np.array, assignment
+    into a padded array, comparison -- on the lazy ScoreList."""
+    from pints_b200 import ScoreList
+    a = np.array([3.5, -1.0, np.inf, 2.25, np.nan])
+    fs = ScoreList(a)
+    plain = a.tolist()
+    assert len(fs) == 5 and fs[1] == -1.0 and type(fs[1]) is float
+    assert fs[-1] != fs[-1]                                     # nan
+    assert isinstance(fs[1:3], ScoreList) and fs[1:3] == plain[1:3]
+    assert list(fs)[:4] == plain[:4] and fs.tolist()[:4] == plain[:4]
+    it = iter(fs)                                # pints/_mcmc/__init__.py:733-735
+    assert next(it) == 3.5 and next(it) == -1.0
+    assert np.array_equal(np.argsort(fs), np.argsort(a))        # _xnes.py:160
+    order = np.argsort(fs)
+    assert fs[order[0]] == -1.0                                 # _xnes.py:177
+    full = np.ones(8) * np.inf                                  # _xnes.py:154-157
+    full[[0, 2, 4, 6, 7]] = fs
+    assert full[2] == -1.0 and full[1] == np.inf
+    arr = np.array(fs)                           # _differential_evolution.py:290
+    assert arr.dtype == np.float64 and arr[3] == 2.25
+    arr[0] = 0.0
+    assert fs[0] == 3.5                          # np.array copies
+    assert np.asarray(fs, dtype=np.float32).dtype == np.float32
+    assert fs == plain and fs == a and not (fs != plain)
+    assert fs == ScoreList(a.copy()) and not (fs == plain[:4])
+    assert ScoreList(np.empty(0)) == [] and not (ScoreList(np.empty(0)) == [1.0])
+    assert fs[:4] + [1.0] == plain[:4] + [1.0]
+    assert [1.0] + fs[:4] == [1.0] + plain[:4]
+    assert min(fs[:4]) == -1.0 and max(fs[:2]) == 3.5
+    assert sorted(fs[:4]) == sorted(plain[:4])
+    assert 2.25 in fs and fs.index(2.25) == 3 and fs.count(3.5) == 1
+    assert list(reversed(fs[:4])) == plain[:4][::-1]
+    assert repr(fs[:2]) == repr(plain[:2])
+    assert float(fs[0]) == 3.5 and -fs[1] == 1.0
+    with pytest.raises(IndexError):
+        fs[7]
+    with pytest.raises(TypeError):
+        hash(fs)
+    # the real consumers, when the reference is importable
+    pints = conftest_reference()
+    if pints is not None:
+        np.random.seed(1)
+        opt = pints.XNES([1.0, 1.0], 0.5, pints.RectangularBoundaries([0, 0], [2, 2]))
+        for _ in range(3):
+            xs = opt.ask()
+            opt.tell(ScoreList(np.sum((np.asarray(xs) - 1.2) ** 2, axis=1)))
+        assert np.isfinite(opt.f_best())
+        de = pints.DifferentialEvolutionMCMC(4, [np.array([0.1, 0.2])] * 4)
+        xs = de.ask()
+        de.tell(ScoreList(-np.sum(np.asarray(xs) ** 2, axis=1)))
+        xs = de.ask()
+        assert de.tell(ScoreList(-np.sum(np.asarray(xs) ** 2, axis=1))) is not None
+
+
+def conftest_reference():
+    from conftest import reference_pints
+    return reference_pints()
+
+
+def test_host_copy_threads_copy_exactly():
+    lib = _lib.load()
+    import ctypes
+    rng = np.random.RandomState(3)
+    for n in (0, 1, 1000, 65536 * 3 + 5):
+        a = rng.rand(n)
+        b = np.zeros(n)
+        for threads in (0, 1, 3, 8):
+            b[:] = 0
+            assert lib.pb200_host_copy(ctypes.c_void_p(b.ctypes.data),
+                                       ctypes.c_void_p(a.ctypes.data),
+                                       a.nbytes, threads) == 0
+            assert np.array_equal(a, b)
+    assert lib.pb200_host_copy(None, None, 8, 1) != 0
