@@ -451,15 +451,34 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
 }
 
 // ---- unfused baseline, second half: objective from stored trajectories ----
-__global__ void __launch_bounds__(WARPS * 32)
+// A streaming kernel: it reads N * n_t * n_o doubles once and writes N scores,
+// so HBM bandwidth bounds it.  One warp per trajectory; the observed series is
+// staged in shared memory (bulk copy, once per persistent block); the lanes
+// sweep the trajectory with 16-byte streaming loads, four in flight per lane
+// (2 KB per warp and trip), so that a resident SM keeps > 100 KB on its way.
+// VEC = 2: two outputs, a double2 is one time point; VEC = 1: one output, a
+// double2 is two time points; VEC = 0: any layout, scalar loads.
+constexpr int ST_WARPS = 8;
+
+template <int VEC>
+__global__ void __launch_bounds__(ST_WARPS * 32)
 score_traj_kernel(const __grid_constant__ ProblemDev P, const double *__restrict__ traj,
                   const double *__restrict__ params, int64_t n, int64_t ld,
-                  double *__restrict__ scores) {
+                  double *__restrict__ scores, int staged) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int row = P.row, no = P.n_outputs, nt = P.n_times;
-    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * WARPS;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * WARPS + warp; i < n;
+    const double *series = P.series;
+    if (staged) {
+        const uint32_t bytes = static_cast<uint32_t>(
+            ((static_cast<int64_t>(nt) + PB200_SENTINEL_ROWS) * row * 8 + 15) & ~15ll);
+        stage_series(smem, P.series, bytes, &bar);
+        series = smem;
+    }
+    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * ST_WARPS;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * ST_WARPS + warp; i < n;
          i += warps_total) {
         double x[PB200_MAX_PARAMS];
 #pragma unroll
@@ -474,15 +493,64 @@ score_traj_kernel(const __grid_constant__ ProblemDev P, const double *__restrict
 #pragma unroll
         for (int o = 0; o < PB200_MAX_OUTPUTS; ++o) ss[o] = 0.0;
         const double *tr = traj + i * static_cast<int64_t>(nt) * no;
-        // flat, coalesced sweep over the nt*no stored values
         const int total = nt * no;
-        for (int q = lane; q < total; q += 32) {
-            const int j = q / no, o = q - j * no;
-            const double r = P.series[j * row + 1 + o] - tr[q];
-            const double sq = r * r;
+        if (VEC == 2) {
+            // pair q = time point q: (output 0, output 1)
+            const double2 *tv = reinterpret_cast<const double2 *>(tr);
+            int q = lane;
+            for (; q + 96 < nt; q += 128) {
+                double2 v[4];
 #pragma unroll
-            for (int oo = 0; oo < PB200_MAX_OUTPUTS; ++oo)
-                if (oo == o) ss[oo] += sq;
+                for (int u = 0; u < 4; ++u) v[u] = __ldcs(tv + q + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double *d = series + (q + 32 * u) * 3 + 1;
+                    const double r0 = d[0] - v[u].x, r1 = d[1] - v[u].y;
+                    ss[0] = fma(r0, r0, ss[0]);
+                    ss[1] = fma(r1, r1, ss[1]);
+                }
+            }
+            for (; q < nt; q += 32) {
+                const double2 v = __ldcs(tv + q);
+                const double *d = series + q * 3 + 1;
+                const double r0 = d[0] - v.x, r1 = d[1] - v.y;
+                ss[0] = fma(r0, r0, ss[0]);
+                ss[1] = fma(r1, r1, ss[1]);
+            }
+        } else if (VEC == 1) {
+            // pair q = time points 2q and 2q + 1 (nt even, checked at launch)
+            const double2 *tv = reinterpret_cast<const double2 *>(tr);
+            const int pairs = nt / 2;
+            int q = lane;
+            for (; q + 96 < pairs; q += 128) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldcs(tv + q + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double *d = series + (q + 32 * u) * 4 + 1;
+                    const double r0 = d[0] - v[u].x, r1 = d[2] - v[u].y;
+                    ss[0] = fma(r0, r0, ss[0]);
+                    ss[0] = fma(r1, r1, ss[0]);
+                }
+            }
+            for (; q < pairs; q += 32) {
+                const double2 v = __ldcs(tv + q);
+                const double *d = series + q * 4 + 1;
+                const double r0 = d[0] - v.x, r1 = d[2] - v.y;
+                ss[0] = fma(r0, r0, ss[0]);
+                ss[0] = fma(r1, r1, ss[0]);
+            }
+        } else {
+            // flat, coalesced sweep over the nt*no stored values
+            for (int q = lane; q < total; q += 32) {
+                const int j = q / no, o = q - j * no;
+                const double r = series[j * row + 1 + o] - __ldcs(tr + q);
+                const double sq = r * r;
+#pragma unroll
+                for (int oo = 0; oo < PB200_MAX_OUTPUTS; ++oo)
+                    if (oo == o) ss[oo] += sq;
+            }
         }
 #pragma unroll
         for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
@@ -514,10 +582,27 @@ int launch_score_traj(const pb200_problem *p, const double *d_traj,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t grid = (n + WARPS - 1) / WARPS;
-    if (grid > static_cast<int64_t>(sms) * 8) grid = static_cast<int64_t>(sms) * 8;
+    const int no = p->dev.n_outputs, nt = p->dev.n_times;
+    const int64_t bytes = ((static_cast<int64_t>(nt) + PB200_SENTINEL_ROWS) * p->dev.row * 8 + 15) & ~15ll;
+    const int staged = bytes <= 48 * 1024 ? 1 : 0;          // else read through L1
+    // persistent grid: 8 blocks of 8 warps per SM (4 when the series is staged
+    // and large), each warp takes every (grid * 8)-th trajectory
+    int per_sm = 8;
+    if (staged && bytes * per_sm > 200 * 1024) per_sm = static_cast<int>(200 * 1024 / bytes);
+    int64_t grid = (n + ST_WARPS - 1) / ST_WARPS;
+    if (grid > static_cast<int64_t>(sms) * per_sm) grid = static_cast<int64_t>(sms) * per_sm;
     if (grid <= 0) return PB200_OK;
-    score_traj_kernel<<<static_cast<unsigned>(grid), WARPS * 32, 0, st>>>(
-        p->dev, d_traj, d_params, n, ld, d_scores);
+    const size_t dyn = staged ? static_cast<size_t>(bytes) : 0;
+    // 16-byte loads need 16-byte aligned trajectories: the buffer itself and,
+    // for one output, an even number of time points
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_traj) & 15) == 0;
+    const int vec = (aligned && no == 2) ? 2 : (aligned && no == 1 && nt % 2 == 0) ? 1 : 0;
+#define PB200_ST(V)                                                                        \
+    score_traj_kernel<V><<<static_cast<unsigned>(grid), ST_WARPS * 32, dyn, st>>>(         \
+        p->dev, d_traj, d_params, n, ld, d_scores, staged)
+    if (vec == 2) PB200_ST(2);
+    else if (vec == 1) PB200_ST(1);
+    else PB200_ST(0);
+#undef PB200_ST
     return pb200_check_cuda(cudaGetLastError(), "score_traj_kernel launch");
 }

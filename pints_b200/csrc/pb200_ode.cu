@@ -31,6 +31,7 @@
 // measured agreement.
 #include "pb200_common.cuh"
 #include <cstdlib>
+#include <type_traits>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -561,11 +562,16 @@ struct BeelerReuterModel {
     __device__ __forceinline__ double cost_key(const double *) const { return gx1; }
 };
 
-// ss += r * r only where `valid`: a predicated DFMA instead of a DFMA plus a
-// 64-bit select (two FSELs on the issue port).
+// ss += r * r only where `valid`.  The compiler turns a predicated DFMA (or a
+// branch) into a DFMA plus a 64-bit select, two FSELs per output and pass.
+// Instead the HIGH word of r is cleared where the slot is not valid (one
+// instruction): what is left is a denormal below 2^-1042 -- also when r was
+// inf or NaN from a sentinel row -- whose square underflows to exactly +0, so
+// the DFMA adds nothing.  (A valid r is never touched.)
 __device__ __forceinline__ void acc_sq_if(double &ss, double r, bool valid) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p fma.rn.f64 %0, %1, %1, %0;\n\t}"
-        : "+d"(ss) : "d"(r), "r"(static_cast<uint32_t>(valid)));
+    const int hi = valid ? __double2hiint(r) : 0;
+    const double rm = __hiloint2double(hi, __double2loint(r));
+    ss = fma(rm, rm, ss);
 }
 
 // Order of two doubles from their bit patterns (integer pipe instead of a
@@ -743,9 +749,19 @@ template <> struct LaunchShape<RepressilatorModel> {
 #define PB200_BIG_UNROLL 2
 #endif
 
-template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE>
-__global__ void __launch_bounds__(MIG ? 512 : LaunchShape<M>::THREADS,
-                                  MIG ? 1 : LaunchShape<M>::BLOCKS)
+// DENSE: register class of the instance.  The loop needs 124 registers to keep
+// everything live, i.e. 16 warps per SM; populations of 16 < warps per SM <= 24
+// (75 776 < N <= 113 664) would then take two waves, the second one nearly
+// empty (48 % of the FP64 peak at N = 100 000 against 55 % at 65 536).  The
+// same code compiled for 640-thread blocks gets 96 registers (12 bytes of
+// spills), for 768-thread blocks 80 registers (114 bytes, outside the stage
+// chain), and holds 20 / 24 warps per SM in ONE wave.
+constexpr int dense_threads(int dense) { return dense == 2 ? 768 : dense == 1 ? 640 : 0; }
+
+template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE, int DENSE = 0>
+__global__ void __launch_bounds__(DENSE ? dense_threads(DENSE)
+                                        : (MIG ? 512 : LaunchShape<M>::THREADS),
+                                  (MIG || DENSE) ? 1 : LaunchShape<M>::BLOCKS)
 ode_kernel(const __grid_constant__ ProblemDev P,
            const __grid_constant__ ModelConsts mc,
            const double *__restrict__ params, int64_t n, int64_t ld,
@@ -832,6 +848,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     const uint32_t end = static_cast<uint32_t>(nt) * ROWB;
     uint32_t off = 0;
     double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * NO : nullptr;
+    const bool traj_vec2 = TRAJ && (reinterpret_cast<uintptr_t>(traj) & 15) == 0;
 
     // observations at (or before) the initial time see the initial state
     if (!idle) {
@@ -911,13 +928,26 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     auto interpolate = [&](double tq, uint32_t row, bool valid) {
         const double th = fma(tq, p_invh, p_c0);
         const double th1 = fma(-tq, p_invh, p_c1);
+        double v[NO];
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
             // y + th (r2 + th1 (r3 + th (r4 + th1 r5)))
-            const double v = fma(th, fma(th1, fma(th, fma(th1, p_r5[o], p_r4[o]), p_r3[o]), p_r2[o]), p_y[o]);
-            const double r = series.at(row + 8 + 8 * o) - v;
-            if (TRAJ) { if (valid) my_traj[row / ROWB * NO + o] = v; }
+            v[o] = fma(th, fma(th1, fma(th, fma(th1, p_r5[o], p_r4[o]), p_r3[o]), p_r2[o]), p_y[o]);
+            const double r = series.at(row + 8 + 8 * o) - v[o];
             acc_sq_if(ss[o], r, valid);
+        }
+        if (TRAJ) {
+            if (valid) {
+                double *dst = my_traj + row / ROWB * NO;
+                if (NO == 2 && traj_vec2) {
+                    // one 16-byte store per time point (a lane's trajectory is
+                    // its own 16 KB region: stores never coalesce across lanes)
+                    *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[NO - 1]);
+                } else {
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) dst[o] = v[o];
+                }
+            }
         }
     };
 
@@ -1621,6 +1651,13 @@ static bool mig_enabled() {
     }();
     return on != 0;
 }
+static bool dense_enabled() {
+    static const int on = [] {
+        const char *e = getenv("PB200_DENSE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
 static double mig_alpha() {
     static const double a = [] {
         const char *e = getenv("PB200_MIGRATE_AT");
@@ -1688,14 +1725,20 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     }
     const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
     // single-wave populations with one or two warps per SM more than a
-    // multiple of four: migrating layout, one block per SM (see MigDev)
+    // multiple of four: migrating layout, one block per SM (see MigDev);
+    // 17 .. 24 warps per SM: the dense register classes (see ode_kernel)
     MigDev mig = {0, 0, 0, 0};
+    int dense = 0;
     if (M::MIGRATES && auto_layout && use_smem && !traj && mig_enabled()) {
         const int64_t warps = (n + 31) / 32;
         const int sms = sm_count();
         const int64_t per_sm = (warps + sms - 1) / sms;
         const int r = static_cast<int>(per_sm % 4);
-        if (per_sm >= 5 && per_sm <= 14 && (r == 1 || r == 2)) {
+        // the dense instances exist for the model's default interpolation loop
+        const bool default_wide = (p->dev.model != PB200_MODEL_FHN) == (s.wide != 0);
+        if (per_sm > 16 && per_sm <= 24 && default_wide && dense_enabled())
+            dense = per_sm <= 20 ? 1 : 2;
+        if (per_sm >= 5 && (per_sm <= 14 || dense) && (r == 1 || r == 2)) {
             mig.q4 = static_cast<int32_t>(per_sm - r);
             mig.r = r;
             const int64_t row = (1 + M::NO) * 8;
@@ -1704,16 +1747,29 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
             mig.off_mid = static_cast<uint32_t>(mid * row);
             mig.buf_off = static_cast<uint32_t>(bytes);
         }
+        if (dense && !mig.r) {
+            // plain layout, one block of per_sm warps per SM
+            block = static_cast<int>(per_sm) * 32;
+        }
     }
 #define PB200_XARG , mig, sc
+    constexpr bool W = !std::is_same<M, FhnModel>::value;      // the model's default loop
     if (mig.r) {
         if constexpr (M::MIGRATES) {
         const int mblock = (mig.q4 + 2 + mig.r) * 32;
         const int64_t per_block = static_cast<int64_t>(mig.q4 + mig.r) * 32;
         const int64_t mgrid = (n + per_block - 1) / per_block;
         const size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
-        if (s.wide) PB200_LAUNCH((ode_kernel<M, true, false, true, true>), mgrid, mblock, mdyn);
+        if (dense == 2) PB200_LAUNCH((ode_kernel<M, true, false, true, W, 2>), mgrid, mblock, mdyn);
+        else if (dense == 1) PB200_LAUNCH((ode_kernel<M, true, false, true, W, 1>), mgrid, mblock, mdyn);
+        else if (s.wide) PB200_LAUNCH((ode_kernel<M, true, false, true, true>), mgrid, mblock, mdyn);
         else PB200_LAUNCH((ode_kernel<M, true, false, true, false>), mgrid, mblock, mdyn);
+        }
+    } else if (dense) {
+        if constexpr (M::MIGRATES) {
+        const int64_t dgrid = (n + block - 1) / block;
+        if (dense == 2) PB200_LAUNCH((ode_kernel<M, true, false, false, W, 2>), dgrid, block, dyn);
+        else PB200_LAUNCH((ode_kernel<M, true, false, false, W, 1>), dgrid, block, dyn);
         }
     } else if (use_smem) {
         if (traj) PB200_LAUNCH((ode_kernel<M, true, true, false, false>), grid, block, dyn);

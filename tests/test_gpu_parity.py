@@ -622,13 +622,15 @@ def test_host_buffer_entry_points(pb):
     assert lib.pb200_copy_async(None, None, -1, 0, stream) == -1
 
 
-@pytest.mark.parametrize('n', [18945, 30000, 47000, 61569, 65536, 66304])
+@pytest.mark.parametrize('n', [18945, 30000, 47000, 61569, 65536, 66304,
+                               80000, 85000, 90000, 97000, 100000, 110000])
 def test_migrating_layout_is_bit_identical(pb, n):
     """Populations of 5..14 warps per SM run one block per SM with warp
-    migration between the schedulers; an explicit block size
-    selects the plain layout.  Same scores and step counts, bit for bit,
-    including vectors decided early (prior box), vectors that fail (NaN) and
-    the ragged last block."""
+    migration between the schedulers; 17..24 warps per SM
+    (the last six sizes) run the dense register classes, with or without
+    migration; an explicit block size selects the plain layout.  Same scores
+    and step counts, bit for bit, including vectors decided early (prior
+    box), vectors that fail (NaN) and the ragged last block."""
     spec = po.headline_fhn_spec()
     rng = np.random.RandomState(n)
     xs = po.headline_fhn_points(n, seed=n % 97)
