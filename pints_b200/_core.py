@@ -1,17 +1,29 @@
 """
-Mirror of the reference's problem layer (pints/_core.py:12-327) with a batched
-``evaluate``: ``problem.evaluate(x)`` for one vector returns what the reference
-returns, ``problem.evaluate(xs)`` for ``(N, d)`` returns ``(N, n_times[,
-n_outputs])`` -- both computed on the GPU through ``pb200_simulate``.
+The problem layer with a batched ``evaluate``: ``problem.evaluate(x)`` for one
+vector returns what the reference returns (pints/_core.py:147-153, :257-265),
+``problem.evaluate(xs)`` for ``(N, d)`` returns ``(N, n_times[, n_outputs])``
+-- both computed on the GPU through ``pb200_simulate`` by the device models of
+``pints_b200.toy``.
+
+Where the reference is importable the classes below ARE the reference's
+(``pints.SingleOutputProblem`` / ``pints.MultiOutputProblem``: constructors,
+validation and accessors are inherited) with ``evaluate`` replaced by the
+batch-aware one.  Without it (``pints_b200`` is standalone) a small generic
+stand-in keeps the same state under the same private names -- ``_model``,
+``_times``, ``_values``, ``_n_parameters``, ``_n_times``, ``_n_outputs``, which
+is what ``_spec.describe`` reads from reference and stand-in objects alike --
+and raises the reference's messages.
 """
 import numpy as np
 
-from ._compat import base
+from ._compat import base, pints_or_none
 from ._util import is_batch, matrix2d, vector
 
 
 class ForwardModel(base('ForwardModel')):
-    """Mirror of ``pints.ForwardModel`` (pints/_core.py:12-56)."""
+    """``pints.ForwardModel`` (pints/_core.py:12-56) when the reference is
+    there, else its interface: ``n_parameters()``, ``simulate(parameters,
+    times)``, ``n_outputs()`` (1 unless overridden)."""
 
     def __init__(self):
         pass
@@ -26,92 +38,74 @@ class ForwardModel(base('ForwardModel')):
         return 1
 
 
-class SingleOutputProblem(base('SingleOutputProblem')):
-    """Mirror of ``pints.SingleOutputProblem`` (pints/_core.py:102-210):
-    times non-negative and strictly increasing, one value per time."""
-
-    def __init__(self, model, times, values):
-        self._model = model
-        if model.n_outputs() != 1:
-            raise ValueError(
-                'Only single-output models can be used for a'
-                ' SingleOutputProblem.')
-        self._times = vector(times)
-        if np.any(self._times < 0):
-            raise ValueError('Times can not be negative.')
-        if np.any(self._times[:-1] >= self._times[1:]):
-            raise ValueError('Times must be increasing.')
-        self._values = vector(values)
-        self._n_parameters = int(model.n_parameters())
-        self._n_times = len(self._times)
-        if len(self._values) != self._n_times:
-            raise ValueError(
-                'Times and values arrays must have same length.')
+class _BatchedEvaluate(object):
+    """``evaluate`` for one parameter vector or a batch of them."""
 
     def evaluate(self, parameters):
         y = np.asarray(self._model.simulate(parameters, self._times))
+        shape = (self._n_times,)
+        if self._multi_output:
+            shape += (self._n_outputs,)
         if is_batch(parameters):
-            return y.reshape((len(parameters), self._n_times))
-        return y.reshape((self._n_times,))
-
-    def model(self):
-        return self._model
-
-    def n_outputs(self):
-        return 1
-
-    def n_parameters(self):
-        return self._n_parameters
-
-    def n_times(self):
-        return self._n_times
-
-    def times(self):
-        return self._times
-
-    def values(self):
-        return self._values
+            shape = (len(parameters),) + shape
+        return y.reshape(shape)
 
 
-class MultiOutputProblem(base('MultiOutputProblem')):
-    """Mirror of ``pints.MultiOutputProblem`` (pints/_core.py:213-327): times
-    non-negative and non-decreasing, values ``(n_times, n_outputs)``."""
+_pints = pints_or_none()
 
-    def __init__(self, model, times, values):
-        self._model = model
-        self._times = vector(times)
-        if np.any(self._times < 0):
-            raise ValueError('Times cannot be negative.')
-        if np.any(self._times[:-1] > self._times[1:]):
-            raise ValueError('Times must be non-decreasing.')
-        self._values = matrix2d(values)
-        self._n_parameters = int(model.n_parameters())
-        self._n_outputs = int(model.n_outputs())
-        self._n_times = len(self._times)
-        if self._values.shape != (self._n_times, self._n_outputs):
-            raise ValueError(
-                'Values array must have shape `(n_times, n_outputs)`.')
+if _pints is not None:
 
-    def evaluate(self, parameters):
-        y = np.asarray(self._model.simulate(parameters, self._times))
-        if is_batch(parameters):
-            return y.reshape(len(parameters), self._n_times, self._n_outputs)
-        return y.reshape(self._n_times, self._n_outputs)
+    class SingleOutputProblem(_BatchedEvaluate, _pints.SingleOutputProblem):
+        """``pints.SingleOutputProblem`` with the batched ``evaluate``."""
+        _multi_output = False
 
-    def model(self):
-        return self._model
+    class MultiOutputProblem(_BatchedEvaluate, _pints.MultiOutputProblem):
+        """``pints.MultiOutputProblem`` with the batched ``evaluate``."""
+        _multi_output = True
 
-    def n_outputs(self):
-        return self._n_outputs
+else:
 
-    def n_parameters(self):
-        return self._n_parameters
+    class _StandInProblem(_BatchedEvaluate):
+        """No reference installed: the state ``_spec.describe`` needs, checked
+        as the reference checks it (pints/_core.py:129-145, :238-255)."""
+        _multi_output = False
 
-    def n_times(self):
-        return self._n_times
+        def __init__(self, model, times, values):
+            single = not self._multi_output
+            if single and model.n_outputs() != 1:
+                raise ValueError('Only single-output models can be used for a'
+                                 ' SingleOutputProblem.')
+            t = vector(times)
+            if np.any(t < 0):
+                raise ValueError('Times can not be negative.' if single
+                                 else 'Times cannot be negative.')
+            steps = np.diff(t)
+            if single and np.any(steps <= 0):
+                raise ValueError('Times must be increasing.')
+            if not single and np.any(steps < 0):
+                raise ValueError('Times must be non-decreasing.')
+            v = vector(values) if single else matrix2d(values)
+            n_out = 1 if single else int(model.n_outputs())
+            if single and len(v) != len(t):
+                raise ValueError(
+                    'Times and values arrays must have same length.')
+            if not single and v.shape != (len(t), n_out):
+                raise ValueError(
+                    'Values array must have shape `(n_times, n_outputs)`.')
+            self._model, self._times, self._values = model, t, v
+            self._n_parameters = int(model.n_parameters())
+            self._n_times, self._n_outputs = len(t), n_out
 
-    def times(self):
-        return self._times
+    # accessors: model(), times(), values(), n_parameters(), n_times(), n_outputs()
+    for _name in ('model', 'times', 'values', 'n_parameters', 'n_times',
+                  'n_outputs'):
+        setattr(_StandInProblem, _name,
+                (lambda attr: lambda self: getattr(self, attr))('_' + _name))
 
-    def values(self):
-        return self._values
+    class SingleOutputProblem(_StandInProblem):
+        """Stand-in for ``pints.SingleOutputProblem`` (pints/_core.py:102-210)."""
+        _multi_output = False
+
+    class MultiOutputProblem(_StandInProblem):
+        """Stand-in for ``pints.MultiOutputProblem`` (pints/_core.py:213-327)."""
+        _multi_output = True

@@ -11,6 +11,7 @@
 //   ConstantModel.simulate             pints/toy/_constant_model.py:75-93
 //   Single/MultiOutputProblem.evaluate pints/_core.py:147-153, :257-265
 //   objective __call__                 see objective_finish()
+#include <cstdlib>
 #include "pb200_common.cuh"
 
 namespace {
@@ -460,7 +461,7 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
 // double2 is two time points; VEC = 0: any layout, scalar loads.
 constexpr int ST_WARPS = 8;
 
-template <int VEC>
+template <int VEC, int U = 4>
 __global__ void __launch_bounds__(ST_WARPS * 32)
 score_traj_kernel(const __grid_constant__ ProblemDev P, const double *__restrict__ traj,
                   const double *__restrict__ params, int64_t n, int64_t ld,
@@ -498,12 +499,12 @@ score_traj_kernel(const __grid_constant__ ProblemDev P, const double *__restrict
             // pair q = time point q: (output 0, output 1)
             const double2 *tv = reinterpret_cast<const double2 *>(tr);
             int q = lane;
-            for (; q + 96 < nt; q += 128) {
-                double2 v[4];
+            for (; q + 32 * (U - 1) < nt; q += 32 * U) {
+                double2 v[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = __ldcs(tv + q + 32 * u);
+                for (int u = 0; u < U; ++u) v[u] = __ldcs(tv + q + 32 * u);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const double *d = series + (q + 32 * u) * 3 + 1;
                     const double r0 = d[0] - v[u].x, r1 = d[1] - v[u].y;
                     ss[0] = fma(r0, r0, ss[0]);
@@ -587,7 +588,11 @@ int launch_score_traj(const pb200_problem *p, const double *d_traj,
     const int staged = bytes <= 48 * 1024 ? 1 : 0;          // else read through L1
     // persistent grid: 8 blocks of 8 warps per SM (4 when the series is staged
     // and large), each warp takes every (grid * 8)-th trajectory
-    int per_sm = 8;
+    static const int blocks_per_sm = [] {
+        const char *e = getenv("PB200_ST_BLOCKS");
+        return e ? atoi(e) : 8;
+    }();
+    int per_sm = blocks_per_sm;
     if (staged && bytes * per_sm > 200 * 1024) per_sm = static_cast<int>(200 * 1024 / bytes);
     int64_t grid = (n + ST_WARPS - 1) / ST_WARPS;
     if (grid > static_cast<int64_t>(sms) * per_sm) grid = static_cast<int64_t>(sms) * per_sm;
@@ -600,7 +605,14 @@ int launch_score_traj(const pb200_problem *p, const double *d_traj,
 #define PB200_ST(V)                                                                        \
     score_traj_kernel<V><<<static_cast<unsigned>(grid), ST_WARPS * 32, dyn, st>>>(         \
         p->dev, d_traj, d_params, n, ld, d_scores, staged)
-    if (vec == 2) PB200_ST(2);
+    static const int unroll = [] {
+        const char *e = getenv("PB200_ST_UNROLL");
+        return e ? atoi(e) : 8;
+    }();
+    if (vec == 2 && unroll == 8)
+        score_traj_kernel<2, 8><<<static_cast<unsigned>(grid), ST_WARPS * 32, dyn, st>>>(
+            p->dev, d_traj, d_params, n, ld, d_scores, staged);
+    else if (vec == 2) PB200_ST(2);
     else if (vec == 1) PB200_ST(1);
     else PB200_ST(0);
 #undef PB200_ST

@@ -1736,7 +1736,10 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
         const int r = static_cast<int>(per_sm % 4);
         // the dense instances exist for the model's default interpolation loop
         const bool default_wide = (p->dev.model != PB200_MODEL_FHN) == (s.wide != 0);
-        if (per_sm > 16 && per_sm <= 24 && default_wide && dense_enabled())
+        // (23 or 24 warps per SM without migration are slower at 80 registers
+        // than two waves at 124: 0.694 against 0.656 ms, profiles/r02i_dense_probe.log)
+        if (per_sm > 16 && per_sm <= 24 && default_wide && dense_enabled() &&
+            (per_sm <= 20 || r == 1 || r == 2))
             dense = per_sm <= 20 ? 1 : 2;
         if (per_sm >= 5 && (per_sm <= 14 || dense) && (r == 1 || r == 2)) {
             mig.q4 = static_cast<int32_t>(per_sm - r);

@@ -151,13 +151,15 @@ def main():
     x0 = np.hstack([p * rng.uniform(0.95, 1.05, (n_ch, 5)),
                     40 * rng.uniform(0.95, 1.05, (n_ch, 1))])
     iters = 100 if quick else 400
-    mc = pb.CudaMCMCController(glh, n_ch, x0, method=pb.HaarioBardenetACMC, seed=1,
-                               sharded=world > 1, device=device)
-    mc.set_max_iterations(iters)
-    mc.set_initial_phase_iterations(50)
-    barrier()
-    mc.run(to_host=False)
-    per_it = max_over_ranks(mc.time() / iters)
+    for n_it in (60, iters):                      # the first run warms up
+        mc = pb.CudaMCMCController(glh, n_ch, x0, method=pb.HaarioBardenetACMC, seed=1,
+                                   sharded=world > 1, device=device)
+        mc.set_max_iterations(n_it)
+        mc.set_initial_phase_iterations(50)
+        barrier()
+        mc.run(to_host=False)
+        per_it = max_over_ranks(mc.time() / n_it)
+        del mc
     out['hh_ik_hbac'] = {'chains': n_ch, 'iterations': iters,
                          'ms_per_iteration': per_it * 1e3,
                          'projected_s_for_1e4_iterations': per_it * 1e4,
@@ -176,12 +178,14 @@ def main():
         x0 = np.hstack([np.array(pp) * rng.uniform(0.98, 1.02, (n_ch, len(pp))),
                         sig * rng.uniform(0.95, 1.05, (n_ch, 2))])
         iters = 100 if quick else 300
-        mc = pb.CudaMCMCController(gl, n_ch, x0, method=pb.DifferentialEvolutionMCMC,
-                                   seed=2, sharded=world > 1, device=device)
-        mc.set_max_iterations(iters)
-        barrier()
-        mc.run(to_host=False)
-        per_it = max_over_ranks(mc.time() / iters)
+        for n_it in (30, iters):                  # the first run warms up
+            mc = pb.CudaMCMCController(gl, n_ch, x0, method=pb.DifferentialEvolutionMCMC,
+                                       seed=2, sharded=world > 1, device=device)
+            mc.set_max_iterations(n_it)
+            barrier()
+            mc.run(to_host=False)
+            per_it = max_over_ranks(mc.time() / n_it)
+            del mc
         out[name + '_de'] = {'chains': n_ch, 'iterations': iters,
                              'ms_per_iteration': per_it * 1e3,
                              'chain_iterations_per_s': n_ch / per_it}
