@@ -253,6 +253,18 @@ class _Lane(object):
             s.synchronize()
 
 
+class _AddTerm(object):
+    """Last item of a pending evaluation: once the lanes before it have been
+    waited for, adds the host-side term of a ``TransformedLogPDF`` (the log
+    Jacobian determinant, pints/_transformation.py:1166-1169) to the scores."""
+
+    def __init__(self, scores, term):
+        self.scores, self.term = scores, term
+
+    def wait(self):
+        np.add(self.scores, self.term, out=self.scores)
+
+
 def pinned_result(n, dtype=torch.float64):
     """A fresh 1-d array in page-locked host memory from torch's caching host
     allocator: the device-to-host copy of a result lands in the array that is
@@ -369,6 +381,14 @@ class CudaEvaluator(Evaluator):
         return self._lanes
 
     def device_problem(self, index=0):
+        """The ``DeviceProblem`` behind this evaluator, for callers that keep
+        their positions on the device.  Its inputs are model-space
+        parameters: an objective wrapped in a transformation can only be
+        scored through :meth:`evaluate`, which maps the rows first."""
+        if self._spec.transform is not None:
+            raise TypeError(
+                'the objective is wrapped in a transformation: device-resident '
+                'callers work in model space; use CudaEvaluator.evaluate')
         return self._setup()[index].problem
 
     # ------------------------------------------------------------------
@@ -400,6 +420,15 @@ class CudaEvaluator(Evaluator):
             return (np.empty(0, dtype=np.float64),
                     np.zeros(0, dtype=np.int32) if return_steps else None, [])
         lanes = self._setup()          # raises when there is no GPU
+        jacobian = None
+        if self._spec.transform is not None:
+            # positions arrive in the search space of the controller's
+            # transformation: map the rows to model space on the host
+            from ._transform import rows_log_jacobian_det, rows_to_model
+            transformation, add_jacobian, outer_sign = self._spec.transform
+            if add_jacobian:
+                jacobian = outer_sign * rows_log_jacobian_det(transformation, xs)
+            xs = rows_to_model(transformation, xs)
         # results land in page-locked arrays that are handed to the caller
         scores = pinned_result(n)
         steps = pinned_result(n, torch.int32) if return_steps else None
@@ -414,6 +443,8 @@ class CudaEvaluator(Evaluator):
                         steps.ctypes.data + lo * 4 if return_steps else None,
                         self._chunk_rows)
             work.append(lane)
+        if jacobian is not None:
+            work.append(_AddTerm(scores, jacobian))
         return scores, steps, work
 
     @staticmethod

@@ -5,7 +5,8 @@ introspection that derives it from an objective object.
 The reference has no evaluator plug-in hook and no operator registry
 (SURVEY.md section 8b): the function handed to an evaluator is an object graph
 
-    [ProbabilityBasedError] -> [LogPosterior] -> SumOfSquaresError |
+    [ProbabilityBasedError] -> [Transformed{ErrorMeasure,LogLikelihood,LogPDF}]
+        -> [LogPosterior] -> SumOfSquaresError |
         GaussianKnownSigmaLogLikelihood | GaussianLogLikelihood
         -> SingleOutputProblem | MultiOutputProblem -> toy model
 
@@ -40,6 +41,8 @@ class ProblemSpec(object):
                  obj_consts, sign=1.0, prior_lower=None, prior_upper=None,
                  log_prior=0.0, multi_output=None, prior_terms=None):
         self.model = int(model)
+        #: host-side transformation of the positions (set by describe())
+        self.transform = None
         self.model_consts = [float(v) for v in model_consts]
         self.times = np.ascontiguousarray(times, dtype=np.float64)
         values = np.asarray(values, dtype=np.float64)
@@ -234,12 +237,24 @@ def describe(function):
     of it is outside the supported hot path."""
     sign = 1.0
     prior = None
+    transform = None           # (transformation, add the Jacobian term?, sign outside)
     f = function
     for _ in range(8):
         kind = _kind(f)
         if kind == 'ProbabilityBasedError':
             sign = -sign
             f = f._log_pdf
+        elif kind in ('TransformedErrorMeasure', 'TransformedLogLikelihood',
+                      'TransformedLogPDF'):
+            # f(to_model(q)) [+ log |det J(q)|]: the rows are mapped on the
+            # host before the launch (pints_b200/_transform.py)
+            if transform is not None or prior is not None:
+                raise TypeError('only one transformation, outside any '
+                                'LogPosterior, is supported')
+            transform = (f._transform, kind == 'TransformedLogPDF', sign)
+            f = getattr(f, {'TransformedErrorMeasure': '_error',
+                            'TransformedLogLikelihood': '_log_likelihood',
+                            'TransformedLogPDF': '_log_pdf'}[kind])
         elif kind == 'LogPosterior':
             if prior is not None:
                 raise TypeError('nested LogPosterior is not supported')
@@ -301,4 +316,8 @@ def describe(function):
                        multi_output=multi, prior_terms=terms)
     if lower is not None and len(lower) != spec.n_parameters():
         raise TypeError('prior and likelihood dimensions differ')
+    if transform is not None and \
+            transform[0].n_parameters() != spec.n_parameters():
+        raise TypeError('transformation and objective dimensions differ')
+    spec.transform = transform
     return spec

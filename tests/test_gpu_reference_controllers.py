@@ -188,3 +188,62 @@ def test_reference_multi_sequential_evaluator_route(pints, pb):
             ev.evaluate(xs[:3])
     assert isinstance(got, list) and len(got) == 5
     assert np.allclose(got, ref, rtol=1e-12, atol=0)
+
+
+def test_reference_controllers_with_a_transformation(pints, pb):
+    """`transformation=...` makes the reference's controllers wrap the
+    objective (pints/_optimisers/__init__.py:392-406, pints/_mcmc/__init__.py:
+    349-361); CudaEvaluator unwraps it, maps the rows on the host and adds the
+    Jacobian term of a TransformedLogPDF: same runs as with SequentialEvaluator."""
+    g = load_golden('logistic')
+    problem = pints.SingleOutputProblem(pints.toy.LogisticModel(), g['times'],
+                                        g['values'])
+    ll = pints.GaussianLogLikelihood(problem)
+    post = pints.LogPosterior(ll, pints.UniformLogPrior([0, 10, 0.1], [1, 100, 10]))
+    t = pints.ComposedTransformation(
+        pints.LogTransformation(1),
+        pints.RectangularBoundariesTransformation([10, 0.1], [100, 10]))
+    # the wrapped objectives themselves, on a batch of search-space points
+    rng = np.random.RandomState(2)
+    qs = np.array([t.to_search(x) for x in
+                   np.array([0.1, 50, 1.0]) * (1 + 0.1 * rng.randn(40, 3))])
+    for f in (t.convert_log_pdf(post), t.convert_log_pdf(ll),
+              pints.ProbabilityBasedError(t.convert_log_pdf(post))):
+        got = np.array(pb.CudaEvaluator(f).evaluate(qs))
+        ref = np.array(pints.SequentialEvaluator(f).evaluate(qs))
+        assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+
+    def optimise(use_cuda):
+        np.random.seed(3)
+        opt = pints.OptimisationController(post, [0.2, 30, 2.0], transformation=t,
+                                           method=pints.XNES)
+        opt.optimiser().set_population_size(64)
+        opt.set_max_iterations(20)
+        opt.set_max_unchanged_iterations(None)
+        opt.set_log_to_screen(False)
+        if use_cuda:
+            with pb.cuda_evaluators():
+                return opt.run() + (np.random.get_state()[1].copy(),)
+        return opt.run() + (np.random.get_state()[1].copy(),)
+
+    x1, f1, s1 = optimise(False)
+    x2, f2, s2 = optimise(True)
+    assert np.array_equal(s1, s2)
+    assert np.allclose(x1, x2, rtol=1e-9, atol=0) and abs(f1 - f2) <= 1e-10 * abs(f1)
+
+    def sample(use_cuda):
+        np.random.seed(4)
+        x0 = [np.array([0.1, 50, 1.0]) * (1 + 0.01 * k) for k in range(4)]
+        mc = pints.MCMCController(post, 4, x0, transformation=t,
+                                  method=pints.HaarioBardenetACMC)
+        mc.set_max_iterations(200)
+        mc.set_initial_phase_iterations(40)
+        mc.set_log_to_screen(False)
+        if use_cuda:
+            with pb.cuda_evaluators():
+                return mc.run()
+        return mc.run()
+
+    a, b = sample(False), sample(True)
+    assert a.shape == b.shape == (4, 200, 3)
+    assert np.allclose(a, b, rtol=1e-9, atol=0)

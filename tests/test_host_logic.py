@@ -434,3 +434,56 @@ def test_host_copy_threads_copy_exactly():
                                        a.nbytes, threads) == 0
             assert np.array_equal(a, b)
     assert lib.pb200_host_copy(None, None, 8, 1) != 0
+
+
+def test_transformations_are_unwrapped_and_mapped_like_the_reference():
+    """Transformed{ErrorMeasure,LogLikelihood,LogPDF} (what the reference's
+    controllers build for `transformation=...`, pints/_optimisers/__init__.py:
+    392-406): describe() peels them, and the batched row mapping equals the
+    transformation's own per-vector arithmetic bit for bit."""
+    pints = conftest_reference()
+    if pints is None:
+        pytest.skip('reference not available')
+    from pints_b200 import _spec
+    from pints_b200._transform import rows_log_jacobian_det, rows_to_model
+    rng = np.random.RandomState(8)
+    q = rng.randn(257, 3)
+    cases = [
+        pints.LogTransformation(3), pints.LogitTransformation(3),
+        pints.IdentityTransformation(3),
+        pints.ScalingTransformation([2.0, 0.5, 10.0]),
+        pints.ScalingTransformation([2.0, 0.5, 10.0], [1.0, -1.0, 0.5]),
+        pints.RectangularBoundariesTransformation([0, 1, 2], [1, 3, 10]),
+        pints.ComposedTransformation(pints.LogTransformation(1),
+                                     pints.RectangularBoundariesTransformation([0, 1], [1, 4])),
+        pints.ComposedTransformation(pints.LogitTransformation(2),
+                                     pints.IdentityTransformation(1)),
+    ]
+    for t in cases:
+        want_p = np.array([t.to_model(row) for row in q])
+        want_j = np.array([t.log_jacobian_det(row) for row in q])
+        assert np.array_equal(rows_to_model(t, q), want_p), type(t).__name__
+        assert np.array_equal(rows_log_jacobian_det(t, q), want_j), type(t).__name__
+    # an unknown transformation object goes row by row through its own methods
+    class Mine(pints.LogTransformation):
+        pass
+    mine = Mine(3)
+    assert np.array_equal(rows_to_model(mine, q), np.exp(q))
+    assert np.array_equal(rows_log_jacobian_det(mine, q),
+                          np.array([np.sum(row) for row in q]))
+
+    g, model, problem = fhn_objects(pints, pints.toy)
+    ll = pints.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    t = pints.LogTransformation(3)
+    spec = _spec.describe(t.convert_log_pdf(ll))
+    assert spec.transform[0] is t and spec.transform[1] is False   # a likelihood: no Jacobian
+    post = pints.LogPosterior(ll, pints.UniformLogPrior([0, 0, 0], [1, 1, 10]))
+    spec = _spec.describe(pints.ProbabilityBasedError(t.convert_log_pdf(post)))
+    assert spec.transform[1] is True and spec.transform[2] == -1.0 and spec.sign == -1.0
+    assert spec.prior_lower is not None
+    spec = _spec.describe(t.convert_error_measure(pints.SumOfSquaresError(problem)))
+    assert spec.transform[1] is False and spec.sign == 1.0
+    with pytest.raises(TypeError):          # two layers
+        _spec.describe(t.convert_log_pdf(t.convert_log_pdf(ll)))
+    with pytest.raises(TypeError, match='model space'):
+        pb.CudaEvaluator(t.convert_log_pdf(ll)).device_problem()
