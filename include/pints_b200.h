@@ -463,6 +463,27 @@ int pb200_ac_tell_it(int32_t variant, int32_t require_finite, double *d_current,
                      const int64_t *d_counter, void *stream);
 int pb200_iter_advance(int64_t *d_counter, void *stream);
 
+/* The whole MCMC loop of the adaptive-covariance family on a closed-form model
+ * in ONE launch (MCMCController.run's loop, pints/_mcmc/__init__.py:706-894, for
+ * samplers whose chains are independent): one persistent warp per chain runs
+ * n_iterations of  ask (pb200_ac_ask's arithmetic)  ->  score the proposal (the
+ * arithmetic of pb200_eval, same reduction order)  ->  tell (pb200_ac_tell's),
+ * reading iteration it's scalars from row first_row + it of the table d_rows
+ * (layout above; the variant of row slot 6 is applied, the store offset of
+ * slot 3 is used when d_samples is given).  Chains are bit-identical to the
+ * launch-per-step loop.  Meant for few chains (up to ~10^3) on a cheap model,
+ * where an iteration of separate launches is launch-latency bound; d must be
+ * the problem's parameter count; all n warps must be resident at once. */
+int pb200_mcmc_chain_run(const pb200_problem *p, int32_t require_finite,
+                         double *d_current, double *d_current_f,
+                         double *d_proposed, double *d_fx, uint8_t *d_accepted,
+                         int64_t *d_acceptance_count, double *d_mu,
+                         double *d_sigma, double *d_log_lambda,
+                         double *d_samples, int64_t sample_stride, int64_t n,
+                         int32_t d, double target, uint64_t seed,
+                         const int64_t *d_rows, int64_t first_row,
+                         int64_t n_iterations, void *stream);
+
 /* Device-resident xNES (pints/_optimisers/_xnes.py:63-91 ask, :147-182 tell).
  * ask: z (n, d) standard normals = pb200_philox_normal(n d, seed, *d_offset)
  * (mean, A and the offset are read from device memory, so that a generation

@@ -31,3 +31,12 @@ def base(name):
     p = pints_or_none()
     cls = getattr(p, name, None) if p is not None else None
     return cls if isinstance(cls, type) else object
+
+
+def is_instance(obj, local_class, name):
+    """``isinstance`` against this package's class or the reference's
+    ``pints.<name>`` -- the latter only where the reference is importable
+    (``base(name)`` is ``object`` otherwise, which everything is)."""
+    ref = base(name)
+    return isinstance(obj, local_class) or \
+        (ref is not object and isinstance(obj, ref))

@@ -778,6 +778,11 @@ class CudaMCMCController(object):
     #: replay the iterations from a CUDA graph (see ``run``);
     #: PB200_MCMC_GRAPH=0 in the environment turns it off
     use_graph = os.environ.get('PB200_MCMC_GRAPH', '1') != '0'
+    #: run independent chains on a closed-form model as one persistent launch
+    #: (``pb200_mcmc_chain_run``); PB200_MCMC_CHAIN_LOOP=0 turns it off
+    use_chain_loop = os.environ.get('PB200_MCMC_CHAIN_LOOP', '1') != '0'
+    #: ... for at most this many chains per GPU (one warp each, all resident)
+    chain_loop_max_chains = 1024
     #: ... for runs with at least this many iterations left: capturing costs
     #: about 2 ms, and only loops whose iteration is shorter on the GPU than
     #: the host's 40-60 us of launch work gain from the replay (7 us per
@@ -915,11 +920,28 @@ class CudaMCMCController(object):
             if sampler.needs_initial_phase() else None
         graph_ok = self.use_graph and pool is None and \
             hasattr(sampler, 'plan_iterations')
+        # independent chains on a closed-form model, few enough for all their
+        # warps to be resident: the whole rest of the run is ONE launch
+        chain_ok = self.use_chain_loop and pool is None and \
+            hasattr(sampler, 'enqueue_chain_loop') and \
+            not problem.spec.is_ode() and \
+            n_local <= self.chain_loop_max_chains
         self.graph_replayed = 0
+        self.chain_loop_iterations = 0
         start = time.perf_counter()
         with torch.cuda.device(device):
             it = 0
             while it < n_iter:
+                if chain_ok and it >= 2 and n_iter - it >= 4 and \
+                        sampler.graph_ready():
+                    k = n_iter - it
+                    rows = torch.from_numpy(sampler.plan_iterations(
+                        k, samples, it, switch_at)).to(device)
+                    sampler.enqueue_chain_loop(problem, fx, samples, rows, k)
+                    self._graph_rows = rows         # alive until the sync below
+                    self.chain_loop_iterations = k
+                    it = n_iter
+                    break
                 if graph_ok and it >= 2 and \
                         n_iter - it >= max(4, self.graph_min_iterations) and \
                         sampler.graph_ready():

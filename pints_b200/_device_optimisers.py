@@ -45,7 +45,10 @@ class DeviceArgsort(object):
         self.device = require_cuda(device)
         self._lib = _lib.load()
         self.native = self.n <= self.MAX
-        self.order = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        # starts as the identity: a sort that gives up (status = 1) leaves its
+        # slice untouched, and what reads `order` next on the stream must find
+        # valid indices until the host has seen the status and sorted again
+        self.order = torch.arange(self.n, dtype=torch.int64, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         nbytes = int(self._lib.pb200_argsort_workspace_bytes(self.n))
         self._ws = torch.empty(max(nbytes, 16), dtype=torch.uint8,

@@ -112,6 +112,10 @@ SIGNATURES = {
                                    _P, _P, _P, _P, c_int64, c_int64, c_int32,
                                    c_double, c_uint64, _P, _P, _P]),
     'pb200_iter_advance': (c_int32, [_P, _P]),
+    'pb200_mcmc_chain_run': (c_int32, [_P, c_int32, _P, _P, _P, _P, _P, _P, _P,
+                                       _P, _P, _P, c_int64, c_int64, c_int32,
+                                       c_double, c_uint64, _P, c_int64,
+                                       c_int64, _P]),
     'pb200_xnes_ask': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64,
                                  c_int32, c_uint64, _P, _P]),
     'pb200_xnes_sums': (c_int32, [_P, _P, _P, _P, c_int32, _P, _P, _P,

@@ -16,7 +16,7 @@ the same numbers reach the kernel).
 """
 import numpy as np
 
-from ._compat import base
+from ._compat import base, is_instance
 from ._util import is_batch, vector
 
 
@@ -129,8 +129,7 @@ class ProbabilityBasedError(_DeviceCallable, ErrorMeasure):
     """``-log_pdf(x)`` (pints/_error_measures.py:164-198)."""
 
     def __init__(self, log_pdf):
-        if not isinstance(log_pdf, LogPDF) and \
-                not isinstance(log_pdf, base('LogPDF')):
+        if not is_instance(log_pdf, LogPDF, 'LogPDF'):
             raise ValueError(
                 'Given log_pdf must be an instance of pints.LogPDF.')
         self._log_pdf = log_pdf
@@ -318,7 +317,7 @@ class ComposedLogPrior(LogPrior):
             raise ValueError('Must have at least one sub-prior')
         self._n_parameters = 0
         for prior in priors:
-            if not isinstance(prior, (LogPrior, base('LogPrior'))):
+            if not is_instance(prior, LogPrior, 'LogPrior'):
                 raise ValueError('All sub-priors must extend pints.LogPrior.')
             self._n_parameters += prior.n_parameters()
         self._priors = priors
@@ -350,7 +349,7 @@ class LogPosterior(_DeviceCallable, LogPDF):
     support is not simulated (pints/_log_pdfs.py:164-241)."""
 
     def __init__(self, log_likelihood, log_prior):
-        if not isinstance(log_prior, (LogPrior, base('LogPrior'))):
+        if not is_instance(log_prior, LogPrior, 'LogPrior'):
             raise ValueError('Given prior must extend pints.LogPrior.')
         if not isinstance(log_likelihood,
                           (LogLikelihood, base('LogLikelihood'))):

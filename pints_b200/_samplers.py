@@ -117,6 +117,17 @@ class _DeviceOps(object):
     def iter_advance(self, counter):
         self._call(self.lib.pb200_iter_advance, _ptr(counter))
 
+    def chain_run(self, problem, cur, cur_f, prop, fx, accepted, acc_count,
+                  mu, sigma, log_lambda, samples, stride, target, seed, rows,
+                  first_row, n_iterations, require_finite=True):
+        n, d = cur.shape
+        self._call(self.lib.pb200_mcmc_chain_run, problem._handle,
+                   1 if require_finite else 0, _ptr(cur), _ptr(cur_f),
+                   _ptr(prop), _ptr(fx), _ptr(accepted), _ptr(acc_count),
+                   _ptr(mu), _ptr(sigma), _ptr(log_lambda), _ptr(samples),
+                   int(stride), n, d, float(target), ctypes.c_uint64(seed),
+                   _ptr(rows), int(first_row), int(n_iterations))
+
     def hbac_adapt(self, cur, accepted, mu, sigma, log_lambda, gamma, target):
         n, d = cur.shape
         self._call(self.lib.pb200_hbac_adapt, _ptr(cur), _ptr(accepted),
@@ -325,6 +336,18 @@ class HaarioBardenetACMC(_GraphIterationsBase):
         self._ops.ac_ask_it(self._current, self._sigma, self._log_lambda,
                             self._proposed, self._rng.seed, rows, counter)
         return self._proposed
+
+    def enqueue_chain_loop(self, problem, fx, samples, rows, k):
+        """The ``k`` planned iterations of ``rows`` in ONE launch: a persistent
+        warp per chain proposes, scores the proposal on ``problem`` (a
+        closed-form ``DeviceProblem``) and accepts / adapts / stores
+        (``pb200_mcmc_chain_run``).  Same chains as ``k`` rounds of
+        ``enqueue_ask_it`` / ``problem.eval`` / ``enqueue_tell_it``."""
+        self._ops.chain_run(problem, self._current, self._current_f,
+                            self._proposed, fx, self._accepted,
+                            self._acceptance_count, self._mu, self._sigma,
+                            self._log_lambda, samples, samples.stride(0),
+                            self._target, self._rng.seed, rows, 0, k)
 
     def enqueue_tell_it(self, fx, samples, rows, counter):
         variant = self._VARIANT if self._VARIANT is not None else -1

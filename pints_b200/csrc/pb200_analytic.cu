@@ -13,6 +13,7 @@
 //   objective __call__                 see objective_finish()
 #include <cstdlib>
 #include "pb200_common.cuh"
+#include "pb200_sampler_dev.cuh"
 
 namespace {
 
@@ -266,13 +267,32 @@ __device__ __forceinline__ double point_value(const E &ev, double t, int o,
 // [one segment table per warp, `table_doubles` each]; the block size is chosen
 // at launch (8 warps for short series, 32 when the series fills most of an SM's
 // shared memory and only one block fits).
-template <class E, bool SMEM, bool TRAJ, bool BIG>
+// CHAIN: the persistent MCMC loop.  Chains of the adaptive-covariance family
+// are independent, so ONE WARP runs one chain through all its iterations
+// without ever leaving the kernel: lane 0 proposes (ac_ask_one), the warp
+// scores the proposal exactly as an evaluation launch would (same code, same
+// reduction order), lane 0 accepts / adapts / stores (ac_tell_one).  No grid
+// barrier, no launch per iteration: for a few chains on a closed-form model an
+// iteration was four dependent launches of a few microseconds each.
+struct ChainDev {
+    double *cur, *cur_f, *prop, *fx, *mu, *sigma, *log_lambda, *samples;
+    uint8_t *accepted;
+    int64_t *acc_count;
+    const int64_t *rows;          // planned iterations, 8 slots each (IterTable)
+    int64_t first_row, n_iter, sample_stride;
+    double target;
+    uint64_t seed;
+    int32_t require_finite, d;
+};
+
+template <class E, bool SMEM, bool TRAJ, bool BIG, bool CHAIN = false>
 __global__ void __launch_bounds__(BIG ? 1024 : 256)
 analytic_kernel(const __grid_constant__ ProblemDev P,
                 const __grid_constant__ ModelConsts mc,
                 const double *__restrict__ params, int64_t n, int64_t ld,
                 double *__restrict__ scores, double *__restrict__ traj,
-                uint32_t table_off, uint32_t table_doubles, const ScatterDev sc) {
+                uint32_t table_off, uint32_t table_doubles, const ScatterDev sc,
+                const ChainDev ch) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ typename E::BlockAux aux;
@@ -302,19 +322,17 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
     const int64_t warps_total = static_cast<int64_t>(gridDim.x) * warps;
     const int n_read = TRAJ ? P.n_model_params : P.n_params;
 
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * warps + warp; i < n;
-         i += warps_total) {
+    // score (or trajectory) of row i, whose parameters are at `prow`; the
+    // score is returned in every lane
+    auto eval_row = [&](int64_t i, const double *prow) -> double {
         double x[PB200_MAX_PARAMS];
 #pragma unroll
         for (int k = 0; k < PB200_MAX_PARAMS; ++k)
-            x[k] = (k < n_read) ? params[i * ld + k] : 0.0;
+            x[k] = (k < n_read) ? (CHAIN ? __ldcg(prow + k) : prow[k]) : 0.0;
 
         if (!TRAJ) {
             double early;
-            if (objective_precheck(P, x, &early)) {     // warp-uniform
-                if (lane == 0) put_score(sc, scores, i, i, early);
-                continue;
-            }
+            if (objective_precheck(P, x, &early)) return early;     // warp-uniform
         }
         E ev;
         ev.prepare(x, mc, table, no, SMEM && E::POINT_AUX, aux);
@@ -392,15 +410,45 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                 }
             }
         }
-        if (!TRAJ) {
+        if (TRAJ) return 0.0;
 #pragma unroll
-            for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
-                if (o < no) ss[o] = warp_sum(ss[o]);
-            if (lane == 0) put_score(sc, scores, i, i, objective_finish(P, ss, x));
+        for (int o = 0; o < PB200_MAX_OUTPUTS; ++o)
+            if (o < no) ss[o] = warp_sum(ss[o]);
+        return objective_finish(P, ss, x);
+    };
+
+    if constexpr (CHAIN) {
+        // chain j = this warp, for all planned iterations
+        const int64_t j = static_cast<int64_t>(blockIdx.x) * warps + warp;
+        if (j < n) {
+            const int d = ch.d;
+            for (int64_t it = 0; it < ch.n_iter; ++it) {
+                const int64_t *r = ch.rows + 8 * (ch.first_row + it);
+                if (lane == 0)
+                    ac_ask_one(ch.cur, ch.sigma, ch.log_lambda, ch.prop, j, d, ch.seed,
+                               static_cast<uint64_t>(r[0]));
+                __syncwarp();
+                const double f_new = eval_row(j, ch.prop + j * d);
+                if (lane == 0) {
+                    ch.fx[j] = f_new;
+                    ac_tell_one(static_cast<int>(r[6]), ch.require_finite, ch.cur, ch.cur_f,
+                                ch.prop, f_new, ch.accepted, ch.acc_count, ch.mu, ch.sigma,
+                                ch.log_lambda, ch.samples, ch.sample_stride, r[3], j, d,
+                                slot_f64(r[5]), ch.target, ch.seed,
+                                static_cast<uint64_t>(r[2]));
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
+    } else {
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * warps + warp; i < n;
+             i += warps_total) {
+            const double score = eval_row(i, params + i * ld);
+            if (!TRAJ && lane == 0) put_score(sc, scores, i, i, score);
+            __syncwarp();
+        }
+        if (!TRAJ) exchange_signal(sc);
     }
-    if (!TRAJ) exchange_signal(sc);
 }
 
 template <class E>
@@ -438,7 +486,7 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
         }                                                                                \
         kern<<<static_cast<unsigned>(grid), warps * 32, dyn, st>>>(                      \
             p->dev, p->mc, d_params, n, ld, d_scores, d_traj,                            \
-            static_cast<uint32_t>(staged), table_doubles, sc);                           \
+            static_cast<uint32_t>(staged), table_doubles, sc, ChainDev{});               \
     } while (0)
     if (warps == 32) {                       // implies use_smem
         if (traj) PB200_LAUNCH(true, true, true); else PB200_LAUNCH(true, false, true);
@@ -449,6 +497,44 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
     }
 #undef PB200_LAUNCH
     return pb200_check_cuda(cudaGetLastError(), "analytic_kernel launch");
+}
+
+// the persistent MCMC loop: one warp per chain, all chains resident at once
+template <class E>
+int launch_chain(const pb200_problem *p, int64_t n, const ChainDev &ch, cudaStream_t st) {
+    const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * p->dev.row * 8 + 15) & ~15ll;
+    const size_t aux_bytes = E::POINT_AUX ? (static_cast<size_t>(p->dev.n_times) + 15) & ~size_t(15) : 0;
+    const uint32_t table_doubles = E::POINT_AUX
+        ? static_cast<uint32_t>((static_cast<int>(p->mc.c[4]) + 1) * SEG_STRIDE) : 0;
+    if (bytes > 100 * 1024) {
+        pb200_set_error("pb200_mcmc_chain_run: the series does not fit shared memory");
+        return PB200_EUNSUPPORTED;
+    }
+    const size_t staged = static_cast<size_t>(bytes) + aux_bytes;
+    const bool big = staged > 48 * 1024;
+    // few chains: spread them over the SMs (one 2-warp block each) rather than
+    // packing eight warps onto one SM
+    const int warps = big ? 32 : (n <= 2 * 148 ? 2 : 8);
+    const size_t dyn = staged + static_cast<size_t>(warps) * table_doubles * 8;
+    const int64_t grid = (n + warps - 1) / warps;
+    const ScatterDev none = {};
+#define PB200_LAUNCH(BG)                                                                 \
+    do {                                                                                 \
+        auto kern = analytic_kernel<E, true, false, BG, true>;                           \
+        if (dyn > 32 * 1024) {                                                           \
+            int rc = pb200_check_cuda(                                                   \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     static_cast<int>(dyn)),                             \
+                "cudaFuncSetAttribute");                                                 \
+            if (rc) return rc;                                                           \
+        }                                                                                \
+        kern<<<static_cast<unsigned>(grid), warps * 32, dyn, st>>>(                      \
+            p->dev, p->mc, nullptr, n, ch.d, ch.fx, nullptr,                             \
+            static_cast<uint32_t>(staged), table_doubles, none, ch);                     \
+    } while (0)
+    if (big) PB200_LAUNCH(true); else PB200_LAUNCH(false);
+#undef PB200_LAUNCH
+    return pb200_check_cuda(cudaGetLastError(), "analytic_kernel (chain loop) launch");
 }
 
 // ---- unfused baseline, second half: objective from stored trajectories ----
@@ -574,6 +660,26 @@ int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
             return launch_eval<ConstantEval>(p, d_params, n, ld, d_scores, d_traj, sc, st);
     }
     pb200_set_error("model %d is not a closed-form model", p->dev.model);
+    return PB200_EUNSUPPORTED;
+}
+
+int pb200_chain_loop(const pb200_problem *p, int64_t n, int32_t d, int32_t require_finite,
+                     double *cur, double *cur_f, double *prop, double *fx, uint8_t *accepted,
+                     int64_t *acc_count, double *mu, double *sigma, double *log_lambda,
+                     double *samples, int64_t sample_stride, double target, uint64_t seed,
+                     const int64_t *rows, int64_t first_row, int64_t n_iter, cudaStream_t st) {
+    ChainDev ch;
+    ch.cur = cur; ch.cur_f = cur_f; ch.prop = prop; ch.fx = fx; ch.mu = mu; ch.sigma = sigma;
+    ch.log_lambda = log_lambda; ch.samples = samples; ch.accepted = accepted;
+    ch.acc_count = acc_count; ch.rows = rows; ch.first_row = first_row; ch.n_iter = n_iter;
+    ch.sample_stride = sample_stride; ch.target = target; ch.seed = seed;
+    ch.require_finite = require_finite; ch.d = d;
+    switch (p->dev.model) {
+        case PB200_MODEL_LOGISTIC: return launch_chain<LogisticEval>(p, n, ch, st);
+        case PB200_MODEL_HH_IK: return launch_chain<HhEval>(p, n, ch, st);
+        case PB200_MODEL_CONSTANT: return launch_chain<ConstantEval>(p, n, ch, st);
+    }
+    pb200_set_error("pb200_mcmc_chain_run: model %d is not a closed-form model", p->dev.model);
     return PB200_EUNSUPPORTED;
 }
 

@@ -483,6 +483,37 @@ int pb200_eval_host(const pb200_problem *p, const double *h_params, int64_t n, i
     return rc;
 }
 
+int pb200_mcmc_chain_run(const pb200_problem *p, int32_t require_finite, double *d_current,
+                         double *d_current_f, double *d_proposed, double *d_fx,
+                         uint8_t *d_accepted, int64_t *d_acceptance_count, double *d_mu,
+                         double *d_sigma, double *d_log_lambda, double *d_samples,
+                         int64_t sample_stride, int64_t n, int32_t d, double target,
+                         uint64_t seed, const int64_t *d_rows, int64_t first_row,
+                         int64_t n_iterations, void *stream) {
+    if (!p) { pb200_set_error("pb200_mcmc_chain_run: problem is NULL"); return PB200_EINVAL; }
+    if (kModels[p->dev.model].ode) {
+        pb200_set_error("pb200_mcmc_chain_run: closed-form models only (an ODE solve per "
+                        "iteration is long enough for separate launches)");
+        return PB200_EUNSUPPORTED;
+    }
+    if (n < 0 || n_iterations < 0 || first_row < 0 || d != p->dev.n_params) {
+        pb200_set_error("pb200_mcmc_chain_run: bad n = %lld, iterations = %lld, first_row = %lld "
+                        "or d = %d (the problem has %d parameters)", (long long)n,
+                        (long long)n_iterations, (long long)first_row, d, p->dev.n_params);
+        return PB200_EINVAL;
+    }
+    if (n == 0 || n_iterations == 0) return PB200_OK;
+    if (!d_current || !d_current_f || !d_proposed || !d_fx || !d_accepted || !d_mu || !d_sigma ||
+        !d_log_lambda || !d_rows || !p->dev.series) {
+        pb200_set_error("pb200_mcmc_chain_run: NULL buffer");
+        return PB200_EINVAL;
+    }
+    return pb200_chain_loop(p, n, d, require_finite, d_current, d_current_f, d_proposed, d_fx,
+                            d_accepted, d_acceptance_count, d_mu, d_sigma, d_log_lambda,
+                            d_samples, sample_stride, target, seed, d_rows, first_row,
+                            n_iterations, static_cast<cudaStream_t>(stream));
+}
+
 int pb200_host_is_pinned(const void *ptr) {
     if (!ptr) return 0;
     cudaPointerAttributes a;

@@ -292,6 +292,11 @@ int launch_analytic(const pb200_problem *p, const double *d_params, int64_t n,
 int launch_score_traj(const pb200_problem *p, const double *d_traj,
                       const double *d_params, int64_t n, int64_t ld,
                       double *d_scores, cudaStream_t st);
+int pb200_chain_loop(const pb200_problem *p, int64_t n, int32_t d, int32_t require_finite,
+                     double *cur, double *cur_f, double *prop, double *fx, uint8_t *accepted,
+                     int64_t *acc_count, double *mu, double *sigma, double *log_lambda,
+                     double *samples, int64_t sample_stride, double target, uint64_t seed,
+                     const int64_t *rows, int64_t first_row, int64_t n_iter, cudaStream_t st);
 int launch_exchange_signal(const ScatterDev &sc, cudaStream_t st);
 int launch_exchange_finish(const void *stage, const void *flags, int n_ranks, int64_t per_rank,
                            int64_t rows_per_rank, unsigned long long epoch, int64_t n_total,

@@ -1615,9 +1615,23 @@ int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
     SortHeader *hdr = static_cast<SortHeader *>(ws);
     float *keys = reinterpret_cast<float *>(hdr + 1);
     int32_t *out = reinterpret_cast<int32_t *>(keys + n);
-    // co-resident blocks only (grid-wide barriers): at most 4 per SM
+    // co-resident blocks only (grid-wide barriers): what the runtime says fits
+    // (registers, 9 KB of static shared memory), at most 4 per SM
     int64_t grid = (n + SORT_THREADS - 1) / SORT_THREADS;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+    static int per_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (!per_sm[dev]) {
+        int fit = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, sort_kernel<M>, SORT_THREADS, 0) !=
+                cudaSuccess || fit < 1) {
+            cudaGetLastError();
+            fit = 1;
+        }
+        per_sm[dev] = fit > 4 ? 4 : fit;
+    }
+    const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm[dev];
     if (grid > cap) grid = cap;
     if (grid > SORT_MAX_BLOCKS) grid = SORT_MAX_BLOCKS;
     void *args[] = {const_cast<ProblemDev *>(&p->dev), const_cast<ModelConsts *>(&p->mc),

@@ -17,6 +17,7 @@
 // round-to-nearest intrinsics (__dmul_rn/__dadd_rn/__dsub_rn), which the
 // compiler never contracts into FMAs: NumPy rounds every product and sum.
 #include "pb200_common.cuh"
+#include "pb200_sampler_dev.cuh"
 
 namespace {
 
@@ -169,31 +170,6 @@ __global__ void de_propose_kernel(const double *__restrict__ cur_all, int64_t fi
     }
 }
 
-// ------------------------------------------------------------------ Philox
-struct U4 { uint32_t x, y, z, w; };
-
-__device__ __forceinline__ U4 philox4x32_10(uint64_t counter, uint64_t stream,
-                                            uint64_t seed) {
-    uint32_t c0 = static_cast<uint32_t>(counter), c1 = static_cast<uint32_t>(counter >> 32);
-    uint32_t c2 = static_cast<uint32_t>(stream), c3 = static_cast<uint32_t>(stream >> 32);
-    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return U4{c0, c1, c2, c3};
-}
-
-// 53-bit uniform in (0, 1)
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-    const uint64_t bits = (static_cast<uint64_t>(hi >> 5) << 26) | (lo >> 6);
-    return (static_cast<double>(bits) + 0.5) * (1.0 / 9007199254740992.0);
-}
-
 __global__ void philox_uniform_kernel(double *out, int64_t n, uint64_t seed,
                                       uint64_t offset) {
     const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -342,38 +318,6 @@ int pb200_de_propose(const double *d_current_all, int64_t first, const double *d
     return pb200_check_cuda(cudaGetLastError(), "de_propose_kernel launch");
 }
 
-// element `idx` of the stream pb200_philox_uniform / pb200_philox_normal would
-// write for (seed, offset): the fused kernels below draw in place and stay
-// bit-identical to the separate launches
-__device__ __forceinline__ double philox_uniform_at(int64_t idx, uint64_t seed, uint64_t offset) {
-    const U4 r = philox4x32_10(offset + (idx >> 1), 1, seed);
-    return (idx & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
-}
-__device__ __forceinline__ double philox_normal_at(int64_t idx, uint64_t seed, uint64_t offset) {
-    const U4 r = philox4x32_10(offset + (idx >> 1), 2, seed);
-    const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    return (idx & 1) ? rad * sn : rad * cs;
-}
-
-// Per-iteration scalars of a sampler loop read from DEVICE memory, so that one
-// captured iteration (ask, solve, tell) can be replayed from a CUDA graph
-// without the host in the loop: row `*counter` of a table planned in advance,
-// eight 64-bit slots per iteration
-//   0 ask offset (normals)   1 second ask offset (DE partner pairs)
-//   2 tell offset (uniforms) 3 sample offset   4 gamma of ask (DE)
-//   5 gamma of tell          6 variant of tell 7 unused
-// and a counter that pb200_iter_advance increments at the end of the
-// iteration.  rows == nullptr: the by-value arguments are used.
-struct IterTable {
-    const int64_t *rows;
-    const int64_t *counter;
-    __device__ __forceinline__ const int64_t *row() const { return rows + 8 * (*counter); }
-};
-__device__ __forceinline__ double slot_f64(int64_t v) { return __longlong_as_double(v); }
-
 __global__ void iter_advance_kernel(int64_t *counter) { *counter += 1; }
 
 // ask of the adaptive-covariance family on the device: normals + Cholesky
@@ -385,28 +329,7 @@ __global__ void ac_ask_kernel(const double *__restrict__ cur, const double *__re
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
     if (it.rows) offset = static_cast<uint64_t>(it.row()[0]);
-    const double scale = exp(log_lambda[j]);
-    const double *sg = sigma + j * static_cast<int64_t>(d) * d;
-    double L[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
-    for (int a = 0; a < d; ++a) {
-        for (int b = 0; b <= a; ++b) {
-            double s = scale * sg[a * d + b];
-            for (int k = 0; k < b; ++k) s -= L[a * d + k] * L[b * d + k];
-            if (a == b) {
-                L[a * d + a] = s > 0.0 ? sqrt(s) : 0.0;
-            } else {
-                const double piv = L[b * d + b];
-                L[a * d + b] = piv > 0.0 ? s / piv : 0.0;
-            }
-        }
-    }
-    double z[PB200_MAX_PARAMS];
-    for (int k = 0; k < d; ++k) z[k] = philox_normal_at(j * d + k, seed, offset);
-    for (int a = 0; a < d; ++a) {
-        double s = cur[j * d + a];
-        for (int k = 0; k <= a; ++k) s = fma(L[a * d + k], z[k], s);
-        prop[j * d + a] = s;
-    }
+    ac_ask_one(cur, sigma, log_lambda, prop, j, d, seed, offset);
 }
 
 // tell of the family on the device, one launch: log-uniform, accept/reject,
@@ -430,47 +353,9 @@ __global__ void ac_tell_kernel(int variant, int require_finite, double *__restri
         gamma = slot_f64(r[5]);
         variant = static_cast<int>(r[6]);
     }
-    const double log_u = log(philox_uniform_at(j, seed, offset));
-    const double f_new = fx[j];
-    const double lr = __dsub_rn(f_new, cur_f[j]);
-    const bool acc = (log_u < lr) && (!require_finite || isfinite(f_new));
-    double x[PB200_MAX_PARAMS], prev[PB200_MAX_PARAMS], y[PB200_MAX_PARAMS];
-    for (int k = 0; k < d; ++k) {
-        prev[k] = cur[j * d + k];
-        y[k] = prop[j * d + k];
-        x[k] = acc ? y[k] : prev[k];
-    }
-    if (acc) {
-        for (int k = 0; k < d; ++k) cur[j * d + k] = x[k];
-        cur_f[j] = f_new;
-    }
-    accepted[j] = acc ? 1 : 0;
-    if (acc_count) acc_count[j] += acc ? 1 : 0;
-    if (samples)
-        for (int k = 0; k < d; ++k) samples[j * sample_stride + sample_offset + k] = x[k];
-    if (variant < 0) return;
-    // adaptation, as ac_adapt_kernel
-    const double keep = __dsub_rn(1.0, gamma);
-    double p = acc ? 1.0 : 0.0;
-    if (variant != PB200_AC_HAARIO_BARDENET) p = lr < 0.0 ? exp(lr) : 1.0;
-    double dev[PB200_MAX_PARAMS];
-    for (int k = 0; k < d; ++k) {
-        const double m = __dadd_rn(__dmul_rn(keep, mu[j * d + k]), __dmul_rn(gamma, x[k]));
-        mu[j * d + k] = m;
-        double v = x[k];
-        if (variant == PB200_AC_RAO_BLACKWELL)
-            v = __dadd_rn(__dmul_rn(p, y[k]), __dmul_rn(__dsub_rn(1.0, p), prev[k]));
-        dev[k] = __dsub_rn(v, m);
-    }
-    double *sg = sigma + j * static_cast<int64_t>(d) * d;
-    for (int a = 0; a < d; ++a)
-        for (int b = 0; b < d; ++b) {
-            const double outer = __dmul_rn(dev[a], dev[b]);
-            sg[a * d + b] = __dadd_rn(__dmul_rn(keep, sg[a * d + b]),
-                                      __dmul_rn(gamma, outer));
-        }
-    if (variant != PB200_AC_RAO_BLACKWELL)
-        log_lambda[j] = __dadd_rn(log_lambda[j], __dmul_rn(gamma, __dsub_rn(p, target)));
+    ac_tell_one(variant, require_finite, cur, cur_f, prop, fx[j], accepted, acc_count, mu, sigma,
+                log_lambda, samples, sample_stride, sample_offset, j, d, gamma, target, seed,
+                offset);
 }
 
 static int ac_ask_impl(const double *d_current, const double *d_sigma,

@@ -585,22 +585,31 @@ def test_mcmc_graph_replay_gives_identical_chains(pb, name):
     n_chains = 24
     x0 = np.array([0.1, 50, 2.0]) * (1 + 0.02 * rng.randn(n_chains, 3))
     chains, rates = [], []
-    for use_graph in (True, False):
+    # the same run three ways: one persistent launch for all iterations after
+    # the second (independent chains on a closed-form model), replay of a
+    # captured iteration from a CUDA graph, and launch by launch
+    independent = name != 'DifferentialEvolutionMCMC'
+    for mode in ('chain loop', 'graph', 'eager'):
         mc = pb.CudaMCMCController(post, n_chains, x0,
                                    method=getattr(pb, name), seed=3)
-        mc.use_graph = use_graph
+        mc.use_chain_loop = mode == 'chain loop'
+        mc.use_graph = mode != 'eager'
         mc.graph_min_iterations = 4
         mc.set_max_iterations(90)
         if mc.sampler().needs_initial_phase():
             mc.set_initial_phase_iterations(30)
         chains.append(mc.run())
-        assert mc.graph_replayed == (88 if use_graph else 0)
+        in_loop = mode == 'chain loop' and independent
+        assert mc.chain_loop_iterations == (88 if in_loop else 0)
+        assert mc.graph_replayed == (88 if mode != 'eager' and not in_loop else 0)
         if hasattr(mc.sampler(), 'acceptance_rate'):
             rates.append(mc.sampler().acceptance_rate())
             assert np.all(rates[-1] >= 0) and np.all(rates[-1] <= 1)
     if rates:                       # same host bookkeeping after the run
         assert np.array_equal(rates[0], rates[1])
+        assert np.array_equal(rates[0], rates[2])
     assert chains[0].shape == (n_chains, 90, 3)
     assert np.array_equal(chains[0], chains[1])
+    assert np.array_equal(chains[0], chains[2])
     assert np.isfinite(chains[0]).all()
     assert len(np.unique(chains[0][:, :, 0])) > n_chains        # they moved
