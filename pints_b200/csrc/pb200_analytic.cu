@@ -283,6 +283,7 @@ struct ChainDev {
     double target;
     uint64_t seed;
     int32_t require_finite, d;
+    uint32_t state_off;           // byte offset of the per-warp chain state in shared memory
 };
 
 template <class E, bool SMEM, bool TRAJ, bool BIG, bool CHAIN = false>
@@ -328,7 +329,7 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
         double x[PB200_MAX_PARAMS];
 #pragma unroll
         for (int k = 0; k < PB200_MAX_PARAMS; ++k)
-            x[k] = (k < n_read) ? (CHAIN ? __ldcg(prow + k) : prow[k]) : 0.0;
+            x[k] = (k < n_read) ? prow[k] : 0.0;
 
         if (!TRAJ) {
             double early;
@@ -418,26 +419,62 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
     };
 
     if constexpr (CHAIN) {
-        // chain j = this warp, for all planned iterations
+        // chain j = this warp, for all planned iterations.  Its state (current
+        // point and score, proposal, mu, sigma, log lambda: 3 d + d^2 + 3
+        // doubles) lives in shared memory for the duration of the loop, so an
+        // iteration makes no dependent round trip to global memory; only the
+        // chain sample is stored (fire and forget).  The d normals of a
+        // proposal are drawn by d lanes at once.
         const int64_t j = static_cast<int64_t>(blockIdx.x) * warps + warp;
         if (j < n) {
-            const int d = ch.d;
+            const int d = ch.d, dd = d * d;
+            double *st = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + ch.state_off) +
+                         static_cast<size_t>(warp) * (3 * d + dd + 3 + PB200_MAX_PARAMS);
+            double *s_cur = st, *s_prop = st + d, *s_mu = st + 2 * d, *s_sig = st + 3 * d;
+            double *s_curf = s_sig + dd, *s_ll = s_curf + 1, *s_z = s_ll + 2;
+            for (int k = lane; k < d; k += 32) {
+                s_cur[k] = ch.cur[j * d + k];
+                s_mu[k] = ch.mu[j * d + k];
+            }
+            for (int k = lane; k < dd; k += 32) s_sig[k] = ch.sigma[j * dd + k];
+            if (lane == 0) { s_curf[0] = ch.cur_f[j]; s_ll[0] = ch.log_lambda[j]; }
+            __syncwarp();
+            int64_t n_acc = 0;
+            bool acc = false;
+            double f_new = 0.0;
             for (int64_t it = 0; it < ch.n_iter; ++it) {
                 const int64_t *r = ch.rows + 8 * (ch.first_row + it);
-                if (lane == 0)
-                    ac_ask_one(ch.cur, ch.sigma, ch.log_lambda, ch.prop, j, d, ch.seed,
-                               static_cast<uint64_t>(r[0]));
+                const uint64_t off_ask = static_cast<uint64_t>(r[0]);
+                if (lane < d) s_z[lane] = philox_normal_at(j * d + lane, ch.seed, off_ask);
                 __syncwarp();
-                const double f_new = eval_row(j, ch.prop + j * d);
+                if (lane == 0)
+                    ac_ask_row(s_cur, s_sig, s_ll, s_prop, j, d, ch.seed, off_ask, s_z);
+                __syncwarp();
+                f_new = eval_row(j, s_prop);
                 if (lane == 0) {
-                    ch.fx[j] = f_new;
-                    ac_tell_one(static_cast<int>(r[6]), ch.require_finite, ch.cur, ch.cur_f,
-                                ch.prop, f_new, ch.accepted, ch.acc_count, ch.mu, ch.sigma,
-                                ch.log_lambda, ch.samples, ch.sample_stride, r[3], j, d,
-                                slot_f64(r[5]), ch.target, ch.seed,
-                                static_cast<uint64_t>(r[2]));
+                    acc = ac_tell_row(static_cast<int>(r[6]), ch.require_finite, s_cur, s_curf,
+                                      s_prop, f_new, s_mu, s_sig, s_ll,
+                                      ch.samples ? ch.samples + j * ch.sample_stride + r[3]
+                                                 : nullptr,
+                                      j, d, slot_f64(r[5]), ch.target, ch.seed,
+                                      static_cast<uint64_t>(r[2]));
+                    n_acc += acc ? 1 : 0;
                 }
                 __syncwarp();
+            }
+            // state back to the arrays the launch-per-step kernels use
+            for (int k = lane; k < d; k += 32) {
+                ch.cur[j * d + k] = s_cur[k];
+                ch.mu[j * d + k] = s_mu[k];
+                ch.prop[j * d + k] = s_prop[k];
+            }
+            for (int k = lane; k < dd; k += 32) ch.sigma[j * dd + k] = s_sig[k];
+            if (lane == 0) {
+                ch.cur_f[j] = s_curf[0];
+                ch.log_lambda[j] = s_ll[0];
+                ch.fx[j] = f_new;
+                ch.accepted[j] = acc ? 1 : 0;
+                if (ch.acc_count) ch.acc_count[j] += n_acc;
             }
         }
     } else {
@@ -501,7 +538,7 @@ int launch_eval(const pb200_problem *p, const double *d_params, int64_t n,
 
 // the persistent MCMC loop: one warp per chain, all chains resident at once
 template <class E>
-int launch_chain(const pb200_problem *p, int64_t n, const ChainDev &ch, cudaStream_t st) {
+int launch_chain(const pb200_problem *p, int64_t n, const ChainDev &ch_in, cudaStream_t st) {
     const int64_t bytes = ((static_cast<int64_t>(p->dev.n_times) + PB200_SENTINEL_ROWS) * p->dev.row * 8 + 15) & ~15ll;
     const size_t aux_bytes = E::POINT_AUX ? (static_cast<size_t>(p->dev.n_times) + 15) & ~size_t(15) : 0;
     const uint32_t table_doubles = E::POINT_AUX
@@ -515,7 +552,17 @@ int launch_chain(const pb200_problem *p, int64_t n, const ChainDev &ch, cudaStre
     // few chains: spread them over the SMs (one 2-warp block each) rather than
     // packing eight warps onto one SM
     const int warps = big ? 32 : (n <= 2 * 148 ? 2 : 8);
-    const size_t dyn = staged + static_cast<size_t>(warps) * table_doubles * 8;
+    const size_t tables = static_cast<size_t>(warps) * table_doubles * 8;
+    const size_t state = static_cast<size_t>(warps) *
+                         (3 * ch_in.d + ch_in.d * ch_in.d + 3 + PB200_MAX_PARAMS) * 8;
+    const size_t dyn = staged + tables + state;
+    if (dyn > 200 * 1024) {
+        pb200_set_error("pb200_mcmc_chain_run: series, tables and chain state need %zu bytes of "
+                        "shared memory", dyn);
+        return PB200_EUNSUPPORTED;
+    }
+    ChainDev ch = ch_in;
+    ch.state_off = static_cast<uint32_t>(staged + tables);
     const int64_t grid = (n + warps - 1) / warps;
     const ScatterDev none = {};
 #define PB200_LAUNCH(BG)                                                                 \

@@ -68,13 +68,15 @@ struct IterTable {
 __device__ __forceinline__ double slot_f64(int64_t v) { return __longlong_as_double(v); }
 
 
-// ask() of chain j: x* = x + chol(sigma e^{log lambda}) z with the normals
-// pb200_philox_normal would write at [j d, (j + 1) d) for (seed, offset)
-__device__ __forceinline__ void ac_ask_one(const double *cur, const double *sigma,
+// ask() of one chain: x* = x + chol(sigma e^{log lambda}) z.  `cur`, `sigma`,
+// `log_lambda`, `prop` point at THIS chain's rows (global memory, or the shared
+// memory copy of the chain loop); z are the normals pb200_philox_normal would
+// write at [j d, (j + 1) d) for (seed, offset), drawn here unless given.
+__device__ __forceinline__ void ac_ask_row(const double *cur, const double *sg,
                                            const double *log_lambda, double *prop, int64_t j,
-                                           int d, uint64_t seed, uint64_t offset) {
-    const double scale = exp(log_lambda[j]);
-    const double *sg = sigma + j * static_cast<int64_t>(d) * d;
+                                           int d, uint64_t seed, uint64_t offset,
+                                           const double *z_given = nullptr) {
+    const double scale = exp(log_lambda[0]);
     double L[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
     for (int a = 0; a < d; ++a) {
         for (int b = 0; b <= a; ++b) {
@@ -89,55 +91,61 @@ __device__ __forceinline__ void ac_ask_one(const double *cur, const double *sigm
         }
     }
     double z[PB200_MAX_PARAMS];
-    for (int k = 0; k < d; ++k) z[k] = philox_normal_at(j * d + k, seed, offset);
+    for (int k = 0; k < d; ++k)
+        z[k] = z_given ? z_given[k] : philox_normal_at(j * d + k, seed, offset);
     for (int a = 0; a < d; ++a) {
-        double s = cur[j * d + a];
+        double s = cur[a];
         for (int k = 0; k <= a; ++k) s = fma(L[a * d + k], z[k], s);
-        prop[j * d + a] = s;
+        prop[a] = s;
     }
 }
 
-// tell() of chain j given the score f_new of its proposal: log-uniform,
-// accept/reject, acceptance count, chain sample, adaptation (variant < 0: none)
-__device__ __forceinline__ void ac_tell_one(int variant, int require_finite, double *cur,
+// the same with the arrays of all chains (row j is used)
+__device__ __forceinline__ void ac_ask_one(const double *cur, const double *sigma,
+                                           const double *log_lambda, double *prop, int64_t j,
+                                           int d, uint64_t seed, uint64_t offset) {
+    ac_ask_row(cur + j * d, sigma + j * static_cast<int64_t>(d) * d, log_lambda + j,
+               prop + j * d, j, d, seed, offset);
+}
+
+// tell() of one chain given the score f_new of its proposal: log-uniform,
+// accept/reject, chain sample, adaptation (variant < 0: none).  `cur`, `cur_f`,
+// `prop`, `mu`, `sg` (sigma), `log_lambda` point at THIS chain's rows; `sample`
+// at where its new current point goes (or NULL).  Returns the decision.
+__device__ __forceinline__ bool ac_tell_row(int variant, int require_finite, double *cur,
                                             double *cur_f, const double *prop, double f_new,
-                                            uint8_t *accepted, int64_t *acc_count, double *mu,
-                                            double *sigma, double *log_lambda, double *samples,
-                                            int64_t sample_stride, int64_t sample_offset,
-                                            int64_t j, int d, double gamma, double target,
-                                            uint64_t seed, uint64_t offset) {
+                                            double *mu, double *sg, double *log_lambda,
+                                            double *sample, int64_t j, int d, double gamma,
+                                            double target, uint64_t seed, uint64_t offset) {
     const double log_u = log(philox_uniform_at(j, seed, offset));
-    const double lr = __dsub_rn(f_new, cur_f[j]);
+    const double lr = __dsub_rn(f_new, cur_f[0]);
     const bool acc = (log_u < lr) && (!require_finite || isfinite(f_new));
     double x[PB200_MAX_PARAMS], prev[PB200_MAX_PARAMS], y[PB200_MAX_PARAMS];
     for (int k = 0; k < d; ++k) {
-        prev[k] = cur[j * d + k];
-        y[k] = prop[j * d + k];
+        prev[k] = cur[k];
+        y[k] = prop[k];
         x[k] = acc ? y[k] : prev[k];
     }
     if (acc) {
-        for (int k = 0; k < d; ++k) cur[j * d + k] = x[k];
-        cur_f[j] = f_new;
+        for (int k = 0; k < d; ++k) cur[k] = x[k];
+        cur_f[0] = f_new;
     }
-    accepted[j] = acc ? 1 : 0;
-    if (acc_count) acc_count[j] += acc ? 1 : 0;
-    if (samples)
-        for (int k = 0; k < d; ++k) samples[j * sample_stride + sample_offset + k] = x[k];
-    if (variant < 0) return;
+    if (sample)
+        for (int k = 0; k < d; ++k) sample[k] = x[k];
+    if (variant < 0) return acc;
     // adaptation, as ac_adapt_kernel
     const double keep = __dsub_rn(1.0, gamma);
     double p = acc ? 1.0 : 0.0;
     if (variant != PB200_AC_HAARIO_BARDENET) p = lr < 0.0 ? exp(lr) : 1.0;
     double dev[PB200_MAX_PARAMS];
     for (int k = 0; k < d; ++k) {
-        const double m = __dadd_rn(__dmul_rn(keep, mu[j * d + k]), __dmul_rn(gamma, x[k]));
-        mu[j * d + k] = m;
+        const double m = __dadd_rn(__dmul_rn(keep, mu[k]), __dmul_rn(gamma, x[k]));
+        mu[k] = m;
         double v = x[k];
         if (variant == PB200_AC_RAO_BLACKWELL)
             v = __dadd_rn(__dmul_rn(p, y[k]), __dmul_rn(__dsub_rn(1.0, p), prev[k]));
         dev[k] = __dsub_rn(v, m);
     }
-    double *sg = sigma + j * static_cast<int64_t>(d) * d;
     for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) {
             const double outer = __dmul_rn(dev[a], dev[b]);
@@ -145,5 +153,24 @@ __device__ __forceinline__ void ac_tell_one(int variant, int require_finite, dou
                                       __dmul_rn(gamma, outer));
         }
     if (variant != PB200_AC_RAO_BLACKWELL)
-        log_lambda[j] = __dadd_rn(log_lambda[j], __dmul_rn(gamma, __dsub_rn(p, target)));
+        log_lambda[0] = __dadd_rn(log_lambda[0], __dmul_rn(gamma, __dsub_rn(p, target)));
+    return acc;
+}
+
+// the same with the arrays of all chains (row j is used), plus the decision
+// flag and the acceptance count
+__device__ __forceinline__ void ac_tell_one(int variant, int require_finite, double *cur,
+                                            double *cur_f, const double *prop, double f_new,
+                                            uint8_t *accepted, int64_t *acc_count, double *mu,
+                                            double *sigma, double *log_lambda, double *samples,
+                                            int64_t sample_stride, int64_t sample_offset,
+                                            int64_t j, int d, double gamma, double target,
+                                            uint64_t seed, uint64_t offset) {
+    const bool acc = ac_tell_row(
+        variant, require_finite, cur + j * d, cur_f + j, prop + j * d, f_new, mu + j * d,
+        sigma + j * static_cast<int64_t>(d) * d, log_lambda + j,
+        samples ? samples + j * sample_stride + sample_offset : nullptr, j, d, gamma, target,
+        seed, offset);
+    accepted[j] = acc ? 1 : 0;
+    if (acc_count) acc_count[j] += acc ? 1 : 0;
 }
