@@ -39,9 +39,9 @@ WORKLOAD = ('FitzhughNagumoModel (3 params, 1000 times on [0,20]) + '
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one ode_kernel launch at this
 # workload, from the `ncu --set full` capture summarised in
-# profiles/r01h_ode_kernel_summary.md (algorithmic HBM traffic: 32 B per
+# profiles/r02_ode_kernel_summary.md (algorithmic HBM traffic: 32 B per
 # evaluation = 2.1 MB per launch; the path is FP64-bound, not HBM-bound)
-TRAFFIC_BYTES_PER_LAUNCH = 1918208
+TRAFFIC_BYTES_PER_LAUNCH = 1923328
 
 
 def hbm_side(kernel_ms):

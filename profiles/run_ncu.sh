@@ -24,6 +24,10 @@ if [ "$WHAT" = headline ] || [ "$WHAT" = all ]; then
       > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -c 600 gpurun_out/plain_$TAG.log
   tail -3 gpurun_out/ncu_full_$TAG.log
+  python profiles/summarize.py gpurun_out/prof_${TAG}_ode_kernel.ncu-rep > gpurun_out/${TAG}_ode_kernel_summary.md
+  ncu -i gpurun_out/prof_${TAG}_ode_kernel.ncu-rep --page source --csv > gpurun_out/src_ode.csv 2>/dev/null &&
+    python profiles/sass_mix.py gpurun_out/src_ode.csv 30 > gpurun_out/${TAG}_ode_kernel_sass_mix.txt
+  rm -f gpurun_out/src_ode.csv
 fi
 if [ "$WHAT" = kernels ] || [ "$WHAT" = all ]; then
   : > gpurun_out/targets_$TAG.log
@@ -32,6 +36,12 @@ if [ "$WHAT" = kernels ] || [ "$WHAT" = all ]; then
     $NCU -k regex:$2 -s $3 -c 1 -o gpurun_out/prof_${TAG}_$4 \
         python tools/ncu_targets.py $1 > gpurun_out/ncu_$4_$TAG.log 2>&1
     tail -1 gpurun_out/ncu_$4_$TAG.log
+    # gpurun brings back at most 64 MiB: keep the text, drop the big report
+    python profiles/summarize.py gpurun_out/prof_${TAG}_$4.ncu-rep > gpurun_out/${TAG}_$4_summary.md
+    ncu -i gpurun_out/prof_${TAG}_$4.ncu-rep --page source --csv > gpurun_out/src_$4.csv 2>/dev/null &&
+      python profiles/sass_mix.py gpurun_out/src_$4.csv 20 > gpurun_out/${TAG}_$4_sass_mix.txt
+    rm -f gpurun_out/src_$4.csv
+    [ $(stat -c %s gpurun_out/prof_${TAG}_$4.ncu-rep) -gt 9000000 ] && rm -f gpurun_out/prof_${TAG}_$4.ncu-rep
   }
   capture unfused  'ode_kernel'         1 unfused_simulate
   capture unfused  'score_traj_kernel'  1 unfused_reduce
@@ -44,6 +54,7 @@ if [ "$WHAT" = kernels ] || [ "$WHAT" = all ]; then
   python tools/ncu_targets.py argsort >> gpurun_out/targets_$TAG.log 2>&1 &&
   $NCU -k regex:argsort -s 35 -c 7 -o gpurun_out/prof_${TAG}_argsort \
       python tools/ncu_targets.py argsort > gpurun_out/ncu_argsort_$TAG.log 2>&1
+  python profiles/summarize.py gpurun_out/prof_${TAG}_argsort.ncu-rep > gpurun_out/${TAG}_argsort_summary.md
   cat gpurun_out/targets_$TAG.log
 fi
 ls -la gpurun_out/ | tail -20
