@@ -266,6 +266,11 @@ class CudaMCMCController(object):
     accept/reject, adapt, store -- is enqueued on the GPU and only the finished
     chains come back to the host.
 
+    ``sharded=True`` (one process per GPU) runs a contiguous block of the chains
+    on every rank with a rank-dependent Philox seed: results are reproducible
+    for a given seed AND world size, and differ (statistically equivalent
+    chains) between world sizes.
+
     Parameters follow the reference: ``log_pdf`` (a supported LogPDF, see
     ``CudaEvaluator``), ``chains``, ``x0`` (``chains`` starting points),
     ``sigma0``, ``method`` (``HaarioBardenetACMC`` (default), ``HaarioACMC``,
@@ -312,7 +317,11 @@ class CudaMCMCController(object):
                                  'the number of ranks.')
             lo, hi, _ = shard_bounds(self._n_chains, world, rank)
             self._first, self._n_local = lo, hi - lo
-            seed = int(seed) + 7919 * rank          # distinct device streams
+            # distinct device streams per rank.  NB: the Philox counters are
+            # indexed by the LOCAL chain number, so a sharded run draws other
+            # numbers than the same chains on one GPU (or on another number of
+            # GPUs): the chains are statistically, not bitwise, the same.
+            seed = int(seed) + 7919 * rank
             if device is None:
                 device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', '0'))
         if self._n_chains < 1:
