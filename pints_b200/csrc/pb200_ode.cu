@@ -613,8 +613,8 @@ __device__ __forceinline__ double step_factor_bits(double sum2, bool cap_at_one)
     // 0x3FF00000 + 2^20 log2(0.9 NS^0.1) - 50000 (centring) + 0x3FF00000 / 10
     constexpr int32_t magic =
         NS == 1 ? 1179753186 : NS == 2 ? 1179858044 : NS == 3 ? 1179919381
-        : NS == 4 ? 1179962902 : NS == 5 ? 1179996658 : 1180024239;
-    static_assert(NS >= 1 && NS <= 6, "magic constant tabulated for 1..6 states");
+        : NS == 4 ? 1179962902 : NS == 5 ? 1179996658 : NS == 6 ? 1180024239 : 1180067762;
+    static_assert((NS >= 1 && NS <= 6) || NS == 8, "magic constant tabulated for 1..6 and 8 states");
     const uint32_t hi = static_cast<uint32_t>(__double2hiint(sum2));
     int32_t hy = magic - static_cast<int32_t>(__umulhi(hi, 0x1999999Au));
     hy = max(hy, 0x3FC99999);                        // 0.2
@@ -650,6 +650,24 @@ struct Series {
     }
 };
 
+#ifndef PB200_TH1_FROM_TH
+#define PB200_TH1_FROM_TH 0     // 1 - theta by subtraction instead of its own affine map
+#endif
+#ifndef PB200_SCALE_FROM_Y
+#define PB200_SCALE_FROM_Y 0    // error weight rtol |y| + atol instead of rtol (|y| + |y_new|) / 2 + atol
+#endif
+#ifndef PB200_MIG_STRIDED
+#define PB200_MIG_STRIDED 1     // migrating layout: warps dealt to the blocks round-robin
+#endif
+#ifndef PB200_STAGGER
+#define PB200_STAGGER 0         // (development) start offset in cycles between a scheduler's warps
+#endif
+#ifndef PB200_TIMELINE
+#define PB200_TIMELINE 0        // (development) per-warp start / end clocks
+#endif
+#if PB200_TIMELINE
+__device__ long long pb200_timeline[160 * 16 * 4];
+#endif
 #ifndef PB200_PIPE_U
 #define PB200_PIPE_U 2          // in-line interpolation slots per step attempt
 #endif
@@ -666,7 +684,7 @@ struct Series {
 #define PB200_LOOP_UNROLL 2
 #endif
 #ifndef PB200_CTRL_BITS
-#define PB200_CTRL_BITS 0       // integer step-size factor (no SFU)
+#define PB200_CTRL_BITS 1       // integer step-size factor (no SFU)
 #endif
 #ifndef PB200_RCP_STEPS
 #define PB200_RCP_STEPS 1
@@ -802,8 +820,25 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         } else if (warp >= mig.q4) {
             role = SOURCE; mig_j = warp - mig.q4;
         }
+#if PB200_MIG_STRIDED
+        // warp v of block b takes warp (v * blocks + b) of the launch order: after
+        // the cost sort a block would otherwise hold 12-14 NEIGHBOURING warps, i.e.
+        // SMs with uniformly cheap or uniformly expensive vectors
+        gi = (static_cast<int64_t>(vw) * gridDim.x + blockIdx.x) * 32 + lane;
+#else
         gi = (static_cast<int64_t>(blockIdx.x) * (mig.q4 + mig.r) + vw) * 32 + lane;
+#endif
     }
+#if PB200_TIMELINE
+    const long long tl_start = clock64();
+#endif
+#if PB200_STAGGER
+    if (MIG) {
+        // warps of one scheduler start a quarter of an attempt apart
+        const long long until = clock64() + static_cast<long long>((threadIdx.x >> 7) & 3) * PB200_STAGGER;
+        while (clock64() < until) { }
+    }
+#endif
     // the role is the same for a whole warp; taking it from a vote tells the
     // compiler so (branches on it stay uniform, constants stay in uniform
     // registers)
@@ -927,7 +962,11 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     // one interpolation of the pending interval at time tq against row `row`
     auto interpolate = [&](double tq, uint32_t row, bool valid) {
         const double th = fma(tq, p_invh, p_c0);
+#if PB200_TH1_FROM_TH
+        const double th1 = 1.0 - th;
+#else
         const double th1 = fma(-tq, p_invh, p_c1);
+#endif
         double v[NO];
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
@@ -1050,7 +1089,13 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
             const double e = fma(E7, K7[j], fma(E6, K6[j], fma(E5, K5[j], fma(E4, K4[j], fma(E3, K3[j], E1 * K1[j])))));
+#if PB200_SCALE_FROM_Y
+            // error weight from the state at the start of the step, as LSODA's
+            // EWT = rtol |y| + atol (the reference's integrator)
+            const double sc = fma(S.rtol, fabs(y[j]), atol);
+#else
             const double sc = fma(half_rtol, fabs(y[j]) + fabs(yn[j]), atol);
+#endif
             const double q = e * rcp_seed(sc);
             sum2 = j == 0 ? q * q : fma(q, q, sum2);
         }
@@ -1123,7 +1168,9 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         }
         p_invh = inv_h;
         p_c0 = -t * inv_h;
+#if !PB200_TH1_FROM_TH
         p_c1 = t_new * inv_h;
+#endif
         t = ok ? t_new : t;
         h *= facd;
 #pragma unroll
@@ -1169,6 +1216,14 @@ ode_kernel(const __grid_constant__ ProblemDev P,
             put_score(sc, scores, slot, i, failed ? NAN : objective_finish(P, ss, x));
         }
     }
+#if PB200_TIMELINE
+    if (MIG && (threadIdx.x & 31) == 0 && blockIdx.x < 160) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *row = pb200_timeline + (blockIdx.x * 16 + (threadIdx.x >> 5)) * 4;
+        row[0] = tl_start; row[1] = clock64(); row[2] = smid; row[3] = role * 1000000 + attempts;
+    }
+#endif
     // multi-GPU launches: the last block to get here raises this rank's flags
     if (!TRAJ) exchange_signal(sc);
 }
@@ -1345,7 +1400,11 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
 
     auto interpolate = [&](double tq, uint32_t row, bool valid) {
         const double th = fma(tq, p_invh, p_c0);
+#if PB200_TH1_FROM_TH
+        const double th1 = 1.0 - th;
+#else
         const double th1 = fma(-tq, p_invh, p_c1);
+#endif
         const double v = fma(th, fma(th1, fma(th, fma(th1, p_r5, p_r4), p_r3), p_r2), p_y);
         const double r = series.at(row + vofs) - v;
         if (TRAJ) { if (valid) my_traj[row / ROWB * NO] = v; }
@@ -1433,7 +1492,9 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
         }
         p_invh = inv_h;
         p_c0 = -t * inv_h;
+#if !PB200_TH1_FROM_TH
         p_c1 = t_new * inv_h;
+#endif
         t = ok ? t_new : t;
         h *= facd;
         y = ok ? yn : y;
@@ -1892,3 +1953,9 @@ int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
 int64_t ode_sort_workspace_bytes(int64_t n) {
     return static_cast<int64_t>(sizeof(SortHeader)) + 8 * (n > 0 ? n : 0);
 }
+
+#if PB200_TIMELINE
+extern "C" int pb200_debug_timeline(long long *host, int n_words) {
+    return (int)cudaMemcpyFromSymbol(host, pb200_timeline, sizeof(long long) * n_words);
+}
+#endif

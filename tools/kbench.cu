@@ -14,6 +14,9 @@
 #include <cuda_runtime.h>
 #include "../include/pints_b200.h"
 
+#if PB200_TIMELINE
+extern "C" int pb200_debug_timeline(long long *host, int n_words);
+#endif
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
     printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 #define PB(x) do { int rc = (x); if (rc) { printf("pb200 error %d: %s\n", rc, pb200_last_error()); exit(1);} } while (0)
@@ -93,5 +96,33 @@ int main(int argc, char **argv) {
     double med = ms[reps / 2];
     printf("sort=%d%d lanes=%d n=%ld block=%d spread=%g nt=%d  median %.4f ms  min %.4f ms  %.3e evals/s  %.2f TFLOP/s  mean_steps %.1f  checksum %.10e  nonfinite %ld\n",
            presort, devsort, lanes, n, block, spread, nt, med, ms[0], n / (med * 1e-3), flops / (med * 1e-3) / 1e12, steps / n, sum / (n - bad), bad);
+#if PB200_TIMELINE
+    {
+        // per-warp start / end clocks of the LAST launch (migrating layout only)
+        std::vector<long long> tl(160 * 16 * 4);
+        if (pb200_debug_timeline(tl.data(), (int)tl.size()) == 0) {
+            long long t0 = -1;
+            for (int b = 0; b < 147; ++b) for (int w = 0; w < 16; ++w) { long long v = tl[(b * 16 + w) * 4]; if (v && (t0 < 0 || v < t0)) t0 = v; }
+            std::vector<double> bend;
+            double sched_sum[4] = {0, 0, 0, 0};
+            for (int b = 0; b < 147; ++b) {
+                long long e = 0;
+                for (int w = 0; w < 16; ++w) { long long v = tl[(b * 16 + w) * 4 + 1]; if (v > e) e = v; }
+                bend.push_back((double)(e - t0));
+                for (int sc = 0; sc < 4; ++sc) { long long m = 0; for (int w = sc; w < 16; w += 4) { long long v = tl[(b * 16 + w) * 4 + 1]; if (v > m) m = v; } sched_sum[sc] += (double)(m - t0); }
+            }
+            std::vector<double> sorted_end = bend; std::sort(sorted_end.begin(), sorted_end.end());
+            double mean = 0; for (double v : bend) mean += v; mean /= bend.size();
+            printf("timeline: block end (cycles after first start) min %.0f  p10 %.0f  median %.0f  mean %.0f  p90 %.0f  max %.0f\n",
+                   sorted_end.front(), sorted_end[14], sorted_end[73], mean, sorted_end[132], sorted_end.back());
+            printf("timeline: mean end of the last warp per scheduler: %.0f %.0f %.0f %.0f\n", sched_sum[0] / 147, sched_sum[1] / 147, sched_sum[2] / 147, sched_sum[3] / 147);
+            for (int b : {0, 36, 73, 110, 146}) {
+                printf("timeline: block %3d sm %3lld:", b, tl[(b * 16) * 4 + 2]);
+                for (int w = 0; w < 16; ++w) printf(" %lld-%lld(%lld)", (tl[(b * 16 + w) * 4] - t0) / 1000, (tl[(b * 16 + w) * 4 + 1] - t0) / 1000, tl[(b * 16 + w) * 4 + 3]);
+                printf("\n");
+            }
+        }
+    }
+#endif
     return 0;
 }
