@@ -61,8 +61,12 @@ const ModelInfo kModels[PB200_N_MODELS] = {
 // log-likelihood error of 1.2e-6 at that tolerance (LSODA itself: 1.9e-5), and
 // the error is proportional to the tolerance (sweep in
 // profiles/r02_lv_tolerance.md), so its default is 5e-9: 3.8e-7, inside the
-// 1e-6 bar with margin, for 23 % more steps.
+// 1e-6 bar with margin, for 23 % more steps.  Beeler-Reuter (the reference:
+// LSODA at rtol 1e-4 / atol 1e-6, 1.7e-3 from the converged log-likelihood)
+// runs on the Rosenbrock integrator at 1e-7: 8.5e-7 from the converged
+// log-likelihood in 1 650 steps (profiles/r02x_br_rosenbrock.log).
 double default_tolerance(int model) {
+    if (model == PB200_MODEL_BEELER_REUTER) return 1e-7;
     return model == PB200_MODEL_LOTKA_VOLTERRA ? 5e-9 : 1.49012e-8;
 }
 

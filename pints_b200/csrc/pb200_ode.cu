@@ -486,7 +486,22 @@ struct BeelerReuterModel {
         h_ = 1.0;
         *t0 = t_first;
     }
-    __device__ __forceinline__ void rhs_t(const double *y, double *f, double time) const {
+    // stimulus current at `time`: (time % period) < length, times are not negative
+    __device__ __forceinline__ double stimulus(double time) const {
+        double ph = fma(-period, floor(time * inv_period), time);
+        if (ph < 0.0) ph += period;
+        if (ph >= period) ph -= period;
+        return ph < length ? amp : 0.0;
+    }
+    // What the arrow-shaped Jacobian of the stiff integrator needs besides one
+    // difference quotient in V: the gates' relaxation rates and three factors.
+    struct Aux {
+        double rate[6];       // alpha + beta of m, h, j, d, f, x1
+        double dECa;          // V - E_Ca
+        double m3, xf;        // m^3; Ix1 = gx1 x1 xf
+    };
+    template <bool AUX>
+    __device__ __forceinline__ void rhs_core(const double *y, double *f, double IStim, Aux *aux) const {
         const double V = y[0], Cai = y[1], m = y[2], hh = y[3], j = y[4], d = y[5],
                      ff = y[6], x1 = y[7];
         // one exponential per distinct rate; the shifted ones are constant
@@ -514,25 +529,31 @@ struct BeelerReuterModel {
         const double inv_e04 = rcp_newton<2>(e_p04);
 #undef PB200_BR_EXP
         // INa and its gates
-        const double INa = (gNa * (m * m * m) * hh * j + gNaC) * (V - e_na);
+        const double m3 = m * m * m;
+        const double INa = (gNa * m3 * hh * j + gNaC) * (V - e_na);
         double al = div_normal(V + 47.0, 1.0 - e_m01);
         double be = 40.0 * e_m056;
         f[2] = al * (1.0 - m) - be * m;
+        if (AUX) aux->rate[0] = al + be;
         al = 0.126 * e_m25;
         be = div_normal(1.7, 1.0 + e_m082);
         f[3] = al * (1.0 - hh) - be * hh;
+        if (AUX) aux->rate[1] = al + be;
         al = div_normal(0.055 * (e_m25 * 0.7788007830714049), 1.0 + e_m2);           // exp(-0.25)
         be = div_normal(0.3, 1.0 + e_m01 * 4.4816890703380645);                       // exp(1.5)
         f[4] = al * (1.0 - j) - be * j;
+        if (AUX) aux->rate[2] = al + be;
         // ICa and its gates
         const double E_Ca = -82.3 - 13.0287 * log(Cai);
         const double ICa = gCa * d * ff * (V - E_Ca);
         al = div_normal(0.095 * e_m01b, e_m072 + 1.0);
         be = div_normal(0.07 * e_m017, e_p05 + 1.0);
         f[5] = al * (1.0 - d) - be * d;
+        if (AUX) aux->rate[3] = al + be;
         al = div_normal(0.012 * e_m008, e_p15 + 1.0);
         be = div_normal(0.0065 * e_m02, e_m2 * 14764.781565577267 + 1.0);             // exp(9.6)
         f[6] = al * (1.0 - ff) - be * ff;
+        if (AUX) aux->rate[4] = al + be;
         f[1] = -1e-7 * ICa + 0.07 * (1e-7 - Cai);
         // IK1: exp(0.04 (V+85)) = e04 exp(1.28), exp(0.08 (V+53)) = e04^2,
         // exp(-0.04 (V+23)) = exp(1.2) / e04
@@ -540,17 +561,16 @@ struct BeelerReuterModel {
             div_normal(4.0 * (e_p04 * 3.5966397255692817 - 1.0), e_p04 * e_p04 + e_p04)
             + div_normal(0.2 * (V + 23.0), 1.0 - 3.3201169227365472 * inv_e04));
         // Ix1: exp(0.04 (V+77)) = e04 exp(0.96), exp(0.04 (V+35)) = e04 exp(-0.72)
-        const double Ix1 = gx1 * x1 * (e_p04 * 2.611696473423118 - 1.0)
-                           * (inv_e04 * 2.0544332106438876);                 // exp(0.72)
+        const double xf = (e_p04 * 2.611696473423118 - 1.0) * (inv_e04 * 2.0544332106438876);   // exp(0.72)
+        const double Ix1 = gx1 * x1 * xf;
         al = div_normal(0.0005 * e_p083, e_p057 + 1.0);
         be = div_normal(0.0013 * e_m06, 1.3674196065680964e-05 * inv_e04 + 1.0);      // exp(-11.2)
         f[7] = al * (1.0 - x1) - be * x1;
-        // stimulus: (time % period) < length, times are not negative
-        double ph = fma(-period, floor(time * inv_period), time);
-        if (ph < 0.0) ph += period;
-        if (ph >= period) ph -= period;
-        const double IStim = ph < length ? amp : 0.0;
+        if (AUX) { aux->rate[5] = al + be; aux->dECa = V - E_Ca; aux->m3 = m3; aux->xf = xf; }
         f[0] = -inv_cm * (IK1 + Ix1 + INa + ICa - IStim);
+    }
+    __device__ __forceinline__ void rhs_t(const double *y, double *f, double time) const {
+        rhs_core<false>(y, f, stimulus(time), nullptr);
     }
     __device__ __forceinline__ void scale(double h) { h_ = h; }
     __device__ __forceinline__ void hrhs_t(const double *y, double *K, double time) const {
@@ -1229,6 +1249,322 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 }
 
 // ======================================================================
+// Stiff integrator for the Beeler-Reuter model: the 4-stage Rosenbrock method
+// of Kaps & Rentrop in Shampine's parameterisation (order 4, embedded order 3;
+// gamma = 1/2), replacing for this model the explicit DP5(4) template above,
+// which is stability-bound by the sodium activation gate (7 700 steps for
+// 400 ms at any tolerance).  The reference's LSODA switches to BDF on this
+// model (pints/toy/_beeler_reuter_model.py:205-222).
+//
+// * Jacobian.  The system is an arrow: the six gates relax towards
+//   voltage-dependent targets (dg/dt = alpha(V)(1-g) - beta(V) g: own diagonal
+//   -(alpha+beta) and a V column), the V row is full and polynomial in the
+//   gates, the Ca row couples to V, Ca, d, f.  The V column costs ONE extra
+//   right-hand side (forward difference); everything else is analytic from
+//   factors the right-hand side computes anyway (BeelerReuterModel::Aux).
+// * Linear algebra.  (I/(gamma h) - J) x = b: the gates are eliminated by
+//   substitution, leaving a 2 x 2 system in (V, Ca); the elimination factors
+//   are prepared once per attempt, each of the four solves is ~40 FMAs.
+// * Stimulus.  Steps are clipped to land exactly on the edges of the
+//   stimulus (k period, k period + length); inside a step it is constant, so
+//   the system is autonomous there (no df/dt term).
+// * Dense output.  Cubic Hermite on (y_n, f_n, y_n+1, f_n+1); f_n+1 is the
+//   next step's first right-hand side, so an attempt costs four right-hand
+//   sides (two stages, the difference quotient, f_n+1).
+// * Error weights atol w_i + rtol |y_i| with w = 1 except 1e-6 for the
+//   calcium concentration (its values are 2e-7 .. 7e-6).
+// Prototype and convergence table: tools/br_rosenbrock_proto.py.
+// ======================================================================
+#ifndef PB200_BRR_THREADS
+#define PB200_BRR_THREADS 128
+#endif
+#ifndef PB200_BRR_BLOCKS
+#define PB200_BRR_BLOCKS 3
+#endif
+
+struct BrArrow {
+    // (a I - J) x = b with the gates eliminated: gate_i = pg_i (b_i + cv_i xV)
+    double pg[6], cv[6];          // 1 / (a - J_ii), column V of the gate rows
+    double rv[6], rc[2];          // J_V,gate_i pg_i ; J_Ca,{d,f} pg_i
+    double i11, i12, i21, i22;    // inverse of the reduced 2 x 2 matrix
+    __device__ __forceinline__ void solve(const double *b, double *x) const {
+        double bV = b[0], bC = b[1];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) bV = fma(rv[i], b[2 + i], bV);
+        bC = fma(rc[0], b[5], bC);
+        bC = fma(rc[1], b[6], bC);
+        const double xV = fma(i11, bV, i12 * bC);
+        x[0] = xV;
+        x[1] = fma(i21, bV, i22 * bC);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[2 + i] = pg[i] * fma(cv[i], xV, b[2 + i]);
+    }
+};
+
+template <bool SMEM, bool TRAJ>
+__global__ void __launch_bounds__(PB200_BRR_THREADS, PB200_BRR_BLOCKS)
+br_rosenbrock_kernel(const __grid_constant__ ProblemDev P,
+                     const __grid_constant__ ModelConsts mc,
+                     const double *__restrict__ params, int64_t n, int64_t ld,
+                     double *__restrict__ scores, double *__restrict__ traj,
+                     int32_t *__restrict__ steps_out, const int32_t *__restrict__ perm,
+                     const SolverDev S, const ScatterDev sc) {
+    using M = BeelerReuterModel;
+    constexpr int NS = 8, NO = 2;
+    constexpr uint32_t ROWB = (1 + NO) * 8;
+    constexpr uint32_t FULL = 0xffffffffu;
+    // Kaps-Rentrop / Shampine
+    constexpr double R_GAM = 0.5, R_A21 = 2.0, R_A31 = 48.0 / 25.0, R_A32 = 6.0 / 25.0;
+    constexpr double R_C21 = -8.0, R_C31 = 372.0 / 25.0, R_C32 = 12.0 / 5.0;
+    constexpr double R_C41 = -112.0 / 125.0, R_C42 = -54.0 / 125.0, R_C43 = -2.0 / 5.0;
+    constexpr double R_B1 = 19.0 / 9.0, R_B2 = 0.5, R_B3 = 25.0 / 108.0, R_B4 = 125.0 / 108.0;
+    constexpr double R_E1 = 17.0 / 54.0, R_E2 = 7.0 / 36.0, R_E4 = 125.0 / 108.0;      // E3 = 0
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    Series<SMEM> series;
+    series.gbase = P.series;
+    series.sbase = 0;
+    if (SMEM) {
+        const uint32_t bytes = static_cast<uint32_t>(
+            ((static_cast<int64_t>(P.n_times) + PB200_SENTINEL_ROWS) * ROWB + 15) & ~15ll);
+        stage_series(smem, P.series, bytes, &bar);
+        series.sbase = launder_u32(smem_u32(smem));
+    }
+    const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool live = gi < n;
+    const int64_t slot = live ? gi : n - 1;
+    const int64_t i = perm ? perm[slot] : slot;
+    const int nt = P.n_times;
+    const int n_read = TRAJ ? P.n_model_params : P.n_params;
+    double x[PB200_MAX_PARAMS];
+#pragma unroll
+    for (int k = 0; k < M::NP + NO; ++k)
+        x[k] = (k < n_read) ? params[i * ld + k] : 0.0;
+
+    bool idle = !live;
+    if (!TRAJ) {
+        double early;
+        if (objective_precheck(P, x, &early)) {
+            if (live) {
+                put_score(sc, scores, slot, i, early);
+                if (steps_out) steps_out[i] = 0;
+            }
+            idle = true;
+        }
+    }
+    M model;
+    double y[NS], t;
+    model.load(x, mc, y, nt > 0 ? series.at(0) : 0.0, &t);
+    double ss[NO] = {0.0, 0.0};
+    const uint32_t end = static_cast<uint32_t>(nt) * ROWB;
+    uint32_t off = 0;
+    double *my_traj = TRAJ ? traj + i * static_cast<int64_t>(nt) * NO : nullptr;
+    if (!idle) {
+        double t_out = series.at(0);
+        while (t_out <= t) {               // observations at the initial time
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                if (TRAJ) my_traj[off / ROWB * NO + o] = y[o];
+                const double r = series.at(off + 8 + 8 * o) - y[o];
+                ss[o] = fma(r, r, ss[o]);
+            }
+            off += ROWB;
+            t_out = series.at(off);
+        }
+    } else {
+        off = end;
+    }
+    const double rtol = S.rtol, atol = S.atol;
+    const double t_last = nt > 0 ? series.at(end - ROWB) : -INFINITY;
+    const double h_min = 1e-13 * fmax(fabs(t_last), 1.0);
+    double h = S.h0 > 0.0 ? S.h0 : 1e-3;
+    double stim = model.stimulus(t);
+    double f0[NS];
+    M::Aux aux;
+    bool have_f0 = false;
+    int attempts = 0;
+    bool failed = false;
+    const int max_steps = S.max_steps;
+
+    for (;;) {
+        const bool fin = (off >= end) || failed;
+        if (__all_sync(FULL, fin)) break;
+        const bool working = !fin;
+        if (working) {
+            if (attempts >= max_steps) failed = true;
+            else ++attempts;
+        }
+        // ---- clip the step at the next edge of the stimulus ----
+        double ph = fma(-model.period, floor(t * model.inv_period), t);
+        if (ph < 0.0) ph += model.period;
+        if (ph >= model.period) ph -= model.period;
+        const double edge = ph < model.length ? (t - ph) + model.length : (t - ph) + model.period;
+        const bool clipped = edge - t < h;
+        const double hs = clipped ? edge - t : h;
+        // ---- f(y), the pieces of the Jacobian, the difference quotient in V ----
+        if (!__all_sync(FULL, have_f0)) {
+            // (first attempt, and lanes whose last step ended on an edge: all
+            // lanes recompute; a lane that had f0 gets the same value again)
+            stim = model.stimulus(fma(0.5, hs, t));
+            model.template rhs_core<true>(y, f0, stim, &aux);
+            have_f0 = true;
+        }
+        double cvV, cvC;
+        BrArrow ar;
+        {
+            const double dV = 1e-6 * fmax(fabs(y[0]), 1.0);
+            double y2[NS], f1[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) y2[k] = y[k];
+            y2[0] = y[0] + dV;
+            model.template rhs_core<false>(y2, f1, stim, nullptr);
+            const double idV = rcp_newton<2>(y2[0] - y[0]);
+            cvV = (f1[0] - f0[0]) * idV;
+            cvC = (f1[1] - f0[1]) * idV;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ar.cv[k] = (f1[2 + k] - f0[2 + k]) * idV;
+        }
+        const double ih = rcp_newton<2>(hs);
+        const double a = ih * (1.0 / R_GAM);
+        {
+            const double V = y[0], Cai = y[1], m = y[2], hh = y[3], j = y[4], d = y[5], ff = y[6];
+            const double dn = V - model.e_na, icm = model.inv_cm;
+            const double dlog = 13.0287 * rcp_newton<2>(Cai);     // d(V - E_Ca) / dCa
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ar.pg[k] = rcp_newton<2>(a + aux.rate[k]);
+            const double jVm = -icm * model.gNa * 3.0 * m * m * hh * j * dn;
+            const double jVh = -icm * model.gNa * aux.m3 * j * dn;
+            const double jVj = -icm * model.gNa * aux.m3 * hh * dn;
+            const double jVd = -icm * model.gCa * ff * aux.dECa;
+            const double jVf = -icm * model.gCa * d * aux.dECa;
+            const double jVx = -icm * model.gx1 * aux.xf;
+            const double jVC = -icm * model.gCa * d * ff * dlog;
+            const double jCC = -1e-7 * model.gCa * d * ff * dlog - 0.07;
+            const double jCd = -1e-7 * model.gCa * ff * aux.dECa;
+            const double jCf = -1e-7 * model.gCa * d * aux.dECa;
+            ar.rv[0] = jVm * ar.pg[0]; ar.rv[1] = jVh * ar.pg[1]; ar.rv[2] = jVj * ar.pg[2];
+            ar.rv[3] = jVd * ar.pg[3]; ar.rv[4] = jVf * ar.pg[4]; ar.rv[5] = jVx * ar.pg[5];
+            ar.rc[0] = jCd * ar.pg[3]; ar.rc[1] = jCf * ar.pg[4];
+            double aVV = a - cvV, aCV = -cvC;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) aVV = fma(-ar.rv[k], ar.cv[k], aVV);
+            aCV = fma(-ar.rc[0], ar.cv[3], aCV);
+            aCV = fma(-ar.rc[1], ar.cv[4], aCV);
+            const double aVC = -jVC, aCC = a - jCC;
+            const double idet = rcp_newton<2>(aVV * aCC - aVC * aCV);
+            ar.i11 = aCC * idet; ar.i12 = -aVC * idet;
+            ar.i21 = -aCV * idet; ar.i22 = aVV * idet;
+        }
+        // ---- four stages ----
+        double g1[NS], g2[NS], g3[NS], g4[NS], w[NS], fw[NS], b[NS];
+        ar.solve(f0, g1);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w[k] = fma(R_A21, g1[k], y[k]);
+        model.template rhs_core<false>(w, fw, stim, nullptr);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) b[k] = fma(R_C21 * ih, g1[k], fw[k]);
+        ar.solve(b, g2);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w[k] = fma(R_A32, g2[k], fma(R_A31, g1[k], y[k]));
+        model.template rhs_core<false>(w, fw, stim, nullptr);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) b[k] = fma(R_C32 * ih, g2[k], fma(R_C31 * ih, g1[k], fw[k]));
+        ar.solve(b, g3);
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            b[k] = fma(R_C43 * ih, g3[k], fma(R_C42 * ih, g2[k], fma(R_C41 * ih, g1[k], fw[k])));
+        ar.solve(b, g4);
+        double yn[NS], sum2 = 0.0;
+        constexpr double wt[NS] = {1.0, 1e-6, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            yn[k] = fma(R_B4, g4[k], fma(R_B3, g3[k], fma(R_B2, g2[k], fma(R_B1, g1[k], y[k]))));
+            const double e = fma(R_E4, g4[k], fma(R_E2, g2[k], R_E1 * g1[k]));
+            const double q = e * rcp_newton<1>(fma(rtol, fabs(y[k]), atol * wt[k]));
+            sum2 = fma(q, q, sum2);
+        }
+        // accepted iff the mean square is <= 1 (NaN: rejected); a negative
+        // calcium concentration is rejected as well (log in the next f)
+        const bool ok = working && sum2 <= static_cast<double>(NS) && yn[1] > 0.0;
+        // 0.9 err^(-1/4) in [0.2, 5]: err^2 = sum2 / NS
+        float fac;
+        {
+            const float n2 = static_cast<float>(sum2 * (1.0 / NS));
+            float l, f;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(n2));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(-0.125f * l));
+            fac = fminf(fmaxf(0.9f * f, 0.2f), 5.0f);
+            if (!(sum2 == sum2) || !(yn[1] > 0.0)) fac = 0.2f;
+            if (!ok) fac = fminf(fac, 1.0f);
+        }
+        const double t_new = clipped ? edge : t + hs;
+        // ---- f(y_new): dense output now, first right-hand side of the next step ----
+        // (junk for a rejected lane, never used)
+        double fn[NS];
+        M::Aux aux_n;
+        model.template rhs_core<true>(yn, fn, stim, &aux_n);
+        // cubic Hermite on [t, t_new]: y + th (d0 + th (c2 + th c3))
+        double c1[NO], c2[NO], c3[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            const double d = yn[o] - y[o], d0 = hs * f0[o], d1 = hs * fn[o];
+            c1[o] = d0;
+            c2[o] = fma(3.0, d, fma(-2.0, d0, -d1));
+            c3[o] = fma(-2.0, d, d0 + d1);
+        }
+        double t_obs = series.at(off);
+        while (__any_sync(FULL, ok && le_bits(t_obs, t_new))) {
+            const bool valid = ok && le_bits(t_obs, t_new);
+            const double th = (t_obs - t) * ih;
+            double v[NO];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                v[o] = fma(th, fma(th, fma(th, c3[o], c2[o]), c1[o]), y[o]);
+                const double r = series.at(off + 8 + 8 * o) - v[o];
+                acc_sq_if(ss[o], r, valid);
+            }
+            if (TRAJ) {
+                if (valid) {
+                    double *dst = my_traj + off / ROWB * NO;
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) dst[o] = v[o];
+                }
+            }
+            off += valid ? ROWB : 0u;
+            t_obs = series.at(off);
+        }
+        // ---- accept / reject ----
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { y[k] = yn[k]; f0[k] = fn[k]; }
+            aux = aux_n;
+            t = t_new;
+            // the stimulus changes at an edge: the next step starts from a new f
+            have_f0 = !clipped;
+        }
+        const double h_try = hs * static_cast<double>(fac);
+        // an accepted, clipped step says nothing against the step it was cut from
+        h = (ok && clipped) ? fmax(h, h_try) : h_try;
+        if (working && !ok && hs < h_min) failed = true;
+    }
+
+    if (!idle) {
+        if (steps_out) steps_out[i] = attempts;
+        if (TRAJ) {
+            if (failed) {
+                const int64_t first = static_cast<int64_t>(off / ROWB) * NO;
+                const int64_t total = static_cast<int64_t>(nt) * NO;
+                for (int64_t q = first; q < total; ++q) my_traj[q] = NAN;
+            }
+        } else {
+            put_score(sc, scores, slot, i, failed ? NAN : objective_finish(P, ss, x));
+        }
+    }
+    if (!TRAJ) exchange_signal(sc);
+}
+
+// ======================================================================
 // Pair kernel: TWO lanes per parameter vector, one per state component
 // (FitzHugh-Nagumo, Lotka-Volterra: NS = NO = 2).  A population of 65 536 on
 // one B200 is only 2048 one-lane warps = 3.5 per scheduler, too few to cover
@@ -1861,6 +2197,43 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     return pb200_check_cuda(cudaGetLastError(), "ode_kernel launch");
 }
 
+// Beeler-Reuter on the stiff integrator (br_rosenbrock_kernel); PB200_BR_EXPLICIT=1
+// keeps the explicit DP5(4) template for comparisons.  Every vector costs the
+// same here (the step size follows the action potential, not the parameters):
+// no cost sort.
+static bool br_explicit() {
+    static const int on = [] {
+        const char *e = getenv("PB200_BR_EXPLICIT");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on != 0;
+}
+int launch_br_rosenbrock(const pb200_problem *p, const double *d_params, int64_t n,
+                         int64_t ld, double *d_scores, double *d_traj, int32_t *d_steps,
+                         const SolverDev &s, const ScatterDev &sc, cudaStream_t st) {
+    const int32_t *perm = nullptr;
+    const int64_t bytes = staged_bytes(p, BeelerReuterModel::NO);
+    const bool use_smem = bytes <= 64 * 1024;
+    const int block = PB200_BRR_THREADS;
+    const int64_t grid = (n + block - 1) / block;
+    if (grid <= 0) return PB200_OK;
+    if (grid > 2147483647ll) {
+        pb200_set_error("too many parameter vectors for one launch: %lld", (long long)n);
+        return PB200_EINVAL;
+    }
+    const size_t dyn = use_smem ? static_cast<size_t>(bytes) : 0;
+#define PB200_XARG , sc
+    if (use_smem) {
+        if (d_traj) PB200_LAUNCH((br_rosenbrock_kernel<true, true>), grid, block, dyn);
+        else PB200_LAUNCH((br_rosenbrock_kernel<true, false>), grid, block, dyn);
+    } else {
+        if (d_traj) PB200_LAUNCH((br_rosenbrock_kernel<false, true>), grid, block, dyn);
+        else PB200_LAUNCH((br_rosenbrock_kernel<false, false>), grid, block, dyn);
+    }
+#undef PB200_XARG
+    return pb200_check_cuda(cudaGetLastError(), "br_rosenbrock_kernel launch");
+}
+
 // two lanes per parameter vector (two-state models)
 template <class L, class M>
 int launch_pair(const pb200_problem *p, const double *d_params, int64_t n,
@@ -1944,7 +2317,9 @@ int launch_ode(const pb200_problem *p, const double *d_params, int64_t n,
         case PB200_MODEL_REPRESSILATOR:
             return launch_model<RepressilatorModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
         case PB200_MODEL_BEELER_REUTER:
-            return launch_model<BeelerReuterModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
+            if (br_explicit())
+                return launch_model<BeelerReuterModel>(p, d_params, n, ld, d_scores, d_traj, d_steps, s, block, sort_ws, sc, st);
+            return launch_br_rosenbrock(p, d_params, n, ld, d_scores, d_traj, d_steps, s, sc, st);
     }
     pb200_set_error("model %d is not an ODE model", p->dev.model);
     return PB200_EUNSUPPORTED;

@@ -463,11 +463,14 @@ class ActionPotentialModel(_DeviceSimulation, ForwardModel):
     (pints/toy/_beeler_reuter_model.py:16-229).  Like ``SIRModel`` it is
     integrated from ``times[0]``.
 
-    ``set_solver_tolerances`` keeps the reference's signature, but the default
-    here is the engine's 1.49e-8 rather than the reference's (1e-4, 1e-6): the
-    explicit integrator is stability-bound on this model (about 7 700 steps
-    for 400 ms at any tolerance), so the tighter solve costs nothing and sits
-    closer to the exact solution than the reference's default run does.
+    The model is stiff (the reference's LSODA switches to BDF on it), so it
+    does not run on the explicit DP5(4) kernel of the other ODE models but on a
+    4-stage Rosenbrock method (``br_rosenbrock_kernel``).
+    ``set_solver_tolerances`` keeps the reference's signature; the default is
+    1e-7 for both rather than the reference's (1e-4, 1e-6): about 1 650 steps
+    for 400 ms and 8.5e-7 from the converged log-likelihood, where the
+    reference's default run is 1.7e-3 away.  The absolute tolerance of the
+    calcium concentration (values of 1e-7 .. 1e-5) is ``atol * 1e-6``.
     """
 
     def __init__(self, y0=None):
@@ -497,7 +500,7 @@ class ActionPotentialModel(_DeviceSimulation, ForwardModel):
         self._cai0 = y0[1]
         self._sim_cache = None
 
-    def set_solver_tolerances(self, rtol=1.49012e-8, atol=1.49012e-8):
+    def set_solver_tolerances(self, rtol=1e-7, atol=1e-7):
         self.set_solver_options(rtol=float(rtol), atol=float(atol))
 
     def n_outputs(self):

@@ -15,7 +15,7 @@ g = np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden',
 model = pb.toy.ActionPotentialModel()
 times, xs = g['times'], g['xs']
 rel = lambda a, b: np.abs(a - b) / np.abs(b)
-for tol in (None, 1e-6, 1e-10, 1e-12):
+for tol in (None, 1e-5, 1e-6, 3e-7, 1e-7, 1e-8, 1e-10):
     if tol:
         model.set_solver_tolerances(tol, tol)
     traj = model.simulate(xs[:8, :5], times)
