@@ -505,6 +505,22 @@ int pb200_xnes_sums(const double *d_z, const int64_t *d_order,
                     const double *d_us, double *d_partial, int32_t n_blocks,
                     double *d_out, const double *d_x, const double *d_fx,
                     int64_t n, int32_t d, void *stream);
+/* The d x d part of the update on the device (one block; replaces the host's
+ * pints/_optimisers/_xnes.py:170-182, and pints/_optimisers/_snes.py:150-166
+ * with separable = 1): d_state = [mu (d), A (d, d) row-major, Philox offset
+ * (uint64)] is updated in place from d_sums (what pb200_xnes_sums wrote):
+ *   mu += eta_mu A Gd,  A = A expm(eta_A / 2 (Gm - sum_us I))
+ * (expm: scaled Taylor series of degree 18 + squaring; separable: the diagonal
+ * of A times exp(eta_A / 2 (Gm_aa - sum_us))), offset += offset_step.
+ * d_best = [f_best, x_best (d), f_guessed, generations] (d + 3 doubles, start
+ * it as [+inf, x0, +inf, 0]) follows :160-165; d_hist (optional, hist_rows
+ * rows of d + 2 doubles) keeps [f_best, x_best, f_guessed] per generation,
+ * row = generation mod hist_rows, for a host that synchronises only every
+ * few generations. */
+int pb200_xnes_update(double *d_state, const double *d_sums, double *d_best,
+                      double *d_hist, int32_t hist_rows, double eta_mu,
+                      double eta_A, double sum_us, int32_t d,
+                      uint64_t offset_step, int32_t separable, void *stream);
 
 /* Ranking of the scores for the device-resident optimisers: ascending argsort
  * of n <= PB200_ARGSORT_MAX doubles (`order = np.argsort(fx)`,

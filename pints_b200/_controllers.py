@@ -167,6 +167,8 @@ class CudaOptimisationController(object):
         self._evaluations = 0
         self._time = None
         self._has_run = False
+        # device-resident optimisers: generations between two synchronisations
+        self._sync_every = 8
 
     def optimiser(self):
         return self._optimiser
@@ -229,33 +231,54 @@ class CudaOptimisationController(object):
             per = (n + world - 1) // world
             lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
             exchange = ScoreExchange(per, problem.device, self._group)
+        best = None
         while True:
+            # f_best after each generation of this round, oldest first
             if exchange is not None:
                 xs = opt.ask()
                 fs = exchange.run(problem, xs[lo:hi], n_total=n)
                 opt.tell(-fs if self._sign < 0 else fs)
-                self._evaluations += len(fs)
+                history = [(opt.f_best(), None, len(fs))]
             elif on_device:
-                # ask + score + tell with one synchronisation (CUDA graph)
-                opt.generation(problem, negate=self._sign < 0)
-                self._evaluations += opt.population_size()
+                # a block of generations (ask + score + tell, replayed from a
+                # CUDA graph) with ONE synchronisation: nothing in a generation
+                # needs the host; the stopping criteria are then applied
+                # generation by generation to the history the device kept
+                block = self._sync_every
+                if self._max_iterations is not None:
+                    block = max(1, min(block, self._max_iterations - self._iterations))
+                rows = opt.generations(problem, block, negate=self._sign < 0)
+                history = [(float(r[0]), r, opt.population_size()) for r in rows]
             else:
                 xs = opt.ask()
                 fs = self._evaluator.evaluate(xs)
                 opt.tell(self._sign * fs if self._sign < 0 else fs)
-                self._evaluations += len(fs)
-            self._iterations += 1
-            f_new = opt.f_best()
-            if np.abs(f_new - f_sig) >= self._unchanged_threshold:
-                unchanged, f_sig = 0, f_new
-            else:
-                unchanged += 1
-            if self._max_iterations is not None and \
-                    self._iterations >= self._max_iterations:
+                history = [(opt.f_best(), None, len(fs))]
+            stop = False
+            for f_new, row, n_evals in history:
+                self._iterations += 1
+                self._evaluations += n_evals
+                best = row
+                if np.abs(f_new - f_sig) >= self._unchanged_threshold:
+                    unchanged, f_sig = 0, f_new
+                else:
+                    unchanged += 1
+                if self._max_iterations is not None and \
+                        self._iterations >= self._max_iterations:
+                    stop = True
+                if self._unchanged_max is not None and \
+                        unchanged >= self._unchanged_max:
+                    stop = True
+                if stop:
+                    break
+            if stop:
                 break
-            if self._unchanged_max is not None and \
-                    unchanged >= self._unchanged_max:
-                break
+        self._time = time.perf_counter() - start
+        if best is not None:
+            # the generation the criteria stopped at (the device may have run
+            # the rest of its block beyond it)
+            d = len(best) - 2
+            return np.array(best[1:1 + d], copy=True), self._sign * float(best[0])
         self._time = time.perf_counter() - start
         return opt.x_best(), self._sign * opt.f_best()
 

@@ -9,7 +9,10 @@ points as a device tensor, ``tell(fx)`` takes their scores as a device tensor.
 At population 65 536 the vectorised host ``XNES`` of this package needs 12 ms
 per generation (6 ms of them NumPy's Mersenne-Twister normals, which identity
 with the reference's random stream requires) against 0.4 ms for scoring the
-population; here a generation's update costs a sort and three small kernels.
+population; here a generation's update costs a sort and four small kernels,
+the d x d part (``expm``) included (``pb200_xnes_update``), so the host only
+reads results back -- every generation, or once per block of generations
+(``generations``).
 
 Same hyper-parameters, utilities and update equations as the reference.  The
 samples come from the counter-based Philox generator of the C ABI instead of
@@ -21,7 +24,6 @@ feeds the device's normals to the host ``XNES`` through ``numpy.random``).
 import ctypes
 
 import numpy as np
-import scipy.linalg
 import torch
 
 from . import _lib
@@ -82,6 +84,9 @@ class DeviceXNES(object):
 
     device_resident = True
     use_graph = True
+    #: generations the device keeps [f_best, x_best, f_guessed] of (the most
+    #: one call of ``generations`` can run between two synchronisations)
+    HISTORY = 64
     #: rank with pb200_argsort_f64 (False: the library sort)
     native_sort = True
 
@@ -195,11 +200,12 @@ class DeviceXNES(object):
         us -= 1 / n
         self._sum_us = float(np.sum(us))
         self._mu = np.array(self._x0, copy=True)
-        self._A = np.eye(d) * self._sigma0
+        self._A = self._initial_A()
         self._I = np.eye(d)
         f64 = dict(dtype=torch.float64, device=dev)
         self._d_us = torch.from_numpy(us).to(dev)
-        self._d_state = torch.empty(d + d * d + 1, **f64)    # mu, A, Philox offset
+        # mu, A, Philox offset: lives on the device, updated there
+        self._d_state = torch.empty(d + d * d + 1, **f64)
         self._d_z = torch.empty((n, d), **f64)
         self._d_x = torch.empty((n, d), **f64)
         self._d_x_eval = torch.empty((n, d), **f64)
@@ -207,12 +213,31 @@ class DeviceXNES(object):
         self._d_inside_bool = self._d_inside.view(torch.bool)
         self._d_inf = torch.full((), float('inf'), **f64)
         self._d_partial = torch.empty(_SUM_BLOCKS * (d + d * d), **f64)
-        # sums, then the best point and its score (one read-back per tell)
+        # sums, then the best point of the generation and its score
         self._d_out = torch.empty(d + d * d + d + 1, **f64)
-        self._h_out = torch.empty(d + d * d + d + 1, dtype=torch.float64,
-                                  pin_memory=True)
+        # [f_best, x_best, f_guessed, generations]; per-generation history
+        self._d_best = torch.empty(d + 3, **f64)
+        self._d_hist = torch.empty((self.HISTORY, d + 2), **f64)
         self._h_state = torch.empty(d + d * d + 1, dtype=torch.float64,
                                     pin_memory=True)
+        self._h_best = torch.empty(d + 3, dtype=torch.float64, pin_memory=True)
+        self._h_hist = torch.empty((self.HISTORY, d + 2), dtype=torch.float64,
+                                   pin_memory=True)
+        self._offset_step = (n * d + 1) // 2 + 1
+        h = self._h_state.numpy()
+        h[:d] = self._mu
+        h[d:d + d * d] = self._A.reshape(-1)
+        h[d + d * d:].view(np.uint64)[0] = self._offset
+        hb = self._h_best.numpy()
+        hb[0] = np.inf
+        hb[1:1 + d] = self._x0
+        hb[d + 1] = np.inf
+        hb[d + 2] = 0.0
+        with torch.cuda.device(dev):
+            self._d_state.copy_(self._h_state, non_blocking=True)
+            self._d_best.copy_(self._h_best, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        self._generations_done = 0
         self._graph = self._graph_key = self._graph_failed = None
         self._eager_generations = 0
         self._sorter = DeviceArgsort(n, dev)
@@ -239,21 +264,12 @@ class DeviceXNES(object):
         """Which of them lie inside the boundaries (uint8)."""
         return self._d_inside
 
-    # -- ask / tell ------------------------------------------------------
-    def _stage_state(self):
-        """mean, A and the Philox offset of the coming generation go to the
-        pinned staging buffer (the kernels read them from device memory, so
-        that a captured generation can be replayed with new values)."""
-        n, d = self._population_size, self._d
-        h = self._h_state.numpy()
-        h[:d] = self._mu
-        h[d:d + d * d] = self._A.reshape(-1)
-        h[d + d * d:].view(np.uint64)[0] = self._offset
-        self._offset += (n * d + 1) // 2 + 1
+    def _initial_A(self):
+        return np.eye(self._d) * self._sigma0
 
+    # -- ask / tell ------------------------------------------------------
     def _enqueue_ask(self):
         n, d = self._population_size, self._d
-        self._d_state.copy_(self._h_state, non_blocking=True)
         state = self._d_state.data_ptr()
         _lib.check(self._lib.pb200_xnes_ask(
             ctypes.c_void_p(state), ctypes.c_void_p(state + 8 * d),
@@ -263,7 +279,13 @@ class DeviceXNES(object):
             ctypes.c_void_p(state + 8 * (d + d * d)),
             _stream_ptr(self._device)))
 
-    def _enqueue_tell(self, fx):
+    #: 1 = the diagonal update of SNES
+    _separable = 0
+
+    def _eta_matrix(self):
+        return self._eta_A
+
+    def _enqueue_tell(self, fx, read_back=True):
         n, d = self._population_size, self._d
         self._last_fx = fx
         if self._d_lower is not None:
@@ -273,45 +295,63 @@ class DeviceXNES(object):
         order = self._sorter(fx.contiguous()) if self.native_sort \
             and self._sorter.native and not self._sort_gave_up \
             else torch.sort(fx)[1]
+        stream = _stream_ptr(self._device)
         _lib.check(self._lib.pb200_xnes_sums(
             _ptr(self._d_z), _ptr(order), _ptr(self._d_us),
             _ptr(self._d_partial), _SUM_BLOCKS, _ptr(self._d_out),
-            _ptr(self._d_x), _ptr(fx), n, d, _stream_ptr(self._device)))
-        self._h_out.copy_(self._d_out, non_blocking=True)
+            _ptr(self._d_x), _ptr(fx), n, d, stream))
+        # the d x d update, the best point so far, the next Philox offset
+        # (pints/_optimisers/_xnes.py:160-182) -- on the device as well
+        _lib.check(self._lib.pb200_xnes_update(
+            _ptr(self._d_state), _ptr(self._d_out), _ptr(self._d_best),
+            _ptr(self._d_hist), self.HISTORY, float(self._eta_mu),
+            float(self._eta_matrix()), self._sum_us, d,
+            ctypes.c_uint64(self._offset_step), self._separable, stream))
+        if read_back:
+            self._enqueue_read_back()
+
+    def _enqueue_read_back(self):
+        self._h_state.copy_(self._d_state, non_blocking=True)
+        self._h_best.copy_(self._d_best, non_blocking=True)
         self._h_status.copy_(self._sorter.status, non_blocking=True)
 
     def _update(self):
-        """The d x d part of tell() on the host
-        (pints/_optimisers/_xnes.py:170-182)."""
-        self._check_sort()
+        """After a synchronisation: the host's copies of what the device has
+        computed (mean, A, best point, scores)."""
         d = self._d
-        m = d + d * d
-        out = self._h_out.numpy()
-        Gd = out[:d]
-        Gm = out[d:m].reshape((d, d)) - self._sum_us * self._I
-        self._mu = self._mu + self._eta_mu * np.dot(self._A, Gd)
-        self._A = np.dot(self._A, scipy.linalg.expm(0.5 * self._eta_A * Gm))
-        self._f_guessed = float(out[m + d])
-        if self._f_guessed < self._f_best:
-            self._f_best = self._f_guessed
-            self._x_best = np.array(out[m:m + d], copy=True)
+        h = self._h_state.numpy()
+        self._mu = np.array(h[:d], copy=True)
+        self._A = np.array(h[d:d + d * d], copy=True).reshape((d, d))
+        hb = self._h_best.numpy()
+        self._f_best = float(hb[0])
+        if np.isfinite(self._f_best) or self._f_best == -np.inf:
+            self._x_best = np.array(hb[1:1 + d], copy=True)
+        self._f_guessed = float(hb[d + 1])
+        self._generations_done = int(hb[d + 2])
 
-    def _check_sort(self):
-        if int(self._h_status[0]) != 0:
-            # never seen: the sample sort met a bucket it cannot hold.  Rank
-            # this generation again with the library sort, and keep to it.
-            self._sort_gave_up = True
-            self._graph = None
-            with torch.cuda.device(self._device):
-                self._sorter.status.zero_()
-                self._enqueue_tell(self._last_fx)
-                torch.cuda.current_stream(self._device).synchronize()
+    def _snapshot(self):
+        return self._d_state.clone(), self._d_best.clone()
+
+    def _restore(self, snap):
+        self._d_state.copy_(snap[0])
+        self._d_best.copy_(snap[1])
+
+    def _sort_failed(self):
+        """True if the sample sort met a bucket it cannot hold (never seen; see
+        ``pb200_argsort_f64``): the library sort takes over for the rest of the
+        run, and the caller repeats the generations concerned from its snapshot
+        of the state."""
+        if int(self._h_status[0]) == 0:
+            return False
+        self._sort_gave_up = True
+        self._graph = None
+        self._sorter.status.zero_()
+        return True
 
     def ask(self):
         if not self._running:
             self._initialise()
         self._ready_for_tell = True
-        self._stage_state()
         with torch.cuda.device(self._device):
             self._enqueue_ask()
         return self._d_x_eval
@@ -323,47 +363,78 @@ class DeviceXNES(object):
             raise Exception('ask() not called before tell()')
         self._ready_for_tell = False
         with torch.cuda.device(self._device):
+            snap = self._snapshot()
             self._enqueue_tell(fx)
             torch.cuda.current_stream(self._device).synchronize()
+            if self._sort_failed():
+                self._restore(snap)
+                self._enqueue_tell(fx)
+                torch.cuda.current_stream(self._device).synchronize()
         self._update()
 
     def generation(self, problem, negate=False):
         """One whole generation -- ask, score on ``problem`` (a
         ``DeviceProblem``), tell -- with a single host synchronisation.
-        ``negate``: maximise the scores.  After two eager generations the
-        device work (state upload, sampling kernel, sort + solve kernels,
-        ranking, sums, read-back: about ten launches) is captured in a CUDA
-        graph and replayed; set ``use_graph = False`` to keep it eager."""
+        ``negate``: maximise the scores."""
+        self.generations(problem, 1, negate)
+
+    def generations(self, problem, count, negate=False):
+        """``count`` (at most ``HISTORY``) whole generations with ONE host
+        synchronisation at the end: nothing in a generation needs the host
+        (sampling, scoring, ranking, the weighted sums and the d x d update
+        are all on the device).  After two eager generations the device work
+        of a generation (sampling kernel, sort + solve kernels, ranking, sums,
+        update: about ten launches) is captured in a CUDA graph and replayed;
+        set ``use_graph = False`` to keep it eager.  Returns the history of the
+        block, an array ``(count, d + 2)`` of ``[f_best, x_best, f_guessed]``
+        after each generation."""
         if not self._running:
             self._initialise()
-        self._stage_state()
+        count = int(count)
+        if not 1 <= count <= self.HISTORY:
+            raise ValueError('count must be between 1 and %d' % self.HISTORY)
         key = (id(problem), bool(negate))
         with torch.cuda.device(self._device):
-            if self._graph is not None and self._graph_key == key:
-                self._graph.replay()
-            elif self.use_graph and self._eager_generations >= 2 \
-                    and self._graph_failed is None:
-                try:
-                    graph = capture_graph(
-                        self._device,
-                        lambda: self._enqueue_generation(problem, negate))
-                    self._graph, self._graph_key = graph, key
-                    graph.replay()
-                except Exception as e:          # keep going without a graph
-                    self._graph_failed = e
-                    self._graph = None
-                    torch.cuda.synchronize(self._device)
-                    self._enqueue_generation(problem, negate)
-            else:
-                self._enqueue_generation(problem, negate)
-                self._eager_generations += 1
-            torch.cuda.current_stream(self._device).synchronize()
+            stream = torch.cuda.current_stream(self._device)
+            snap = self._snapshot()
+            first = self._generations_done
+            for attempt in range(2):
+                for _ in range(count):
+                    self._one_generation(problem, negate, key)
+                self._enqueue_read_back()
+                self._h_hist.copy_(self._d_hist, non_blocking=True)
+                stream.synchronize()
+                if not self._sort_failed():
+                    break
+                self._restore(snap)       # and again, with the library sort
         self._update()
+        rows = [(first + k) % self.HISTORY for k in range(count)]
+        return np.array(self._h_hist.numpy()[rows], copy=True)
+
+    def _one_generation(self, problem, negate, key):
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+        elif self.use_graph and self._eager_generations >= 2 \
+                and self._graph_failed is None:
+            try:
+                graph = capture_graph(
+                    self._device,
+                    lambda: self._enqueue_generation(problem, negate))
+                self._graph, self._graph_key = graph, key
+                graph.replay()
+            except Exception as e:          # keep going without a graph
+                self._graph_failed = e
+                self._graph = None
+                torch.cuda.synchronize(self._device)
+                self._enqueue_generation(problem, negate)
+        else:
+            self._enqueue_generation(problem, negate)
+            self._eager_generations += 1
 
     def _enqueue_generation(self, problem, negate):
         self._enqueue_ask()
         fx = problem.eval(self._d_x_eval)
-        self._enqueue_tell(-fx if negate else fx)
+        self._enqueue_tell(-fx if negate else fx, read_back=False)
 
 
 class DeviceSNES(DeviceXNES):
@@ -376,25 +447,20 @@ class DeviceSNES(DeviceXNES):
     def name(cls):
         return 'Seperable Natural Evolution Strategy (SNES), device resident'
 
+    _separable = 1
+
     def _initialise(self):
-        super()._initialise()
         d = self._d
         self._eta_sigmas = 0.2 * (3 + np.log(d)) * d ** -0.5
-        self._sigmas = np.array(self._sigma0, copy=True)
-        self._A = np.diag(self._sigmas)
+        super()._initialise()
+
+    def _initial_A(self):
+        return np.diag(self._sigma0)
+
+    def _eta_matrix(self):
+        return self._eta_sigmas
 
     def _update(self):
-        # pints/_optimisers/_snes.py:150-166
-        self._check_sort()
-        d = self._d
-        m = d + d * d
-        out = self._h_out.numpy()
-        Gd = out[:d]
-        Gs = np.diagonal(out[d:m].reshape((d, d))) - self._sum_us
-        self._mu = self._mu + self._eta_mu * self._sigmas * Gd
-        self._sigmas = self._sigmas * np.exp(0.5 * self._eta_sigmas * Gs)
-        self._A = np.diag(self._sigmas)
-        self._f_guessed = float(out[m + d])
-        if self._f_guessed < self._f_best:
-            self._f_best = self._f_guessed
-            self._x_best = np.array(out[m:m + d], copy=True)
+        # pints/_optimisers/_snes.py:150-166, computed by pb200_xnes_update
+        super()._update()
+        self._sigmas = np.array(np.diagonal(self._A), copy=True)

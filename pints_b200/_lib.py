@@ -120,6 +120,8 @@ SIGNATURES = {
                                  c_int32, c_uint64, _P, _P]),
     'pb200_xnes_sums': (c_int32, [_P, _P, _P, _P, c_int32, _P, _P, _P,
                                   c_int64, c_int32, _P]),
+    'pb200_xnes_update': (c_int32, [_P, _P, _P, _P, c_int32, c_double, c_double,
+                                    c_double, c_int32, c_uint64, c_int32, _P]),
     'pb200_argsort_workspace_bytes': (c_int64, [c_int64]),
     'pb200_argsort_f64': (c_int32, [_P, _P, c_int64, _P, c_int64, _P, _P]),
     'pb200_hbac_adapt': (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32,

@@ -601,6 +601,117 @@ __global__ void xnes_sums_final_kernel(const double *__restrict__ partial, doubl
     out[q] = acc;
 }
 
+// The d x d part of tell() (pints/_optimisers/_xnes.py:170-182; SNES:
+// pints/_optimisers/_snes.py:150-166) in one block, so that the host is out of
+// the generation loop:
+//   mu <- mu + eta_mu A Gd,   A <- A expm(eta_A / 2 (Gm - sum(u) I))
+// expm by scaling and squaring of the Taylor series: the argument is divided by
+// 2^s until its 1-norm is at most 1/2, the series is summed to degree 18 in
+// Horner form (remainder below 2e-23), the result squared s times.
+// `state` = [mu (d), A (d, d), Philox offset (u64)], `sums` = what
+// pb200_xnes_sums wrote, `best` = [f_best, x_best (d), f_guessed,
+// generations (as double)], `hist` (optional) row g mod hist_rows receives
+// [f_best, x_best (d), f_guessed] after generation g.
+constexpr int XNES_TAYLOR = 18;
+__global__ void xnes_update_kernel(double *__restrict__ state, const double *__restrict__ sums,
+                                   double *__restrict__ best, double *__restrict__ hist,
+                                   int hist_rows, double eta_mu, double eta_A, double sum_us,
+                                   int d, uint64_t offset_step, int separable) {
+    __shared__ double M[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
+    __shared__ double E[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
+    __shared__ double T[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
+    __shared__ double A0[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
+    __shared__ double col[PB200_MAX_PARAMS];
+    __shared__ int s_shift;
+    const int q = threadIdx.x, dd = d * d, m = d + dd;
+    const int a = q / d, b = q % d;
+    double *mu = state, *A = state + d;
+    if (q < dd) A0[q] = A[q];
+    __syncthreads();
+    if (separable) {
+        // sigma <- sigma exp(eta / 2 (Gm_aa - sum(u))), mu <- mu + eta_mu sigma Gd
+        if (q < d) {
+            const double sigma = A0[q * d + q];
+            mu[q] = mu[q] + eta_mu * sigma * sums[q];
+            A[q * d + q] = sigma * exp(0.5 * eta_A * (sums[d + q * d + q] - sum_us));
+        }
+    } else {
+        if (q < dd) M[q] = 0.5 * eta_A * (sums[d + q] - (a == b ? sum_us : 0.0));
+        __syncthreads();
+        if (q < d) {
+            double c = 0.0;
+            for (int r = 0; r < d; ++r) c += fabs(M[r * d + q]);
+            col[q] = c;
+        }
+        __syncthreads();
+        if (q == 0) {
+            double norm = 0.0;
+            for (int k = 0; k < d; ++k) norm = fmax(norm, col[k]);
+            int sh = 0;
+            // NaN or inf: no scaling, the NaNs travel on as they do on the host
+            while (norm > 0.5 && sh < 60 && norm < INFINITY) { norm *= 0.5; ++sh; }
+            s_shift = sh;
+        }
+        __syncthreads();
+        const int sh = s_shift;
+        if (q < dd) {
+            M[q] = ldexp(M[q], -sh);
+            E[q] = a == b ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        // E = I + M / k E, k = degree .. 1
+        for (int k = XNES_TAYLOR; k >= 1; --k) {
+            double acc = 0.0;
+            if (q < dd) {
+                for (int r = 0; r < d; ++r) acc = fma(M[a * d + r], E[r * d + b], acc);
+                acc = acc / static_cast<double>(k) + (a == b ? 1.0 : 0.0);
+            }
+            __syncthreads();
+            if (q < dd) E[q] = acc;
+            __syncthreads();
+        }
+        for (int k = 0; k < sh; ++k) {
+            double acc = 0.0;
+            if (q < dd)
+                for (int r = 0; r < d; ++r) acc = fma(E[a * d + r], E[r * d + b], acc);
+            __syncthreads();
+            if (q < dd) E[q] = acc;
+            __syncthreads();
+        }
+        if (q < dd) {
+            double acc = 0.0;
+            for (int r = 0; r < d; ++r) acc = fma(A0[a * d + r], E[r * d + b], acc);
+            T[q] = acc;
+        }
+        if (q < d) {
+            double acc = 0.0;
+            for (int r = 0; r < d; ++r) acc = fma(A0[q * d + r], sums[r], acc);
+            mu[q] = mu[q] + eta_mu * acc;
+        }
+        __syncthreads();
+        if (q < dd) A[q] = T[q];
+    }
+    // best point so far (pints/_optimisers/_xnes.py:160-165) and bookkeeping
+    __syncthreads();
+    const double f_gen = sums[m + d];
+    const bool better = f_gen < best[0];
+    const double generation = best[d + 2];
+    if (q < d && better) best[1 + q] = sums[m + q];
+    __syncthreads();
+    if (q == 0) {
+        if (better) best[0] = f_gen;
+        best[d + 1] = f_gen;
+        best[d + 2] = generation + 1.0;
+        uint64_t *offset = reinterpret_cast<uint64_t *>(state + d + dd);
+        *offset += offset_step;
+    }
+    __syncthreads();
+    if (hist && q < d + 2) {
+        const int row = static_cast<int>(static_cast<long long>(generation) % hist_rows);
+        hist[row * (d + 2) + q] = best[q];
+    }
+}
+
 int pb200_xnes_ask(const double *d_mu, const double *d_A, const double *d_lower,
                    const double *d_upper, double *d_z, double *d_x, double *d_x_eval,
                    uint8_t *d_inside, int64_t n, int32_t d, uint64_t seed,
@@ -633,6 +744,22 @@ int pb200_xnes_sums(const double *d_z, const int64_t *d_order, const double *d_u
     xnes_sums_final_kernel<<<1, threads, 0, st>>>(d_partial, d_out, n_blocks, m, d_order,
                                                   (d_x && d_fx) ? d_x : nullptr, d_fx, d);
     return pb200_check_cuda(cudaGetLastError(), "xnes_sums_kernel launch");
+}
+
+int pb200_xnes_update(double *d_state, const double *d_sums, double *d_best, double *d_hist,
+                      int32_t hist_rows, double eta_mu, double eta_A, double sum_us, int32_t d,
+                      uint64_t offset_step, int32_t separable, void *stream) {
+    if (d < 1 || d > PB200_MAX_PARAMS || !d_state || !d_sums || !d_best ||
+        (d_hist && hist_rows < 1)) {
+        pb200_set_error("pb200_xnes_update: bad d=%d, NULL buffer or hist_rows=%d", d, hist_rows);
+        return PB200_EINVAL;
+    }
+    int threads = (d * d + 31) & ~31;
+    if (threads < 32) threads = 32;
+    xnes_update_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_state, d_sums, d_best, d_hist, hist_rows, eta_mu, eta_A, sum_us, d, offset_step,
+        separable);
+    return pb200_check_cuda(cudaGetLastError(), "xnes_update_kernel launch");
 }
 
 int pb200_philox_normal(double *d_out, int64_t n, uint64_t seed, uint64_t offset,

@@ -463,25 +463,34 @@ def test_cuda_optimisation_controller_with_device_xnes(pb):
             runs.append(ctl.run())
         assert np.allclose(runs[0][0], runs[1][0], rtol=1e-9)
         assert np.isclose(runs[0][1], runs[1][1], rtol=1e-12)
-    # had the sample sort given up (status != 0), the generation is ranked
-    # again with the library sort and the run carries on with it
-    opt = pb.DeviceXNES([0.3, 0.7, 2.5], boundaries=b)
-    opt.native_sort = True
-    opt.set_population_size(6000)
+    # had the sample sort given up (status != 0), the state is put back, the
+    # generation is ranked again with the library sort and the run carries on
+    # with it: same result as a run that never saw the flag
     problem_dev = pb.CudaEvaluator(ll, as_list=False).device_problem()
-    opt.generation(problem_dev, negate=True)
-    before = opt.x_guessed().copy()
-    xs = opt.ask()
-    fx = -problem_dev.eval(xs)
-    opt._ready_for_tell = False
-    with torch.cuda.device(xs.device):
-        opt._enqueue_tell(fx)
-        torch.cuda.synchronize()
-    want = host(opt._d_out).copy()
-    opt._h_status[0] = 1                       # pretend
-    opt._update()
-    assert opt._sort_gave_up and np.allclose(host(opt._d_out), want, rtol=1e-12)
-    assert not np.array_equal(opt.x_guessed(), before)
+    twins = []
+    for pretend in (False, True):
+        opt = pb.DeviceXNES([0.3, 0.7, 2.5], boundaries=b)
+        opt.native_sort = True
+        opt.set_population_size(6000)
+        opt.generation(problem_dev, negate=True)
+        before = opt.x_guessed().copy()
+        if pretend:
+            real, seen = opt._sort_failed, []
+
+            def flagged(real=real, seen=seen, opt=opt):
+                if not seen:
+                    seen.append(1)
+                    opt._h_status[0] = 1
+                return real()
+            opt._sort_failed = flagged
+        hist = opt.generations(problem_dev, 3, negate=True)
+        assert hist.shape == (3, 5) and hist[-1, 0] == opt.f_best()
+        assert opt._sort_gave_up == pretend
+        assert not np.array_equal(opt.x_guessed(), before)
+        assert opt._generations_done == 4
+        twins.append((opt.x_guessed().copy(), opt.f_best(), opt.x_best().copy()))
+    assert np.allclose(twins[0][0], twins[1][0], rtol=1e-9)
+    assert np.isclose(twins[0][1], twins[1][1], rtol=1e-12)
     # minimising the error measure of the same problem finds the same point
     opt = pb.CudaOptimisationController(
         pb.SumOfSquaresError(problem), [0.3, 0.7, 2.5], boundaries=b,
