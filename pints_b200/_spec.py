@@ -124,12 +124,13 @@ class ProblemSpec(object):
         if self.model == _lib.MODEL_REPRESSILATOR:
             return (6 * 64 + 6 * 27 + 10 + 108) * steps + 35.0 * nt
         if self.model == _lib.MODEL_BEELER_REUTER:
-            # Rosenbrock 4(3) attempt: four right-hand sides (27 exp + 1 log,
+            # Rosenbrock 4(3) attempt: three right-hand sides (27 exp + 1 log,
             # counted 1 each as the reference writes them, + 19 divisions +
-            # 106 add/mul = 153), Jacobian pieces and elimination factors 110,
+            # 106 add/mul = 153), analytic V column 90, other Jacobian pieces and
+            # elimination factors 110,
             # four arrow solves 180, stage sums, new state and error 208,
             # Hermite coefficients 20; per observation 2 + 8 per output
-            return (4 * 153 + 518) * steps + 18.0 * nt
+            return (3 * 153 + 90 + 518) * steps + 18.0 * nt
         if self.model == _lib.MODEL_HH_IK:
             return 0.0 * steps + 12.0 * nt + 750.0
         return 0.0 * steps + 8.0 * nt * self.n_outputs
