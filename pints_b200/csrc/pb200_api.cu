@@ -342,7 +342,10 @@ int pb200_problem_set_prior_terms(pb200_problem *p, int32_t n_terms, const int32
     return PB200_OK;
 }
 
-void pb200_problem_destroy(pb200_problem *p) { delete p; }
+void pb200_problem_destroy(pb200_problem *p) {
+    if (p && p->sort_hint) cudaFreeHost(p->sort_hint);
+    delete p;
+}
 
 int32_t pb200_problem_n_parameters(const pb200_problem *p) {
     return p ? p->dev.n_params : -1;

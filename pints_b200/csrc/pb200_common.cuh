@@ -66,6 +66,12 @@ struct pb200_problem {
     ModelConsts mc;
     int32_t n_model_consts;
     int64_t series_bytes;         // bytes staged into shared memory
+    // One word of page-locked, device-mapped host memory (allocated at the first
+    // sorted launch): the kernels that see the cost keys of a population leave
+    // 1 = narrow, 2 = wide here, and the NEXT launch picks its sort by it
+    // (launch_model in pb200_ode.cu); no synchronisation, a stale value only
+    // costs a per cent or two of speed, never a result.
+    mutable int32_t *sort_hint = nullptr;
 };
 
 // Where a score goes.  n = 0: the caller's d_scores[i].  n > 0: the exchange
@@ -159,8 +165,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ void stage_series(double *dst, const double *src,
-                                             uint32_t bytes, uint64_t *bar) {
+// Issue: barrier initialisation (one block-wide barrier) and the copies.
+__device__ __forceinline__ void stage_series_begin(double *dst, const double *src,
+                                                   uint32_t bytes, uint64_t *bar) {
     const uint32_t bar_a = smem_u32(bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
@@ -184,7 +191,11 @@ __device__ __forceinline__ void stage_series(double *dst, const double *src,
             done += nb;
         }
     }
-    // wait for phase 0 to complete
+}
+
+// Wait for phase 0 of the barrier (every thread that reads the series).
+__device__ __forceinline__ void stage_series_wait(uint64_t *bar) {
+    const uint32_t bar_a = smem_u32(bar);
     uint32_t ok = 0;
     while (!ok) {
         asm volatile(
@@ -195,6 +206,12 @@ __device__ __forceinline__ void stage_series(double *dst, const double *src,
             : "r"(bar_a)
             : "memory");
     }
+}
+
+__device__ __forceinline__ void stage_series(double *dst, const double *src,
+                                             uint32_t bytes, uint64_t *bar) {
+    stage_series_begin(dst, src, bytes, bar);
+    stage_series_wait(bar);
 }
 
 // ---------------------------------------------------------------------------

@@ -12,7 +12,9 @@
 //   ode_kernel        one lane per vector; plain layout (64-thread blocks) or
 //                     the migrating layout (one block per SM, MigDev)
 //   ode_pair_kernel   two lanes per vector (option, two-state models)
-//   sort_kernel       cost-coherent scheduling (cooperative counting sort)
+//   sort_kernel       cost-coherent scheduling (cooperative counting sort);
+//                     local_cost_sort: the block-by-block sort inside
+//                     ode_kernel where the launch is one block per SM
 //   launchers         layout selection, launch_ode
 // DESIGN.md section 3 has the measurements each choice rests on.
 //
@@ -31,6 +33,7 @@
 // measured agreement.
 #include "pb200_common.cuh"
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -724,6 +727,9 @@ struct Series {
 #ifndef PB200_STAGGER
 #define PB200_STAGGER 0         // (development) start offset in cycles between a scheduler's warps
 #endif
+#ifndef PB200_LSORT_STRIDED
+#define PB200_LSORT_STRIDED 2   // block-local sort: 2 = runs of 32 rows dealt round-robin, 1 = rows b, b + blocks, ..., 0 = one contiguous run
+#endif
 #ifndef PB200_TIMELINE
 #define PB200_TIMELINE 0        // (development) per-warp start / end clocks
 #endif
@@ -838,6 +844,145 @@ template <> struct LaunchShape<RepressilatorModel> {
 // chain), and holds 20 / 24 warps per SM in ONE wave.
 constexpr int dense_threads(int dense) { return dense == 2 ? 768 : dense == 1 ? 640 : 0; }
 
+// ---------------------------------------------------------------------------
+// Cost sort inside the evaluation kernel (one block per SM: migrating and dense
+// layouts).  What the lock step of a warp needs is 32 vectors of similar cost
+// in every warp; it does not need a GLOBAL order.  Block b takes the vectors
+// b, b + blocks, b + 2 blocks, ... (a systematic sample of the population,
+// whatever order the caller's rows are in) and sorts THOSE by the cost key in
+// shared memory (counting
+// sort over 1024 bins between the block's own smallest and largest key, no
+// order inside a bin), under the bulk copy of the series: no launch of its own,
+// no grid-wide barrier, no permutation in global memory.  Emulated on the
+// headline population (tools/step_emulation.py): 3.71 interpolation passes per
+// attempt for blocks of 448 vectors against 3.59 for the global sort and 4.60
+// unsorted, i.e. 1.1 % more issue cycles than the global order -- against the
+// 13.7 us (3.7 % of the step) that sort_kernel takes in front of the solve.
+// A block's warps are in increasing order of cost, as the strided deal of the
+// globally sorted order gave them, and every block holds an even sample of
+// the population, so the SMs stay balanced as long as the costs of a
+// population differ by a few per cent (an optimiser's or sampler's population).
+// On a wide prior box (costs 1 : 5) the SMs' sums differ by a few per cent and
+// the global order wins by 2 %: PB200_LOCAL_SORT=0 keeps sort_kernel.
+// ---------------------------------------------------------------------------
+constexpr int SORT_BINS = 1024;
+struct LocalSortDev {
+    int32_t on;                    // 0: launch order / perm as given
+    uint32_t scratch_off;          // byte offset of LOCAL_SORT_WORDS words in dynamic shared memory
+    int32_t *hint;                 // pb200_problem::sort_hint (or nullptr)
+};
+
+// The spread of a population's cost keys, from the keys at 10 % and 90 % of
+// their order: narrow (1) when (k90 - k10) / (k90 + k10) < 0.1, else wide (2).
+// Measured on FitzHugh-Nagumo (key = c, population 65 536, profiles/
+// r02ac_local_sort.log): Gaussian populations of relative width 2 / 5 / 10 /
+// 20 % have ratios 0.026 / 0.064 / 0.13 / 0.26 and the block-local sort is
+// 9 us faster / 6 us faster / even / 14 us slower than sort_kernel.
+__device__ __forceinline__ int32_t spread_hint(float k10, float k90) {
+    return (k90 - k10) < 0.1f * (k90 + k10) ? 1 : 2;
+}
+constexpr int LOCAL_SORT_MAX = 768;          // vectors per block (the largest block shape)
+constexpr int LOCAL_SORT_WORDS = SORT_BINS + LOCAL_SORT_MAX + 64;
+
+// Returns the block-local index of the vector that takes local slot j; m is
+// the number of vectors of this block (local index t is vector
+// blockIdx.x + gridDim.x * t).
+// row of the population that is local vector t of this block
+__device__ __forceinline__ int64_t local_row(int t, int per_block) {
+#if PB200_LSORT_STRIDED == 2
+    // runs of 32 rows dealt to the blocks round-robin: coalesced, and still a
+    // sample from all over the population
+    return ((static_cast<int64_t>(t >> 5) * gridDim.x + blockIdx.x) << 5) + (t & 31);
+#elif PB200_LSORT_STRIDED
+    return blockIdx.x + static_cast<int64_t>(gridDim.x) * t;
+#else
+    return static_cast<int64_t>(blockIdx.x) * per_block + t;
+#endif
+}
+
+template <class M>
+__device__ __forceinline__ int local_cost_sort(const ProblemDev &P, const ModelConsts &mc,
+                                               const double *__restrict__ params,
+                                               int m, int m_full, int64_t ld, uint32_t *sh, int j,
+                                               int32_t *hint) {
+    uint32_t *hist = sh, *sorted = sh + SORT_BINS, *red = sh + SORT_BINS + LOCAL_SORT_MAX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    const int t = threadIdx.x;
+    const bool have = t < m;
+    for (int b = t; b < SORT_BINS; b += blockDim.x) hist[b] = 0u;
+    float key = 0.0f;
+    if (have) {
+        double x[PB200_MAX_PARAMS];
+#pragma unroll
+        for (int k = 0; k < M::NP + M::NO; ++k)
+            x[k] = (k < P.n_params) ? params[local_row(t, m_full) * ld + k] : 0.0;
+        double early;
+        if (!objective_precheck(P, x, &early)) {      // decided vectors keep key 0
+            M model;
+            double y[M::NS], t0;
+            model.load(x, mc, y, P.n_times > 0 ? P.series[0] : 0.0, &t0);
+            key = static_cast<float>(model.cost_key(y));
+            if (!(key >= 0.0f)) key = 0.0f;            // NaN
+            key = fminf(key, 3.0e38f);
+        }
+    }
+    // keys are >= 0: their bit patterns order like the values
+    uint32_t hi = have ? __float_as_uint(key) : 0u;
+    uint32_t lo = have ? ~__float_as_uint(key) : 0u;
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    lo = __reduce_max_sync(0xffffffffu, lo);
+    if (lane == 0) { red[warp] = hi; red[32 + warp] = lo; }
+    __syncthreads();
+    hi = lane < nwarps ? red[lane] : 0u;
+    lo = lane < nwarps ? red[32 + lane] : 0u;
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    lo = __reduce_max_sync(0xffffffffu, lo);
+    const float kmin = __uint_as_float(~lo), kmax = __uint_as_float(hi);
+    const float scale = kmax > kmin ? static_cast<float>(SORT_BINS) / (kmax - kmin) : 0.0f;
+    int bin = static_cast<int>((key - kmin) * scale);
+    bin = min(max(bin, 0), SORT_BINS - 1);
+    uint32_t rank = 0;
+    if (have) rank = atomicAdd(&hist[bin], 1u);
+    __syncthreads();
+    // exclusive scan of the bins in place: threads 0..127 take eight bins each
+    constexpr int PER = SORT_BINS / 128;
+    uint32_t cnt[PER], run = 0, inc = 0;
+    if (t < 128) {
+        const uint4 a = reinterpret_cast<const uint4 *>(hist)[t * 2];
+        const uint4 b = reinterpret_cast<const uint4 *>(hist)[t * 2 + 1];
+        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
+        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) run += cnt[k];
+        inc = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) red[warp] = inc;
+    }
+    __syncthreads();
+    if (t < 128) {
+        uint32_t before = inc - run;
+        for (int w = 0; w < warp; ++w) before += red[w];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { hist[t * PER + k] = before; before += cnt[k]; }
+    }
+    __syncthreads();
+    const uint32_t pos = hist[bin] + rank;
+    if (have) sorted[pos] = static_cast<uint32_t>(t);
+    __syncthreads();
+    if (hint != nullptr && blockIdx.x == 0) {          // uniform
+        if (have && pos == static_cast<uint32_t>(m / 10)) red[0] = __float_as_uint(key);
+        if (have && pos == static_cast<uint32_t>(m - 1 - m / 10)) red[1] = __float_as_uint(key);
+        __syncthreads();
+        if (t == 0) *hint = spread_hint(__uint_as_float(red[0]), __uint_as_float(red[1]));
+    }
+    return static_cast<int>(sorted[min(j, m - 1)]);
+}
+
 template <class M, bool SMEM, bool TRAJ, bool MIG, bool WIDE, int DENSE = 0>
 __global__ void __launch_bounds__(DENSE ? dense_threads(DENSE)
                                         : (MIG ? 512 : LaunchShape<M>::THREADS),
@@ -847,11 +992,13 @@ ode_kernel(const __grid_constant__ ProblemDev P,
            const double *__restrict__ params, int64_t n, int64_t ld,
            double *__restrict__ scores, double *__restrict__ traj,
            int32_t *__restrict__ steps_out, const int32_t *__restrict__ perm,
-           const SolverDev S, const MigDev mig, const ScatterDev sc) {
+           const SolverDev S, const MigDev mig, const ScatterDev sc,
+           const LocalSortDev ls) {
     constexpr int NS = M::NS, NO = M::NO, OUT0 = M::OUT0;
     constexpr uint32_t ROWB = (1 + NO) * 8;          // bytes per series row
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr int U = PB200_PIPE_U;
+    constexpr bool LSORT = (MIG || DENSE != 0) && !TRAJ;     // instances that can sort in the block
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     // role of this warp in the migrating layout
@@ -864,13 +1011,13 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     if (SMEM) {
         const uint32_t bytes = static_cast<uint32_t>(
             ((static_cast<int64_t>(P.n_times) + PB200_SENTINEL_ROWS) * ROWB + 15) & ~15ll);
-        stage_series(smem, P.series, bytes, &bar);
-        series.sbase = launder_u32(smem_u32(smem));
+        stage_series_begin(smem, P.series, bytes, &bar);     // waited for below
     }
 
     // lanes past the end of the population shadow the last vector and write
     // nothing: whole warps stay convergent for the votes below
     int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int lj = static_cast<int>(threadIdx.x);           // block-local slot (block-local sort)
     bool filler = false;
     if (MIG) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -890,6 +1037,40 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 #else
         gi = (static_cast<int64_t>(blockIdx.x) * (mig.q4 + mig.r) + vw) * 32 + lane;
 #endif
+        lj = vw * 32 + lane;
+    }
+    // the block's own vectors in order of cost (see local_cost_sort)
+    int li = -1, l_full = 0;
+    if constexpr (LSORT) {
+        if (ls.on) {
+            l_full = MIG ? (mig.q4 + mig.r) * 32 : static_cast<int>(blockDim.x);
+#if PB200_LSORT_STRIDED == 2
+            // valid local vectors are a prefix (rows grow with the local index)
+            const int m = __syncthreads_count(static_cast<int>(threadIdx.x) < l_full &&
+                                              local_row(threadIdx.x, l_full) < n);
+#elif PB200_LSORT_STRIDED
+            // vectors b, b + G, ...: n / G of them, one more in the first n % G blocks
+            const int64_t q = n / gridDim.x, rem = n % gridDim.x, b = blockIdx.x;
+            const int m = static_cast<int>(q + (b < rem ? 1 : 0));
+            const int64_t first_slot = b * q + (b < rem ? b : rem);
+#else
+            const int64_t first_slot = static_cast<int64_t>(blockIdx.x) * l_full;
+            const int m = n - first_slot < l_full ? static_cast<int>(n - first_slot) : l_full;
+#endif
+            li = local_cost_sort<M>(P, mc, params, m, l_full, ld,
+                                    reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(smem) + ls.scratch_off),
+                                    lj, ls.hint);
+            // position in the launch order: 32 consecutive ones per warp (put_score)
+#if PB200_LSORT_STRIDED == 2
+            gi = lj < m ? local_row(lj, l_full) : n;
+#else
+            gi = lj < m ? first_slot + lj : n;
+#endif
+        }
+    }
+    if (SMEM) {
+        stage_series_wait(&bar);
+        series.sbase = launder_u32(smem_u32(smem));
     }
 #if PB200_TIMELINE
     const long long tl_start = clock64();
@@ -910,7 +1091,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     // `perm` (optional) lists the vectors in order of a cost key, so that the
     // lanes of a warp integrate similar dynamics (see sort_* below)
     const int64_t slot = gi < n ? gi : n - 1;
-    const int64_t i = perm ? perm[slot] : slot;
+    const int64_t i = (LSORT && li >= 0) ? local_row(li, l_full) : (perm ? perm[slot] : slot);
 
     const int nt = P.n_times;
     const int n_read = TRAJ ? P.n_model_params : P.n_params;
@@ -1093,7 +1274,8 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     for (;;) {
         const bool fin = (off >= end) || failed;
         if (__all_sync(FULL, fin)) break;
-        if (is_source && __any_sync(FULL, off >= mig.off_mid)) break;
+        // (lanes without a vector sit at off = end from the start: they do not count)
+        if (is_source && __any_sync(FULL, !idle && off >= mig.off_mid)) break;
         // an attempt counts (and may fail the vector) only while the solution
         // has not reached the last observation; a lane that has consumed all its
         // observations is frozen (its attempts are forced to "rejected", so t, y
@@ -1903,7 +2085,6 @@ ode_pair_kernel(const __grid_constant__ ProblemDev P,
 // enough (no order is needed inside a bin) and is one cooperative launch.
 // ======================================================================
 static int sm_count();
-constexpr int SORT_BINS = 1024;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_MAX_BLOCKS = 1024;
 
@@ -1925,8 +2106,9 @@ sort_kernel(const __grid_constant__ ProblemDev P,
             const __grid_constant__ ModelConsts mc,
             const double *__restrict__ params, int64_t n, int64_t ld,
             float *__restrict__ keys, SortHeader *__restrict__ hdr,
-            int32_t *__restrict__ perm) {
+            int32_t *__restrict__ perm, int32_t *hint) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t sh_q[2];              // C: bins of the 10 % and 90 % quantiles
     __shared__ uint32_t sh_a[SORT_BINS];      // B: histogram      C: scan of the histogram
     __shared__ uint32_t sh_b[SORT_BINS];      // C: this block's count per bin, then its start
     __shared__ uint32_t sh_w[2 * SORT_THREADS / 32];
@@ -2016,8 +2198,22 @@ sort_kernel(const __grid_constant__ ProblemDev P,
     __syncthreads();
     uint32_t before = inc - run;
     for (int w = 0; w < warp; ++w) before += sh_w[w];
+    const uint32_t r10 = static_cast<uint32_t>(n / 10), r90 = static_cast<uint32_t>(n - 1 - n / 10);
 #pragma unroll
-    for (int k = 0; k < PER; ++k) { sh_a[threadIdx.x * PER + k] = before; before += v[k]; }
+    for (int k = 0; k < PER; ++k) {
+        sh_a[threadIdx.x * PER + k] = before;
+        if (before <= r10 && r10 < before + v[k]) sh_q[0] = threadIdx.x * PER + k;
+        if (before <= r90 && r90 < before + v[k]) sh_q[1] = threadIdx.x * PER + k;
+        before += v[k];
+    }
+    // what the population's keys look like, for the next launch (see spread_hint)
+    if (hint != nullptr && blockIdx.x == 0) {          // uniform
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float w = scale > 0.0f ? 1.0f / scale : 0.0f;
+            *hint = spread_hint(kmin + (sh_q[0] + 0.5f) * w, kmin + (sh_q[1] + 0.5f) * w);
+        }
+    }
     // ranks inside this block (one round of the grid-stride loop at a time)
     for (int64_t base_i = static_cast<int64_t>(blockIdx.x) * blockDim.x; base_i < n; base_i += stride) {
         const int64_t i = base_i + threadIdx.x;
@@ -2041,7 +2237,8 @@ sort_kernel(const __grid_constant__ ProblemDev P,
 // returns the device pointer to it through *perm.
 template <class M>
 int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
-                      int64_t ld, void *ws, const int32_t **perm, cudaStream_t st) {
+                      int64_t ld, void *ws, const int32_t **perm, cudaStream_t st,
+                      int32_t *hint = nullptr) {
     SortHeader *hdr = static_cast<SortHeader *>(ws);
     float *keys = reinterpret_cast<float *>(hdr + 1);
     int32_t *out = reinterpret_cast<int32_t *>(keys + n);
@@ -2065,7 +2262,7 @@ int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
     if (grid > cap) grid = cap;
     if (grid > SORT_MAX_BLOCKS) grid = SORT_MAX_BLOCKS;
     void *args[] = {const_cast<ProblemDev *>(&p->dev), const_cast<ModelConsts *>(&p->mc),
-                    &d_params, &n, &ld, &keys, &hdr, &out};
+                    &d_params, &n, &ld, &keys, &hdr, &out, &hint};
     int rc = pb200_check_cuda(
         cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sort_kernel<M>),
                                     dim3(static_cast<unsigned>(grid)), dim3(SORT_THREADS),
@@ -2094,6 +2291,37 @@ static bool mig_enabled() {
         return (e && e[0] == '0') ? 0 : 1;
     }();
     return on != 0;
+}
+// PB200_LOCAL_SORT: 0 = always sort_kernel, 1 = always the block-local sort,
+// anything else = by the spread of the previous population (sort_hint)
+static int local_sort_mode() {
+    static const int mode = [] {
+        const char *e = getenv("PB200_LOCAL_SORT");
+        return (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
+    }();
+    return mode;
+}
+// The problem's hint word (allocated on first use, never while the stream is
+// being captured); nullptr when there is none.
+static int32_t *sort_hint_of(const pb200_problem *p, cudaStream_t st) {
+    if (p->sort_hint) return p->sort_hint;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (p->sort_hint) return p->sort_hint;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    int32_t *w = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&w), 64, cudaHostAllocMapped | cudaHostAllocPortable) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    w[0] = 0;
+    p->sort_hint = w;
+    return w;
 }
 static bool dense_enabled() {
     static const int on = [] {
@@ -2138,10 +2366,6 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
                  int32_t *d_steps, const SolverDev &s, int block,
                  void *sort_ws, const ScatterDev &sc, cudaStream_t st) {
     const int32_t *perm = nullptr;
-    if (sort_ws) {
-        int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st);
-        if (rc) return rc;
-    }
     const int64_t bytes = staged_bytes(p, M::NO);
 #ifdef PB200_NO_SMEM
     const bool use_smem = false;
@@ -2199,14 +2423,40 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
             block = static_cast<int>(per_sm) * 32;
         }
     }
-#define PB200_XARG , mig, sc
+    // one block per SM: the cost sort runs inside the launch, block by block
+    // (local_cost_sort); everywhere else sort_kernel builds a global permutation
+    // Which of the two: the block-local sort is 6-9 us faster on populations
+    // whose costs differ by a few per cent (an optimiser's or sampler's
+    // population), the global order is up to 14 us faster on wide ones; both
+    // kernels leave the spread of the keys they saw in the problem's hint word
+    // and the next launch goes by it (the first one takes the global sort).
+    const bool one_block_per_sm = (mig.r != 0) || (dense != 0);
+    size_t sort_dyn = 0;
+    LocalSortDev ls = {0, 0, nullptr};
+    if (sort_ws && one_block_per_sm && local_sort_mode() != 0) {
+        ls.hint = sort_hint_of(p, st);
+        const int seen = ls.hint ? *static_cast<volatile int32_t *>(ls.hint) : 0;
+        if (local_sort_mode() == 1 || seen == 1) {
+            ls.on = 1;
+            sort_dyn = static_cast<size_t>(LOCAL_SORT_WORDS) * 4 + 16;
+        }
+    }
+    if (sort_ws && !ls.on) {
+        int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st, ls.hint);
+        if (rc) return rc;
+    }
+#define PB200_XARG , mig, sc, ls
     constexpr bool W = !std::is_same<M, FhnModel>::value;      // the model's default loop
     if (mig.r) {
         if constexpr (M::MIGRATES) {
         const int mblock = (mig.q4 + 2 + mig.r) * 32;
         const int64_t per_block = static_cast<int64_t>(mig.q4 + mig.r) * 32;
         const int64_t mgrid = (n + per_block - 1) / per_block;
-        const size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
+        size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
+        if (ls.on) {
+            ls.scratch_off = static_cast<uint32_t>((mdyn + 15) & ~static_cast<size_t>(15));
+            mdyn = ls.scratch_off + sort_dyn;
+        }
         if (dense == 2) PB200_LAUNCH((ode_kernel<M, true, false, true, W, 2>), mgrid, mblock, mdyn);
         else if (dense == 1) PB200_LAUNCH((ode_kernel<M, true, false, true, W, 1>), mgrid, mblock, mdyn);
         else if (s.wide) PB200_LAUNCH((ode_kernel<M, true, false, true, true>), mgrid, mblock, mdyn);
@@ -2215,8 +2465,13 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     } else if (dense) {
         if constexpr (M::MIGRATES) {
         const int64_t dgrid = (n + block - 1) / block;
-        if (dense == 2) PB200_LAUNCH((ode_kernel<M, true, false, false, W, 2>), dgrid, block, dyn);
-        else PB200_LAUNCH((ode_kernel<M, true, false, false, W, 1>), dgrid, block, dyn);
+        size_t ddyn = dyn;
+        if (ls.on) {
+            ls.scratch_off = static_cast<uint32_t>((ddyn + 15) & ~static_cast<size_t>(15));
+            ddyn = ls.scratch_off + sort_dyn;
+        }
+        if (dense == 2) PB200_LAUNCH((ode_kernel<M, true, false, false, W, 2>), dgrid, block, ddyn);
+        else PB200_LAUNCH((ode_kernel<M, true, false, false, W, 1>), dgrid, block, ddyn);
         }
     } else if (use_smem) {
         if (traj) PB200_LAUNCH((ode_kernel<M, true, true, false, false>), grid, block, dyn);

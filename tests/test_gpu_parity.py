@@ -393,6 +393,42 @@ def test_cost_sorted_scheduling_changes_nothing(pb):
                           evaluate(pb, f, g['xs'], sort=False))
 
 
+def test_block_local_sort_and_its_hint(pb):
+    """One-block-per-SM launches sort inside the kernel, block by block, when
+    the previous population's cost keys were narrow, and with sort_kernel when
+    they were wide (pb200_problem::sort_hint); whichever runs, scores and step
+    counts are per vector, bit for bit those of the unsorted launch.  Sizes:
+    migrating layout (65 536, 20 000: 14 and 5 warps per SM), dense classes
+    (80 000, 100 000), a ragged last run of rows."""
+    import torch
+    spec = po.headline_fhn_spec()
+    problem = pb.MultiOutputProblem(pb.toy.FitzhughNagumoModel(), spec.times,
+                                    spec.values)
+    ll = pb.GaussianKnownSigmaLogLikelihood(problem, 0.5)
+    rng = np.random.RandomState(11)
+    narrow = po.headline_fhn_points(100000)
+    wide = rng.uniform([0, 0, 1], [1, 1, 5], (65536, 3))
+    for n in (65536, 20000 - 7, 80000, 100000):
+        dp_s = pb.CudaEvaluator(ll, sort=True).device_problem()
+        dp_u = pb.CudaEvaluator(ll, sort=False).device_problem()
+        d_x = torch.from_numpy(np.ascontiguousarray(narrow[:n])).cuda()
+        want = dp_u.eval(d_x).cpu().numpy()
+        for _ in range(3):          # global sort, then (hint = narrow) the block-local one
+            got = dp_s.eval(d_x).cpu().numpy()
+            torch.cuda.synchronize()
+            assert np.array_equal(got, want, equal_nan=True), n
+    # a wide population in between flips the hint back and forth
+    dp_s = pb.CudaEvaluator(ll, sort=True).device_problem()
+    dp_u = pb.CudaEvaluator(ll, sort=False).device_problem()
+    for xs in (narrow[:65536], narrow[:65536], wide, wide, narrow[:65536], narrow[:65536]):
+        xs = xs.copy()
+        xs[123, 2] = -1.0                          # NaN key
+        d_x = torch.from_numpy(np.ascontiguousarray(xs)).cuda()
+        got = dp_s.eval(d_x).cpu().numpy()
+        torch.cuda.synchronize()
+        assert np.array_equal(got, dp_u.eval(d_x).cpu().numpy(), equal_nan=True)
+
+
 def test_mean_squared_and_root_mean_squared_errors(pb):
     """(f) row 3: MeanSquaredError / RootMeanSquaredError /
     NormalisedRootMeanSquaredError epilogues (pints/_error_measures.py:74-161,
