@@ -611,6 +611,9 @@ def run_ours(args):
         return {'median': float(np.median(x)), 'p95': float(np.percentile(x, 95)),
                 'mean': float(np.mean(x)), 'max': float(np.max(x))}
 
+    # which cost sort the timed steps ran with (the hint is set by the warm-up
+    # steps and the population does not change)
+    sort_in_kernel = dp.sort_hint() == 1 and os.environ.get('PB200_LOCAL_SORT', '') != '0'
     mine = {'rank': rank, 'step_ms_each': [round(float(v), 4) for v in whole],
             'step_ms': stats(whole), 'kernel_ms': stats(first),
             'exchange_wait_ms': stats(rest), 'sum_step_ms': float(whole.sum()),
@@ -676,9 +679,12 @@ def run_ours(args):
                 'hbm': hbm_side(kern_ms / K)},
             'e2e': e2e,
             'parity': parity,
-            # per step and rank: the counting-sort kernel + the fused ODE
-            # kernel (+ the reading side of the exchange)
-            'gpu_launches': K * world * (2 if world == 1 else 3),
+            # per step and rank: the fused ODE kernel (+ the reading side of
+            # the exchange), and the counting-sort kernel in front of it unless
+            # the population's cost keys were narrow (sort inside the kernel)
+            'gpu_launches': K * world * ((1 if world == 1 else 2) + (0 if sort_in_kernel else 1)),
+            'cost_sort': ('inside the evaluation kernel, block by block (narrow cost keys)'
+                          if sort_in_kernel else 'sort kernel in front of the evaluation kernel'),
             'clocks': clocks,
             'wall_s_timed_region': wall,
             # where the time of a step goes, per rank: kernel_ms = sort +

@@ -201,8 +201,19 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n,
  * row positions and do not depend on the grouping.  d_sort_ws is a 16-byte
  * aligned device workspace of pb200_sort_workspace_bytes(n) bytes owned by the
  * caller (NULL = no sorting, i.e. pb200_eval).
+ *
+ * Launches with one block per SM (the single-wave populations of the
+ * migrating and dense layouts) can also sort inside the evaluation kernel,
+ * block by block in shared memory, which saves the sort kernel's launch; that
+ * pays when the costs of a population differ by a few per cent only, so both
+ * sorts leave the spread of the keys they saw in a word of the problem and the
+ * next launch chooses by it.  pb200_problem_sort_hint reads that word:
+ * 0 = nothing seen yet, 1 = narrow (next one-block-per-SM launch sorts in the
+ * kernel), 2 = wide (sort kernel).  Environment PB200_LOCAL_SORT=0 / 1 forces
+ * either.  Scores never depend on the choice.
  */
 int64_t pb200_sort_workspace_bytes(int64_t n);
+int32_t pb200_problem_sort_hint(const pb200_problem *p);
 int pb200_eval_sorted(const pb200_problem *p, const double *d_params, int64_t n,
                       int64_t ld, double *d_scores, int32_t *d_steps,
                       const pb200_solver_opts *opts, void *d_sort_ws,

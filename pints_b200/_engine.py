@@ -156,6 +156,12 @@ class DeviceProblem(object):
             return n >= self.SORT_MIN_ROWS
         return bool(self.sort)
 
+    def sort_hint(self):
+        """What the last sorted launch saw (``pb200_problem_sort_hint``): 0
+        nothing yet, 1 narrow cost keys (the next one-block-per-SM launch sorts
+        inside the evaluation kernel), 2 wide (sort kernel)."""
+        return int(self._lib.pb200_problem_sort_hint(self._handle))
+
     def sort_workspace(self, n, key=0):
         """Device workspace of ``pb200_sort_workspace_bytes(n)`` bytes, cached
         per ``key`` (one per stream that may run concurrently)."""

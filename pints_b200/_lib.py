@@ -75,6 +75,7 @@ SIGNATURES = {
     'pb200_eval': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                              POINTER(SolverOpts), _P]),
     'pb200_sort_workspace_bytes': (c_int64, [c_int64]),
+    'pb200_problem_sort_hint': (c_int32, [c_void_p]),
     'pb200_eval_sorted': (c_int32, [_P, _P, c_int64, c_int64, _P, _P,
                                     POINTER(SolverOpts), _P, c_int64, _P]),
     'pb200_eval_exchange': (c_int32, [_P, _P, c_int64, c_int64, _P,

@@ -347,6 +347,10 @@ void pb200_problem_destroy(pb200_problem *p) {
     delete p;
 }
 
+int32_t pb200_problem_sort_hint(const pb200_problem *p) {
+    return (p && p->sort_hint) ? *static_cast<volatile int32_t *>(p->sort_hint) : 0;
+}
+
 int32_t pb200_problem_n_parameters(const pb200_problem *p) {
     return p ? p->dev.n_params : -1;
 }
