@@ -2323,6 +2323,13 @@ static int32_t *sort_hint_of(const pb200_problem *p, cudaStream_t st) {
     p->sort_hint = w;
     return w;
 }
+static bool local_plain_enabled() {
+    static const int on = [] {
+        const char *e = getenv("PB200_LOCAL_PLAIN");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
 static bool dense_enabled() {
     static const int on = [] {
         const char *e = getenv("PB200_DENSE");
@@ -2396,6 +2403,8 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     // multiple of four: migrating layout, one block per SM (see MigDev);
     // 17 .. 24 warps per SM: the dense register classes (see ode_kernel)
     MigDev mig = {0, 0, 0, 0};
+    LocalSortDev ls = {0, 0, nullptr};
+    bool use_mig = false, want_local = false;
     int dense = 0;
     if (M::MIGRATES && auto_layout && use_smem && !traj && mig_enabled()) {
         const int64_t warps = (n + 31) / 32;
@@ -2409,7 +2418,20 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
         if (per_sm > 16 && per_sm <= 24 && default_wide && dense_enabled() &&
             (per_sm <= 20 || r == 1 || r == 2))
             dense = per_sm <= 20 ? 1 : 2;
+        // Which cost sort (if any).  The block-local sort (local_cost_sort) is
+        // 6-9 us faster on populations whose costs differ by a few per cent
+        // (an optimiser's or sampler's population), the global order of
+        // sort_kernel is up to 14 us faster on wide ones; both leave the spread
+        // of the keys they saw in the problem's hint word and the next launch
+        // goes by it (the first one takes the global sort).
+        const bool single_wave = per_sm >= 5 && (per_sm <= 16 || dense);
+        if (sort_ws && single_wave && local_sort_mode() != 0) {
+            ls.hint = sort_hint_of(p, st);
+            const int seen = ls.hint ? *static_cast<volatile int32_t *>(ls.hint) : 0;
+            want_local = local_sort_mode() == 1 || seen == 1;
+        }
         if (per_sm >= 5 && (per_sm <= 14 || dense) && (r == 1 || r == 2)) {
+            use_mig = true;
             mig.q4 = static_cast<int32_t>(per_sm - r);
             mig.r = r;
             const int64_t row = (1 + M::NO) * 8;
@@ -2417,29 +2439,30 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
             mid = mid < 1 ? 1 : mid;
             mig.off_mid = static_cast<uint32_t>(mid * row);
             mig.buf_off = static_cast<uint32_t>(bytes);
+        } else if (single_wave && !dense && local_plain_enabled()) {
+            // nothing to migrate (the schedulers carry equal numbers of warps, or
+            // three of them one more): the same one-block-per-SM kernel without
+            // extra workers.  Its round-robin deal of the sorted warps keeps the
+            // SMs level where 64-thread blocks land wherever a slot frees up
+            // (population 73 000, 16 warps per SM: 0.441 -> 0.422 ms, wide prior
+            // box 0.702 -> 0.643 ms), and the sort can run inside it (0.416 ms;
+            // profiles/r02af_local_plain*.log)
+            use_mig = true;
+            mig.q4 = static_cast<int32_t>(per_sm);
+            mig.r = 0;
+            mig.off_mid = 0xffffffffu;
+            mig.buf_off = static_cast<uint32_t>(bytes);
         }
-        if (dense && !mig.r) {
+        if (dense && !use_mig) {
             // plain layout, one block of per_sm warps per SM
             block = static_cast<int>(per_sm) * 32;
         }
     }
-    // one block per SM: the cost sort runs inside the launch, block by block
-    // (local_cost_sort); everywhere else sort_kernel builds a global permutation
-    // Which of the two: the block-local sort is 6-9 us faster on populations
-    // whose costs differ by a few per cent (an optimiser's or sampler's
-    // population), the global order is up to 14 us faster on wide ones; both
-    // kernels leave the spread of the keys they saw in the problem's hint word
-    // and the next launch goes by it (the first one takes the global sort).
-    const bool one_block_per_sm = (mig.r != 0) || (dense != 0);
+    const bool one_block_per_sm = use_mig || (dense != 0);
     size_t sort_dyn = 0;
-    LocalSortDev ls = {0, 0, nullptr};
-    if (sort_ws && one_block_per_sm && local_sort_mode() != 0) {
-        ls.hint = sort_hint_of(p, st);
-        const int seen = ls.hint ? *static_cast<volatile int32_t *>(ls.hint) : 0;
-        if (local_sort_mode() == 1 || seen == 1) {
-            ls.on = 1;
-            sort_dyn = static_cast<size_t>(LOCAL_SORT_WORDS) * 4 + 16;
-        }
+    if (want_local && one_block_per_sm) {
+        ls.on = 1;
+        sort_dyn = static_cast<size_t>(LOCAL_SORT_WORDS) * 4 + 16;
     }
     if (sort_ws && !ls.on) {
         int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st, ls.hint);
@@ -2447,9 +2470,9 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
     }
 #define PB200_XARG , mig, sc, ls
     constexpr bool W = !std::is_same<M, FhnModel>::value;      // the model's default loop
-    if (mig.r) {
+    if (use_mig) {
         if constexpr (M::MIGRATES) {
-        const int mblock = (mig.q4 + 2 + mig.r) * 32;
+        const int mblock = (mig.q4 + (mig.r ? 2 + mig.r : 0)) * 32;
         const int64_t per_block = static_cast<int64_t>(mig.q4 + mig.r) * 32;
         const int64_t mgrid = (n + per_block - 1) / per_block;
         size_t mdyn = dyn + static_cast<size_t>(mig.r) * (2 * M::NS + 2 + M::NO + 2) * 32 * 8;
