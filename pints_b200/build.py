@@ -45,6 +45,8 @@ def build(force=False, verbose=False):
            *ARCH]
     if verbose:
         cmd += ['-Xptxas', '-v']
+    # development: extra -D flags for kernel variants (PB200_NVCC_FLAGS="-DPB200_X=1 ...")
+    cmd += os.environ.get('PB200_NVCC_FLAGS', '').split()
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True)

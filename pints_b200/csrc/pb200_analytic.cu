@@ -18,6 +18,15 @@
 namespace {
 
 constexpr int WARPS = 8;                 // warps per block
+#ifndef PB200_CHAIN_T_ASK
+#define PB200_CHAIN_T_ASK 1
+#endif
+#ifndef PB200_CHAIN_T_TELL
+#define PB200_CHAIN_T_TELL 1
+#endif
+#ifndef PB200_POINT_W
+#define PB200_POINT_W 8                  // points per lane and trip of the one-output loop
+#endif
 constexpr int SEG_STRIDE = 11;           // doubles per HH-IK segment record
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -398,6 +407,40 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                 }
             }
             ss[0] = acc;
+        } else if (no == 1) {
+            // One output (the usual closed-form problem): PB200_POINT_W of a
+            // lane's points per trip, so that their exponentials and divisions
+            // -- a few hundred cycles of dependent arithmetic each -- overlap.
+            // Slots past the end read the last row and add +0 (which leaves any
+            // sum as it is); the squares are added in the order of the points:
+            // the score is bit for bit that of the one-point loop below.  (A
+            // warp of the persistent chain loop has nothing else to hide that
+            // latency with: 20 -> 15 us per MCMC iteration at four per trip.)
+            constexpr int W = PB200_POINT_W;
+            double acc = 0.0;
+            for (int j0 = lane; j0 < nt; j0 += 32 * W) {
+                double tt[W], dd[W], vv[W];
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const int jj = j0 + 32 * u;
+                    const int jc = jj < nt ? jj : nt - 1;
+                    tt[u] = series[jc * row];
+                    dd[u] = series[jc * row + 1];
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u)
+                    vv[u] = point_value<E, SMEM>(ev, tt[u], 0, table, seg_of, j0 + 32 * u);
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const int jj = j0 + 32 * u;
+                    const bool valid = jj < nt;
+                    if (TRAJ) { if (valid) my_traj[jj] = vv[u]; }
+                    double r = __dsub_rn(dd[u], vv[u]);
+                    r = valid ? r : 0.0;
+                    acc = __dadd_rn(acc, __dmul_rn(r, r));
+                }
+            }
+            ss[0] = acc;
         } else
         for (int j = lane; j < nt; j += 32) {
             const double t = series[j * row];
@@ -447,17 +490,32 @@ analytic_kernel(const __grid_constant__ ProblemDev P,
                 const uint64_t off_ask = static_cast<uint64_t>(r[0]);
                 if (lane < d) s_z[lane] = philox_normal_at(j * d + lane, ch.seed, off_ask);
                 __syncwarp();
-                if (lane == 0)
-                    ac_ask_row(s_cur, s_sig, s_ll, s_prop, j, d, ch.seed, off_ask, s_z);
+                // (the serial part, one lane: dimension known at compile time up to 6)
+                if (lane == 0) {
+                    switch (PB200_CHAIN_T_ASK ? d : 0) {
+#define PB200_ASK(D) case D: ac_ask_row<D>(s_cur, s_sig, s_ll, s_prop, j, d, ch.seed, off_ask, s_z); break
+                        PB200_ASK(1); PB200_ASK(2); PB200_ASK(3); PB200_ASK(4); PB200_ASK(5); PB200_ASK(6);
+#undef PB200_ASK
+                        default: ac_ask_row<0>(s_cur, s_sig, s_ll, s_prop, j, d, ch.seed, off_ask, s_z);
+                    }
+                }
                 __syncwarp();
                 f_new = eval_row(j, s_prop);
                 if (lane == 0) {
-                    acc = ac_tell_row(static_cast<int>(r[6]), ch.require_finite, s_cur, s_curf,
-                                      s_prop, f_new, s_mu, s_sig, s_ll,
-                                      ch.samples ? ch.samples + j * ch.sample_stride + r[3]
-                                                 : nullptr,
-                                      j, d, slot_f64(r[5]), ch.target, ch.seed,
-                                      static_cast<uint64_t>(r[2]));
+                    double *sample = ch.samples ? ch.samples + j * ch.sample_stride + r[3] : nullptr;
+                    const int variant = static_cast<int>(r[6]);
+                    const double gamma = slot_f64(r[5]);
+                    const uint64_t off_tell = static_cast<uint64_t>(r[2]);
+                    switch (PB200_CHAIN_T_TELL ? d : 0) {
+#define PB200_TELL(D) case D: acc = ac_tell_row<D>(variant, ch.require_finite, s_cur, s_curf, s_prop,  \
+                                                   f_new, s_mu, s_sig, s_ll, sample, j, d, gamma,      \
+                                                   ch.target, ch.seed, off_tell); break
+                        PB200_TELL(1); PB200_TELL(2); PB200_TELL(3); PB200_TELL(4); PB200_TELL(5); PB200_TELL(6);
+#undef PB200_TELL
+                        default: acc = ac_tell_row<0>(variant, ch.require_finite, s_cur, s_curf, s_prop,
+                                                      f_new, s_mu, s_sig, s_ll, sample, j, d, gamma,
+                                                      ch.target, ch.seed, off_tell);
+                    }
                     n_acc += acc ? 1 : 0;
                 }
                 __syncwarp();

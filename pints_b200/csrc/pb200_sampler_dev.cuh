@@ -9,6 +9,20 @@
 #pragma once
 #include "pb200_common.cuh"
 
+// The library's exp / log / sincospi are inlined as sequences of separately
+// rounded multiplications and additions that the assembler may or may not
+// contract into FMAs depending on the code around them: inlined into the
+// unrolled ask / tell of the chain loop, exp(log lambda) came out one ulp away
+// from the copy in the one-thread-per-chain kernels (chains differing in the
+// last bit from iteration 46 on).  The samplers therefore call them through
+// these non-inlined functions: one body each, whatever the caller looks like
+// (a call costs ~30 cycles, four times per iteration of a chain).
+static __device__ __noinline__ double sampler_exp(double x) { return exp(x); }
+static __device__ __noinline__ double sampler_log(double x) { return log(x); }
+static __device__ __noinline__ void sampler_sincospi(double x, double *sn, double *cs) {
+    sincospi(x, sn, cs);
+}
+
 // ------------------------------------------------------------------ Philox
 struct U4 { uint32_t x, y, z, w; };
 
@@ -45,9 +59,9 @@ __device__ __forceinline__ double philox_uniform_at(int64_t idx, uint64_t seed, 
 __device__ __forceinline__ double philox_normal_at(int64_t idx, uint64_t seed, uint64_t offset) {
     const U4 r = philox4x32_10(offset + (idx >> 1), 2, seed);
     const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1));
+    const double rad = sqrt(-2.0 * sampler_log(u1));
     double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
+    sampler_sincospi(2.0 * u2, &sn, &cs);
     return (idx & 1) ? rad * sn : rad * cs;
 }
 
@@ -72,16 +86,28 @@ __device__ __forceinline__ double slot_f64(int64_t v) { return __longlong_as_dou
 // `log_lambda`, `prop` point at THIS chain's rows (global memory, or the shared
 // memory copy of the chain loop); z are the normals pb200_philox_normal would
 // write at [j d, (j + 1) d) for (seed, offset), drawn here unless given.
+// D > 0: the dimension at compile time (d == D): the loops unroll, the factor
+// stays in registers and nothing branches -- the same expressions in the same
+// order, so the same bits as D = 0 (the chain loop's serial part: one lane runs
+// this between two evaluations, and every branch of the generic loops is a
+// stall of the whole warp).
+template <int D = 0>
 __device__ __forceinline__ void ac_ask_row(const double *cur, const double *sg,
                                            const double *log_lambda, double *prop, int64_t j,
-                                           int d, uint64_t seed, uint64_t offset,
+                                           int d_, uint64_t seed, uint64_t offset,
                                            const double *z_given = nullptr) {
-    const double scale = exp(log_lambda[0]);
-    double L[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
+    const int d = D > 0 ? D : d_;
+    const double scale = sampler_exp(log_lambda[0]);
+    double L[(D > 0 ? D * D : PB200_MAX_PARAMS * PB200_MAX_PARAMS)];
+#pragma unroll
     for (int a = 0; a < d; ++a) {
+#pragma unroll
         for (int b = 0; b <= a; ++b) {
-            double s = scale * sg[a * d + b];
-            for (int k = 0; k < b; ++k) s -= L[a * d + k] * L[b * d + k];
+            // (explicit roundings: an unrolled `scale * sg - L * L` may contract
+            // either product into the FMA, the loop form contracts the second)
+            double s = __dmul_rn(scale, sg[a * d + b]);
+#pragma unroll
+            for (int k = 0; k < b; ++k) s = fma(-L[a * d + k], L[b * d + k], s);
             if (a == b) {
                 L[a * d + a] = s > 0.0 ? sqrt(s) : 0.0;
             } else {
@@ -90,11 +116,14 @@ __device__ __forceinline__ void ac_ask_row(const double *cur, const double *sg,
             }
         }
     }
-    double z[PB200_MAX_PARAMS];
+    double z[D > 0 ? D : PB200_MAX_PARAMS];
+#pragma unroll
     for (int k = 0; k < d; ++k)
         z[k] = z_given ? z_given[k] : philox_normal_at(j * d + k, seed, offset);
+#pragma unroll
     for (int a = 0; a < d; ++a) {
         double s = cur[a];
+#pragma unroll
         for (int k = 0; k <= a; ++k) s = fma(L[a * d + k], z[k], s);
         prop[a] = s;
     }
@@ -112,32 +141,41 @@ __device__ __forceinline__ void ac_ask_one(const double *cur, const double *sigm
 // accept/reject, chain sample, adaptation (variant < 0: none).  `cur`, `cur_f`,
 // `prop`, `mu`, `sg` (sigma), `log_lambda` point at THIS chain's rows; `sample`
 // at where its new current point goes (or NULL).  Returns the decision.
+// D as in ac_ask_row.
+template <int D = 0>
 __device__ __forceinline__ bool ac_tell_row(int variant, int require_finite, double *cur,
                                             double *cur_f, const double *prop, double f_new,
                                             double *mu, double *sg, double *log_lambda,
-                                            double *sample, int64_t j, int d, double gamma,
+                                            double *sample, int64_t j, int d_, double gamma,
                                             double target, uint64_t seed, uint64_t offset) {
-    const double log_u = log(philox_uniform_at(j, seed, offset));
+    const int d = D > 0 ? D : d_;
+    constexpr int DM = D > 0 ? D : PB200_MAX_PARAMS;
+    const double log_u = sampler_log(philox_uniform_at(j, seed, offset));
     const double lr = __dsub_rn(f_new, cur_f[0]);
     const bool acc = (log_u < lr) && (!require_finite || isfinite(f_new));
-    double x[PB200_MAX_PARAMS], prev[PB200_MAX_PARAMS], y[PB200_MAX_PARAMS];
+    double x[DM], prev[DM], y[DM];
+#pragma unroll
     for (int k = 0; k < d; ++k) {
         prev[k] = cur[k];
         y[k] = prop[k];
         x[k] = acc ? y[k] : prev[k];
     }
     if (acc) {
+#pragma unroll
         for (int k = 0; k < d; ++k) cur[k] = x[k];
         cur_f[0] = f_new;
     }
-    if (sample)
+    if (sample) {
+#pragma unroll
         for (int k = 0; k < d; ++k) sample[k] = x[k];
+    }
     if (variant < 0) return acc;
     // adaptation, as ac_adapt_kernel
     const double keep = __dsub_rn(1.0, gamma);
     double p = acc ? 1.0 : 0.0;
-    if (variant != PB200_AC_HAARIO_BARDENET) p = lr < 0.0 ? exp(lr) : 1.0;
-    double dev[PB200_MAX_PARAMS];
+    if (variant != PB200_AC_HAARIO_BARDENET) p = lr < 0.0 ? sampler_exp(lr) : 1.0;
+    double dev[DM];
+#pragma unroll
     for (int k = 0; k < d; ++k) {
         const double m = __dadd_rn(__dmul_rn(keep, mu[k]), __dmul_rn(gamma, x[k]));
         mu[k] = m;
@@ -146,7 +184,9 @@ __device__ __forceinline__ bool ac_tell_row(int variant, int require_finite, dou
             v = __dadd_rn(__dmul_rn(p, y[k]), __dmul_rn(__dsub_rn(1.0, p), prev[k]));
         dev[k] = __dsub_rn(v, m);
     }
+#pragma unroll
     for (int a = 0; a < d; ++a)
+#pragma unroll
         for (int b = 0; b < d; ++b) {
             const double outer = __dmul_rn(dev[a], dev[b]);
             sg[a * d + b] = __dadd_rn(__dmul_rn(keep, sg[a * d + b]),

@@ -99,7 +99,7 @@ __global__ void ac_adapt_kernel(int variant, const double *__restrict__ cur,
     double p = accepted[j] ? 1.0 : 0.0;
     if (variant != PB200_AC_HAARIO_BARDENET) {
         const double lr = log_ratio[j];
-        p = lr < 0.0 ? exp(lr) : 1.0;
+        p = lr < 0.0 ? sampler_exp(lr) : 1.0;
     }
     double dev[PB200_MAX_PARAMS];
     for (int k = 0; k < d; ++k) {
@@ -130,7 +130,7 @@ __global__ void hbac_propose_kernel(const double *__restrict__ cur,
                                     double *__restrict__ prop, int64_t n, int d) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const double scale = exp(log_lambda[j]);
+    const double scale = sampler_exp(log_lambda[j]);
     const double *sg = sigma + j * static_cast<int64_t>(d) * d;
     double L[PB200_MAX_PARAMS * PB200_MAX_PARAMS];
     // in-thread Cholesky of scale * sigma (lower), semi-definite tolerant
@@ -185,9 +185,9 @@ __global__ void philox_normal_kernel(double *out, int64_t n, uint64_t seed,
     if (2 * t >= n) return;
     const U4 r = philox4x32_10(offset + t, 2, seed);
     const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
-    const double rad = sqrt(-2.0 * log(u1));
+    const double rad = sqrt(-2.0 * sampler_log(u1));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    sampler_sincospi(2.0 * u2, &s, &c);
     out[2 * t] = rad * c;
     if (2 * t + 1 < n) out[2 * t + 1] = rad * s;
 }
