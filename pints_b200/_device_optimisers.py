@@ -238,7 +238,8 @@ class DeviceXNES(object):
             self._d_best.copy_(self._h_best, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
         self._generations_done = 0
-        self._graph = self._graph_key = self._graph_failed = None
+        self._graphs = {}             # (problem, sign, cost sort of the launch) -> captured generation
+        self._graph_failed = None
         self._eager_generations = 0
         self._sorter = DeviceArgsort(n, dev)
         self._sort_gave_up = False
@@ -344,7 +345,7 @@ class DeviceXNES(object):
         if int(self._h_status[0]) == 0:
             return False
         self._sort_gave_up = True
-        self._graph = None
+        self._graphs = {}
         self._sorter.status.zero_()
         return True
 
@@ -411,20 +412,33 @@ class DeviceXNES(object):
         rows = [(first + k) % self.HISTORY for k in range(count)]
         return np.array(self._h_hist.numpy()[rows], copy=True)
 
+    @property
+    def _graph(self):
+        """A captured generation (any of them), or None."""
+        return next(iter(self._graphs.values()), None)
+
     def _one_generation(self, problem, negate, key):
-        if self._graph is not None and self._graph_key == key:
-            self._graph.replay()
+        # which cost sort the evaluation launch takes is decided when it is
+        # ENQUEUED (from the spread of the previous population's keys,
+        # pb200_problem_sort_hint), i.e. it is baked into a captured graph: one
+        # graph per choice, so that a population that has narrowed since the
+        # first generations moves to the sort inside the kernel
+        hint = getattr(problem, 'sort_hint', None)
+        key = key + (hint() == 1 if hint is not None else False,)
+        graph = self._graphs.get(key)
+        if graph is not None:
+            graph.replay()
         elif self.use_graph and self._eager_generations >= 2 \
                 and self._graph_failed is None:
             try:
                 graph = capture_graph(
                     self._device,
                     lambda: self._enqueue_generation(problem, negate))
-                self._graph, self._graph_key = graph, key
+                self._graphs[key] = graph
                 graph.replay()
             except Exception as e:          # keep going without a graph
                 self._graph_failed = e
-                self._graph = None
+                self._graphs = {}
                 torch.cuda.synchronize(self._device)
                 self._enqueue_generation(problem, negate)
         else:
