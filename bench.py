@@ -596,8 +596,18 @@ def run_ours(args):
         np.copyto(xs_pinned, xs)
         e2e_private_s = e2e_loop(ev, xs_pinned)
         total = pop * world * K
+        hg = getattr(sharded, '_host_gather', None)
+        on_host = hg is not None and hg.ok
         e2e = {'h2d_bytes_per_step': int(xs.nbytes) * world,
-               'd2h_bytes_per_step': int(pop * world * 8) * world,
+               # gathered on the host: every score crosses PCIe once; gathered
+               # by the GPUs: every rank reads all scores back
+               'd2h_bytes_per_step': int(pop * 8) * world * (1 if on_host else world),
+               'exchange': ('host: every rank copies its block of scores into a shared, '
+                            'page-locked host segment, epoch flags, copy-out (HostGather%s)'
+                            % ('' if hg.pinned else ', segment NOT registered with CUDA')
+                            if on_host else
+                            'device: scores stored into every rank\'s staging array by the '
+                            'kernel over NVLink, every rank reads all of them back'),
                'api': 'ShardedEvaluator(f, as_list=False).evaluate(all '
                       'positions, page-locked) on every rank -> all scores in '
                       'every rank\'s host memory (exchange included)',

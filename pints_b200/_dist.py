@@ -9,8 +9,11 @@ update, which is O(population) and stays on the CPU -- sees all of them.  This
 replaces the task/result queues of ``ParallelEvaluator``
 (pints/_evaluation.py:284-372, :489-565).
 """
+import contextlib
 import ctypes
 import os
+import socket
+import time
 
 import numpy as np
 import torch
@@ -165,6 +168,170 @@ class ScoreExchange(object):
         return every[:total]
 
 
+def _boot_id():
+    try:
+        with open('/proc/sys/kernel/random/boot_id') as f:
+            return f.read().strip()
+    except OSError:
+        return ''
+
+
+class HostGather(object):
+    """All-gather of the ranks' score blocks on the HOST, for ranks of one
+    node: one POSIX shared-memory segment mapped by every process (and
+    registered with CUDA as page-locked, so a rank's device-to-host copy lands
+    in it directly), ``SLOTS`` result areas used in turn and one epoch flag per
+    rank.  A call: every rank copies ITS block of scores into the current
+    area, raises its flag, waits for the flags of the others and copies the
+    whole area out.
+
+    Why: ``ShardedEvaluator.evaluate`` hands ALL scores to EVERY rank's host.
+    Reading them back from each GPU moves world x n x 8 bytes over PCIe in
+    lock step (8 ranks x 4 MB: +0.33 ms per call on an 8-GPU box); here every
+    score crosses PCIe once and the rest is a host memory copy.  As measured
+    so far that copy and the flag wait cost more than they save (see
+    ``ShardedEvaluator._host_gather_possible``), so this path is opt-in.
+
+    The segment is unlinked as soon as all ranks have mapped it (nothing is
+    left behind if a process dies).  Flags and data are ordinary stores and
+    loads: the copy into the area is complete (stream synchronised) before a
+    rank's flag is raised, and x86 keeps stores, and loads, in order.  A rank
+    can be at most one call ahead of the slowest one (it needs everybody's
+    flag to return), so two areas would do.  ``ok`` is False (and ``error``
+    says why) when the ranks are not on one node or the segment cannot be
+    set up; the decision is collective.
+    """
+
+    SLOTS = 3
+    HEADER = 4096
+
+    def __init__(self, capacity, group=None, device=None, timeout=120.0):
+        from multiprocessing import resource_tracker, shared_memory
+        self.group = group
+        self.capacity = int(capacity)           # doubles per result area
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.timeout = float(timeout)
+        self.epoch = 0
+        self.ok = False
+        self.error = None
+        self.pinned = False
+        self._shm = None
+        if self.world * 64 > self.HEADER:
+            self.error = 'too many ranks'
+            return
+        cuda = device is not None and torch.device(device).type == 'cuda'
+        ctx = torch.cuda.device(device) if cuda else contextlib.nullcontext()
+        size = self.HEADER + self.SLOTS * self.capacity * 8
+        shm = None
+        with ctx:
+            where = [None] * self.world
+            dist.all_gather_object(where, (socket.gethostname(), _boot_id()), group=group)
+            name = None
+            if len(set(where)) == 1 and self.rank == 0:
+                try:
+                    shm = shared_memory.SharedMemory(create=True, size=size)
+                    name = shm.name
+                except Exception as e:                  # no /dev/shm, too small, ...
+                    self.error = e
+            box = [name]
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=group)
+            name = box[0]
+            mapped = False
+            if name is not None:
+                try:
+                    if self.rank != 0:
+                        # this process did not create the segment and must not
+                        # unlink it at exit: attach without telling the resource
+                        # tracker (Python < 3.13 has no track=False)
+                        register = resource_tracker.register
+                        resource_tracker.register = lambda *a, **k: None
+                        try:
+                            shm = shared_memory.SharedMemory(name=name)
+                        finally:
+                            resource_tracker.register = register
+                    mapped = shm.size >= size
+                except Exception as e:
+                    self.error = e
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, bool(mapped), group=group)
+            if self.rank == 0 and shm is not None:
+                try:
+                    shm.unlink()
+                except Exception:
+                    pass
+        if not all(everyone):
+            if shm is not None:
+                shm.close()
+            if self.error is None:
+                self.error = 'the ranks are not on one node' if name is None \
+                    else 'a rank could not map the segment'
+            return
+        self._shm = shm
+        self.flags = np.ndarray((self.world, 8), dtype=np.int64, buffer=shm.buf)
+        self.data = np.ndarray((self.SLOTS, self.capacity), dtype=np.float64,
+                               buffer=shm.buf, offset=self.HEADER)
+        self.base = self.data.ctypes.data
+        if cuda:
+            try:
+                with torch.cuda.device(device):
+                    rc = torch.cuda.cudart().cudaHostRegister(
+                        self.base - self.HEADER, size, 0)
+                self.pinned = int(rc) == 0
+            except Exception as e:      # still correct: the copies are staged by the driver
+                self.error = e
+        self.ok = True
+
+    def area(self, epoch):
+        """Address of the result area of call ``epoch``."""
+        return self.base + (epoch % self.SLOTS) * self.capacity * 8
+
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch
+
+    def publish(self, epoch):
+        self.flags[self.rank, 0] = epoch
+
+    def wait(self, epoch):
+        """Until every rank has published ``epoch``; raises after ``timeout``
+        seconds instead of hanging."""
+        col = self.flags[:, 0]
+        spins, t0 = 0, None
+        while not (col >= epoch).all():
+            spins += 1
+            if (spins & 1023) == 0:
+                now = time.monotonic()
+                if t0 is None:
+                    t0 = now
+                elif now - t0 > self.timeout:
+                    raise RuntimeError(
+                        'HostGather: ranks %s have not delivered call %d after %g s'
+                        % (np.nonzero(col < epoch)[0].tolist(), epoch, self.timeout))
+
+    def close(self):
+        shm, self._shm = self._shm, None
+        if shm is None:
+            return
+        if self.pinned:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.base - self.HEADER)
+            except Exception:
+                pass
+        self.flags = self.data = None
+        try:
+            shm.close()
+        except Exception:
+            pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedEvaluator(Evaluator):
     """Every rank calls ``evaluate(positions)`` with the same positions (as an
     SPMD controller loop does); each scores its own block on its own GPU and
@@ -193,6 +360,7 @@ class ShardedEvaluator(Evaluator):
         self._local = None
         self._buffers = {}
         self._exchange = None
+        self._host_gather = None
 
     # -- overridable pieces (the gloo tests replace the launch) ----------
     def _make_local(self):
@@ -244,6 +412,17 @@ class ShardedEvaluator(Evaluator):
             return np.empty(0)
         lo, hi, per = shard_bounds(n, world, rank)
         device = self._collective_device()
+        if self._host_gather_possible(device):
+            # ranks of one node: every score crosses PCIe once, into a host
+            # segment all ranks map (HostGather)
+            hg = self._host_gather
+            if hg is None or (hg.ok and hg.capacity < per * world):
+                if hg is not None:
+                    hg.close()
+                hg = self._host_gather = HostGather(
+                    max(per * world, 4096), self._group, device)
+            if hg.ok:
+                return self._evaluate_host_gather(hg, xs, lo, hi, per, n)
         if self._fused_possible(device):
             # fused exchange: the kernel stores the scores into every rank's
             # staging array (symmetric memory over NVLink)
@@ -262,6 +441,38 @@ class ShardedEvaluator(Evaluator):
             self._local_scores(np.ascontiguousarray(xs[lo:hi]), mine)
         dist.all_gather_into_tensor(every, mine, group=self._group)
         return every[:n].cpu().numpy() if per * world >= n else None
+
+    def _host_gather_possible(self, device):
+        # Opt-in (PB200_HOST_GATHER=1).  Measured with bench.py's end-to-end
+        # loop (profiles/r02d_*): 2 GPUs 2.70e8 against 2.64e8 evaluations/s
+        # for the device-side exchange, 4 GPUs 3.76e8 against 4.38e8, 8 GPUs
+        # 4.45e8 against 6.58e8 -- the copy-out of the whole area by every
+        # rank and the flag wait in Python cost more than the PCIe traffic
+        # they save on those boxes (32 host cores for 8 ranks).
+        return torch.device(device).type == 'cuda' and \
+            os.environ.get('PB200_HOST_GATHER', '0') == '1' and \
+            type(self)._local_scores is ShardedEvaluator._local_scores
+
+    def _evaluate_host_gather(self, hg, xs, lo, hi, per, n):
+        """H2D of this rank's rows, ONE fused launch, D2H of its block of
+        scores into the shared result area; then the flags, and the whole area
+        is copied out into a fresh array (the library's copy threads)."""
+        lane = self._local._setup()[0]
+        lib = self._local._lib
+        epoch = hg.next_epoch()
+        area = hg.area(epoch)
+        if hi > lo:
+            lane.launch(lib, xs[lo:hi], area + lo * 8, None, 1 << 62)
+            lane.wait()
+        hg.publish(epoch)
+        hg.wait(epoch)
+        # (a block of torch's caching host allocator: mapped and touched already,
+        # where a fresh 4 MB ndarray would fault its pages in during the copy)
+        from ._evaluation import pinned_result
+        scores = pinned_result(n)
+        _lib.check(lib.pb200_host_copy(ctypes.c_void_p(scores.ctypes.data),
+                                       ctypes.c_void_p(area), n * 8, 0))
+        return scores
 
     def _evaluate_fused(self, ex, xs, lo, hi, per, n):
         """H2D of this rank's rows, evaluation kernel with the exchange fused

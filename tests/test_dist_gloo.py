@@ -129,3 +129,60 @@ def test_score_exchange_falls_back_to_all_gather_on_cpu():
         p.join(120)
         assert p.exitcode == 0
     assert list(out) == [1] * world
+
+
+def _host_gather_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import time
+        from pints_b200._dist import HostGather, shard_bounds
+
+        n = 11
+        hg = HostGather(16, None, None, timeout=2.0)
+        ok = hg.ok and not hg.pinned and hg.capacity == 16
+        for gen in range(7):                   # more calls than result areas
+            lo, hi, per = shard_bounds(n, world, rank)
+            epoch = hg.next_epoch()
+            slot = epoch % HostGather.SLOTS
+            if rank == 1:
+                time.sleep(0.02)               # the other rank has to wait
+            hg.data[slot, lo:hi] = np.arange(lo, hi) + 100.0 * gen
+            ok = ok and hg.area(epoch) == hg.data[slot].ctypes.data
+            hg.publish(epoch)
+            hg.wait(epoch)
+            ok = ok and np.array_equal(hg.data[slot, :n], np.arange(n) + 100.0 * gen)
+        # a rank that never delivers: the other one gives up with an error
+        # naming it instead of hanging
+        dist.barrier()
+        epoch = hg.next_epoch()
+        if rank == 0:
+            hg.publish(epoch)
+            try:
+                hg.wait(epoch)
+                ok = False
+            except RuntimeError as e:
+                ok = ok and 'ranks [1]' in str(e)
+        dist.barrier()
+        hg.close()
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_gather_world_size_2():
+    """The host-side all-gather of ShardedEvaluator (ranks of one node): one
+    shared segment, result areas used in turn, epoch flags, time-out."""
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + 977
+    out = mp.get_context('spawn').Array('i', [0, 0])
+    procs = [mp.get_context('spawn').Process(
+        target=_host_gather_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1, 1]
