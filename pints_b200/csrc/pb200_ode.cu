@@ -2337,13 +2337,19 @@ static bool dense_enabled() {
     }();
     return on != 0;
 }
-static double mig_alpha() {
-    static const double a = [] {
+// Hand-over point of the extra workers as a fraction of the observations, by
+// the number of warps a scheduler carries without them: 0.55 for three or
+// four, 0.60 for two, 0.65 for one (swept at populations 65 536 / 58 000,
+// 47 000 / 43 000 and 24 000 / 20 000: profiles/r02ap_migrate_at*.log; the
+// differences are below 1 %).  PB200_MIGRATE_AT overrides.
+static double mig_alpha(int warps_per_scheduler) {
+    static const double forced = [] {
         const char *e = getenv("PB200_MIGRATE_AT");
         const double v = e ? atof(e) : 0.0;
-        return (v > 0.0 && v < 1.0) ? v : 0.55;
+        return (v > 0.0 && v < 1.0) ? v : 0.0;
     }();
-    return a;
+    if (forced > 0.0) return forced;
+    return warps_per_scheduler >= 3 ? 0.55 : warps_per_scheduler == 2 ? 0.60 : 0.65;
 }
 
 // series rows + the +inf sentinel rows, in whole 16-byte units
@@ -2435,7 +2441,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
             mig.q4 = static_cast<int32_t>(per_sm - r);
             mig.r = r;
             const int64_t row = (1 + M::NO) * 8;
-            int64_t mid = static_cast<int64_t>(mig_alpha() * p->dev.n_times);
+            int64_t mid = static_cast<int64_t>(mig_alpha(mig.q4 / 4) * p->dev.n_times);
             mid = mid < 1 ? 1 : mid;
             mig.off_mid = static_cast<uint32_t>(mid * row);
             mig.buf_off = static_cast<uint32_t>(bytes);
