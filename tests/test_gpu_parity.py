@@ -417,16 +417,40 @@ def test_block_local_sort_and_its_hint(pb):
             got = dp_s.eval(d_x).cpu().numpy()
             torch.cuda.synchronize()
             assert np.array_equal(got, want, equal_nan=True), n
+    # the models with the generic cost key (and the wide interpolation loop)
+    for name, model in (('lotka_volterra', pb.toy.LotkaVolterraModel()),
+                        ('sir', pb.toy.SIRModel())):
+        g = load_golden(name)
+        f = pb.GaussianLogLikelihood(pb.MultiOutputProblem(model, g['times'], g['values']))
+        centre = g['xs'][0]
+        for spread in (0.01, 0.2):              # narrow keys, wide keys
+            xs = centre * (1 + spread * rng.uniform(-1, 1, (30000, len(centre))))
+            if name == 'sir':
+                xs[:, 2] = np.round(xs[:, 2])
+            d_x = torch.from_numpy(np.ascontiguousarray(xs)).cuda()
+            dp_s = pb.CudaEvaluator(f, sort=True).device_problem()
+            want = pb.CudaEvaluator(f, sort=False).device_problem().eval(d_x).cpu().numpy()
+            hints = []
+            for _ in range(3):
+                got = dp_s.eval(d_x).cpu().numpy()
+                torch.cuda.synchronize()
+                hints.append(dp_s.sort_hint())
+                assert np.array_equal(got, want, equal_nan=True), (name, spread)
+            assert hints[-1] in (1, 2), hints
     # a wide population in between flips the hint back and forth
     dp_s = pb.CudaEvaluator(ll, sort=True).device_problem()
     dp_u = pb.CudaEvaluator(ll, sort=False).device_problem()
+    seen = []
     for xs in (narrow[:65536], narrow[:65536], wide, wide, narrow[:65536], narrow[:65536]):
         xs = xs.copy()
         xs[123, 2] = -1.0                          # NaN key
         d_x = torch.from_numpy(np.ascontiguousarray(xs)).cuda()
         got = dp_s.eval(d_x).cpu().numpy()
         torch.cuda.synchronize()
+        seen.append(dp_s.sort_hint())
         assert np.array_equal(got, dp_u.eval(d_x).cpu().numpy(), equal_nan=True)
+    # what each launch saw: 1 = narrow keys, 2 = wide keys
+    assert seen == [1, 1, 2, 2, 1, 1], seen
 
 
 def test_mean_squared_and_root_mean_squared_errors(pb):
