@@ -691,9 +691,9 @@ def run_ours(args):
             'parity': parity,
             # per step and rank: the fused ODE kernel (+ the reading side of
             # the exchange), and the counting-sort kernel in front of it unless
-            # the population's cost keys were narrow (sort inside the kernel)
+            # the previous launch found the population's costs close together (sort inside the kernel)
             'gpu_launches': K * world * ((1 if world == 1 else 2) + (0 if sort_in_kernel else 1)),
-            'cost_sort': ('inside the evaluation kernel, block by block (narrow cost keys)'
+            'cost_sort': ('inside the evaluation kernel, block by block (costs of the population close together)'
                           if sort_in_kernel else 'sort kernel in front of the evaluation kernel'),
             'clocks': clocks,
             'wall_s_timed_region': wall,

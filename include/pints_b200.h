@@ -205,8 +205,9 @@ int pb200_eval(const pb200_problem *p, const double *d_params, int64_t n,
  * Launches with one block per SM (the single-wave populations of the
  * migrating and dense layouts) can also sort inside the evaluation kernel,
  * block by block in shared memory, which saves the sort kernel's launch; that
- * pays when the costs of a population differ by a few per cent only, so both
- * sorts leave the spread of the keys they saw in a word of the problem and the
+ * pays when the costs of a population differ by a few per cent only, so every
+ * such launch leaves what it measured (the spread of its vectors' attempted
+ * steps, weighted with the kernel's duration) in a word of the problem and the
  * next launch chooses by it.  pb200_problem_sort_hint reads that word:
  * 0 = nothing seen yet, 1 = narrow (next one-block-per-SM launch sorts in the
  * kernel), 2 = wide (sort kernel).  Environment PB200_LOCAL_SORT=0 / 1 forces

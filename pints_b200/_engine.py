@@ -158,7 +158,7 @@ class DeviceProblem(object):
 
     def sort_hint(self):
         """What the last sorted launch saw (``pb200_problem_sort_hint``): 0
-        nothing yet, 1 narrow cost keys (the next one-block-per-SM launch sorts
+        nothing yet, 1 costs close together (the next one-block-per-SM launch sorts
         inside the evaluation kernel), 2 wide (sort kernel)."""
         return int(self._lib.pb200_problem_sort_hint(self._handle))
 

@@ -67,8 +67,8 @@ struct pb200_problem {
     int32_t n_model_consts;
     int64_t series_bytes;         // bytes staged into shared memory
     // One word of page-locked, device-mapped host memory (allocated at the first
-    // sorted launch): the kernels that see the cost keys of a population leave
-    // 1 = narrow, 2 = wide here, and the NEXT launch picks its sort by it
+    // sorted launch): a one-block-per-SM launch leaves 1 = costs narrow, 2 = wide
+    // here (from its vectors' attempted steps), and the NEXT launch picks its sort by it
     // (launch_model in pb200_ode.cu); no synchronisation, a stale value only
     // costs a per cent or two of speed, never a result.
     mutable int32_t *sort_hint = nullptr;

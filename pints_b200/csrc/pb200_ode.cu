@@ -872,15 +872,20 @@ struct LocalSortDev {
     int32_t *hint;                 // pb200_problem::sort_hint (or nullptr)
 };
 
-// The spread of a population's cost keys, from the keys at 10 % and 90 % of
-// their order: narrow (1) when (k90 - k10) / (k90 + k10) < 0.1, else wide (2).
-// Measured on FitzHugh-Nagumo (key = c, population 65 536, profiles/
-// r02ac_local_sort.log): Gaussian populations of relative width 2 / 5 / 10 /
-// 20 % have ratios 0.026 / 0.064 / 0.13 / 0.26 and the block-local sort is
-// 9 us faster / 6 us faster / even / 14 us slower than sort_kernel.
-__device__ __forceinline__ int32_t spread_hint(float k10, float k90) {
-    return (k90 - k10) < 0.1f * (k90 + k10) ? 1 : 2;
-}
+// Which sort pays is decided from what the previous launch measured (block 0 of
+// every one-block-per-SM launch, at its end): the block-local sort costs about
+// 1.2 x (relative mean absolute deviation of the attempted steps) x (kernel
+// time) in lock-step waste and SM imbalance, the sort kernel 13.7 us in front
+// of the solve.  Fitted on FitzHugh-Nagumo populations of relative width 2 /
+// 5 / 10 / 20 % (deviation 0.8 / 1.6 / 3.0 / 6.8 % of 385 steps; local sort
+// 9 us faster / 6 us faster / even / 14 us slower at 0.37-0.40 ms), and it
+// predicts the other models: Lotka-Volterra and SIR populations of width 5 %
+// (3.7 / 4.4 % of their steps, but kernels of 0.21 / 0.17 ms) run 3.5 % faster
+// with the block-local sort (profiles/r02ac_local_sort.log, r02aq_*).  In SM
+// cycles: local while deviation x elapsed cycles < PB200_LOCAL_SORT_CYCLES.
+#ifndef PB200_LOCAL_SORT_CYCLES
+#define PB200_LOCAL_SORT_CYCLES 22000.0f
+#endif
 constexpr int LOCAL_SORT_MAX = 768;          // vectors per block (the largest block shape)
 constexpr int LOCAL_SORT_WORDS = SORT_BINS + LOCAL_SORT_MAX + 64;
 
@@ -903,8 +908,7 @@ __device__ __forceinline__ int64_t local_row(int t, int per_block) {
 template <class M>
 __device__ __forceinline__ int local_cost_sort(const ProblemDev &P, const ModelConsts &mc,
                                                const double *__restrict__ params,
-                                               int m, int m_full, int64_t ld, uint32_t *sh, int j,
-                                               int32_t *hint) {
+                                               int m, int m_full, int64_t ld, uint32_t *sh, int j) {
     uint32_t *hist = sh, *sorted = sh + SORT_BINS, *red = sh + SORT_BINS + LOCAL_SORT_MAX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = (blockDim.x + 31) >> 5;
@@ -974,12 +978,6 @@ __device__ __forceinline__ int local_cost_sort(const ProblemDev &P, const ModelC
     const uint32_t pos = hist[bin] + rank;
     if (have) sorted[pos] = static_cast<uint32_t>(t);
     __syncthreads();
-    if (hint != nullptr && blockIdx.x == 0) {          // uniform
-        if (have && pos == static_cast<uint32_t>(m / 10)) red[0] = __float_as_uint(key);
-        if (have && pos == static_cast<uint32_t>(m - 1 - m / 10)) red[1] = __float_as_uint(key);
-        __syncthreads();
-        if (t == 0) *hint = spread_hint(__uint_as_float(red[0]), __uint_as_float(red[1]));
-    }
     return static_cast<int>(sorted[min(j, m - 1)]);
 }
 
@@ -998,9 +996,17 @@ ode_kernel(const __grid_constant__ ProblemDev P,
     constexpr uint32_t ROWB = (1 + NO) * 8;          // bytes per series row
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr int U = PB200_PIPE_U;
-    constexpr bool LSORT = (MIG || DENSE != 0) && !TRAJ;     // instances that can sort in the block
+    constexpr bool LSORT = (MIG || DENSE != 0) && !TRAJ;     // one-block-per-SM scoring instances
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ long long hint_t0;                 // LSORT: clock at the start (block 0)
+    __shared__ float hint_sum[3];                 // LSORT: attempts, vectors, |deviations|
+    if constexpr (LSORT) {
+        if (threadIdx.x == 0) {
+            hint_t0 = clock64();
+            hint_sum[0] = hint_sum[1] = hint_sum[2] = 0.0f;
+        }
+    }
     // role of this warp in the migrating layout
     enum { WORKER = 0, SOURCE = 1, RECEIVER = 2 };
     int role = WORKER, mig_j = 0;
@@ -1059,7 +1065,7 @@ ode_kernel(const __grid_constant__ ProblemDev P,
 #endif
             li = local_cost_sort<M>(P, mc, params, m, l_full, ld,
                                     reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(smem) + ls.scratch_off),
-                                    lj, ls.hint);
+                                    lj);
             // position in the launch order: 32 consecutive ones per warp (put_score)
 #if PB200_LSORT_STRIDED == 2
             gi = lj < m ? local_row(lj, l_full) : n;
@@ -1468,6 +1474,34 @@ ode_kernel(const __grid_constant__ ProblemDev P,
         row[0] = tl_start; row[1] = clock64(); row[2] = smid; row[3] = role * 1000000 + attempts;
     }
 #endif
+    // what the next launch's choice of cost sort goes by (see PB200_LOCAL_SORT_CYCLES):
+    // block 0 leaves the spread of its vectors' attempted steps, weighted with the
+    // kernel's duration, in the problem's hint word
+    if constexpr (LSORT) {
+        if (ls.hint != nullptr && blockIdx.x == 0) {        // uniform
+            const bool counted = !is_source && live && !idle && !failed;
+            const float a = counted ? static_cast<float>(attempts) : 0.0f;
+            float sa = a, sc_ = counted ? 1.0f : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sa += __shfl_xor_sync(FULL, sa, o);
+                sc_ += __shfl_xor_sync(FULL, sc_, o);
+            }
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&hint_sum[0], sa); atomicAdd(&hint_sum[1], sc_); }
+            __syncthreads();
+            const float cnt = fmaxf(hint_sum[1], 1.0f), mean = hint_sum[0] / cnt;
+            float dv = counted ? fabsf(a - mean) : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dv += __shfl_xor_sync(FULL, dv, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&hint_sum[2], dv);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const float rel = hint_sum[2] / (cnt * fmaxf(mean, 1.0f));
+                const float cycles = static_cast<float>(clock64() - hint_t0);
+                *ls.hint = rel * cycles < PB200_LOCAL_SORT_CYCLES ? 1 : 2;
+            }
+        }
+    }
     // multi-GPU launches: the last block to get here raises this rank's flags
     if (!TRAJ) exchange_signal(sc);
 }
@@ -2106,9 +2140,8 @@ sort_kernel(const __grid_constant__ ProblemDev P,
             const __grid_constant__ ModelConsts mc,
             const double *__restrict__ params, int64_t n, int64_t ld,
             float *__restrict__ keys, SortHeader *__restrict__ hdr,
-            int32_t *__restrict__ perm, int32_t *hint) {
+            int32_t *__restrict__ perm) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ uint32_t sh_q[2];              // C: bins of the 10 % and 90 % quantiles
     __shared__ uint32_t sh_a[SORT_BINS];      // B: histogram      C: scan of the histogram
     __shared__ uint32_t sh_b[SORT_BINS];      // C: this block's count per bin, then its start
     __shared__ uint32_t sh_w[2 * SORT_THREADS / 32];
@@ -2198,22 +2231,8 @@ sort_kernel(const __grid_constant__ ProblemDev P,
     __syncthreads();
     uint32_t before = inc - run;
     for (int w = 0; w < warp; ++w) before += sh_w[w];
-    const uint32_t r10 = static_cast<uint32_t>(n / 10), r90 = static_cast<uint32_t>(n - 1 - n / 10);
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        sh_a[threadIdx.x * PER + k] = before;
-        if (before <= r10 && r10 < before + v[k]) sh_q[0] = threadIdx.x * PER + k;
-        if (before <= r90 && r90 < before + v[k]) sh_q[1] = threadIdx.x * PER + k;
-        before += v[k];
-    }
-    // what the population's keys look like, for the next launch (see spread_hint)
-    if (hint != nullptr && blockIdx.x == 0) {          // uniform
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const float w = scale > 0.0f ? 1.0f / scale : 0.0f;
-            *hint = spread_hint(kmin + (sh_q[0] + 0.5f) * w, kmin + (sh_q[1] + 0.5f) * w);
-        }
-    }
+    for (int k = 0; k < PER; ++k) { sh_a[threadIdx.x * PER + k] = before; before += v[k]; }
     // ranks inside this block (one round of the grid-stride loop at a time)
     for (int64_t base_i = static_cast<int64_t>(blockIdx.x) * blockDim.x; base_i < n; base_i += stride) {
         const int64_t i = base_i + threadIdx.x;
@@ -2237,8 +2256,7 @@ sort_kernel(const __grid_constant__ ProblemDev P,
 // returns the device pointer to it through *perm.
 template <class M>
 int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
-                      int64_t ld, void *ws, const int32_t **perm, cudaStream_t st,
-                      int32_t *hint = nullptr) {
+                      int64_t ld, void *ws, const int32_t **perm, cudaStream_t st) {
     SortHeader *hdr = static_cast<SortHeader *>(ws);
     float *keys = reinterpret_cast<float *>(hdr + 1);
     int32_t *out = reinterpret_cast<int32_t *>(keys + n);
@@ -2262,7 +2280,7 @@ int build_permutation(const pb200_problem *p, const double *d_params, int64_t n,
     if (grid > cap) grid = cap;
     if (grid > SORT_MAX_BLOCKS) grid = SORT_MAX_BLOCKS;
     void *args[] = {const_cast<ProblemDev *>(&p->dev), const_cast<ModelConsts *>(&p->mc),
-                    &d_params, &n, &ld, &keys, &hdr, &out, &hint};
+                    &d_params, &n, &ld, &keys, &hdr, &out};
     int rc = pb200_check_cuda(
         cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sort_kernel<M>),
                                     dim3(static_cast<unsigned>(grid)), dim3(SORT_THREADS),
@@ -2471,7 +2489,7 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
         sort_dyn = static_cast<size_t>(LOCAL_SORT_WORDS) * 4 + 16;
     }
     if (sort_ws && !ls.on) {
-        int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st, ls.hint);
+        int rc = build_permutation<M>(p, d_params, n, ld, sort_ws, &perm, st);
         if (rc) return rc;
     }
 #define PB200_XARG , mig, sc, ls

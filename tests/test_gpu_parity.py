@@ -395,8 +395,9 @@ def test_cost_sorted_scheduling_changes_nothing(pb):
 
 def test_block_local_sort_and_its_hint(pb):
     """One-block-per-SM launches sort inside the kernel, block by block, when
-    the previous population's cost keys were narrow, and with sort_kernel when
-    they were wide (pb200_problem::sort_hint); whichever runs, scores and step
+    the previous launch found its vectors' costs (attempted steps) close
+    together, and with sort_kernel when they were far apart
+    (pb200_problem::sort_hint); whichever runs, scores and step
     counts are per vector, bit for bit those of the unsorted launch.  Sizes:
     migrating layout (65 536, 20 000: 14 and 5 warps per SM), dense classes
     (80 000, 100 000), a ragged last run of rows."""
@@ -423,7 +424,7 @@ def test_block_local_sort_and_its_hint(pb):
         g = load_golden(name)
         f = pb.GaussianLogLikelihood(pb.MultiOutputProblem(model, g['times'], g['values']))
         centre = g['xs'][0]
-        for spread in (0.01, 0.2):              # narrow keys, wide keys
+        for spread in (0.01, 0.2):              # costs close together, far apart
             xs = centre * (1 + spread * rng.uniform(-1, 1, (30000, len(centre))))
             if name == 'sir':
                 xs[:, 2] = np.round(xs[:, 2])
@@ -449,7 +450,7 @@ def test_block_local_sort_and_its_hint(pb):
         torch.cuda.synchronize()
         seen.append(dp_s.sort_hint())
         assert np.array_equal(got, dp_u.eval(d_x).cpu().numpy(), equal_nan=True)
-    # what each launch saw: 1 = narrow keys, 2 = wide keys
+    # what each launch measured: 1 = costs close together, 2 = far apart
     assert seen == [1, 1, 2, 2, 1, 1], seen
 
 

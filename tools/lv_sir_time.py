@@ -25,5 +25,5 @@ for name, ll, x in problems():
         e0.record()
         for _ in range(50): dp.eval(d, out=out)
         e1.record(); e1.synchronize()
-        out_line.append('%s N=%d %.1f us' % (name, n, e0.elapsed_time(e1) / 50 * 1e3))
+        out_line.append('%s N=%d %.1f us (sort hint %d)' % (name, n, e0.elapsed_time(e1) / 50 * 1e3, dp.sort_hint()))
 print('; '.join(out_line))
