@@ -2445,9 +2445,10 @@ int launch_model(const pb200_problem *p, const double *d_params, int64_t n,
         // Which cost sort (if any).  The block-local sort (local_cost_sort) is
         // 6-9 us faster on populations whose costs differ by a few per cent
         // (an optimiser's or sampler's population), the global order of
-        // sort_kernel is up to 14 us faster on wide ones; both leave the spread
-        // of the keys they saw in the problem's hint word and the next launch
-        // goes by it (the first one takes the global sort).
+        // sort_kernel is up to 14 us faster on wide ones; every one-block-per-SM
+        // launch leaves what it measured in the problem's hint word (see
+        // PB200_LOCAL_SORT_CYCLES) and the next launch goes by it (the first one
+        // takes the global sort).
         const bool single_wave = per_sm >= 5 && (per_sm <= 16 || dense);
         if (sort_ws && single_wave && local_sort_mode() != 0) {
             ls.hint = sort_hint_of(p, st);
